@@ -1,0 +1,793 @@
+// C-ABI of libdebvader_b200: context, weights, layer plans and the network entry points.
+// See include/debvader_b200.h for the contract and the reference citations.
+#include "kernels.h"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cmath>
+
+namespace dbv {
+
+std::atomic<long long> g_launches{0};
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+enum LayerKind { L_CONV = 0, L_CONVT = 1, L_DENSE = 2 };
+
+// static description of one GEMM-shaped layer of the DC2 network
+struct LayerDesc {
+  const char* name;
+  int kind, stride;
+  int Hin, Cin, Hout, Cout;  // square images
+  int enc;                   // 1: encoder model (layer_with_weights-0), 0: decoder model
+  int wn, an, a2n;           // checkpoint indices of kernel/bias, alpha, second alpha (-1: none)
+  int relu_head;             // decoder head
+};
+
+static const LayerDesc kLayers[] = {
+    {"enc_conv1", L_CONV, 1, 59, 6, 59, 32, 1, 1, 2, -1, 0},
+    {"enc_conv2", L_CONV, 2, 59, 32, 30, 32, 1, 3, 4, -1, 0},
+    {"enc_conv3", L_CONV, 1, 30, 32, 30, 64, 1, 5, 6, -1, 0},
+    {"enc_conv4", L_CONV, 2, 30, 64, 15, 64, 1, 7, 8, -1, 0},
+    {"enc_conv5", L_CONV, 1, 15, 64, 15, 128, 1, 9, 10, -1, 0},
+    {"enc_conv6", L_CONV, 2, 15, 128, 8, 128, 1, 11, 12, -1, 0},
+    {"enc_conv7", L_CONV, 1, 8, 128, 8, 256, 1, 13, 14, -1, 0},
+    {"enc_conv8", L_CONV, 2, 8, 256, 4, 256, 1, 15, 16, 17, 0},  // + Flatten PReLU (alpha2)
+    {"enc_dense", L_DENSE, 1, 1, 4096, 1, 560, 1, 18, -1, -1, 0},
+    {"dec_dense1", L_DENSE, 1, 1, 32, 1, 560, 0, 1, 2, -1, 0},
+    {"dec_dense2", L_DENSE, 1, 1, 560, 1, 4096, 0, 3, 4, -1, 0},
+    {"dec_convT1", L_CONVT, 2, 4, 256, 8, 256, 0, 5, 6, -1, 0},
+    {"dec_convT2", L_CONVT, 1, 8, 256, 8, 256, 0, 7, 8, -1, 0},
+    {"dec_convT3", L_CONVT, 2, 8, 256, 16, 128, 0, 9, 10, -1, 0},
+    {"dec_convT4", L_CONVT, 1, 16, 128, 16, 128, 0, 11, 12, -1, 0},
+    {"dec_convT5", L_CONVT, 2, 16, 128, 32, 64, 0, 13, 14, -1, 0},
+    {"dec_convT6", L_CONVT, 1, 32, 64, 32, 64, 0, 15, 16, -1, 0},
+    {"dec_convT7", L_CONVT, 2, 32, 64, 64, 32, 0, 17, 18, -1, 0},
+    {"dec_convT8", L_CONVT, 1, 64, 32, 64, 32, 0, 19, 20, -1, 0},
+    {"dec_head", L_CONV, 1, 64, 32, 64, 12, 0, 21, -1, -1, 1},
+};
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_HEAD = 19 };
+
+static std::string wkey(int enc, int n, const char* nm) {
+  char buf[128];
+  snprintf(buf, sizeof buf, "layer_with_weights-%d/layer_with_weights-%d/%s", enc ? 0 : 1, n, nm);
+  return buf;
+}
+
+static int same_pad_before(int n, int k, int s) {
+  const int out = (n + s - 1) / s;
+  const int total = std::max((out - 1) * s + k - n, 0);
+  return total / 2;
+}
+
+// tensor-core configuration of a layer
+struct TcGeom {
+  int CBK, NT, TW, TH, TB;
+  int tc;  // 0: runs on the SIMT kernel even in tensor-core modes
+};
+static const TcGeom kTc[kNumLayers] = {
+    {0, 0, 0, 0, 0, 0},      // enc_conv1 (Cin=6): SIMT, BN fused
+    {32, 32, 30, 4, 1, 1},   // enc_conv2
+    {32, 64, 30, 4, 1, 1},   // enc_conv3
+    {64, 64, 15, 8, 1, 1},   // enc_conv4
+    {64, 128, 15, 8, 1, 1},  // enc_conv5
+    {64, 128, 8, 8, 2, 1},   // enc_conv6
+    {64, 256, 8, 8, 2, 1},   // enc_conv7
+    {64, 256, 4, 4, 8, 1},   // enc_conv8
+    {64, 112, 1, 1, 128, 1}, // enc_dense
+    {0, 0, 0, 0, 0, 0},      // dec_dense1 (K=32): SIMT
+    {64, 256, 1, 1, 128, 1}, // dec_dense2
+    {64, 256, 4, 4, 8, 1},   // dec_convT1 (class space 4x4)
+    {64, 256, 8, 8, 2, 1},   // dec_convT2
+    {64, 128, 8, 8, 2, 1},   // dec_convT3 (class space 8x8)
+    {64, 128, 16, 8, 1, 1},  // dec_convT4
+    {64, 64, 16, 8, 1, 1},   // dec_convT5 (class space 16x16)
+    {64, 64, 32, 4, 1, 1},   // dec_convT6
+    {64, 32, 32, 4, 1, 1},   // dec_convT7 (class space 32x32)
+    {32, 32, 64, 2, 1, 1},   // dec_convT8
+    {32, 16, 64, 2, 1, 1},   // dec_head
+};
+
+struct LayerRt {
+  // device weights
+  float* w_gather = nullptr;       // SIMT gather form [taps][Cin][CoutP]
+  __nv_bfloat16* w_packed = nullptr;  // tcgen05 packed blocks [nblk][Ntot][CBK]
+  float* bias = nullptr;
+  float* alpha = nullptr;
+  float* alpha2 = nullptr;
+  int CoutP = 0;
+  // output activation buffer
+  void* out = nullptr;
+  size_t out_bytes_per_stamp = 0;
+  OutSpec ospec{};
+  // tcgen05 plan
+  TcLayer tc{};
+  bool has_tc = false;
+};
+
+}  // namespace dbv
+
+using namespace dbv;
+
+struct dbv_ctx {
+  int device = 0;
+  int precision = DBV_PREC_FP32;
+  long long chunk = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host_w;
+  LayerRt rt[kNumLayers];
+  float* bn_scale = nullptr;
+  float* bn_shift = nullptr;
+  float* dec_alpha0 = nullptr;
+  // per-chunk scratch
+  float* params = nullptr;  // [chunk][560]
+  float* z = nullptr;       // [chunk][32]
+  float* zp = nullptr;      // [chunk][32]
+  std::vector<void*> allocs;
+  long long launches = 0;
+  // host-buffer pipeline
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  void* stage_in[2] = {nullptr, nullptr};   // raw host dtype
+  float* stage_x[2] = {nullptr, nullptr};
+  float* stage_mean[2] = {nullptr, nullptr};
+  float* stage_std[2] = {nullptr, nullptr};
+  float* stage_z[2] = {nullptr, nullptr};
+  float* stage_eps[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  bool pipe_ready = false;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  int prof_n = 0;
+};
+
+namespace dbv {
+
+static int dev_alloc(dbv_ctx* c, void** p, size_t bytes, bool zero) {
+  DBV_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  c->allocs.push_back(*p);
+  if (zero) DBV_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return DBV_OK;
+}
+template <typename T>
+static int upload(dbv_ctx* c, T** dst, const std::vector<T>& v) {
+  int r = dev_alloc(c, (void**)dst, v.size() * sizeof(T), false);
+  if (r) return r;
+  DBV_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return DBV_OK;
+}
+
+static const HostTensor* find_w(dbv_ctx* c, const std::string& k) {
+  auto it = c->host_w.find(k);
+  return it == c->host_w.end() ? nullptr : &it->second;
+}
+
+static int check_shape(dbv_ctx* c, const std::string& k, std::initializer_list<int64_t> want, const HostTensor** out) {
+  const HostTensor* t = find_w(c, k);
+  if (!t) return fail(DBV_ERR_INVALID, "missing weight tensor '%s'", k.c_str());
+  if (t->shape.size() != want.size() || !std::equal(want.begin(), want.end(), t->shape.begin())) {
+    std::string got, exp;
+    for (auto d : t->shape) got += std::to_string(d) + ",";
+    for (auto d : want) exp += std::to_string(d) + ",";
+    return fail(DBV_ERR_UNSUPPORTED, "weight '%s' has shape [%s], the DC2 architecture needs [%s]", k.c_str(), got.c_str(),
+                exp.c_str());
+  }
+  *out = t;
+  return DBV_OK;
+}
+
+// W(ky,kx,ci,co) accessor in *gather form* for a layer: value multiplying in[.., ci] for output co at tap (ky,kx)
+// of the checkpoint tensor.  Conv2D kernels are HWIO, Conv2DTranspose kernels are HWOI, Dense is IO.
+static inline float w_at(const LayerDesc& L, const HostTensor& W, int ky, int kx, int ci, int co) {
+  if (L.kind == L_CONV) return W.data[(((size_t)ky * 3 + kx) * L.Cin + ci) * L.Cout + co];
+  if (L.kind == L_CONVT) return W.data[(((size_t)ky * 3 + kx) * L.Cout + co) * L.Cin + ci];
+  return W.data[(size_t)ci * L.Cout + co];
+}
+
+// tap table of a layer in gather form.  For each tap: which checkpoint (ky,kx) it uses and where its
+// input pixel sits relative to the output pixel (tile space), plus parity plane for stride-2 Conv2D
+// and output class for stride-2 Conv2DTranspose.
+struct Tap {
+  int ky, kx, dy, dx, plane, cls;
+};
+static std::vector<Tap> make_taps(const LayerDesc& L) {
+  std::vector<Tap> t;
+  if (L.kind == L_DENSE) {
+    t.push_back({0, 0, 0, 0, 0, 0});
+    return t;
+  }
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      Tap a{ky, kx, 0, 0, 0, 0};
+      if (L.kind == L_CONV && L.stride == 1) {
+        a.dy = ky - 1;
+        a.dx = kx - 1;
+      } else if (L.kind == L_CONV) {  // stride 2: input row 2y + ky - pb lives in parity plane (ky-pb)&1 at row y + ((ky-pb)>>1)
+        const int pb = same_pad_before(L.Hin, 3, 2);
+        const int ry = ky - pb, rx = kx - pb;
+        a.plane = (ry & 1) * 2 + (rx & 1);
+        a.dy = ry >> 1;  // arithmetic shift: floor
+        a.dx = rx >> 1;
+      } else if (L.stride == 1) {  // Conv2DTranspose s1, pb=1: in row = y - ky + 1
+        a.dy = 1 - ky;
+        a.dx = 1 - kx;
+      } else {  // Conv2DTranspose s2, pb=0: y = 2i + ky -> class py = ky&1, in row i - (ky-py)/2
+        const int py = ky & 1, px = kx & 1;
+        a.cls = py * 2 + px;
+        a.dy = -((ky - py) / 2);
+        a.dx = -((kx - px) / 2);
+      }
+      t.push_back(a);
+    }
+  return t;
+}
+
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// describe how layer li's OUTPUT is stored in the tensor-core modes
+static void tc_out_layout(int li, int planes, OutSpec* o) {
+  const LayerDesc& L = kLayers[li];
+  o->planes = planes;
+  o->OH = L.Hout;
+  o->OW = L.Hout;
+  o->Cout = L.Cout;
+  o->Cpad = L.Cout;
+  o->PH = o->PW = 0;
+  o->mode = OUT_BF16_NHWC;
+  const bool next_is_s2_conv = (li + 1 < kNumLayers) && kLayers[li + 1].kind == L_CONV && kLayers[li + 1].stride == 2;
+  if (next_is_s2_conv) {
+    o->mode = OUT_BF16_PARITY;
+    o->PH = o->PW = (L.Hout + 1) / 2;
+  }
+  if (li == I_ENC_DENSE) { o->mode = OUT_F32_NHWC; o->planes = 1; }
+  if (li == I_DENSE1) o->Cpad = 576;                    // K of dec_dense2 padded to 9 x 64
+  if (li == I_DENSE2) { o->OH = o->OW = 4; o->Cout = o->Cpad = 256; }  // Reshape(4,4,256), model/model.py:119
+  if (li == I_HEAD) { o->mode = OUT_HEAD; o->planes = 1; }
+}
+
+static size_t out_elems_per_stamp(const OutSpec& o) {
+  if (o.mode == OUT_HEAD) return 0;
+  if (o.mode == OUT_BF16_PARITY) return (size_t)4 * o.PH * o.PW * o.planes * o.Cpad;
+  return (size_t)o.OH * o.OW * o.planes * o.Cpad;
+}
+
+static int build_tc_layer(dbv_ctx* c, int li) {
+  const LayerDesc& L = kLayers[li];
+  const TcGeom& G = kTc[li];
+  LayerRt& R = c->rt[li];
+  const bool x3 = c->precision == DBV_PREC_BF16X3;
+  const HostTensor* W = find_w(c, wkey(L.enc, L.wn, "kernel"));
+  // ---- input tensor (previous layer's output buffer) -------------------------------------------
+  const LayerRt& P = c->rt[li - 1];
+  const OutSpec& in = P.ospec;
+  const int in_cpad = in.Cpad, in_planes = in.planes;
+  // enc_dense reads conv8's (4,4,256) map: 16 "taps" at pixel offsets; everything else via make_taps
+  std::vector<Tap> taps;
+  if (li == I_ENC_DENSE) {
+    for (int p = 0; p < 16; ++p) taps.push_back({p, 0, p / 4, p % 4, 0, 0});
+  } else {
+    taps = make_taps(L);
+  }
+  const int cin_tap = (li == I_ENC_DENSE) ? 256 : L.Cin;  // channels per tap in the input tensor
+  const int nchunk = (cin_tap + G.CBK - 1) / G.CBK;
+  const int Ntot = ((L.Cout + G.NT - 1) / G.NT) * G.NT;
+  const int parts_w = x3 ? 2 : 1;
+  // ---- pack weights: block (tap, chunk, part) = [Ntot][CBK] bf16, K contiguous ------------------
+  const size_t blk_elems = (size_t)Ntot * G.CBK;
+  const size_t nblk = taps.size() * nchunk * parts_w;
+  std::vector<uint16_t> packed(nblk * blk_elems, 0);
+  for (size_t ti = 0; ti < taps.size(); ++ti)
+    for (int ch = 0; ch < nchunk; ++ch)
+      for (int n = 0; n < L.Cout; ++n)
+        for (int k = 0; k < G.CBK; ++k) {
+          const int ci = ch * G.CBK + k;
+          if (ci >= cin_tap) continue;
+          float w;
+          if (li == I_ENC_DENSE) w = W->data[((size_t)taps[ti].ky * 256 + ci) * L.Cout + n];  // flat (h,w,c) index
+          else w = w_at(L, *W, taps[ti].ky, taps[ti].kx, ci, n);
+          const uint16_t hi = f2bf(w);
+          const size_t b0 = ((ti * nchunk + ch) * parts_w) * blk_elems + (size_t)n * G.CBK + k;
+          packed[b0] = hi;
+          if (x3) packed[b0 + blk_elems] = f2bf(w - bf2f(hi));
+        }
+  {
+    std::vector<__nv_bfloat16> tmp(packed.size());
+    memcpy(tmp.data(), packed.data(), packed.size() * 2);
+    int r = upload(c, &R.w_packed, tmp);
+    if (r) return r;
+  }
+  // ---- k-block table ------------------------------------------------------------------------------
+  TcLayer& T = R.tc;
+  memset(&T, 0, sizeof T);
+  const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
+  T.n_cls = ncls;
+  int nkb = 0;
+  for (int cl = 0; cl < ncls; ++cl) {
+    T.cls[cl].kb_begin = nkb;
+    for (size_t ti = 0; ti < taps.size(); ++ti) {
+      if (taps[ti].cls != cl) continue;
+      for (int ch = 0; ch < nchunk; ++ch) {
+        // pairings: (a_hi, w_hi) [, (a_hi, w_lo), (a_lo, w_hi)]
+        const int npair = x3 ? 3 : 1;
+        for (int pr = 0; pr < npair; ++pr) {
+          if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: k-block table overflow", L.name);
+          const int a_lo = (pr == 2), w_lo = (pr == 1);
+          if (a_lo && in_planes < 2) return fail(DBV_ERR_STATE, "%s: input has no lo plane", L.name);
+          TcKBlock& K = T.kb[nkb++];
+          K.dx = (int16_t)taps[ti].dx;
+          K.dy = (int16_t)taps[ti].dy;
+          K.plane = (int16_t)taps[ti].plane;
+          K.c_off = (int16_t)(ch * G.CBK + (a_lo ? in_cpad : 0));
+          K.b_row = (int32_t)(((ti * nchunk + ch) * parts_w + w_lo) * Ntot);
+        }
+      }
+    }
+    T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
+    const int py = cl >> 1, px = cl & 1;
+    T.cls[cl].oy0 = ncls == 4 ? py : 0;
+    T.cls[cl].ox0 = ncls == 4 ? px : 0;
+    T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
+  }
+  // ---- geometry -----------------------------------------------------------------------------------
+  T.TW = G.TW; T.TH = G.TH; T.TB = G.TB;
+  const int space = (ncls == 4) ? L.Hin : L.Hout;  // class space of a s2 transposed conv = its input grid
+  T.SH = T.SW = (L.kind == L_DENSE) ? 1 : space;
+  T.tiles_x = (T.SW + T.TW - 1) / T.TW;
+  T.tiles_y = (T.SH + T.TH - 1) / T.TH;
+  T.n_tiles_n = Ntot / G.NT;
+  T.nt_pixel_mode = (li == I_DENSE2);
+  T.a_bytes = G.CBK * 2 * G.TW * G.TH * G.TB;
+  T.b_bytes = G.NT * G.CBK * 2;
+  // ---- tensor maps ----------------------------------------------------------------------------------
+  {
+    // input viewed as (C, W, H, P, B)
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)G.TW, (uint32_t)G.TH, 1u, (uint32_t)G.TB};
+    const uint64_t Ct = (uint64_t)in_planes * in_cpad;
+    uint64_t Wd, Hd, Pd;
+    if (in.mode == OUT_BF16_PARITY) { Wd = in.PW; Hd = in.PH; Pd = 4; }
+    else { Wd = in.OW; Hd = in.OH; Pd = 1; }
+    dims[0] = Ct; dims[1] = Wd; dims[2] = Hd; dims[3] = Pd; dims[4] = (uint64_t)c->chunk;
+    str[0] = Ct * 2; str[1] = str[0] * Wd; str[2] = str[1] * Hd; str[3] = str[2] * Pd;
+    int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, G.CBK * 2);
+    if (r) return r;
+    uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};
+    uint64_t bs[1] = {(uint64_t)G.CBK * 2};
+    uint32_t bb[2] = {(uint32_t)G.CBK, (uint32_t)G.NT};
+    r = encode_tmap(&T.tmB, R.w_packed, 2, bd, bs, bb, G.CBK * 2);
+    if (r) return r;
+  }
+  if (!tc_layer_supported(G.CBK, G.NT)) return fail(DBV_ERR_UNSUPPORTED, "%s: no kernel for CBK=%d NT=%d", L.name, G.CBK, G.NT);
+  R.has_tc = true;
+  return DBV_OK;
+}
+
+static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, float* head_mean, float* head_std, float* params_out,
+                     cudaStream_t st) {
+  const LayerDesc& L = kLayers[li];
+  LayerRt& R = c->rt[li];
+  OutSpec o = R.ospec;
+  if (li == I_HEAD) { o.out = head_mean; o.out2 = head_std; }
+  if (li == I_ENC_DENSE && params_out) o.out = params_out;
+  if (R.has_tc) {
+    TcLayer T = R.tc;
+    T.B = B;
+    T.o = o;
+    const long long btiles = (B + T.TB - 1) / T.TB;
+    T.tiles_per_cls = btiles * T.tiles_x * T.tiles_y * T.n_tiles_n;
+    T.total_tiles = T.tiles_per_cls * T.n_cls;
+    return launch_tc_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
+  }
+  SimtConv p{};
+  p.in = (const float*)input_f32;
+  p.w = R.w_gather;
+  p.B = B;
+  p.Hin = p.Win = L.Hin;
+  p.Cin = L.Cin;
+  p.Hout = p.Wout = L.Hout;
+  p.CoutP = R.CoutP;
+  p.ksz = L.kind == L_DENSE ? 1 : 3;
+  p.mode = (L.kind == L_CONVT && L.stride == 2) ? 1 : 0;
+  p.stride = (L.kind == L_CONV) ? L.stride : 1;
+  p.pb = L.kind == L_DENSE ? 0 : (L.kind == L_CONV ? same_pad_before(L.Hin, 3, L.stride) : 1);
+  if (li == I_CONV1) { p.in_scale = c->bn_scale; p.in_shift = c->bn_shift; }
+  p.o = o;
+  return launch_simt_conv(p, st);
+}
+
+static void prof_mark(dbv_ctx* c, const char* name, cudaStream_t st) {
+  if (!c->profiling) return;
+  if ((int)c->prof_ev.size() <= c->prof_n) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->prof_ev.push_back(e);
+    c->prof_names.push_back("");
+  }
+  c->prof_names[c->prof_n] = name;
+  cudaEventRecord(c->prof_ev[c->prof_n], st);
+  c->prof_n++;
+}
+
+// one chunk (B <= ctx->chunk) through the requested stages
+static int run_chunk(dbv_ctx* c, const float* x, long long B, const float* eps, uint64_t seed, int sample, long long first_stamp,
+                     float* params_out, float* z_io, float* loc_out, float* zstd_out, float* mean, float* stddev, bool do_enc,
+                     bool do_lat, bool do_dec, cudaStream_t st) {
+  const bool fp32 = c->precision == DBV_PREC_FP32;
+  int r;
+  if (c->profiling) { c->prof_n = 0; prof_mark(c, "start", st); }
+  float* params = c->params;
+  if (do_enc) {
+    const void* in = x;
+    for (int li = I_CONV1; li <= I_ENC_DENSE; ++li) {
+      float* pout = (li == I_ENC_DENSE) ? (params_out && !do_lat ? params_out : params) : nullptr;
+      r = run_layer(c, li, in, B, nullptr, nullptr, pout, st);
+      if (r) return r;
+      prof_mark(c, kLayers[li].name, st);
+      in = fp32 ? c->rt[li].out : nullptr;  // tensor-core layers find their input through the tensor map
+    }
+    if (params_out && do_lat) DBV_CUDA(cudaMemcpyAsync(params_out, params, (size_t)B * NPAR * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  float* z = c->z;
+  if (do_lat) {
+    const float* pin = do_enc ? params : params_out;  // dbv_latent passes the caller's params through params_out
+    r = launch_latent(pin, eps, seed, sample, first_stamp, B, z_io ? z_io : z, loc_out, zstd_out, c->zp, c->dec_alpha0, st);
+    if (r) return r;
+    prof_mark(c, "latent", st);
+  } else if (do_dec) {
+    r = launch_prelu_vec(z_io, c->dec_alpha0, B * LAT, LAT, c->zp, st);
+    if (r) return r;
+  }
+  if (do_dec) {
+    const void* in = c->zp;
+    for (int li = I_DENSE1; li <= I_HEAD; ++li) {
+      // in tensor-core modes dense1 runs on the SIMT kernel from zp, the rest read through tensor maps
+      r = run_layer(c, li, in, B, mean, stddev, nullptr, st);
+      if (r) return r;
+      prof_mark(c, kLayers[li].name, st);
+      in = fp32 ? c->rt[li].out : nullptr;
+    }
+  }
+  return DBV_OK;
+}
+
+static int check_ready(dbv_ctx* c, const char* fn) {
+  if (!c) return fail(DBV_ERR_INVALID, "%s: null ctx", fn);
+  if (!c->finalized) return fail(DBV_ERR_STATE, "%s: weights not finalized (call dbv_finalize_weights)", fn);
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail(DBV_ERR_CUDA, "%s: cudaSetDevice(%d): %s", fn, c->device, cudaGetErrorString(e));
+  return DBV_OK;
+}
+
+}  // namespace dbv
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" int dbv_abi_version(void) { return DBV_ABI_VERSION; }
+extern "C" const char* dbv_last_error(void) { return last_error().c_str(); }
+extern "C" int64_t dbv_global_launch_count(void) { return g_launches.load(); }
+extern "C" int64_t dbv_launch_count(const dbv_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chunk) {
+  DBV_REQUIRE(out, "dbv_create: null out");
+  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_BF16X3, "dbv_create: bad precision %d", precision);
+  DBV_REQUIRE(chunk >= 0 && chunk <= (1 << 20), "dbv_create: bad chunk %lld", (long long)chunk);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(DBV_ERR_CUDA, "dbv_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  DBV_REQUIRE(device >= 0 && device < ndev, "dbv_create: device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  DBV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(DBV_ERR_UNSUPPORTED, "dbv_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  DBV_CUDA(cudaSetDevice(device));
+  dbv_ctx* c = new dbv_ctx();
+  c->device = device;
+  c->precision = precision;
+  c->chunk = chunk > 0 ? chunk : 512;
+  *out = c;
+  return DBV_OK;
+}
+
+extern "C" int dbv_destroy(dbv_ctx* c) {
+  if (!c) return DBV_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  for (auto e : c->prof_ev) cudaEventDestroy(e);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  delete c;
+  return DBV_OK;
+}
+
+extern "C" int dbv_set_weights(dbv_ctx* c, const char* key, const float* host, const int64_t* shape, int ndim) {
+  DBV_REQUIRE(c && key && host && shape, "dbv_set_weights: null argument");
+  DBV_REQUIRE(ndim >= 1 && ndim <= 4, "dbv_set_weights: bad ndim %d for '%s'", ndim, key);
+  if (c->finalized) return fail(DBV_ERR_STATE, "dbv_set_weights: ctx already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DBV_REQUIRE(shape[i] > 0, "dbv_set_weights: bad shape for '%s'", key);
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(host, host + n);
+  std::string k(key);
+  const std::string suffix = "/.ATTRIBUTES/VARIABLE_VALUE";
+  if (k.size() > suffix.size() && k.compare(k.size() - suffix.size(), suffix.size(), suffix) == 0) k.resize(k.size() - suffix.size());
+  c->host_w[k] = std::move(t);
+  return DBV_OK;
+}
+
+extern "C" int dbv_finalize_weights(dbv_ctx* c) {
+  DBV_REQUIRE(c, "dbv_finalize_weights: null ctx");
+  if (c->finalized) return fail(DBV_ERR_STATE, "dbv_finalize_weights: already finalized");
+  DBV_CUDA(cudaSetDevice(c->device));
+  const bool fp32 = c->precision == DBV_PREC_FP32;
+  const int planes = c->precision == DBV_PREC_BF16X3 ? 2 : 1;
+  int r;
+  // ---- BatchNorm (model/model.py:79; Keras eps 1e-3) folded to scale/shift -----------------------
+  {
+    const HostTensor *g, *b, *m, *v;
+    if ((r = check_shape(c, wkey(1, 0, "gamma"), {6}, &g))) return r;
+    if ((r = check_shape(c, wkey(1, 0, "beta"), {6}, &b))) return r;
+    if ((r = check_shape(c, wkey(1, 0, "moving_mean"), {6}, &m))) return r;
+    if ((r = check_shape(c, wkey(1, 0, "moving_variance"), {6}, &v))) return r;
+    std::vector<float> sc(8, 0.f), sh(8, 0.f);
+    for (int i = 0; i < 6; ++i) {
+      sc[i] = g->data[i] / sqrtf(v->data[i] + 1e-3f);
+      sh[i] = b->data[i] - m->data[i] * sc[i];
+    }
+    if ((r = upload(c, &c->bn_scale, sc))) return r;
+    if ((r = upload(c, &c->bn_shift, sh))) return r;
+    const HostTensor* a0;
+    if ((r = check_shape(c, wkey(0, 0, "alpha"), {32}, &a0))) return r;
+    if ((r = upload(c, &c->dec_alpha0, a0->data))) return r;
+  }
+  // ---- per-layer weights ------------------------------------------------------------------------
+  for (int li = 0; li < kNumLayers; ++li) {
+    const LayerDesc& L = kLayers[li];
+    LayerRt& R = c->rt[li];
+    const HostTensor *W, *Bv, *A = nullptr, *A2 = nullptr;
+    if (L.kind == L_CONV) r = check_shape(c, wkey(L.enc, L.wn, "kernel"), {3, 3, L.Cin, L.Cout}, &W);
+    else if (L.kind == L_CONVT) r = check_shape(c, wkey(L.enc, L.wn, "kernel"), {3, 3, L.Cout, L.Cin}, &W);
+    else r = check_shape(c, wkey(L.enc, L.wn, "kernel"), {L.Cin, L.Cout}, &W);
+    if (r) return r;
+    if ((r = check_shape(c, wkey(L.enc, L.wn, "bias"), {L.Cout}, &Bv))) return r;
+    if (L.an >= 0) {
+      if (L.kind == L_DENSE) r = check_shape(c, wkey(L.enc, L.an, "alpha"), {L.Cout}, &A);
+      else r = check_shape(c, wkey(L.enc, L.an, "alpha"), {L.Hout, L.Hout, L.Cout}, &A);
+      if (r) return r;
+    }
+    if (L.a2n >= 0 && (r = check_shape(c, wkey(L.enc, L.a2n, "alpha"), {(int64_t)L.Hout * L.Hout * L.Cout}, &A2))) return r;
+    if ((r = upload(c, &R.bias, Bv->data))) return r;
+    if (A && (r = upload(c, &R.alpha, A->data))) return r;
+    if (A2 && (r = upload(c, &R.alpha2, A2->data))) return r;
+    R.CoutP = (L.Cout + 3) & ~3;
+    const bool simt = fp32 || !kTc[li].tc;
+    if (simt) {
+      const int ksz = L.kind == L_DENSE ? 1 : 3;
+      std::vector<float> g((size_t)ksz * ksz * L.Cin * R.CoutP, 0.f);
+      for (int ky = 0; ky < ksz; ++ky)
+        for (int kx = 0; kx < ksz; ++kx) {
+          // stride-1 transposed conv = conv with the kernel flipped (in row = y + (2-ky) - 1)
+          const bool flip = (L.kind == L_CONVT && L.stride == 1);
+          const int sy = flip ? 2 - ky : ky, sx = flip ? 2 - kx : kx;
+          for (int ci = 0; ci < L.Cin; ++ci)
+            for (int co = 0; co < L.Cout; ++co)
+              g[(((size_t)ky * ksz + kx) * L.Cin + ci) * R.CoutP + co] = w_at(L, *W, sy, sx, ci, co);
+        }
+      if ((r = upload(c, &R.w_gather, g))) return r;
+    }
+    // output buffer + spec
+    OutSpec& o = R.ospec;
+    memset(&o, 0, sizeof o);
+    if (fp32) {
+      o.mode = (li == I_HEAD) ? OUT_HEAD : OUT_F32_NHWC;
+      o.planes = 1;
+      o.OH = o.OW = L.Hout;
+      o.Cout = o.Cpad = L.Cout;
+    } else {
+      tc_out_layout(li, planes, &o);
+    }
+    o.bias = R.bias;
+    o.alpha = R.alpha;
+    o.alpha2 = R.alpha2;
+    o.relu = L.relu_head;
+    const size_t el = out_elems_per_stamp(o);
+    const size_t esz = (o.mode == OUT_F32_NHWC) ? 4 : 2;
+    R.out_bytes_per_stamp = el * esz;
+    if (li == I_ENC_DENSE) {
+      if ((r = dev_alloc(c, (void**)&c->params, (size_t)c->chunk * NPAR * 4, true))) return r;
+      R.out = c->params;
+    } else if (el) {
+      if ((r = dev_alloc(c, &R.out, (size_t)c->chunk * R.out_bytes_per_stamp, true))) return r;
+    }
+    o.out = R.out;
+  }
+  if ((r = dev_alloc(c, (void**)&c->z, (size_t)c->chunk * LAT * 4, true))) return r;
+  if ((r = dev_alloc(c, (void**)&c->zp, (size_t)c->chunk * LAT * 4, true))) return r;
+  // ---- tensor-core plans ------------------------------------------------------------------------
+  if (!fp32)
+    for (int li = 0; li < kNumLayers; ++li)
+      if (kTc[li].tc && (r = build_tc_layer(c, li))) return r;
+  DBV_CUDA(cudaDeviceSynchronize());
+  c->finalized = true;
+  c->host_w.clear();
+  return DBV_OK;
+}
+
+static int chunked(dbv_ctx* c, const char* fn, const float* x, int64_t B, const float* eps, uint64_t seed, int sample,
+                   int64_t first_stamp, float* params, float* z, float* loc, float* zstd, float* mean, float* stddev, bool enc,
+                   bool lat, bool dec, void* stream) {
+  int r = check_ready(c, fn);
+  if (r) return r;
+  DBV_REQUIRE(B >= 0, "%s: negative B", fn);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long before = g_launches.load();
+  for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
+    const long long nb = std::min<long long>(c->chunk, B - b0);
+    r = run_chunk(c, x ? x + b0 * STAMP_ELTS : nullptr, nb, eps ? eps + b0 * LAT : nullptr, seed, sample, first_stamp + b0,
+                  params ? params + b0 * NPAR : nullptr, z ? z + b0 * LAT : nullptr, loc ? loc + b0 * LAT : nullptr,
+                  zstd ? zstd + b0 * LAT : nullptr, mean ? mean + b0 * STAMP_ELTS : nullptr,
+                  stddev ? stddev + b0 * STAMP_ELTS : nullptr, enc, lat, dec, st);
+    if (r) return r;
+  }
+  c->launches += g_launches.load() - before;
+  return DBV_OK;
+}
+
+extern "C" int dbv_encode(dbv_ctx* c, const float* x, int64_t B, float* params, void* stream) {
+  DBV_REQUIRE(x && params, "dbv_encode: null buffer");
+  return chunked(c, "dbv_encode", x, B, nullptr, 0, 0, 0, params, nullptr, nullptr, nullptr, nullptr, nullptr, true, false, false, stream);
+}
+
+extern "C" int dbv_latent(dbv_ctx* c, const float* params, const float* eps, uint64_t seed, int sample, int64_t first_stamp,
+                          int64_t B, float* z, float* loc, float* zstd, void* stream) {
+  DBV_REQUIRE(params && z, "dbv_latent: null buffer");
+  return chunked(c, "dbv_latent", nullptr, B, eps, seed, sample, first_stamp, const_cast<float*>(params), z, loc, zstd, nullptr,
+                 nullptr, false, true, false, stream);
+}
+
+extern "C" int dbv_decode(dbv_ctx* c, const float* z, int64_t B, float* mean, float* stddev, void* stream) {
+  DBV_REQUIRE(z && mean, "dbv_decode: null buffer");
+  return chunked(c, "dbv_decode", nullptr, B, nullptr, 0, 0, 0, nullptr, const_cast<float*>(z), nullptr, nullptr, mean, stddev,
+                 false, false, true, stream);
+}
+
+extern "C" int dbv_deblend(dbv_ctx* c, const float* x, int64_t B, const float* eps, uint64_t seed, int sample, float* mean,
+                           float* stddev, float* z, void* stream) {
+  DBV_REQUIRE(x && mean, "dbv_deblend: null buffer");
+  return chunked(c, "dbv_deblend", x, B, eps, seed, sample, 0, nullptr, z, nullptr, nullptr, mean, stddev, true, true, true, stream);
+}
+
+// ---- host-buffer pipeline ----------------------------------------------------------------------------
+static int ensure_pipe(dbv_ctx* c) {
+  if (c->pipe_ready) return DBV_OK;
+  DBV_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  DBV_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  DBV_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  int r;
+  for (int i = 0; i < 2; ++i) {
+    if ((r = dev_alloc(c, &c->stage_in[i], (size_t)c->chunk * STAMP_ELTS * 8, false))) return r;
+    if ((r = dev_alloc(c, (void**)&c->stage_x[i], (size_t)c->chunk * STAMP_ELTS * 4, false))) return r;
+    if ((r = dev_alloc(c, (void**)&c->stage_mean[i], (size_t)c->chunk * STAMP_ELTS * 4, false))) return r;
+    if ((r = dev_alloc(c, (void**)&c->stage_std[i], (size_t)c->chunk * STAMP_ELTS * 4, false))) return r;
+    if ((r = dev_alloc(c, (void**)&c->stage_z[i], (size_t)c->chunk * LAT * 4, false))) return r;
+    if ((r = dev_alloc(c, (void**)&c->stage_eps[i], (size_t)c->chunk * LAT * 4, false))) return r;
+    DBV_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    DBV_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+    DBV_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+  }
+  c->pipe_ready = true;
+  return DBV_OK;
+}
+
+extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int64_t B, const float* eps_host, uint64_t seed,
+                                int sample, float* mean_host, float* stddev_host, float* z_host) {
+  int r = check_ready(c, "dbv_deblend_host");
+  if (r) return r;
+  DBV_REQUIRE(x_host && mean_host, "dbv_deblend_host: null buffer");
+  DBV_REQUIRE(x_dtype == DBV_F32 || x_dtype == DBV_F64, "dbv_deblend_host: bad dtype %d", x_dtype);
+  DBV_REQUIRE(B >= 0, "dbv_deblend_host: negative B");
+  if ((r = ensure_pipe(c))) return r;
+  const long long before = g_launches.load();
+  const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
+  int k = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += c->chunk, ++k) {
+    const int s = k & 1;
+    const long long nb = std::min<long long>(c->chunk, B - b0);
+    const size_t n = (size_t)nb * STAMP_ELTS;
+    // slot s is free for new input once the compute that used it (chunk k-2) is done, and its
+    // outputs are free once the D2H of chunk k-2 is done
+    if (k >= 2) {
+      DBV_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[s], 0));
+      DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[s], 0));
+    }
+    void* dst = x_dtype == DBV_F64 ? c->stage_in[s] : (void*)c->stage_x[s];
+    DBV_CUDA(cudaMemcpyAsync(dst, (const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, n * esz, cudaMemcpyHostToDevice, c->s_h2d));
+    if (eps_host)
+      DBV_CUDA(cudaMemcpyAsync(c->stage_eps[s], eps_host + b0 * LAT, (size_t)nb * LAT * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    DBV_CUDA(cudaEventRecord(c->ev_in[s], c->s_h2d));
+    DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[s], 0));
+    if (x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return r;
+    r = run_chunk(c, c->stage_x[s], nb, eps_host ? c->stage_eps[s] : nullptr, seed, sample, b0, nullptr, c->stage_z[s], nullptr,
+                  nullptr, c->stage_mean[s], stddev_host ? c->stage_std[s] : nullptr, true, true, true, c->s_comp);
+    if (r) return r;
+    DBV_CUDA(cudaEventRecord(c->ev_comp[s], c->s_comp));
+    DBV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
+    DBV_CUDA(cudaMemcpyAsync(mean_host + (size_t)b0 * STAMP_ELTS, c->stage_mean[s], n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (stddev_host)
+      DBV_CUDA(cudaMemcpyAsync(stddev_host + (size_t)b0 * STAMP_ELTS, c->stage_std[s], n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (z_host) DBV_CUDA(cudaMemcpyAsync(z_host + b0 * LAT, c->stage_z[s], (size_t)nb * LAT * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    DBV_CUDA(cudaEventRecord(c->ev_out[s], c->s_d2h));
+  }
+  DBV_CUDA(cudaStreamSynchronize(c->s_d2h));
+  DBV_CUDA(cudaStreamSynchronize(c->s_comp));
+  DBV_CUDA(cudaStreamSynchronize(c->s_h2d));
+  c->launches += g_launches.load() - before;
+  return DBV_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+extern "C" int dbv_set_profiling(dbv_ctx* c, int enabled) {
+  DBV_REQUIRE(c, "dbv_set_profiling: null ctx");
+  c->profiling = enabled != 0;
+  c->prof_n = 0;
+  return DBV_OK;
+}
+
+extern "C" int dbv_layer_times(dbv_ctx* c, int max_layers, float* ms_out, char* names_out) {
+  DBV_REQUIRE(c && ms_out && names_out, "dbv_layer_times: null argument");
+  int n = 0;
+  for (int i = 1; i < c->prof_n && n < max_layers; ++i, ++n) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&ms, c->prof_ev[i - 1], c->prof_ev[i]);
+    if (e != cudaSuccess) return fail(DBV_ERR_CUDA, "dbv_layer_times: %s", cudaGetErrorString(e));
+    ms_out[n] = ms;
+    strncpy(names_out + 32 * n, c->prof_names[i].c_str(), 31);
+    names_out[32 * n + 31] = 0;
+  }
+  return n;
+}
+
+extern "C" int dbv_debug_activation(dbv_ctx* c, const char* name, int64_t B, float* out, void* stream) {
+  int r = check_ready(c, "dbv_debug_activation");
+  if (r) return r;
+  DBV_REQUIRE(name && out && B >= 0 && B <= c->chunk, "dbv_debug_activation: bad argument");
+  for (int li = 0; li < kNumLayers; ++li)
+    if (!strcmp(name, kLayers[li].name)) {
+      if (li == I_HEAD) return fail(DBV_ERR_INVALID, "dbv_debug_activation: the head writes the caller's buffers");
+      return launch_act_to_f32(c->rt[li].ospec, B, out, (cudaStream_t)stream);
+    }
+  return fail(DBV_ERR_INVALID, "dbv_debug_activation: unknown layer '%s'", name);
+}

@@ -1,0 +1,173 @@
+// Output addressing + bias / PReLU / ReLU epilogue shared by the SIMT and the tcgen05 kernels.
+//
+// Activation tensors between layers are NHWC.  Three storage forms:
+//   OUT_F32_NHWC     fp32 [B][OH][OW][Cstore]                       (fp32 path, encoder params)
+//   OUT_BF16_NHWC    bf16 [B][OH][OW][planes*Cpad]                  (consumer is a stride-1 layer)
+//   OUT_BF16_PARITY  bf16 [B][4][PH][PW][planes*Cpad], plane = (y&1)*2+(x&1), row y>>1, col x>>1
+//                    (consumer is a stride-2 Conv2D: each of its taps then reads ONE plane with
+//                    unit stride, so a plain tiled TMA box + out-of-bounds zero fill implements
+//                    TF "SAME" padding; rows/cols a plane lacks stay zero from allocation)
+//   OUT_HEAD         decoder head (model/model.py:137-159): ReLU, crop [2:61]^2 of the 64x64 map,
+//                    channels 0-5 -> mean, 6-11 -> 1e-4 + v -> stddev, both fp32 (B,59,59,6)
+// planes = 2 stores a hi/lo bf16 split (v ~= hi + lo) at channel offsets [0,Cpad) and [Cpad,2Cpad).
+#pragma once
+#include "common.cuh"
+
+namespace dbv {
+
+enum OutMode { OUT_F32_NHWC = 0, OUT_BF16_NHWC = 1, OUT_BF16_PARITY = 2, OUT_HEAD = 3 };
+
+struct OutSpec {
+  void* out;
+  void* out2;          // OUT_HEAD: stddev
+  int mode;
+  int planes;          // bf16 modes: 1 or 2
+  int OH, OW;          // full output image extents (addressing + alpha indexing)
+  int Cout;            // real channels
+  int Cpad;            // channels per plane as stored (>= Cout)
+  int PH, PW;          // OUT_BF16_PARITY plane extents
+  const float* bias;   // [Cout]
+  const float* alpha;  // [OH][OW][Cout] or null
+  const float* alpha2; // second PReLU (encoder Flatten PReLU, model/model.py:95) or null
+  int relu;
+};
+
+__device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
+
+// element offset of channel 0 of pixel (b,y,x); OUT_HEAD handled by the callers
+__device__ __forceinline__ long long pixel_offset(const OutSpec& o, long long b, int y, int x) {
+  const int cs = o.planes * o.Cpad;
+  if (o.mode == OUT_BF16_PARITY) {
+    const long long plane = b * 4 + ((y & 1) * 2 + (x & 1));
+    return ((plane * o.PH + (y >> 1)) * o.PW + (x >> 1)) * cs;
+  }
+  return ((b * o.OH + y) * o.OW + x) * (long long)cs;
+}
+
+// bias + PReLU(+PReLU) / ReLU on NV consecutive channels starting at c of pixel (y,x).
+// bias_off shifts the bias index only (Dense -> Reshape layers whose N tile is a pixel).
+template <int NV>
+__device__ __forceinline__ void apply_act(const OutSpec& o, int y, int x, int c, float (&v)[NV], int bias_off = 0) {
+  const long long pix = (long long)y * o.OW + x;
+  if (c + NV <= o.Cout && (o.Cout & 3) == 0) {  // fast path: 16-byte loads (c is a multiple of 4)
+    const float4* bp = reinterpret_cast<const float4*>(o.bias + bias_off + c);
+    const float4* ap = o.alpha ? reinterpret_cast<const float4*>(o.alpha + pix * o.Cout + c) : nullptr;
+    const float4* a2p = o.alpha2 ? reinterpret_cast<const float4*>(o.alpha2 + pix * o.Cout + c) : nullptr;
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+      const float4 bb = __ldg(bp + (j >> 2));
+      v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+      if (ap) {
+        const float4 a = __ldg(ap + (j >> 2));
+        v[j] = prelu_f(v[j], a.x); v[j + 1] = prelu_f(v[j + 1], a.y); v[j + 2] = prelu_f(v[j + 2], a.z); v[j + 3] = prelu_f(v[j + 3], a.w);
+      }
+      if (a2p) {
+        const float4 a = __ldg(a2p + (j >> 2));
+        v[j] = prelu_f(v[j], a.x); v[j + 1] = prelu_f(v[j + 1], a.y); v[j + 2] = prelu_f(v[j + 2], a.z); v[j + 3] = prelu_f(v[j + 3], a.w);
+      }
+      if (o.relu) {
+        v[j] = fmaxf(v[j], 0.f); v[j + 1] = fmaxf(v[j + 1], 0.f); v[j + 2] = fmaxf(v[j + 2], 0.f); v[j + 3] = fmaxf(v[j + 3], 0.f);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (c + j < o.Cout) {
+      float t = v[j] + __ldg(o.bias + bias_off + c + j);
+      if (o.alpha) t = prelu_f(t, __ldg(o.alpha + pix * o.Cout + c + j));
+      if (o.alpha2) t = prelu_f(t, __ldg(o.alpha2 + pix * o.Cout + c + j));
+      if (o.relu) t = fmaxf(t, 0.f);
+      v[j] = t;
+    } else {
+      v[j] = 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// store NV (multiple of 4, c multiple of 4) activated channels of pixel (b,y,x)
+template <int NV>
+__device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, int x, int c, const float (&v)[NV]) {
+  if (o.mode == OUT_HEAD) {
+    if (y < 2 || y >= 61 || x < 2 || x >= 61) return;
+    const long long base = ((b * 59 + (y - 2)) * 59 + (x - 2)) * 6;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int cc = c + j;
+      if (cc < 6) reinterpret_cast<float*>(o.out)[base + cc] = v[j];
+      else if (cc < 12 && o.out2) reinterpret_cast<float*>(o.out2)[base + cc - 6] = 1e-4f + v[j];
+    }
+    return;
+  }
+  const long long off = pixel_offset(o, b, y, x);
+  if (o.mode == OUT_F32_NHWC) {
+    float* p = reinterpret_cast<float*>(o.out) + off + c;
+    if (c + NV <= o.Cout && (o.Cpad & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c + j < o.Cout) p[j] = v[j];
+    }
+    return;
+  }
+  // bf16 (hi[/lo]) — Cpad is a multiple of 8 and c of 4, so 8-byte stores are aligned
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + off + c;
+  const bool full = c + NV <= o.Cpad;
+  if (full) {
+    if constexpr (NV % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(p + j) = q;
+      }
+      if (o.planes == 2) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(v[j] - bf16_round(v[j]), v[j + 1] - bf16_round(v[j + 1]));
+          q.y = pack_bf16x2(v[j + 2] - bf16_round(v[j + 2]), v[j + 3] - bf16_round(v[j + 3]));
+          q.z = pack_bf16x2(v[j + 4] - bf16_round(v[j + 4]), v[j + 5] - bf16_round(v[j + 5]));
+          q.w = pack_bf16x2(v[j + 6] - bf16_round(v[j + 6]), v[j + 7] - bf16_round(v[j + 7]));
+          *reinterpret_cast<uint4*>(p + o.Cpad + j) = q;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) {
+        uint2 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        *reinterpret_cast<uint2*>(p + j) = q;
+        if (o.planes == 2) {
+          uint2 r;
+          r.x = pack_bf16x2(v[j] - bf16_round(v[j]), v[j + 1] - bf16_round(v[j + 1]));
+          r.y = pack_bf16x2(v[j + 2] - bf16_round(v[j + 2]), v[j + 3] - bf16_round(v[j + 3]));
+          *reinterpret_cast<uint2*>(p + o.Cpad + j) = r;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (c + j < o.Cpad) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+        p[j] = h;
+        if (o.planes == 2) p[o.Cpad + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+}  // namespace dbv

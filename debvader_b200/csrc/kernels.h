@@ -1,0 +1,73 @@
+// Internal (non-ABI) declarations shared between the .cu files of libdebvader_b200.
+#pragma once
+#include "epilogue.cuh"
+#include <cuda.h>
+
+namespace dbv {
+
+// ---- fp32 SIMT gather convolution (simt_kernels.cu) ----------------------------------------------
+struct SimtConv {
+  const float* in;  // NHWC fp32 [B][Hin][Win][Cin]
+  const float* w;   // gather form [ksz*ksz][Cin][CoutP]
+  long long B;
+  int Hin, Win, Cin, Hout, Wout, CoutP;
+  int mode;         // 0: iy = stride*y + ky - pb    1: stride-2 transposed conv (iy = (y-ky)/2)
+  int stride, pb, ksz;
+  const float* in_scale;  // BatchNorm folded to scale/shift, applied to in-bounds pixels only
+  const float* in_shift;
+  OutSpec o;
+};
+int launch_simt_conv(const SimtConv& p, cudaStream_t st);
+int launch_latent(const float* params, const float* eps, unsigned long long seed, int sample, long long first_stamp,
+                  long long B, float* z, float* loc, float* std_out, float* zp, const float* alpha0, cudaStream_t st);
+int launch_prelu_vec(const float* z, const float* alpha, long long n, int C, float* out, cudaStream_t st);
+int launch_cast_f64_f32(const double* in, float* out, long long n, cudaStream_t st);
+int launch_act_to_f32(const OutSpec& o, long long B, float* out, cudaStream_t st);
+
+// ---- tcgen05 implicit-GEMM convolution (tc_conv.cu) ------------------------------------------------
+// One k-block = one (tap, channel chunk[, hi/lo pairing]) : an A box of the activation tensor and a
+// B box of the packed weights, multiplied by CB/16 tcgen05.mma of K=16.
+struct TcKBlock {
+  int16_t dx, dy;     // offset of the A box relative to the output tile origin (pixels)
+  int16_t plane;      // parity plane of the input tensor (0 for plain tensors)
+  int16_t c_off;      // first channel of the A box (hi plane: [0,Cin), lo plane: [Cpad,Cpad+Cin))
+  int32_t b_row;      // first row of the B box in the packed weight tensor
+};
+
+constexpr int TC_MAX_KB = 192;  // enc_dense in bf16x3: 16 pixels x 4 chunks x 3 pairings
+constexpr int TC_MAX_CLS = 4;
+
+struct TcClass {
+  int kb_begin, nkb;  // slice of the k-block table
+  int oy0, ox0;       // output pixel = (oy0 + osy*ty, ox0 + osx*tx) for tile-space pixel (ty,tx)
+  int osy, osx;
+};
+
+struct TcLayer {
+  CUtensorMap tmA;    // 5D (C, W, H, P, B) bf16
+  CUtensorMap tmB;    // 2D (CBK, rows) bf16 packed weights
+  TcKBlock kb[TC_MAX_KB];
+  TcClass cls[TC_MAX_CLS];
+  int n_cls;
+  int TW, TH, TB;     // tile box in tile space (TW*TH*TB <= 128 rows)
+  int SH, SW;         // tile-space image extents (valid outputs)
+  int tiles_x, tiles_y;
+  int n_tiles_n;      // N tiling (dense layers); channel offset = nt * NT
+  int nt_pixel_mode;  // Dense -> Reshape(4,4,256): N tile nt IS output pixel nt (channel offset 0, bias offset nt*NT)
+  long long B;        // stamps in this launch
+  long long tiles_per_cls;
+  long long total_tiles;
+  int a_bytes, b_bytes;  // expect_tx per k-block
+  OutSpec o;
+};
+
+// CBK: K elements per k-block (32 -> 64-byte rows / SWIZZLE_64B, 64 -> 128-byte rows / SWIZZLE_128B)
+// NT : MMA N (multiple of 16, 16..256)
+int launch_tc_layer(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+bool tc_layer_supported(int CBK, int NT);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int swizzle_bytes);
+
+}  // namespace dbv

@@ -1,0 +1,147 @@
+/*
+ * debvader_b200 — C-ABI of the B200-native debvader hot path.
+ *
+ * The reference (astrodeepnet/debvader) has no FFI: the path sits behind plain
+ * Python functions that call TensorFlow/Keras/TFP/scipy.  This header is the
+ * boundary a maintainer would bind (ctypes/cffi) directly
+ * beneath those functions.  Each entry point cites the reference code it
+ * replaces (paths relative to the reference's src/debvader/).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types; every function returns
+ *     0 on success or a negative dbv_status, never throws; the message of the
+ *     last failure on the calling thread is dbv_last_error().
+ *   - "dev" pointers are device memory on the ctx's device, "host" pointers are
+ *     host memory (pinned memory makes the copies asynchronous and fast).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream).  All device-pointer calls only enqueue work on it; no hidden
+ *     synchronisation.  The *_host calls are synchronous.
+ *   - the caller owns every buffer; the ctx owns repacked weights + workspace.
+ *   - one ctx per device, not re-entrant.
+ *   - tensors are dense, row-major, NHWC: stamps (B,59,59,6), fields (1,F,F,C).
+ */
+#ifndef DEBVADER_B200_H
+#define DEBVADER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBV_ABI_VERSION 1
+
+typedef enum {
+  DBV_OK = 0,
+  DBV_ERR_INVALID = -1,     /* bad argument / shape / key */
+  DBV_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  DBV_ERR_STATE = -3,       /* e.g. compute before dbv_finalize_weights */
+  DBV_ERR_UNSUPPORTED = -4  /* not the DC2 architecture, not an sm_100 device, ... */
+} dbv_status;
+
+/* arithmetic of the network path */
+typedef enum {
+  DBV_PREC_FP32 = 0,   /* fp32 SIMT kernels: <=1e-5 of peak flux vs the fp64 oracle        */
+  DBV_PREC_BF16 = 1,   /* tcgen05 bf16 x bf16 -> fp32, activations stored once in bf16      */
+  DBV_PREC_BF16X3 = 2  /* tcgen05, hi/lo bf16 split of activations and weights (3 MMAs per
+                          product, ~16-bit mantissa): <=1e-3 of peak flux                   */
+} dbv_precision;
+
+typedef enum { DBV_F32 = 0, DBV_F64 = 1 } dbv_dtype;
+
+typedef struct dbv_ctx dbv_ctx;
+
+/* ---- housekeeping ------------------------------------------------------------------- */
+int dbv_abi_version(void);
+const char* dbv_last_error(void);
+
+/* Replaces create_model_vae / load_deblender's graph construction (model/model.py:164-218,
+ * 221-259): allocates the workspace for `chunk` stamps per pass (0 = default). */
+int dbv_create(dbv_ctx** out, int device, int precision, int64_t chunk);
+int dbv_destroy(dbv_ctx* ctx);
+
+/* Replaces net.load_weights (model/model.py:262-266).  `key` is the TF2 checkpoint key
+ * without the "/.ATTRIBUTES/VARIABLE_VALUE" suffix, e.g.
+ * "layer_with_weights-0/layer_with_weights-1/kernel"; data is host fp32 in the
+ * checkpoint's own layout (Conv2D HWIO, Conv2DTranspose HWOI, Dense IO, PReLU HWC). */
+int dbv_set_weights(dbv_ctx* ctx, const char* key, const float* host, const int64_t* shape, int ndim);
+/* Validates the 64 tensors against the DC2 architecture, repacks and uploads them. */
+int dbv_finalize_weights(dbv_ctx* ctx);
+
+/* ---- network: device buffers ------------------------------------------------------------ */
+/* encoder(x): model/model.py:61-100.  x (B,59,59,6) f32 -> params (B,560) f32. */
+int dbv_encode(dbv_ctx* ctx, const float* x_dev, int64_t B, float* params_dev, void* stream);
+
+/* tfp.layers.MultivariateNormalTriL(32) / MvNormal.__call__: model/model.py:43-58, 211-214.
+ * z = loc + L eps.  eps_dev (B,32) or NULL; with NULL, `sample`!=0 draws eps ~ N(0,1) from a
+ * Philox stream keyed by (seed, first_stamp + row) and `sample`==0 gives z = loc.
+ * Optional outputs: loc (B,32), stddev (B,32) = sqrt(sum_j L_ij^2). */
+int dbv_latent(dbv_ctx* ctx, const float* params_dev, const float* eps_dev, uint64_t seed, int sample,
+               int64_t first_stamp, int64_t B, float* z_dev, float* loc_dev, float* stddev_dev, void* stream);
+
+/* decoder(z): model/model.py:103-161.  z (B,32) -> mean, stddev (B,59,59,6) f32
+ * (Normal(loc=t[...,:6], scale=1e-4+t[...,6:]) of model/model.py:154-159). */
+int dbv_decode(dbv_ctx* ctx, const float* z_dev, int64_t B, float* mean_dev, float* stddev_dev, void* stream);
+
+/* net(x) as deblend() uses it: deblend_cutout/deblender.py:18,24.  The benchmarked unit.
+ * stddev_dev / z_dev may be NULL. */
+int dbv_deblend(dbv_ctx* ctx, const float* x_dev, int64_t B, const float* eps_dev, uint64_t seed, int sample,
+                float* mean_dev, float* stddev_dev, float* z_dev, void* stream);
+
+/* ---- network: host buffers (the end-to-end call of deblend()) ----------------------------- */
+/* deblend_cutout/deblender.py:6-24 including tf.cast(images, tf.float32) (x_dtype = DBV_F32 or
+ * DBV_F64; the cast is done on the device) and outimg.mean().numpy().  Chunks are pipelined:
+ * H2D of chunk k+1, compute of chunk k and D2H of chunk k-1 overlap on three streams.
+ * stddev_host / z_host / eps_host may be NULL.  Synchronous. */
+int dbv_deblend_host(dbv_ctx* ctx, const void* x_host, int x_dtype, int64_t B, const float* eps_host,
+                     uint64_t seed, int sample, float* mean_host, float* stddev_host, float* z_host);
+
+/* ---- field operators: device buffers -------------------------------------------------------- */
+/* extract_cutouts: extract/extraction.py:21-36.  For k in [0,N): copies the window of `field`
+ * (1,F,F,C) whose first row/col is (sx[k], sy[k]) into out[slot[k]] (S,S,C).  flags[k] bit0 / bit1
+ * = the source has length 1 along rows / cols and is broadcast (numpy assignment semantics).
+ * The host planner (which applies int() truncation and slice.indices) owns acceptance.
+ * sx, sy (int32), flags (uint8), slot (int64) are device arrays.  out is f64 (reference-faithful)
+ * or f32 (fused tf.cast of deblender.py:18). */
+int dbv_extract(const void* field_dev, int field_dtype, int64_t F, int C, const int32_t* sx_dev,
+                const int32_t* sy_dev, const uint8_t* flags_dev, const int64_t* slot_dev, int64_t N, int S,
+                void* out_dev, int out_dtype, void* stream);
+
+/* get_residual_field / get_predicted_field with integer positions: deblend/field_deblender.py:46-97,
+ * 99-189.  out = in + alpha * sum_k paste(stamps[k] at rows x0[k].., cols y0[k]..), clipped to the
+ * field; in_dev == NULL means zeros; in_dev may equal out_dev.  Contributions are applied to each
+ * pixel in ascending k with one rounding per addition (no atomics, no FMA contraction), so the
+ * result is bit-identical to the sequential numpy loop.  stamps (N,S,S,C) f32. */
+int dbv_window_axpy(const void* in_dev, void* out_dev, int field_dtype, int64_t F, int C, const float* stamps_dev,
+                    const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S, double alpha, void* stream);
+
+/* mse of the centre window: deblend/field_deblender.py:323-332.  out[k] = mean over
+ * [lo,hi)x[lo,hi)xC of (cutouts[k] - mean[k])^2 in fp64. */
+int dbv_center_mse(const void* cutouts_dev, int cutouts_dtype, const float* mean_dev, int64_t N, int S, int C,
+                   int lo, int hi, double* out_dev, void* stream);
+
+/* training/metrics.py:4-12 on two fields (deblend_iterative/iterative_deblender.py:52,75):
+ * out[0] = mean((a-b)^2) over n elements, fp64, fixed reduction order. */
+int dbv_mse(const void* a_dev, const void* b_dev, int dtype, int64_t n, double* out_dev, void* scratch_dev,
+            int64_t scratch_bytes, void* stream);
+int64_t dbv_mse_scratch_bytes(void);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */
+int64_t dbv_launch_count(const dbv_ctx* ctx);
+int64_t dbv_global_launch_count(void);
+/* name / elapsed ms of the per-layer CUDA-event timers of the last dbv_deblend call made with
+ * profiling enabled; returns the number of layers. */
+int dbv_set_profiling(dbv_ctx* ctx, int enabled);
+int dbv_layer_times(dbv_ctx* ctx, int max_layers, float* ms_out, char* names_out /* max_layers*32 bytes */);
+/* copy an internal activation buffer (debug / per-layer parity): writes fp32 NHWC */
+int dbv_debug_activation(dbv_ctx* ctx, const char* name, int64_t B, float* out_dev, void* stream);
+
+/* tcgen05 / TMA self-test kernels (descriptor conventions this library relies on).  `which`
+ * selects the probe; out_dev receives the kernel result, see csrc/tc_probe.cu. */
+int dbv_probe(int which, const void* a_dev, const void* b_dev, float* out_dev, int M, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEBVADER_B200_H */

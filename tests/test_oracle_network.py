@@ -1,0 +1,74 @@
+"""Self-consistency of the network oracle: explicit numpy restatement vs torch-CPU library convs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vae_numpy as vn
+from oracle import weights as ow
+from oracle.vae_torch import TorchOracle
+
+
+@pytest.fixture(scope="module")
+def wts():
+    return ow.make_random_weights(seed=1234)
+
+
+def test_same_pad_rule():
+    # 59->30 pad (1,1); 30->15 pad (0,1); 15->8 pad (1,1); 8->4 pad (0,1)
+    assert vn.same_pad(59, 3, 2) == (30, 1, 1)
+    assert vn.same_pad(30, 3, 2) == (15, 0, 1)
+    assert vn.same_pad(15, 3, 2) == (8, 1, 1)
+    assert vn.same_pad(8, 3, 2) == (4, 0, 1)
+    assert vn.same_pad(59, 3, 1) == (59, 1, 1)
+
+
+def test_fill_triangular_index_form():
+    # rows 0-15 L[i,j]=t[64+32i+j]; rows 16-31 L[i,j]=t[1055-32i-j]
+    t = np.arange(560, dtype=np.float64)
+    L = vn.fill_triangular_lower(t[32:])
+    for i in range(32):
+        for j in range(i + 1):
+            exp = t[64 + 32 * i + j] if i < 16 else t[1055 - 32 * i - j]
+            assert L[i, j] == exp
+    assert np.all(np.triu(L, 1) == 0)
+
+
+def test_transposed_conv_tiny_bruteforce():
+    rng = np.random.default_rng(0)
+    for s in (1, 2):
+        x = rng.normal(size=(1, 3, 3, 2))
+        w = rng.normal(size=(3, 3, 4, 2))
+        b = rng.normal(size=4)
+        y = vn.conv2d_transpose_same(x, w, b, s)
+        pb = 0 if s == 2 else 1
+        ref = np.zeros((1, 3 * s, 3 * s, 4)) + b
+        for i in range(3):
+            for j in range(3):
+                for ky in range(3):
+                    for kx in range(3):
+                        yy, xx = s * i + ky - pb, s * j + kx - pb
+                        if 0 <= yy < 3 * s and 0 <= xx < 3 * s:
+                            ref[0, yy, xx] += w[ky, kx] @ x[0, i, j]
+        np.testing.assert_allclose(y, ref, atol=1e-12)
+
+
+def test_numpy_vs_torch_fp64(wts):
+    x = ow.synthetic_stamps(3, seed=5, dtype=np.float64)
+    eps = np.random.default_rng(1).normal(size=(3, 32))
+    a = vn.forward(wts, x, eps)
+    b = TorchOracle(wts, dtype=torch.float64).forward(x, eps)
+    for k in ("params", "z", "z_stddev", "mean", "stddev"):
+        np.testing.assert_allclose(a[k], b[k].numpy(), rtol=1e-9, atol=1e-9, err_msg=k)
+    assert a["mean"].shape == (3, 59, 59, 6) and a["stddev"].shape == (3, 59, 59, 6)
+    assert a["mean"].min() >= 0 and a["stddev"].min() >= 1e-4
+    assert a["mean"].max() > 0.05, "random init must produce a non-trivial output"
+
+
+def test_fp32_vs_fp64_within_north_star_tolerance(wts):
+    x = ow.synthetic_stamps(4, seed=6)
+    eps = np.random.default_rng(2).normal(size=(4, 32)).astype(np.float32)
+    a = TorchOracle(wts, dtype=torch.float64).forward(x.astype(np.float64), eps.astype(np.float64))
+    b = TorchOracle(wts, dtype=torch.float32).forward(x, eps)
+    peak = float(a["mean"].abs().max())
+    err = float((a["mean"] - b["mean"].double()).abs().max())
+    assert err <= 1e-5 * max(peak, 1.0), (err, peak)
