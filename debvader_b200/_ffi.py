@@ -1,0 +1,98 @@
+"""ctypes binding of libdebvader_b200.so (the C-ABI in include/debvader_b200.h).
+
+There is no CPU path: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdebvader_b200.so")
+
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+F32, F64 = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+
+c_i64 = C.c_int64
+c_vp = C.c_void_p
+
+
+class DbvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"debvader_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _declare(lib):
+    sig = {
+        "dbv_abi_version": (C.c_int, []),
+        "dbv_last_error": (C.c_char_p, []),
+        "dbv_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, c_i64]),
+        "dbv_destroy": (C.c_int, [c_vp]),
+        "dbv_set_weights": (C.c_int, [c_vp, C.c_char_p, c_vp, C.POINTER(c_i64), C.c_int]),
+        "dbv_finalize_weights": (C.c_int, [c_vp]),
+        "dbv_encode": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+        "dbv_latent": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+        "dbv_decode": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+        "dbv_deblend": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+        "dbv_deblend_host": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+        "dbv_extract": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
+        "dbv_window_axpy": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
+        "dbv_center_mse": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+        "dbv_mse": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
+        "dbv_mse_scratch_bytes": (c_i64, []),
+        "dbv_launch_count": (c_i64, [c_vp]),
+        "dbv_global_launch_count": (c_i64, []),
+        "dbv_set_profiling": (C.c_int, [c_vp, C.c_int]),
+        "dbv_layer_times": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
+        "dbv_debug_activation": (C.c_int, [c_vp, C.c_char_p, c_i64, c_vp, c_vp]),
+        "dbv_probe": (C.c_int, [C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTS = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib, EXPORTS
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing. Build it with `python -m debvader_b200._build` "
+                        "(needs nvcc); debvader_b200 has no CPU fallback."
+                    )
+                l = C.CDLL(LIB_PATH)
+                EXPORTS = _declare(l)
+                if l.dbv_abi_version() != 1:
+                    raise ImportError("libdebvader_b200.so ABI version mismatch; rebuild it")
+                _lib = l
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise DbvError(rc, lib().dbv_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,194 @@
+"""Host side of the field operators: index planning (bit-identical to the reference by
+construction) and thin wrappers that enqueue the CUDA kernels through the C-ABI.
+
+Index planning restates extract/extraction.py:26-32 literally (int() truncation toward zero,
+Python slice clipping / negative wrap-around via the same arithmetic as ``slice.indices``, numpy's
+"length S or length 1 broadcasts" assignment rule), vectorised for ndarray input.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+_DT = {torch.float32: _ffi.F32, torch.float64: _ffi.F64}
+
+
+# ---------------------------------------------------------------------------------------------
+# planning (host, integer-exact)
+# ---------------------------------------------------------------------------------------------
+def _slice_norm(v, n):
+    """start/stop normalisation of slice(start, stop).indices(n) for step 1."""
+    v = np.where(v < 0, v + n, v)
+    return np.clip(v, 0, n)
+
+
+def plan_windows(galaxy_distances_to_center, cutout_size: int, field_size: int):
+    """For every centre: source window start (row, col), its lengths, and acceptance.
+
+    Returns dict of arrays: sx, sy (int64 start row/col), lx, ly (int64), ok (bool).
+    """
+    S, F_ = int(cutout_size), int(field_size)
+    half = int(S / 2)
+    fh = int(F_ / 2)
+    n = len(galaxy_distances_to_center)
+    xi = np.zeros(n, dtype=np.int64)
+    yi = np.zeros(n, dtype=np.int64)
+    valid = np.ones(n, dtype=bool)
+    arr = None
+    if isinstance(galaxy_distances_to_center, np.ndarray) and galaxy_distances_to_center.dtype.kind in "iuf":
+        arr = galaxy_distances_to_center
+    if arr is not None and arr.ndim == 2 and arr.shape[1] >= 2 and (arr.dtype.kind in "iu" or np.isfinite(arr[:, :2]).all()):
+        xi = np.trunc(arr[:, 0]).astype(np.int64)  # int() truncates toward zero
+        yi = np.trunc(arr[:, 1]).astype(np.int64)
+    else:
+        for i in range(n):
+            try:
+                c = galaxy_distances_to_center[i]
+                xi[i], yi[i] = int(c[0]), int(c[1])
+            except ValueError:  # int(nan): numpy raises ValueError, which the reference swallows (extraction.py:35)
+                valid[i] = False
+    xs = -half + xi + fh
+    ys = -half + yi + fh
+    W = 2 * half + 1  # x_end - x_start (extraction.py:27)
+    sx, ex = _slice_norm(xs, F_), _slice_norm(xs + W, F_)
+    sy, ey = _slice_norm(ys, F_), _slice_norm(ys + W, F_)
+    lx = np.maximum(ex - sx, 0)
+    ly = np.maximum(ey - sy, 0)
+    ok = valid & ((lx == S) | (lx == 1)) & ((ly == S) | (ly == 1))
+    return {"sx": sx, "sy": sy, "lx": lx, "ly": ly, "ok": ok}
+
+
+def subtract_offset(field_size: int, cutout_size: int) -> int:
+    """pos_offset of get_residual_field (deblend/field_deblender.py:72)."""
+    return int((int(field_size) - int(cutout_size)) / 2)
+
+
+def integer_positions(dist, shifts, what="positions"):
+    """x_pos = distance + shift (field_deblender.py:83-90) as int64; raises for sub-pixel values."""
+    p = np.asarray(dist, dtype=np.float64) + np.asarray(shifts, dtype=np.float64)
+    r = np.rint(p)
+    if not np.array_equal(r, p):
+        raise NotImplementedError(
+            f"{what} are not integer-valued: the sub-pixel cubic-spline placement of the reference "
+            "(scipy.ndimage.shift) is not part of the B200 hot path; round the centres first "
+            "(detect_objects already does)"
+        )
+    return r.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------
+def _require_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{name} must be a CUDA tensor")
+    if t.dtype not in _DT:
+        raise TypeError(f"{name} must be float32 or float64, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def to_device_field(field_image, device=None):
+    """(1,F,F,C) array-like -> contiguous CUDA tensor, dtype kept (float64 for the reference's fields)."""
+    if isinstance(field_image, torch.Tensor):
+        t = field_image
+    else:
+        a = np.asarray(field_image)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return t.to(device).contiguous()
+
+
+def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch.float64):
+    """Gather the accepted windows of `plan` into a zero-initialised (N,S,S,nb) CUDA tensor."""
+    _require_cuda(field_dev, "field")
+    S = int(cutout_size)
+    n = len(plan["ok"])
+    F_ = field_dev.shape[1]
+    Cf = field_dev.shape[3]
+    out = torch.zeros((n, S, S, nb_of_bands), device=field_dev.device, dtype=out_dtype)
+    ok = plan["ok"]
+    if Cf != nb_of_bands:
+        if Cf != 1:  # numpy cannot broadcast (.., Cf) into (.., nb): every stamp raises ValueError in the reference
+            return out, []
+        field_dev = field_dev.expand(1, F_, F_, nb_of_bands).contiguous()
+    idx = np.nonzero(ok)[0]
+    if idx.size == 0:
+        return out, []
+    flags = ((plan["lx"][idx] == 1) & (S != 1)).astype(np.uint8) | (((plan["ly"][idx] == 1) & (S != 1)).astype(np.uint8) << 1)
+    dev = field_dev.device
+    sx = torch.from_numpy(plan["sx"][idx].astype(np.int32)).to(dev)
+    sy = torch.from_numpy(plan["sy"][idx].astype(np.int32)).to(dev)
+    fl = torch.from_numpy(flags).to(dev)
+    slot = torch.from_numpy(idx.astype(np.int64)).to(dev)
+    with torch.cuda.device(dev):
+        _ffi.check(
+            _ffi.lib().dbv_extract(_ffi.ptr(field_dev), _DT[field_dev.dtype], F_, nb_of_bands, _ffi.ptr(sx), _ffi.ptr(sy), _ffi.ptr(fl),
+                                   _ffi.ptr(slot), int(idx.size), S, _ffi.ptr(out), _DT[out_dtype], _ffi.stream_ptr())
+        )
+    return out, [int(i) for i in idx]
+
+
+def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64):
+    """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy)."""
+    _require_cuda(stamps, "stamps")
+    if stamps.dtype != torch.float32:
+        raise TypeError("stamps must be float32 (the network's output dtype)")
+    dev = stamps.device
+    if field_in is not None:
+        _require_cuda(field_in, "field")
+        shape, dtype = tuple(field_in.shape), field_in.dtype
+    else:
+        shape = tuple(field_shape)
+    F_, Cc = shape[-3], shape[-1]
+    n, S = stamps.shape[0], stamps.shape[1]
+    if out is None:
+        out = torch.empty(shape, device=dev, dtype=dtype)
+    xs = torch.from_numpy(np.asarray(x0, dtype=np.int32)).to(dev)
+    ys = torch.from_numpy(np.asarray(y0, dtype=np.int32)).to(dev)
+    with torch.cuda.device(dev):
+        _ffi.check(
+            _ffi.lib().dbv_window_axpy(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _ffi.ptr(xs), _ffi.ptr(ys),
+                                       n, S, float(alpha), _ffi.stream_ptr())
+        )
+    return out
+
+
+def center_mse(cutouts, means, lo: int, hi: int):
+    """(N,) float64 CUDA tensor of the centre-window MSE (field_deblender.py:323-332)."""
+    _require_cuda(cutouts, "cutouts")
+    _require_cuda(means, "means")
+    n, S, _, Cc = cutouts.shape
+    out = torch.empty((n,), device=cutouts.device, dtype=torch.float64)
+    with torch.cuda.device(cutouts.device):
+        _ffi.check(
+            _ffi.lib().dbv_center_mse(_ffi.ptr(cutouts), _DT[cutouts.dtype], _ffi.ptr(means), n, S, Cc, int(lo), int(hi), _ffi.ptr(out),
+                                      _ffi.stream_ptr())
+        )
+    return out
+
+
+def mse(a, b) -> float:
+    """training/metrics.py:4-12 on the device (uploads host arrays)."""
+    dev = a.device if isinstance(a, torch.Tensor) and a.is_cuda else (b.device if isinstance(b, torch.Tensor) and b.is_cuda else None)
+    ta, tb = to_device_field(a, dev), to_device_field(b, dev)
+    if ta.shape != tb.shape:
+        ta, tb = torch.broadcast_tensors(ta, tb)
+        ta, tb = ta.contiguous(), tb.contiguous()
+    if ta.dtype != tb.dtype:
+        ta, tb = ta.double(), tb.double()
+    n = ta.numel()
+    lib = _ffi.lib()
+    sb = int(lib.dbv_mse_scratch_bytes())
+    scratch = torch.empty((sb // 8,), device=ta.device, dtype=torch.float64)
+    out = torch.empty((1,), device=ta.device, dtype=torch.float64)
+    with torch.cuda.device(ta.device):
+        _ffi.check(lib.dbv_mse(_ffi.ptr(ta), _ffi.ptr(tb), _DT[ta.dtype], n, _ffi.ptr(out), _ffi.ptr(scratch), sb, _ffi.stream_ptr()))
+    return float(out.item())

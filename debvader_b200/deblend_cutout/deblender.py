@@ -1,0 +1,37 @@
+"""B200-native drop-in for reference deblend_cutout/deblender.py:6-24."""
+import numpy as np
+import torch
+
+from .._dist import NormalOutput
+from ..model.model import Deblender
+from ..normalize.normalize import denormalize_non_linear, normalize_non_linear
+
+
+def deblend(net, images, normalise=False, **kw):
+    """Deblend the images with the network; returns ``(mean ndarray float32, distribution)``.
+
+    net: a ``Deblender`` from ``load_deblender`` (any other callable is invoked exactly as the
+         reference does, ``net(float32 images)``, and must return an object with
+         ``.mean().numpy()``).
+    images: (B,59,59,6) array-like, any float dtype; host arrays go through the pipelined
+         host entry point (H2D, kernels and D2H overlap), CUDA tensors stay on the device.
+    normalise: tanh(arcsinh) the input and invert it on the output mean.  NB in the reference
+         this branch replaces the distribution by an ndarray and then calls ``.mean()`` on it
+         (deblender.py:20-24), which cannot work; the intended semantics are implemented.
+    kw: extensions — eps=(B,32) latent draw, sample=False for z=loc, seed=int.
+    """
+    if normalise:
+        images = normalize_non_linear(np.asarray(images.detach().cpu() if isinstance(images, torch.Tensor) else images))
+    if isinstance(net, Deblender):
+        if isinstance(images, torch.Tensor) and images.is_cuda:
+            dist = net(images, **kw)
+            mean = dist.mean().numpy()
+        else:
+            mean, std = net.deblend_host(images, **kw)
+            dist = NormalOutput(torch.from_numpy(mean), torch.from_numpy(std))
+    else:  # a foreign model object: call it the way the reference does (deblender.py:18)
+        dist = net(np.asarray(images, dtype=np.float32))
+        mean = dist.mean().numpy()
+    if normalise:
+        mean = denormalize_non_linear(mean)
+    return (mean, dist)

@@ -1,0 +1,293 @@
+"""B200-native drop-in for reference ``debvader.model.model`` (model/model.py).
+
+``load_deblender`` / ``create_model_vae`` keep the reference signatures
+(model/model.py:164-172, 221-229) and return callables with the same surface as
+the Keras models (``net(x)`` -> distribution with ``.mean()/.stddev()/.sample()/
+.log_prob()``, ``encoder(x)`` -> (B,560), ``decoder(z)``, ``z(x)``), but every
+call runs hand-written sm_100a kernels through the C-ABI in
+``include/debvader_b200.h``.  Only the DC2 architecture is compiled in; any
+other configuration raises (there is no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from .. import _ffi
+from .._dist import MVNTriLOutput, NormalOutput, Value
+from . import ckpt, spec
+
+S, NB, LAT, NPAR = 59, 6, 32, 560
+DEFAULT_PRECISION = os.environ.get("DEBVADER_B200_PRECISION", "bf16x3")
+
+
+def _as_device_f32(x, device):
+    """tf.cast(images, tf.float32) (deblend_cutout/deblender.py:18) onto `device`."""
+    if isinstance(x, Value):
+        x = x.tensor
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    x = x.to(device, non_blocking=True)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+class Deblender:
+    """``net`` of create_model_vae (model/model.py:216): encoder -> MultivariateNormalTriL -> decoder."""
+
+    def __init__(self, weights: dict, precision: str | None = None, device: int | None = None, chunk: int = 0, seed: int = 0):
+        precision = precision or DEFAULT_PRECISION
+        if precision not in _ffi.PREC:
+            raise ValueError(f"precision must be one of {sorted(_ffi.PREC)}, got {precision!r}")
+        lib = _ffi.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("debvader_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.precision = precision
+        self._seed = int(seed)
+        self._calls = 0
+        self._ctx = C.c_void_p()
+        _ffi.check(lib.dbv_create(C.byref(self._ctx), self.device_index, _ffi.PREC[precision], int(chunk)))
+        table = dict(spec.tensor_table())
+        missing = [k for k in table if k not in weights]
+        if missing:
+            raise KeyError(f"weights are missing {len(missing)} tensors, e.g. {missing[0]}")
+        for key in table:
+            a = np.ascontiguousarray(np.asarray(weights[key], dtype=np.float32))
+            shp = (C.c_int64 * a.ndim)(*a.shape)
+            _ffi.check(lib.dbv_set_weights(self._ctx, key.encode(), a.ctypes.data_as(C.c_void_p), shp, a.ndim))
+        _ffi.check(lib.dbv_finalize_weights(self._ctx))
+        self.trainable = False
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            _ffi.lib().dbv_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed: int):
+        self._seed, self._calls = int(seed), 0
+
+    def _next_seed(self, seed):
+        if seed is not None:
+            return int(seed) & (2**64 - 1)
+        self._calls += 1
+        return (self._seed * 0x9E3779B97F4A7C15 + self._calls) & (2**64 - 1)
+
+    @property
+    def launches(self) -> int:
+        return int(_ffi.lib().dbv_launch_count(self._ctx))
+
+    # ---- stages on device tensors ---------------------------------------------------------------
+    def encode(self, x) -> torch.Tensor:
+        """encoder(x): model/model.py:61-100.  (B,59,59,6) -> (B,560) fp32 on the device."""
+        x = self._check_x(_as_device_f32(x, self.device))
+        with torch.cuda.device(self.device):
+            out = torch.empty((x.shape[0], NPAR), device=self.device, dtype=torch.float32)
+            _ffi.check(_ffi.lib().dbv_encode(self._ctx, _ffi.ptr(x), x.shape[0], _ffi.ptr(out), _ffi.stream_ptr()))
+        return out
+
+    def latent(self, params, eps=None, sample=True, seed=None):
+        """MultivariateNormalTriL(32): model/model.py:43-58, 211-214 -> (z, loc, stddev)."""
+        params = _as_device_f32(params, self.device)
+        B = params.shape[0]
+        if eps is not None:
+            eps = _as_device_f32(eps, self.device)
+            if tuple(eps.shape) != (B, LAT):
+                raise ValueError(f"eps must have shape {(B, LAT)}, got {tuple(eps.shape)}")
+        with torch.cuda.device(self.device):
+            z = torch.empty((B, LAT), device=self.device, dtype=torch.float32)
+            loc = torch.empty_like(z)
+            std = torch.empty_like(z)
+            _ffi.check(
+                _ffi.lib().dbv_latent(self._ctx, _ffi.ptr(params), _ffi.ptr(eps), self._next_seed(seed), int(bool(sample)), 0, B,
+                                      _ffi.ptr(z), _ffi.ptr(loc), _ffi.ptr(std), _ffi.stream_ptr())
+            )
+        return z, loc, std
+
+    def decode(self, z) -> NormalOutput:
+        """decoder(z): model/model.py:103-161."""
+        z = _as_device_f32(z, self.device)
+        if z.ndim != 2 or z.shape[1] != LAT:
+            raise ValueError(f"z must have shape (B,{LAT}), got {tuple(z.shape)}")
+        B = z.shape[0]
+        with torch.cuda.device(self.device):
+            mean = torch.empty((B, S, S, NB), device=self.device, dtype=torch.float32)
+            std = torch.empty_like(mean)
+            _ffi.check(_ffi.lib().dbv_decode(self._ctx, _ffi.ptr(z), B, _ffi.ptr(mean), _ffi.ptr(std), _ffi.stream_ptr()))
+        return NormalOutput(mean, std)
+
+    def __call__(self, x, eps=None, sample=True, seed=None, return_z=False):
+        """net(x) (deblend_cutout/deblender.py:18) on device-resident data.
+
+        By default z is *sampled* like the reference (the TFP layer's convert_to_tensor_fn is
+        Distribution.sample); pass ``eps=`` for a given draw or ``sample=False`` for z = loc."""
+        x = self._check_x(_as_device_f32(x, self.device))
+        B = x.shape[0]
+        if eps is not None:
+            eps = _as_device_f32(eps, self.device)
+            if tuple(eps.shape) != (B, LAT):
+                raise ValueError(f"eps must have shape {(B, LAT)}, got {tuple(eps.shape)}")
+        with torch.cuda.device(self.device):
+            mean = torch.empty((B, S, S, NB), device=self.device, dtype=torch.float32)
+            std = torch.empty_like(mean)
+            z = torch.empty((B, LAT), device=self.device, dtype=torch.float32) if return_z else None
+            _ffi.check(
+                _ffi.lib().dbv_deblend(self._ctx, _ffi.ptr(x), B, _ffi.ptr(eps), self._next_seed(seed), int(bool(sample)),
+                                       _ffi.ptr(mean), _ffi.ptr(std), _ffi.ptr(z), _ffi.stream_ptr())
+            )
+        out = NormalOutput(mean, std)
+        return (out, z) if return_z else out
+
+    # ---- host buffers: the end-to-end call ---------------------------------------------------------
+    def deblend_host(self, images, eps=None, sample=True, seed=None, want_stddev=True, out_mean=None, out_stddev=None):
+        """Host ndarray in, host ndarrays out, H2D / compute / D2H pipelined inside the C-ABI
+        (dbv_deblend_host).  float64 input is cast on the device.  Returns (mean, stddev|None)."""
+        a = images if isinstance(images, np.ndarray) else np.asarray(images)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32)
+        a = np.ascontiguousarray(a)
+        self._check_x(a)
+        B = a.shape[0]
+        mean = out_mean if out_mean is not None else np.empty((B, S, S, NB), dtype=np.float32)
+        std = (out_stddev if out_stddev is not None else np.empty((B, S, S, NB), dtype=np.float32)) if want_stddev else None
+        e = None
+        if eps is not None:
+            e = np.ascontiguousarray(np.asarray(eps, dtype=np.float32))
+            if e.shape != (B, LAT):
+                raise ValueError(f"eps must have shape {(B, LAT)}, got {e.shape}")
+        vp = lambda arr: None if arr is None else arr.ctypes.data_as(C.c_void_p)
+        _ffi.check(
+            _ffi.lib().dbv_deblend_host(self._ctx, vp(a), _ffi.F64 if a.dtype == np.float64 else _ffi.F32, B, vp(e),
+                                        self._next_seed(seed), int(bool(sample)), vp(mean), vp(std), None)
+        )
+        return mean, std
+
+    # ---- diagnostics ------------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        _ffi.check(_ffi.lib().dbv_set_profiling(self._ctx, int(bool(on))))
+
+    def layer_times(self):
+        """[(layer name, ms)] of the last chunk run with profiling on (CUDA events)."""
+        n = 64
+        ms = (C.c_float * n)()
+        names = C.create_string_buffer(32 * n)
+        torch.cuda.synchronize(self.device)
+        k = _ffi.check(_ffi.lib().dbv_layer_times(self._ctx, n, ms, names))
+        return [(names.raw[32 * i : 32 * i + 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(k)]
+
+    def debug_activation(self, name: str, B: int, shape):
+        out = torch.empty((B,) + tuple(shape), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().dbv_debug_activation(self._ctx, name.encode(), B, _ffi.ptr(out), _ffi.stream_ptr()))
+        return out
+
+    @staticmethod
+    def _check_x(x):
+        if x.ndim != 4 or tuple(x.shape[1:]) != (S, S, NB):
+            raise ValueError(f"images must have shape (B,{S},{S},{NB}) (the DC2 deblender), got {tuple(x.shape)}")
+        return x
+
+
+class EncoderModel:
+    """``encoder`` of create_model_vae (model/model.py:182-189): x -> (B,560)."""
+
+    def __init__(self, net: Deblender):
+        self.net = net
+
+    def __call__(self, x):
+        return Value(self.net.encode(x))
+
+
+class DecoderModel:
+    """``decoder`` of create_model_vae (model/model.py:191-199): z -> Normal(loc, scale)."""
+
+    def __init__(self, net: Deblender):
+        self.net = net
+        self.trainable = False
+
+    def __call__(self, z):
+        if isinstance(z, MVNTriLOutput):
+            z = z.sample().tensor
+        return self.net.decode(z)
+
+
+class LatentModel:
+    """``Model(inputs=x_input, outputs=z)`` (model/model.py:218): x -> MultivariateNormalTriL."""
+
+    def __init__(self, net: Deblender):
+        self.net = net
+
+    def __call__(self, x, eps=None, sample=True, seed=None):
+        p = self.net.encode(x)
+        z, loc, std = self.net.latent(p, eps=eps, sample=sample, seed=seed)
+        return MVNTriLOutput(loc, std, z)
+
+
+def _resolve_weights(survey, weights):
+    if isinstance(weights, dict):
+        return weights
+    if isinstance(weights, str) and weights.startswith("random"):
+        seed = int(weights.split(":", 1)[1]) if ":" in weights else 1234
+        return spec.random_weights(seed)
+    if isinstance(weights, str) and weights.endswith(".npz"):
+        with np.load(weights) as f:
+            return {k: f[k] for k in f.files}
+    dirs = []
+    if isinstance(weights, str):
+        dirs.append(weights)
+    if os.environ.get("DEBVADER_WEIGHTS_DIR"):
+        dirs.append(os.path.join(os.environ["DEBVADER_WEIGHTS_DIR"], survey))
+    dirs.append(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "weights", survey))
+    errors = []
+    for d in dirs:
+        print(d)  # the reference prints the loading path (model/model.py:264)
+        latest = ckpt.latest_checkpoint(d) if os.path.isdir(d) else (d if os.path.exists(d + ".index") else None)
+        if latest is None:
+            errors.append(f"{d}: no checkpoint")
+            continue
+        try:
+            return ckpt.load_checkpoint(latest)
+        except FileNotFoundError as e:  # index present, tensor data missing
+            errors.append(str(e))
+    raise FileNotFoundError(
+        f"no usable '{survey}' checkpoint found ({'; '.join(errors)}). Pass weights=<dict | .npz | checkpoint dir>, "
+        "set DEBVADER_WEIGHTS_DIR, or use weights='random[:seed]' for random-init weights of the same architecture."
+    )
+
+
+def create_model_vae(input_shape, latent_dim, filters, kernels, conv_activation=None, dense_activation=None, for_onnx=False,
+                     *, weights="random", precision=None, device=None, chunk=0, seed=0):
+    """Reference signature model/model.py:164-172; returns (net, encoder, decoder, z-model)."""
+    if not spec.is_dc2(input_shape, latent_dim, filters, kernels):
+        raise NotImplementedError(
+            "debvader_b200 is specialised for the DC2 deblender: input_shape=(59,59,6), latent_dim=32, "
+            f"filters=[32,64,128,256], kernels=[3,3,3,3]; got {input_shape}, {latent_dim}, {list(filters)}, {list(kernels)}"
+        )
+    if conv_activation is not None or dense_activation is not None:
+        raise NotImplementedError("only the reference's activation=None configuration is implemented")
+    net = Deblender(_resolve_weights("dc2", weights), precision=precision, device=device, chunk=chunk, seed=seed)
+    return net, EncoderModel(net), DecoderModel(net), LatentModel(net)
+
+
+def load_deblender(survey, input_shape, latent_dim, filters, kernels, return_encoder_decoder_z=False, for_onnx=False,
+                   *, weights=None, precision=None, device=None, chunk=0, seed=0):
+    """Reference signature model/model.py:221-229.  Extension kwargs are keyword-only:
+    weights (dict | .npz | checkpoint dir | 'random[:seed]'), precision ('fp32'|'bf16'|'bf16x3'), device, chunk, seed."""
+    if not spec.is_dc2(input_shape, latent_dim, filters, kernels):
+        raise NotImplementedError("debvader_b200 implements the DC2 deblender architecture only (no fallback)")
+    net = Deblender(_resolve_weights(survey, weights), precision=precision, device=device, chunk=chunk, seed=seed)
+    if return_encoder_decoder_z:
+        return net, EncoderModel(net), DecoderModel(net), LatentModel(net)
+    return net

@@ -33,6 +33,8 @@ class TorchOracle:
             torch.set_num_threads(threads)
         self.dtype = dtype
         self.emulate = emulate
+        self.keep_acts = False  # when True, forward() records every layer's NHWC output in self.acts
+        self.acts = {}
         self.w = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in weights.items()}
         w = self.w
         self.enc_convs = []
@@ -73,9 +75,13 @@ class TorchOracle:
             h = torch.clamp_min(h, 0) + alpha * torch.clamp_max(h, 0)
             if i != last:  # the last conv's epilogue also applies the Flatten PReLU before storing
                 h = _q(h, em)
+                if self.keep_acts:
+                    self.acts["enc_conv%d" % (i + 1)] = h.permute(0, 2, 3, 1).contiguous()
         h = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)  # Flatten (h,w,c)
         h = torch.clamp_min(h, 0) + self.enc_flat_alpha * torch.clamp_max(h, 0)
         h = _q(h, em)
+        if self.keep_acts:
+            self.acts["enc_conv8"] = h.reshape(-1, 4, 4, 256)
         return h @ self.enc_dense[0] + self.enc_dense[1]
 
     # ---- latent: model.py:43-58 ---------------------------------------------------
@@ -97,18 +103,24 @@ class TorchOracle:
         # the GPU tensor-core path keeps Dense(32->560) in fp32 SIMT, so no rounding here
         h = pr(h @ w[D % (1, "kernel")] + w[D % (1, "bias")], w[D % (2, "alpha")])
         h = _q(h, em)
+        if self.keep_acts:
+            self.acts["dec_dense1"] = h.reshape(-1, 1, 1, h.shape[1])
         h = pr(h @ _q(w[D % (3, "kernel")], em) + w[D % (3, "bias")], w[D % (4, "alpha")])
         h = _q(h, em)
+        if self.keep_acts:
+            self.acts["dec_dense2"] = h.reshape(-1, 4, 4, 256)
         cin = self.dec_convs[0][0].shape[0]
         ww = int(round((h.shape[1] // cin) ** 0.5))
         h = h.reshape(-1, ww, ww, cin).permute(0, 3, 1, 2)
-        for k, bias, alpha, s in self.dec_convs:
+        for i, (k, bias, alpha, s) in enumerate(self.dec_convs):
             n = h.shape[2]
             if s == 2:
                 h = F.conv_transpose2d(h, k, bias, stride=2, padding=0)[:, :, : 2 * n, : 2 * n]
             else:
                 h = F.conv_transpose2d(h, k, bias, stride=1, padding=1)
             h = _q(pr(h, alpha), em)
+            if self.keep_acts:
+                self.acts["dec_convT%d" % (i + 1)] = h.permute(0, 2, 3, 1).contiguous()
         k, bias = self.head
         h = torch.relu(F.conv2d(F.pad(h, (1, 1, 1, 1)), k, bias))
         S = 59

@@ -1,0 +1,55 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/debvader_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from debvader_b200 import _build, _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _ffi.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "debvader_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dbv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/debvader_b200.h but not exported"
+    assert set(names) == set(_ffi.EXPORTS), "ctypes signatures out of sync with the header"
+
+
+def test_abi_version(lib):
+    assert lib.dbv_abi_version() == 1
+    assert lib.dbv_mse_scratch_bytes() > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu(lib):
+    ctx = ctypes.c_void_p()
+    rc = lib.dbv_create(ctypes.byref(ctx), 0, 0, 0)
+    assert rc < 0
+    assert b"no CUDA device" in lib.dbv_last_error() or b"CPU" in lib.dbv_last_error()
+    from debvader_b200.model.model import load_deblender
+
+    with pytest.raises(RuntimeError):
+        load_deblender("dc2", (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights="random")
+
+
+def test_non_dc2_architecture_is_refused():
+    from debvader_b200.model.model import load_deblender
+
+    with pytest.raises(NotImplementedError):
+        load_deblender("dc2", (64, 64, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights="random")

@@ -1,0 +1,98 @@
+"""Pure-Python TF tensor-bundle reader: round trip on a synthetic bundle written in the same format,
+and the architecture golden parsed from the shipped DC2 index (tests/golden/architecture.json)."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from debvader_b200.model import ckpt, spec
+
+
+def _varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _block(entries):
+    # no prefix compression, a single restart point
+    body = b"".join(_varint(0) + _varint(len(k)) + _varint(len(v)) + k + v for k, v in entries)
+    return body + struct.pack("<I", 0) + struct.pack("<I", 1)
+
+
+def _entry(shape, offset, size, shard=0):
+    dims = b"".join(b"\x12" + _varint(len(d)) + d for d in (b"\x08" + _varint(s) for s in shape))
+    return b"\x08\x01" + b"\x12" + _varint(len(dims)) + dims + b"\x18" + _varint(shard) + b"\x20" + _varint(offset) + b"\x28" + _varint(size)
+
+
+def write_bundle(prefix, tensors):
+    data = bytearray()
+    entries = []
+    for key in sorted(tensors):
+        a = np.ascontiguousarray(tensors[key], dtype="<f4")
+        entries.append(((key + "/.ATTRIBUTES/VARIABLE_VALUE").encode(), _entry(a.shape, len(data), a.nbytes)))
+        data += a.tobytes()
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    blk = _block(entries)
+    trailer = b"\x00" + b"\x00\x00\x00\x00"
+    f = bytearray(blk + trailer)
+    handle = _varint(0) + _varint(len(blk))
+    idx = _block([(entries[-1][0], handle)])
+    idx_off = len(f)
+    f += idx + trailer
+    meta = _block([])
+    meta_off = len(f)
+    f += meta + trailer
+    footer = _varint(meta_off) + _varint(len(meta)) + _varint(idx_off) + _varint(len(idx))
+    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", 0xDB4775248B80FB57)
+    f += footer
+    open(prefix + ".index", "wb").write(bytes(f))
+    open(os.path.join(os.path.dirname(prefix), "checkpoint"), "w").write(f'model_checkpoint_path: "{os.path.basename(prefix)}"\n')
+
+
+def test_bundle_round_trip(tmp_path):
+    w = spec.random_weights(seed=3)
+    small = {k: v for k, v in w.items() if v.size < 40000}
+    prefix = str(tmp_path / "w.ckpt")
+    write_bundle(prefix, small)
+    assert ckpt.latest_checkpoint(str(tmp_path)) == prefix
+    got = ckpt.load_checkpoint(prefix)
+    assert set(got) == set(small)
+    for k in small:
+        np.testing.assert_array_equal(got[k], small[k])
+
+
+def test_missing_data_shard_is_a_clear_error(tmp_path):
+    prefix = str(tmp_path / "w.ckpt")
+    write_bundle(prefix, {"layer_with_weights-0/layer_with_weights-0/gamma": np.ones(6, np.float32)})
+    os.remove(prefix + ".data-00000-of-00001")
+    with pytest.raises(FileNotFoundError):
+        ckpt.load_checkpoint(prefix)
+
+
+def test_spec_matches_shipped_checkpoint_index(golden_dir):
+    a = json.load(open(os.path.join(golden_dir, "architecture.json")))
+    table = spec.tensor_table()
+    assert len(table) == 64
+    for key, shape in table:
+        assert a["tensors"][key] == list(shape), key
+    w = spec.random_weights(1)
+    enc = sum(v.size for k, v in w.items() if k.startswith("layer_with_weights-0/"))
+    dec = sum(v.size for k, v in w.items() if k.startswith("layer_with_weights-1/"))
+    assert {"encoder": enc, "decoder": dec, "total": enc + dec} == a["net_summary_params"]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/debvader/data/weights/dc2/checkpoint"), reason="build container only")
+def test_reader_on_the_real_index():
+    d = "/root/reference/src/debvader/data/weights/dc2"
+    latest = ckpt.latest_checkpoint(d)
+    entries = ckpt.read_index(latest + ".index")
+    assert {k: tuple(e["shape"]) for k, e in entries.items()} == dict(spec.tensor_table())
+    with pytest.raises(FileNotFoundError):  # the 99.8 MB data shard is not part of the snapshot
+        ckpt.load_checkpoint(latest)

@@ -1,0 +1,83 @@
+"""-m gpu: DeblendField / IterativeDeblendField end to end on the device (BASELINE cfg 0 inputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import field_numpy as fo
+from oracle import weights as ow
+from oracle.vae_torch import TorchOracle
+
+pytestmark = pytest.mark.gpu
+CFG = ("dc2", (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3])
+
+
+@pytest.fixture(scope="module")
+def wts():
+    return ow.make_random_weights(seed=1234)
+
+
+def test_deblend_field_on_the_packaged_dc2_field(wts, golden_dir):
+    from debvader import DeblendField  # reference import path (src/debvader/__init__.py:1)
+    from debvader.model.model import load_deblender
+
+    g = np.load(os.path.join(golden_dir, "dc2_field2.npz"))
+    field, centres = g["field"], g["centres"]
+    net = load_deblender(*CFG, weights=wts, precision="bf16x3", seed=3)
+    obj = DeblendField(net, field)
+    # the reference samples z; pin the draw by seeding, and compare with the oracle at the SAME z
+    rec = obj.deblend_field(centres)
+    assert list(rec["list_idx"]) == list(g["list_idx"])  # order contract
+    assert rec.dtype.names == ("cutout_images", "output_images_mean", "output_images_stddev", "shifts", "list_idx",
+                               "galaxy_distances_to_center_x", "galaxy_distances_to_center_y", "epistemic_uncertainty", "passed_cuts")
+    cut_ref, idx_ref = fo.extract_cutouts(field, 259, centres, 59, 6)
+    cuts = np.stack(list(rec["cutout_images"]))
+    np.testing.assert_array_equal(cuts, cut_ref[idx_ref])
+    means = np.stack(list(rec["output_images_mean"]))
+    stds = np.stack(list(rec["output_images_stddev"]))
+    assert means.dtype == np.float32 and means.shape == (len(idx_ref), 59, 59, 6) and (stds >= 1e-4).all()
+    # centre-window MSE / passed_cuts recomputed by the oracle from the same arrays
+    m = fo.center_mse(cuts, means)
+    assert list(rec["passed_cuts"]) == [not (v > 100.0) for v in m]
+    # residual: bit-identical to the sequential slice-subtract of the same means
+    res = obj.get_residual_field()
+    want = fo.residual_field(field, means, np.array(list(rec["galaxy_distances_to_center_x"])), np.array(list(rec["galaxy_distances_to_center_y"])))
+    np.testing.assert_array_equal(res, want)
+    pf = obj.get_predicted_field()
+    wpf = fo.predicted_fields(259, 6, means, stds, None, centres[idx_ref, 0], centres[idx_ref, 1])
+    np.testing.assert_array_equal(pf["predicted_mean_field"], wpf["predicted_mean_field"])
+    np.testing.assert_array_equal(pf["predicted_stddev_field"], wpf["predicted_stddev_field"])
+    assert float(np.abs(pf["predicted_epistemic_field"]).max()) == 0.0
+    # network parity on these real cutouts (z = loc to remove the draw)
+    o = TorchOracle(wts, dtype=torch.float64).forward(cuts)
+    d = net(cuts, sample=False)
+    peak = float(o["mean"].abs().max())
+    assert float((d.mean().tensor.double().cpu() - o["mean"]).abs().max()) <= 1e-3 * peak
+    net.close()
+
+
+def test_iterative_deblending_on_device(wts):
+    from debvader import IterativeDeblendField
+    from debvader.model.model import load_deblender
+
+    rng = np.random.default_rng(5)
+    F = 260  # even field size: extraction and subtraction windows differ by one pixel
+    field = rng.normal(0, 0.3, (1, F, F, 6))
+    steps = [np.array([[0.0, 0.0], [40.0, -35.0]]), np.array([[10.0, 10.0], [-50.0, 20.0], [60.0, 60.0]]), np.array([[5.0, 5.0]])]
+    calls = []
+
+    def detector(f):
+        calls.append(1)
+        return steps[min(len(calls) - 1, 2)]
+
+    net = load_deblender(*CFG, weights=wts, precision="bf16x3", seed=1)
+    obj = IterativeDeblendField(net, field, detector=detector)
+    rec = obj.iterative_deblending()
+    assert obj.nb_of_deblended_galaxies == [2, 3, 1] and list(rec["list_idx"]) == [0, 1, 2, 3, 4, 5]
+    assert len(obj.mse) == 3 and all(np.isfinite(obj.mse))
+    res = obj.get_residual_field()
+    means = np.stack(list(rec["output_images_mean"]))
+    want = fo.residual_field(field, means, np.array(list(rec["galaxy_distances_to_center_x"])), np.array(list(rec["galaxy_distances_to_center_y"])))
+    np.testing.assert_array_equal(res, want)
+    net.close()

@@ -1,0 +1,58 @@
+"""Host-side index planning of debvader_b200 vs the oracle and the reference-generated goldens (no GPU)."""
+import json
+import os
+
+import numpy as np
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from debvader_b200 import _fieldops
+from oracle import field_numpy as fo
+
+
+def _ok_list(plan):
+    return [int(i) for i in np.nonzero(plan["ok"])[0]]
+
+
+def test_planner_matches_reference_goldens(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "extraction_cases.json")))
+    for c in g["cases"]:
+        for centres in (c["centres"], np.array(c["centres"], dtype=np.float64)):
+            plan = _fieldops.plan_windows(centres, c["S"], c["F"])
+            assert _ok_list(plan) == c["list_idx"], c["seed"]
+
+
+@settings(max_examples=200, deadline=None)
+@given(
+    F=st.integers(3, 70),
+    S=st.sampled_from([1, 3, 5, 9, 59]),
+    centres=st.lists(st.tuples(st.floats(-150, 150, allow_nan=False), st.floats(-150, 150, allow_nan=False)), min_size=1, max_size=8),
+)
+def test_planner_matches_oracle_windows(F, S, centres):
+    ora = fo.plan_windows(centres, S, F)
+    for inp in (centres, np.array(centres)):
+        plan = _fieldops.plan_windows(inp, S, F)
+        for i, (sx, lx, sy, ly, ok) in enumerate(ora):
+            assert bool(plan["ok"][i]) == ok
+            if ok:
+                assert (plan["sx"][i], plan["lx"][i], plan["sy"][i], plan["ly"][i]) == (sx, lx, sy, ly)
+
+
+def test_planner_nan_is_skipped_like_the_reference():
+    plan = _fieldops.plan_windows([[float("nan"), 0.0], [0, 0]], 5, 15)
+    assert _ok_list(plan) == [1]
+
+
+def test_subtract_offset_even_odd():
+    # for even F the subtract window sits one pixel up-left of the extraction window
+    assert _fieldops.subtract_offset(259, 59) == 100 == int(259 / 2) - int(59 / 2)
+    assert _fieldops.subtract_offset(260, 59) == 100 == int(260 / 2) - int(59 / 2) - 1
+    assert fo.subtract_offset(260, 59) == 100
+
+
+def test_integer_positions_rejects_subpixel():
+    import pytest
+
+    assert list(_fieldops.integer_positions([1.0, -3.0], [0, 0])) == [1, -3]
+    with pytest.raises(NotImplementedError):
+        _fieldops.integer_positions([1.5], [0])
