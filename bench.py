@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the debvader hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3]
+
+A "step" is one pass of the hot path (encode -> latent -> decode of BASELINE cfg 2: a batch of
+4096 synthetic 59x59x6 stamps, 342 MB of fp32 input per step, i.e. larger than the 126 MB L2, so
+consecutive steps never find their input in cache) on each GPU.  One process per GPU (torchrun for
+N>1), stamps shard with no data-path collective -> weak scaling.  Prints ONE JSON line (rank 0):
+
+  value      deblended stamps/s, whole job, inputs resident in HBM, timed with CUDA events on the
+             launching stream between barrier+synchronize, max over ranks
+  e2e        the same metric through the public call deblend(net, images) with HOST buffers:
+             H2D of the step's input from pinned memory + D2H of mean and stddev inside the
+             timed region (wall clock around the synchronous call)
+  roofline   the dominant kernel (the slowest layer) against the measured tensor-core peak
+  cpu_baseline  the CPU oracle (torch-CPU restatement of the reference model — a stand-in, NOT
+             TensorFlow, which is not installable here) on a bounded sample of the same workload
+  field      extras: extraction / scatter kernels in GB/s against measured HBM bandwidth, and ms per
+             4096^2 field with 2000 sources
+
+--impl reference times the reference's CPU path stand-in (oracle port) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "deblended stamps/sec (encode+decode)"
+UNIT = "stamps/s"
+BATCH = 4096
+CFG = ("dc2", (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3])
+STAMP_ELTS = 59 * 59 * 6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_stamps_device(n, seed, device):
+    """SURVEY §8d cfg 2/3 generator on the device: sky noise N(0,0.3) + a centred elliptical blob."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn((n, 59, 59, 6), device=device, generator=g) * 0.3
+    yy, xx = torch.meshgrid(torch.arange(59, device=device, dtype=torch.float32), torch.arange(59, device=device, dtype=torch.float32), indexing="ij")
+    peak = 10 ** (torch.rand((n, 1, 1), device=device, generator=g) * 2 - 0.5)
+    sx = 1.5 + 3.5 * torch.rand((n, 1, 1), device=device, generator=g)
+    sy = 1.5 + 3.5 * torch.rand((n, 1, 1), device=device, generator=g)
+    prof = peak * torch.exp(-0.5 * (((xx - 29) / sx) ** 2 + ((yy - 29) / sy) ** 2))
+    sed = 0.3 + 0.7 * torch.rand((n, 1, 1, 6), device=device, generator=g)
+    return (x + prof[..., None] * sed).contiguous()
+
+
+def cpu_reference_rate(sample, threads=None):
+    """stamps/s of the oracle port (torch-CPU restatement of reference model/model.py) on host cores."""
+    from oracle import weights as ow
+    from oracle.vae_torch import TorchOracle
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    o = TorchOracle(ow.make_random_weights(seed=1234), dtype=torch.float32)
+    x = torch.from_numpy(ow.synthetic_stamps(min(sample, 256), seed=0))
+    eps = torch.randn((x.shape[0], 32))
+    o.forward(x[:32], eps[:32])  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while done < sample:
+        o.forward(x, eps)
+        done += x.shape[0]
+    dt = time.perf_counter() - t0
+    return done / dt, threads, done, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = 256
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, threads, done, dt = cpu_reference_rate(sample)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batched deblend() of synthetic 59x59x6 stamps (BASELINE cfg 2), CPU", "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} stamps per step in one batch; torch-CPU restatement of the reference model (stand-in, not TensorFlow: TF 2.13 is not installable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def field_extras(net, device, pk, quick=False):
+    """Extraction / scatter kernels (GB/s vs measured HBM) and ms per 4096^2 field (BASELINE cfg 3)."""
+    from debvader_b200 import _fieldops
+
+    F, S, C, N = 4096, 59, 6, 2000
+    g = torch.Generator(device=device).manual_seed(5)
+    field = (torch.randn((1, F, F, C), device=device, generator=g, dtype=torch.float32) * 0.6).double()
+    rng = np.random.default_rng(5)
+    centres = rng.integers(-(F // 2 - 30), F // 2 - 30, size=(N, 2)).astype(np.float64)
+    plan = _fieldops.plan_windows(centres, S, F)
+    off = _fieldops.subtract_offset(F, S)
+    x0, y0 = off + centres[:, 0].astype(np.int64), off + centres[:, 1].astype(np.int64)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = {}
+
+    def timeit(fn, iters=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    # many more stamps than one field has, so the gather is timed over >L2 of traffic: 16k stamps x 334 KB = 5.5 GB
+    big_c = rng.integers(-(F // 2 - 30), F // 2 - 30, size=(16384, 2)).astype(np.float64)
+    big_plan = _fieldops.plan_windows(big_c, S, F)
+    t = timeit(lambda: _fieldops.extract(field, big_plan, S, C, out_dtype=torch.float64))
+    out["extract_f64"] = {"GBps": 16384 * STAMP_ELTS * 16 / t / 1e6, "ms": t, "stamps": 16384, "bytes_per_stamp": STAMP_ELTS * 16}
+    t = timeit(lambda: _fieldops.extract(field, big_plan, S, C, out_dtype=torch.float32))
+    out["extract_f64_to_f32"] = {"GBps": 16384 * STAMP_ELTS * 12 / t / 1e6, "ms": t, "stamps": 16384, "bytes_per_stamp": STAMP_ELTS * 12}
+    stamps32, _ = _fieldops.extract(field, plan, S, C, out_dtype=torch.float32)
+    res = torch.empty_like(field)
+    t = timeit(lambda: _fieldops.window_axpy(field, stamps32, x0, y0, -1.0, out=res))
+    alg = N * STAMP_ELTS * 20  # stamp read + f64 field window RMW
+    full = 2 * field.numel() * 8 + N * STAMP_ELTS * 4  # what the owner-computes kernel really moves: whole field in+out, stamps once
+    out["window_axpy_f64"] = {"GBps_algorithmic": alg / t / 1e6, "GBps_moved": full / t / 1e6, "ms": t, "stamps": N}
+    for k in out.values():
+        for kk in list(k):
+            if kk.startswith("GBps"):
+                k["frac" + kk[4:]] = round(k[kk] / pk["hbm_gbs"], 4)
+    if not quick:
+        def one_field():
+            cut, idx = _fieldops.extract(field, plan, S, C, out_dtype=torch.float32)
+            d = net(cut)
+            _fieldops.center_mse(cut, d.mean().tensor, 24, 34)
+            r = _fieldops.window_axpy(field, d.mean().tensor, x0, y0, -1.0, out=res)
+            return _fieldops.mse(field, r)
+        out["ms_per_field"] = {"value": timeit(one_field, iters=3), "field": "4096x4096x6 f64", "sources": N,
+                               "includes": "extract+cast, net, centre MSE, residual subtract, field MSE (device resident; detection excluded)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / field / alternative-precision extras")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    from debvader_b200 import _ffi
+    from debvader_b200.deblend_cutout.deblender import deblend
+    from debvader_b200.model import spec
+    from debvader_b200.model.model import load_deblender
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU path)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    pk = peaks()
+    B = args.batch
+    net = load_deblender(*CFG, weights="random:1234", precision=args.precision, chunk=args.chunk, seed=rank)
+    x = synthetic_stamps_device(B, 1000 + rank, device)
+    mean = torch.empty((B, 59, 59, 6), device=device)
+    std = torch.empty_like(mean)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        net.deblend_into(x, mean, std)
+    net.set_profiling(True)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = _ffi.lib().dbv_global_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        net.deblend_into(x, mean, std)
+    e1.record()
+    barrier()
+    launches = int(_ffi.lib().dbv_global_launch_count() - l0)
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+    layers = net.layer_times()  # last timed step, summed over its chunks
+    net.set_profiling(False)
+
+    # ---- e2e through the public API with host buffers ------------------------------------------------
+    x_host = torch.empty((B, 59, 59, 6), dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x)
+    xh = x_host.numpy()
+    for _ in range(2):
+        m, d = deblend(net, xh)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        m, d = deblend(net, xh)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = world * B * e2e_steps / float(t_e2e.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peak_tf = pk["bf16_tflops_sustained"]  # kernels timed inside a long step: sustained figure
+    lay = []
+    for name, lms in layers:
+        macs = spec.LAYER_MACS.get(name, 0)
+        tf = 2 * macs * B / (lms / 1e3) / 1e12 if lms > 0 else 0.0
+        lay.append({"layer": name, "ms": round(lms, 4), "tflops": round(tf, 2), "frac": round(tf / peak_tf, 4)})
+    tc_lay = [l for l in lay if spec.LAYER_MACS.get(l["layer"], 0) > 0]
+    top = max(tc_lay, key=lambda l: l["ms"]) if tc_lay else {"layer": None, "tflops": 0.0, "ms": 0.0}
+    sum_ms = sum(l["ms"] for l in lay) or 1.0
+    net_tf = value / world * spec.FLOP_PER_STAMP / 1e12
+    roofline = {"bound": "tensor", "kernel": f"tc_conv_kernel[{top['layer']}]", "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(top["tflops"] / peak_tf, 4), "traffic": None, "share_of_step": round(top["ms"] / sum_ms, 4),
+                "peak_source": pk["source"] + " bf16 sustained", "flops": "algorithmic (nominal 2*MACs of the layer; bf16x3 executes 3x that on the tensor pipe)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": "batched deblend() of 4096 synthetic 59x59x6 stamps per GPU (BASELINE cfg 2), random-init DC2 weights",
+                   "stamps_per_gpu_per_step": B, "precision": args.precision, "l2": "step input 342 MB > 126 MB L2 (inputs larger than L2)",
+                   "parallelism": f"dp{world} (stamps sharded, no data-path collective)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * STAMP_ELTS * 4, "d2h_bytes_per_step": 2 * B * STAMP_ELTS * 4,
+                "api": "debvader_b200.deblend_cutout.deblender.deblend(net, host ndarray) -> dbv_deblend_host", "timing": "wall clock, max over ranks"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "network": {"tflops_algorithmic": round(net_tf, 2), "frac_of_bf16_sustained": round(net_tf / pk["bf16_tflops_sustained"], 4),
+                    "frac_of_bf16_burst": round(net_tf / pk["bf16_tflops"], 4), "flop_per_stamp": spec.FLOP_PER_STAMP},
+        "layers": lay,
+    }
+    if not args.no_extras:
+        try:
+            alt = {}
+            for prec in [p for p in ("bf16", "bf16x3") if p != args.precision]:
+                n2 = load_deblender(*CFG, weights="random:1234", precision=prec, chunk=args.chunk)
+                for _ in range(3):
+                    n2.deblend_into(x, mean, std)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    n2.deblend_into(x, mean, std)
+                b.record()
+                torch.cuda.synchronize()
+                alt[prec] = {"value": B * 5 / (a.elapsed_time(b) / 1e3), "unit": UNIT, "n_gpus": 1,
+                             "note": "single-pass bf16: ~1e-2 of peak flux, does NOT meet the 1e-3 tolerance" if prec == "bf16" else "meets 1e-3"}
+                n2.close()
+            line["alt_precision"] = alt
+        except Exception as e:  # extras never break the contract line
+            line["alt_precision"] = {"error": repr(e)}
+        try:
+            line["field"] = field_extras(net, device, pk)
+        except Exception as e:
+            line["field"] = {"error": repr(e)}
+        try:
+            v, threads, done, dt = cpu_reference_rate(1024)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{done} stamps in batches of 256 ({dt:.1f} s); torch-CPU restatement of the reference model (stand-in, not TensorFlow)"}
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -434,7 +434,7 @@ static int run_chunk(dbv_ctx* c, const float* x, long long B, const float* eps, 
                      bool do_lat, bool do_dec, cudaStream_t st) {
   const bool fp32 = c->precision == DBV_PREC_FP32;
   int r;
-  if (c->profiling) { c->prof_n = 0; prof_mark(c, "start", st); }
+  if (c->profiling) prof_mark(c, "start", st);
   float* params = c->params;
   if (do_enc) {
     const void* in = x;
@@ -654,6 +654,7 @@ static int chunked(dbv_ctx* c, const char* fn, const float* x, int64_t B, const 
   DBV_REQUIRE(B >= 0, "%s: negative B", fn);
   cudaStream_t st = (cudaStream_t)stream;
   const long long before = g_launches.load();
+  c->prof_n = 0;
   for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
     const long long nb = std::min<long long>(c->chunk, B - b0);
     r = run_chunk(c, x ? x + b0 * STAMP_ELTS : nullptr, nb, eps ? eps + b0 * LAT : nullptr, seed, sample, first_stamp + b0,
@@ -768,13 +769,24 @@ extern "C" int dbv_set_profiling(dbv_ctx* c, int enabled) {
 
 extern "C" int dbv_layer_times(dbv_ctx* c, int max_layers, float* ms_out, char* names_out) {
   DBV_REQUIRE(c && ms_out && names_out, "dbv_layer_times: null argument");
-  int n = 0;
-  for (int i = 1; i < c->prof_n && n < max_layers; ++i, ++n) {
+  // sum over chunks, layers in order of first appearance; "start" marks open a new chunk
+  std::vector<std::string> names;
+  std::vector<float> tot;
+  for (int i = 1; i < c->prof_n; ++i) {
+    if (c->prof_names[i] == "start") continue;
     float ms = 0.f;
     cudaError_t e = cudaEventElapsedTime(&ms, c->prof_ev[i - 1], c->prof_ev[i]);
     if (e != cudaSuccess) return fail(DBV_ERR_CUDA, "dbv_layer_times: %s", cudaGetErrorString(e));
-    ms_out[n] = ms;
-    strncpy(names_out + 32 * n, c->prof_names[i].c_str(), 31);
+    size_t k = 0;
+    for (; k < names.size(); ++k)
+      if (names[k] == c->prof_names[i]) break;
+    if (k == names.size()) { names.push_back(c->prof_names[i]); tot.push_back(0.f); }
+    tot[k] += ms;
+  }
+  int n = 0;
+  for (; n < (int)names.size() && n < max_layers; ++n) {
+    ms_out[n] = tot[n];
+    strncpy(names_out + 32 * n, names[n].c_str(), 31);
     names_out[32 * n + 31] = 0;
   }
   return n;

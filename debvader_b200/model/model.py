@@ -150,6 +150,13 @@ class Deblender:
         out = NormalOutput(mean, std)
         return (out, z) if return_z else out
 
+    def deblend_into(self, x, mean, stddev=None, z=None, eps=None, sample=True, seed=None):
+        """net(x) into caller-provided CUDA tensors (no allocation; what bench.py times)."""
+        _ffi.check(
+            _ffi.lib().dbv_deblend(self._ctx, _ffi.ptr(x), x.shape[0], _ffi.ptr(eps), self._next_seed(seed), int(bool(sample)),
+                                   _ffi.ptr(mean), _ffi.ptr(stddev), _ffi.ptr(z), _ffi.stream_ptr())
+        )
+
     # ---- host buffers: the end-to-end call ---------------------------------------------------------
     def deblend_host(self, images, eps=None, sample=True, seed=None, want_stddev=True, out_mean=None, out_stddev=None):
         """Host ndarray in, host ndarrays out, H2D / compute / D2H pipelined inside the C-ABI
@@ -160,8 +167,11 @@ class Deblender:
         a = np.ascontiguousarray(a)
         self._check_x(a)
         B = a.shape[0]
-        mean = out_mean if out_mean is not None else np.empty((B, S, S, NB), dtype=np.float32)
-        std = (out_stddev if out_stddev is not None else np.empty((B, S, S, NB), dtype=np.float32)) if want_stddev else None
+        # outputs live in pinned host memory (torch's caching host allocator recycles the blocks), so the
+        # D2H copies of the pipeline are asynchronous DMA transfers
+        new = lambda: torch.empty((B, S, S, NB), dtype=torch.float32, pin_memory=True).numpy()
+        mean = out_mean if out_mean is not None else new()
+        std = (out_stddev if out_stddev is not None else new()) if want_stddev else None
         e = None
         if eps is not None:
             e = np.ascontiguousarray(np.asarray(eps, dtype=np.float32))

@@ -109,3 +109,16 @@ def random_weights(seed: int = 1234, dtype=np.float32):
             v = rng.uniform(0.05, 0.15, size=shape)
         w[key] = np.ascontiguousarray(v.astype(dtype))
     return w
+
+
+# nominal MACs per stamp of each GEMM-shaped layer (padded taps counted), keyed by the
+# layer names the library reports in dbv_layer_times
+LAYER_MACS = {
+    "enc_conv1": 6_015_168, "enc_conv2": 8_294_400, "enc_conv3": 16_588_800, "enc_conv4": 8_294_400,
+    "enc_conv5": 16_588_800, "enc_conv6": 9_437_184, "enc_conv7": 18_874_368, "enc_conv8": 9_437_184,
+    "enc_dense": 2_293_760, "latent": 0, "dec_dense1": 17_920, "dec_dense2": 2_293_760,
+    "dec_convT1": 9_437_184, "dec_convT2": 37_748_736, "dec_convT3": 18_874_368, "dec_convT4": 37_748_736,
+    "dec_convT5": 18_874_368, "dec_convT6": 37_748_736, "dec_convT7": 18_874_368, "dec_convT8": 37_748_736,
+    "dec_head": 14_155_776,
+}
+assert 2 * sum(LAYER_MACS.values()) == FLOP_PER_STAMP
