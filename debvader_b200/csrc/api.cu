@@ -110,6 +110,9 @@ struct LayerRt {
   // tcgen05 plan
   TcLayer tc{};
   bool has_tc = false;
+  // resident-halo plan (preferred when it exists)
+  HaloLayer halo{};
+  bool has_halo = false;
 };
 
 }  // namespace dbv
@@ -382,6 +385,109 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   return DBV_OK;
 }
 
+// Resident-halo plan for the stride-1 Conv2D / Conv2DTranspose layers (and stride-2 transposed convs as 4
+// classes over one halo) whose packed weights fit in shared memory next to the halo ring.
+static int build_halo_layer(dbv_ctx* c, int li) {
+  const LayerDesc& L = kLayers[li];
+  const TcGeom& G = kTc[li];
+  LayerRt& R = c->rt[li];
+  if (getenv("DBV_NO_HALO")) return DBV_OK;
+  if (!R.has_tc || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
+  if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
+  const LayerRt& P = c->rt[li - 1];
+  const OutSpec& in = P.ospec;
+  if (in.mode != OUT_BF16_NHWC) return DBV_OK;
+  const bool x3 = c->precision == DBV_PREC_BF16X3;
+  const int ROWB = G.CBK * 2;
+  const std::vector<Tap> taps = make_taps(L);
+  const int nchunk = (L.Cin + G.CBK - 1) / G.CBK;
+  const int parts_w = x3 ? 2 : 1;
+  const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
+  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2;
+  const int n_wblk = (int)taps.size() * nchunk * parts_w;
+  const int w_bytes = ((n_wblk * G.NT * ROWB + 1023) / 1024) * 1024;
+  const int n_regions = in.planes * nchunk;
+  if (n_regions > 8) return DBV_OK;
+  const int tail_pad = ((129 * ROWB + 1023) / 1024) * 1024;
+  int bestR = 0, bestBuf = 0;
+  double best = 0.0;
+  for (int nbuf = 2; nbuf >= 1; --nbuf)
+    for (int r = 1; r <= H; ++r) {
+      const int ntiles = (r * WP + 127) / 128;
+      if (ncls * ntiles * G.NT > 256) continue;
+      if (r + 2 > 256 || WP > 256) continue;
+      const long long region = (((long long)(r + 2) * WP * ROWB + 1023) / 1024) * 1024;
+      const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 128;
+      if (smem > HALO_MAX_SMEM) continue;
+      const int bands = (H + r - 1) / r;
+      double eff = (double)H * W / ((double)bands * ntiles * 128.0);
+      eff *= (double)r / (r + 2.0) * 0.15 + 0.85;  // mild preference for a smaller halo overhead
+      if (nbuf == 1) eff *= 0.85;                  // exposed TMA latency per band
+      if (eff > best + 1e-9) { best = eff; bestR = r; bestBuf = nbuf; }
+    }
+  if (!bestR) return DBV_OK;
+  HaloLayer& T = R.halo;
+  memset(&T, 0, sizeof T);
+  T.n_cls = ncls;
+  int nkb = 0;
+  for (int cl = 0; cl < ncls; ++cl) {
+    T.cls[cl].kb_begin = nkb;
+    for (size_t ti = 0; ti < taps.size(); ++ti) {
+      if (taps[ti].cls != cl) continue;
+      for (int ch = 0; ch < nchunk; ++ch)
+        for (int pr = 0; pr < (x3 ? 3 : 1); ++pr) {
+          if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: halo k-block table overflow", L.name);
+          const int a_lo = (pr == 2), w_lo = (pr == 1);
+          TcKBlock& K = T.kb[nkb++];
+          K.dx = K.dy = 0;
+          K.plane = (int16_t)(a_lo * nchunk + ch);
+          K.dx = (int16_t)((taps[ti].dy + 1) * WP + taps[ti].dx + 1);  // row offset of the tap in the halo tile
+          K.b_row = (int32_t)((ti * nchunk + ch) * parts_w + w_lo);      // weight block index (patched below)
+        }
+    }
+    T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
+    T.cls[cl].oy0 = ncls == 4 ? (cl >> 1) : 0;
+    T.cls[cl].ox0 = ncls == 4 ? (cl & 1) : 0;
+    T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
+  }
+  T.W = W; T.H = H; T.R = bestR; T.WP = WP;
+  T.ntiles = (bestR * WP + 127) / 128;
+  T.n_regions = n_regions;
+  for (int r = 0; r < n_regions; ++r) T.region_coff[r] = (r / nchunk) * in.Cpad + (r % nchunk) * G.CBK;
+  T.a_box_bytes = (bestR + 2) * WP * ROWB;
+  T.region_bytes = ((T.a_box_bytes + 1023) / 1024) * 1024;
+  T.n_wblk = n_wblk;
+  T.w_rows_per_blk = G.NT;  // conv layers are not N-tiled: Ntot == NT
+  T.w_bytes = w_bytes;
+  T.nbuf = bestBuf;
+  T.tail_pad = tail_pad;
+  T.smem_bytes = 1024 + w_bytes + bestBuf * n_regions * T.region_bytes + tail_pad + 128;
+  T.bands_per_img = (H + bestR - 1) / bestR;
+  // descriptor offsets in 16-byte units, ready to be added to the low descriptor word by the MMA issuer
+  for (int i = 0; i < nkb; ++i) {
+    TcKBlock& K = T.kb[i];
+    const long long a_off = (long long)K.plane * T.region_bytes + (long long)K.dx * ROWB;
+    const long long b_off = (long long)K.b_row * G.NT * ROWB;
+    if ((a_off >> 4) > 0x7fff || (b_off >> 4) > 0x3fff) return fail(DBV_ERR_UNSUPPORTED, "%s: halo descriptor offset overflow", L.name);
+    K.c_off = (int16_t)(a_off >> 4);
+    K.b_row = (int32_t)(b_off >> 4);
+  }
+  {
+    const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
+    uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
+    uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
+    uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bestR + 2), 1u, 1u};
+    int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, ROWB);
+    if (r) return r;
+    T.tmB = R.tc.tmB;
+  }
+  if (getenv("DBV_VERBOSE"))
+    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d ntiles=%d regions=%d wblk=%d smem=%d eff=%.3f\n", L.name, bestR, bestBuf, T.ntiles,
+            n_regions, n_wblk, T.smem_bytes, best);
+  R.has_halo = true;
+  return DBV_OK;
+}
+
 static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, float* head_mean, float* head_std, float* params_out,
                      cudaStream_t st) {
   const LayerDesc& L = kLayers[li];
@@ -389,6 +495,13 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
   OutSpec o = R.ospec;
   if (li == I_HEAD) { o.out = head_mean; o.out2 = head_std; }
   if (li == I_ENC_DENSE && params_out) o.out = params_out;
+  if (R.has_halo) {
+    HaloLayer T = R.halo;
+    T.B = B;
+    T.o = o;
+    T.total_bands = B * T.bands_per_img;
+    return launch_halo_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
+  }
   if (R.has_tc) {
     TcLayer T = R.tc;
     T.B = B;
@@ -639,7 +752,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   // ---- tensor-core plans ------------------------------------------------------------------------
   if (!fp32)
     for (int li = 0; li < kNumLayers; ++li)
-      if (kTc[li].tc && (r = build_tc_layer(c, li))) return r;
+      if (kTc[li].tc && ((r = build_tc_layer(c, li)) || (r = build_halo_layer(c, li)))) return r;
   DBV_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
   c->host_w.clear();

@@ -85,11 +85,68 @@ __device__ __forceinline__ void apply_act(const OutSpec& o, int y, int x, int c,
   }
 }
 
+// ---- the same epilogue with its global loads hoisted: bias / alpha vectors are fetched into registers
+// (act_prefetch) BEFORE the accumulator is waited for, so their L2 latency overlaps the MMA / TMEM wait.
+template <int NV>
+struct ActRegs {
+  float4 a[NV / 4];  // PReLU alpha of this thread's pixel (the bias is warp-uniform and L1-resident: loaded late)
+  bool fast;
+};
+
+template <int NV>
+__device__ __forceinline__ void act_prefetch(const OutSpec& o, bool ok, int y, int x, int c, int bias_off, ActRegs<NV>& r) {
+  r.fast = ok && (c + NV <= o.Cout) && ((o.Cout & 3) == 0) && o.alpha != nullptr;
+  if (r.fast) {
+    const long long pix = (long long)y * o.OW + x;
+    const float4* ap = reinterpret_cast<const float4*>(o.alpha + pix * o.Cout + c);
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) r.a[j] = __ldg(ap + j);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void act_apply(const OutSpec& o, int y, int x, int c, int bias_off, const ActRegs<NV>& r, float (&v)[NV]) {
+  if (!r.fast) {
+    apply_act<NV>(o, y, x, c, v, bias_off);
+    return;
+  }
+  const float4* bp = reinterpret_cast<const float4*>(o.bias + bias_off + c);
+#pragma unroll
+  for (int j = 0; j < NV / 4; ++j) {
+    const float4 bb = __ldg(bp + j);
+    v[4 * j + 0] = prelu_f(v[4 * j + 0] + bb.x, r.a[j].x);
+    v[4 * j + 1] = prelu_f(v[4 * j + 1] + bb.y, r.a[j].y);
+    v[4 * j + 2] = prelu_f(v[4 * j + 2] + bb.z, r.a[j].z);
+    v[4 * j + 3] = prelu_f(v[4 * j + 3] + bb.w, r.a[j].w);
+  }
+  if (o.alpha2) {
+    const float4* a2p = reinterpret_cast<const float4*>(o.alpha2 + ((long long)y * o.OW + x) * o.Cout + c);
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+      const float4 a = __ldg(a2p + j);
+      v[4 * j + 0] = prelu_f(v[4 * j + 0], a.x);
+      v[4 * j + 1] = prelu_f(v[4 * j + 1], a.y);
+      v[4 * j + 2] = prelu_f(v[4 * j + 2], a.z);
+      v[4 * j + 3] = prelu_f(v[4 * j + 3], a.w);
+    }
+  }
+  if (o.relu) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+// hi = bf16x2(a,b); lo = bf16x2(a - hi.a, b - hi.b): 6 instructions per pair
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(a - ha, b - hb);
+}
 
 // store NV (multiple of 4, c multiple of 4) activated channels of pixel (b,y,x)
 template <int NV>
@@ -123,24 +180,26 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
   const bool full = c + NV <= o.Cpad;
   if (full) {
     if constexpr (NV % 8 == 0) {
-#pragma unroll
-      for (int j = 0; j < NV; j += 8) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]);
-        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(p + j) = q;
-      }
       if (o.planes == 2) {
 #pragma unroll
         for (int j = 0; j < NV; j += 8) {
+          uint4 q, l;
+          split_bf16x2(v[j], v[j + 1], q.x, l.x);
+          split_bf16x2(v[j + 2], v[j + 3], q.y, l.y);
+          split_bf16x2(v[j + 4], v[j + 5], q.z, l.z);
+          split_bf16x2(v[j + 6], v[j + 7], q.w, l.w);
+          *reinterpret_cast<uint4*>(p + j) = q;
+          *reinterpret_cast<uint4*>(p + o.Cpad + j) = l;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV; j += 8) {
           uint4 q;
-          q.x = pack_bf16x2(v[j] - bf16_round(v[j]), v[j + 1] - bf16_round(v[j + 1]));
-          q.y = pack_bf16x2(v[j + 2] - bf16_round(v[j + 2]), v[j + 3] - bf16_round(v[j + 3]));
-          q.z = pack_bf16x2(v[j + 4] - bf16_round(v[j + 4]), v[j + 5] - bf16_round(v[j + 5]));
-          q.w = pack_bf16x2(v[j + 6] - bf16_round(v[j + 6]), v[j + 7] - bf16_round(v[j + 7]));
-          *reinterpret_cast<uint4*>(p + o.Cpad + j) = q;
+          q.x = pack_bf16x2(v[j], v[j + 1]);
+          q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(p + j) = q;
         }
       }
     } else {

@@ -58,6 +58,8 @@ struct TcLayer {
   long long tiles_per_cls;
   long long total_tiles;
   int a_bytes, b_bytes;  // expect_tx per k-block
+  int dbg_shift_rows;    // probe only: A box loaded dbg_shift_rows batch rows early, descriptor start advanced to compensate
+  int dbg_base_mode;     // probe only: 0 = base_offset field 0, 1 = (start_addr >> 7) & 7
   OutSpec o;
 };
 
@@ -65,6 +67,34 @@ struct TcLayer {
 // NT : MMA N (multiple of 16, 16..256)
 int launch_tc_layer(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
 bool tc_layer_supported(int CBK, int NT);
+
+// ---- tcgen05 convolution with a resident halo tile (tc_halo.cu) ----------------------------------------
+// kb[] entries are repurposed: c_off = byte offset >> 4 of the tap's window inside one halo buffer
+// (region * region_bytes + ((dy+1)*(W+2) + dx+1) * ROWB), b_row = byte offset >> 4 of the resident weight block.
+constexpr int HALO_MAX_SMEM = 232448;  // 227 KB
+struct HaloLayer {
+  CUtensorMap tmA;  // 5D (C, W, H, 1, B) bf16, box (CBK, W+2, R+2, 1, 1)
+  CUtensorMap tmB;  // packed weights, box (CBK, NT)
+  TcKBlock kb[TC_MAX_KB];
+  TcClass cls[TC_MAX_CLS];
+  int n_cls;
+  int W, H;          // tile-space extents (valid outputs sx < W, sy < H)
+  int R, WP;         // output rows per band, W + 2
+  int ntiles;        // ceil(R * WP / 128)
+  int n_regions;     // planes * channel chunks
+  int region_coff[8];
+  int region_bytes;  // (R+2) * WP * ROWB rounded up to 1024
+  int a_box_bytes;   // (R+2) * WP * ROWB
+  int n_wblk, w_rows_per_blk, w_bytes;
+  int nbuf;          // halo buffers in the ring (1 or 2)
+  int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)
+  int smem_bytes;
+  int bands_per_img;
+  long long B, total_bands;
+  OutSpec o;
+};
+int launch_halo_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+bool halo_layer_supported(int CBK, int NT);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -18,121 +18,12 @@
 //
 // Reference semantics implemented: model/model.py:80-98 (encoder convs + Dense),
 // :117-137 (decoder Dense + Conv2DTranspose stack + head), with TF padding rules.
-#include "kernels.h"
+#include "tc_ptx.cuh"
 #include <mutex>
 
 namespace dbv {
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, M=128
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// smem matrix descriptor, K-major operand, rows of ROWB bytes packed densely, 8-row swizzle atoms.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-//  layout [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-template <int ROWB>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t layout = (ROWB == 128) ? 2ull : (ROWB == 64 ? 4ull : 6ull);
-  constexpr uint64_t sbo = (8 * ROWB) >> 4;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-constexpr int tmem_cols_for(int n2) { return n2 <= 32 ? 32 : n2 <= 64 ? 64 : n2 <= 128 ? 128 : n2 <= 256 ? 256 : 512; }
-
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 template <int CBK, int NT>
 struct TcCfg {
@@ -188,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const int tiles_img = L.tiles_x * L.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < total; t += gridDim.x) {
@@ -204,14 +95,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const TcKBlock K = L.kb[cl.kb_begin + kb];
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(L.a_bytes + L.b_bytes));
-          tma_load_5d(sA + stage * Cfg::A_STAGE, &L.tmA, bar_full + 8 * stage, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0);
+          tma_load_5d(sA + stage * Cfg::A_STAGE, &L.tmA, bar_full + 8 * stage, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
           tma_load_2d(sB + stage * Cfg::B_STAGE, &L.tmB, bar_full + 8 * stage, 0, K.b_row + nt * NT);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -225,7 +116,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc<Cfg::ROWB>(sA + stage * Cfg::A_STAGE);
+          uint64_t adesc = make_smem_desc<Cfg::ROWB>(sA + stage * Cfg::A_STAGE + L.dbg_shift_rows * Cfg::ROWB);
+          if (L.dbg_base_mode == 1)
+            adesc |= (uint64_t)(((sA + stage * Cfg::A_STAGE + L.dbg_shift_rows * Cfg::ROWB) >> 7) & 7u) << 49;
           const uint64_t bdesc = make_smem_desc<Cfg::ROWB>(sB + stage * Cfg::B_STAGE);
 #pragma unroll
           for (int k = 0; k < CBK / 16; ++k)
@@ -239,61 +132,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
     }
   } else {
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains accumulator
+    // buffer g (every other tile), so two tiles are in the epilogue at once.
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int rows_img = L.TW * L.TH;
     const int tb = row / rows_img;
     const int rr = row - tb * rows_img;
     const int ty = rr / L.TW, tx = rr - ty * L.TW;
     const bool row_ok = tb < L.TB;
+    constexpr int NV = (NT % 32 == 0) ? 32 : 16;
+    constexpr int NCHK = NT / NV;
     int as = 0;
     uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      const int c = (int)(t / L.tiles_per_cls);
-      long long r = t - (long long)c * L.tiles_per_cls;
-      const int nt = (int)(r % L.n_tiles_n);
-      r /= L.n_tiles_n;
-      const int ti = (int)(r % tiles_img);
-      const int bt = (int)(r / tiles_img);
-      const int sx = (ti % L.tiles_x) * L.TW + tx, sy = (ti / L.tiles_x) * L.TH + ty;
-      const long long b = (long long)bt * L.TB + tb;
-      const TcClass cl = L.cls[c];
-      const bool ok = row_ok && b < L.B && sx < L.SW && sy < L.SH;
-      int oy = cl.oy0 + cl.osy * sy, ox = cl.ox0 + cl.osx * sx;
-      int cbase = nt * NT, boff = 0;
-      if (L.nt_pixel_mode) {
-        oy = nt / L.o.OW;
-        ox = nt - oy * L.o.OW;
-        cbase = 0;
-        boff = nt * NT;
-      }
-      mbar_wait(bar_tfull + 8 * as, aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * NT);
-      if constexpr (NT % 32 == 0) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-          float v[32];
-          tmem_ld_x32(taddr + c0, v);
-          if (ok) {
-            apply_act<32>(L.o, oy, ox, cbase + c0, v, boff);
-            store_act<32>(L.o, b, oy, ox, cbase + c0, v);
-          }
+      if (as == half) {
+        const int c = (int)(t / L.tiles_per_cls);
+        long long r = t - (long long)c * L.tiles_per_cls;
+        const int nt = (int)(r % L.n_tiles_n);
+        r /= L.n_tiles_n;
+        const int ti = (int)(r % tiles_img);
+        const int bt = (int)(r / tiles_img);
+        const int sx = (ti % L.tiles_x) * L.TW + tx, sy = (ti / L.tiles_x) * L.TH + ty;
+        const long long b = (long long)bt * L.TB + tb;
+        const TcClass cl = L.cls[c];
+        const bool ok = row_ok && b < L.B && sx < L.SW && sy < L.SH;
+        int oy = cl.oy0 + cl.osy * sy, ox = cl.ox0 + cl.osx * sx;
+        int cbase = nt * NT, boff = 0;
+        if (L.nt_pixel_mode) {
+          oy = nt / L.o.OW;
+          ox = nt - oy * L.o.OW;
+          cbase = 0;
+          boff = nt * NT;
         }
-      } else {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * NT);
+        ActRegs<NV> rc;
+        act_prefetch<NV>(L.o, ok, oy, ox, cbase, boff, rc);
+        mbar_wait(bar_tfull + 8 * as, aphase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          float v[16];
-          tmem_ld_x16(taddr + c0, v);
+        for (int q = 0; q < NCHK; ++q) {
+          ActRegs<NV> rn;
+          rn.fast = false;
+          if (q + 1 < NCHK) act_prefetch<NV>(L.o, ok, oy, ox, cbase + (q + 1) * NV, boff, rn);
+          float v[NV];
+          tmem_ld<NV>(taddr + q * NV, v);
           if (ok) {
-            apply_act<16>(L.o, oy, ox, cbase + c0, v, boff);
-            store_act<16>(L.o, b, oy, ox, cbase + c0, v);
+            act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, rc, v);
+            store_act<NV>(L.o, b, oy, ox, cbase + q * NV, v);
           }
+          rc = rn;
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

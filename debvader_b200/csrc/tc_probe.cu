@@ -11,6 +11,9 @@ using namespace dbv;
 
 extern "C" int dbv_probe(int which, const void* a_dev, const void* b_dev, float* out_dev, int M, int N, int K, void* stream) {
   DBV_REQUIRE(a_dev && b_dev && out_dev, "dbv_probe: null pointer");
+  // which: bits 0-7 = 0 (CBK 64) | 1 (CBK 32); bits 8-15 = A row shift; bits 16-19 = base_offset mode
+  const int shift = (which >> 8) & 0xff, base_mode = (which >> 16) & 0xf;
+  which &= 0xff;
   const int CBK = which == 0 ? 64 : 32;
   DBV_REQUIRE(which == 0 || which == 1, "dbv_probe: unknown probe %d", which);
   DBV_REQUIRE(M > 0 && K > 0 && K % CBK == 0 && K / CBK <= TC_MAX_KB, "dbv_probe: bad K=%d for CBK=%d", K, CBK);
@@ -50,6 +53,8 @@ extern "C" int dbv_probe(int which, const void* a_dev, const void* b_dev, float*
   T.total_tiles = T.tiles_per_cls;
   T.a_bytes = CBK * 2 * 128;
   T.b_bytes = N * CBK * 2;
+  T.dbg_shift_rows = shift;
+  T.dbg_base_mode = base_mode;
   OutSpec& o = T.o;
   o.out = out_dev;
   o.mode = OUT_F32_NHWC;

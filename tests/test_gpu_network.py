@@ -235,3 +235,29 @@ def test_cfg2_batch_4096_properties(wts):
     peak = float(o["mean"].abs().max())
     assert float((a[sub].double().cpu() - o["mean"]).abs().max()) <= 1e-3 * peak
     net.close()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_probe_descriptor_row_shift(which):
+    """Records (does not assert) how tcgen05 treats an operand whose start address is not aligned to the
+    swizzle atom: needed to read 3x3 taps as shifted windows of ONE resident halo tile."""
+    from debvader_b200 import _ffi
+
+    CBK = 64 if which == 0 else 32
+    M, N, K = 256, 64, 2 * CBK
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    b = torch.randn((N, K), device="cuda", generator=g).bfloat16()
+    bp = b.reshape(N, K // CBK, CBK).permute(1, 0, 2).contiguous()
+    want = a.float() @ b.float().T
+    res = {}
+    for shift in (0, 1, 2, 3, 4, 7, 8, 9, 17):
+        for mode in (0, 1):
+            out = torch.zeros((M, N), device="cuda")
+            _ffi.check(_ffi.lib().dbv_probe(which | (shift << 8) | (mode << 16), _ffi.ptr(a), _ffi.ptr(bp), _ffi.ptr(out), M, N, K, _ffi.stream_ptr()))
+            torch.cuda.synchronize()
+            ok_rows = 128 - shift  # rows of each tile whose shifted source row is still inside the stage
+            e = max(float((out[t * 128 : t * 128 + ok_rows] - want[t * 128 : t * 128 + ok_rows]).abs().max()) for t in range(2))
+            res[(shift, mode)] = e / float(want.abs().max())
+    print(f"ROWSHIFT CBK={CBK}: " + " ".join(f"s{s}m{m}={'OK' if v < 1e-4 else 'BAD(%.2g)' % v}" for (s, m), v in res.items()))
+    assert res[(0, 0)] < 1e-4 and res[(8, 0)] < 1e-4
