@@ -73,7 +73,7 @@ struct TcGeom {
   int tc;  // 0: runs on the SIMT kernel even in tensor-core modes
 };
 static const TcGeom kTc[kNumLayers] = {
-    {0, 0, 0, 0, 0, 0},      // enc_conv1 (Cin=6): SIMT, BN fused
+    {64, 32, 59, 2, 1, 1},   // enc_conv1: BN + im2col (K = 9 taps x 6 bands = 54 -> 64) by a SIMT pre-kernel, then a 1-tap GEMM
     {32, 32, 30, 4, 1, 1},   // enc_conv2
     {32, 64, 30, 4, 1, 1},   // enc_conv3
     {64, 64, 15, 8, 1, 1},   // enc_conv4
@@ -133,6 +133,7 @@ struct dbv_ctx {
   float* params = nullptr;  // [chunk][560]
   float* z = nullptr;       // [chunk][32]
   float* zp = nullptr;      // [chunk][32]
+  LayerRt im2col;           // tensor-core modes: conv1's operand, bf16 [chunk][59][59][planes*64]
   std::vector<void*> allocs;
   long long launches = 0;
   // host-buffer pipeline
@@ -281,17 +282,19 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   const bool x3 = c->precision == DBV_PREC_BF16X3;
   const HostTensor* W = find_w(c, wkey(L.enc, L.wn, "kernel"));
   // ---- input tensor (previous layer's output buffer) -------------------------------------------
-  const LayerRt& P = c->rt[li - 1];
+  const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
   const int in_cpad = in.Cpad, in_planes = in.planes;
   // enc_dense reads conv8's (4,4,256) map: 16 "taps" at pixel offsets; everything else via make_taps
   std::vector<Tap> taps;
   if (li == I_ENC_DENSE) {
     for (int p = 0; p < 16; ++p) taps.push_back({p, 0, p / 4, p % 4, 0, 0});
+  } else if (li == I_CONV1) {
+    taps.push_back({0, 0, 0, 0, 0, 0});  // the 9 taps are already unrolled along K by the im2col pre-kernel
   } else {
     taps = make_taps(L);
   }
-  const int cin_tap = (li == I_ENC_DENSE) ? 256 : L.Cin;  // channels per tap in the input tensor
+  const int cin_tap = (li == I_ENC_DENSE) ? 256 : (li == I_CONV1 ? 64 : L.Cin);  // channels per tap in the input tensor
   const int nchunk = (cin_tap + G.CBK - 1) / G.CBK;
   const int Ntot = ((L.Cout + G.NT - 1) / G.NT) * G.NT;
   const int parts_w = x3 ? 2 : 1;
@@ -307,6 +310,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
           if (ci >= cin_tap) continue;
           float w;
           if (li == I_ENC_DENSE) w = W->data[((size_t)taps[ti].ky * 256 + ci) * L.Cout + n];  // flat (h,w,c) index
+          else if (li == I_CONV1) w = ci < 54 ? W->data[(size_t)ci * L.Cout + n] : 0.f;  // HWIO flattened: k = (ky*3+kx)*6 + band
           else w = w_at(L, *W, taps[ti].ky, taps[ti].kx, ci, n);
           const uint16_t hi = f2bf(w);
           const size_t b0 = ((ti * nchunk + ch) * parts_w) * blk_elems + (size_t)n * G.CBK + k;
@@ -394,16 +398,19 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   if (getenv("DBV_NO_HALO")) return DBV_OK;
   if (!R.has_tc || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
-  const LayerRt& P = c->rt[li - 1];
+  const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
   if (in.mode != OUT_BF16_NHWC) return DBV_OK;
   const bool x3 = c->precision == DBV_PREC_BF16X3;
   const int ROWB = G.CBK * 2;
-  const std::vector<Tap> taps = make_taps(L);
-  const int nchunk = (L.Cin + G.CBK - 1) / G.CBK;
+  std::vector<Tap> taps = make_taps(L);
+  if (li == I_CONV1) taps.assign(1, Tap{0, 0, 0, 0, 0, 0});  // taps already unrolled along K by the im2col pre-kernel
+  const int pad = (li == I_CONV1) ? 0 : 1;
+  const int cin = (li == I_CONV1) ? 64 : L.Cin;
+  const int nchunk = (cin + G.CBK - 1) / G.CBK;
   const int parts_w = x3 ? 2 : 1;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
-  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2;
+  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2 * pad;
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
   const int w_bytes = ((n_wblk * G.NT * ROWB + 1023) / 1024) * 1024;
   const int n_regions = in.planes * nchunk;
@@ -414,14 +421,14 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   for (int nbuf = 2; nbuf >= 1; --nbuf)
     for (int r = 1; r <= H; ++r) {
       const int ntiles = (r * WP + 127) / 128;
-      if (ncls * ntiles * G.NT > 256) continue;
-      if (r + 2 > 256 || WP > 256) continue;
-      const long long region = (((long long)(r + 2) * WP * ROWB + 1023) / 1024) * 1024;
+      if (ncls * ntiles * G.NT * (x3 ? 2 : 1) > 256) continue;
+      if (r + 2 * pad > 256 || WP > 256) continue;
+      const long long region = (((long long)(r + 2 * pad) * WP * ROWB + 1023) / 1024) * 1024;
       const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 128;
       if (smem > HALO_MAX_SMEM) continue;
       const int bands = (H + r - 1) / r;
       double eff = (double)H * W / ((double)bands * ntiles * 128.0);
-      eff *= (double)r / (r + 2.0) * 0.15 + 0.85;  // mild preference for a smaller halo overhead
+      eff *= (double)r / (r + 2.0 * pad) * 0.15 + 0.85;  // mild preference for a smaller halo overhead
       if (nbuf == 1) eff *= 0.85;                  // exposed TMA latency per band
       if (eff > best + 1e-9) { best = eff; bestR = r; bestBuf = nbuf; }
     }
@@ -435,14 +442,16 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     for (size_t ti = 0; ti < taps.size(); ++ti) {
       if (taps[ti].cls != cl) continue;
       for (int ch = 0; ch < nchunk; ++ch)
-        for (int pr = 0; pr < (x3 ? 3 : 1); ++pr) {
+        // bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of N = 2*NT (the hi and lo weight blocks are adjacent in
+        // shared memory) + (A_lo x B_hi): the A_hi window is fetched once instead of twice
+        for (int pr = 0; pr < (x3 ? 2 : 1); ++pr) {
           if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: halo k-block table overflow", L.name);
-          const int a_lo = (pr == 2), w_lo = (pr == 1);
+          const int a_lo = (pr == 1);
           TcKBlock& K = T.kb[nkb++];
-          K.dx = K.dy = 0;
+          K.dy = (int16_t)((x3 && pr == 0) ? 1 : 0);  // wide MMA
           K.plane = (int16_t)(a_lo * nchunk + ch);
-          K.dx = (int16_t)((taps[ti].dy + 1) * WP + taps[ti].dx + 1);  // row offset of the tap in the halo tile
-          K.b_row = (int32_t)((ti * nchunk + ch) * parts_w + w_lo);      // weight block index (patched below)
+          K.dx = (int16_t)((taps[ti].dy + pad) * WP + taps[ti].dx + pad);  // row offset of the tap in the halo tile
+          K.b_row = (int32_t)((ti * nchunk + ch) * parts_w);             // weight block index (patched below)
         }
     }
     T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
@@ -450,16 +459,18 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     T.cls[cl].ox0 = ncls == 4 ? (cl & 1) : 0;
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
-  T.W = W; T.H = H; T.R = bestR; T.WP = WP;
+  T.W = W; T.H = H; T.R = bestR; T.WP = WP; T.pad = pad;
   T.ntiles = (bestR * WP + 127) / 128;
   T.n_regions = n_regions;
   for (int r = 0; r < n_regions; ++r) T.region_coff[r] = (r / nchunk) * in.Cpad + (r % nchunk) * G.CBK;
-  T.a_box_bytes = (bestR + 2) * WP * ROWB;
+  T.a_box_bytes = (bestR + 2 * pad) * WP * ROWB;
   T.region_bytes = ((T.a_box_bytes + 1023) / 1024) * 1024;
   T.n_wblk = n_wblk;
   T.w_rows_per_blk = G.NT;  // conv layers are not N-tiled: Ntot == NT
   T.w_bytes = w_bytes;
   T.nbuf = bestBuf;
+  T.dbg_skip = getenv("DBV_HALO_SKIP") ? atoi(getenv("DBV_HALO_SKIP")) : 0;
+  T.wide = x3 ? 1 : 0;
   T.tail_pad = tail_pad;
   T.smem_bytes = 1024 + w_bytes + bestBuf * n_regions * T.region_bytes + tail_pad + 128;
   T.bands_per_img = (H + bestR - 1) / bestR;
@@ -476,7 +487,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
     uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
     uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
-    uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bestR + 2), 1u, 1u};
+    uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bestR + 2 * pad), 1u, 1u};
     int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, ROWB);
     if (r) return r;
     T.tmB = R.tc.tmB;
@@ -495,6 +506,10 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
   OutSpec o = R.ospec;
   if (li == I_HEAD) { o.out = head_mean; o.out2 = head_std; }
   if (li == I_ENC_DENSE && params_out) o.out = params_out;
+  if (li == I_CONV1 && R.has_tc) {
+    int r = launch_im2col_conv1((const float*)input_f32, c->bn_scale, c->bn_shift, B, c->im2col.ospec, st);
+    if (r) return r;
+  }
   if (R.has_halo) {
     HaloLayer T = R.halo;
     T.B = B;
@@ -749,6 +764,16 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   }
   if ((r = dev_alloc(c, (void**)&c->z, (size_t)c->chunk * LAT * 4, true))) return r;
   if ((r = dev_alloc(c, (void**)&c->zp, (size_t)c->chunk * LAT * 4, true))) return r;
+  if (!fp32) {
+    OutSpec& o = c->im2col.ospec;
+    memset(&o, 0, sizeof o);
+    o.mode = OUT_BF16_NHWC;
+    o.planes = planes;
+    o.OH = o.OW = S_;
+    o.Cout = o.Cpad = 64;
+    if ((r = dev_alloc(c, &c->im2col.out, (size_t)c->chunk * S_ * S_ * planes * 64 * 2, true))) return r;
+    o.out = c->im2col.out;
+  }
   // ---- tensor-core plans ------------------------------------------------------------------------
   if (!fp32)
     for (int li = 0; li < kNumLayers; ++li)

@@ -34,6 +34,18 @@ struct OutSpec {
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // element offset of channel 0 of pixel (b,y,x); OUT_HEAD handled by the callers
 __device__ __forceinline__ long long pixel_offset(const OutSpec& o, long long b, int y, int x) {
   const int cs = o.planes * o.Cpad;
@@ -98,9 +110,16 @@ __device__ __forceinline__ void act_prefetch(const OutSpec& o, bool ok, int y, i
   r.fast = ok && (c + NV <= o.Cout) && ((o.Cout & 3) == 0) && o.alpha != nullptr;
   if (r.fast) {
     const long long pix = (long long)y * o.OW + x;
-    const float4* ap = reinterpret_cast<const float4*>(o.alpha + pix * o.Cout + c);
+    const float* ap = o.alpha + pix * o.Cout + c;
+    if constexpr (NV % 8 == 0) {
+      if ((o.Cout & 7) == 0) {  // 32-byte aligned: 256-bit loads halve the L1 wavefronts of this per-lane-line pattern
 #pragma unroll
-    for (int j = 0; j < NV / 4; ++j) r.a[j] = __ldg(ap + j);
+        for (int j = 0; j < NV / 8; ++j) ldg256(ap + 8 * j, r.a[2 * j], r.a[2 * j + 1]);
+        return;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) r.a[j] = __ldg(reinterpret_cast<const float4*>(ap) + j);
   }
 }
 
@@ -179,27 +198,42 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
   __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + off + c;
   const bool full = c + NV <= o.Cpad;
   if (full) {
-    if constexpr (NV % 8 == 0) {
-      if (o.planes == 2) {
+    if constexpr (NV % 16 == 0) {
+      // 16 channels = 32 bytes per plane: 256-bit stores when the pixel base is 32-byte aligned (Cpad % 16 == 0)
+      const bool a32 = (o.Cpad & 15) == 0 && (c & 15) == 0;
 #pragma unroll
-        for (int j = 0; j < NV; j += 8) {
-          uint4 q, l;
-          split_bf16x2(v[j], v[j + 1], q.x, l.x);
-          split_bf16x2(v[j + 2], v[j + 3], q.y, l.y);
-          split_bf16x2(v[j + 4], v[j + 5], q.z, l.z);
-          split_bf16x2(v[j + 6], v[j + 7], q.w, l.w);
-          *reinterpret_cast<uint4*>(p + j) = q;
-          *reinterpret_cast<uint4*>(p + o.Cpad + j) = l;
+      for (int j = 0; j < NV; j += 16) {
+        uint4 q0, q1, l0, l1;
+        if (o.planes == 2) {
+          split_bf16x2(v[j], v[j + 1], q0.x, l0.x);
+          split_bf16x2(v[j + 2], v[j + 3], q0.y, l0.y);
+          split_bf16x2(v[j + 4], v[j + 5], q0.z, l0.z);
+          split_bf16x2(v[j + 6], v[j + 7], q0.w, l0.w);
+          split_bf16x2(v[j + 8], v[j + 9], q1.x, l1.x);
+          split_bf16x2(v[j + 10], v[j + 11], q1.y, l1.y);
+          split_bf16x2(v[j + 12], v[j + 13], q1.z, l1.z);
+          split_bf16x2(v[j + 14], v[j + 15], q1.w, l1.w);
+        } else {
+          q0.x = pack_bf16x2(v[j], v[j + 1]);
+          q0.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          q0.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          q0.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          q1.x = pack_bf16x2(v[j + 8], v[j + 9]);
+          q1.y = pack_bf16x2(v[j + 10], v[j + 11]);
+          q1.z = pack_bf16x2(v[j + 12], v[j + 13]);
+          q1.w = pack_bf16x2(v[j + 14], v[j + 15]);
+          l0 = l1 = make_uint4(0u, 0u, 0u, 0u);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NV; j += 8) {
-          uint4 q;
-          q.x = pack_bf16x2(v[j], v[j + 1]);
-          q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(p + j) = q;
+        if (a32) {
+          stg256(p + j, q0, q1);
+          if (o.planes == 2) stg256(p + o.Cpad + j, l0, l1);
+        } else {
+          *reinterpret_cast<uint4*>(p + j) = q0;
+          *reinterpret_cast<uint4*>(p + j + 8) = q1;
+          if (o.planes == 2) {
+            *reinterpret_cast<uint4*>(p + o.Cpad + j) = l0;
+            *reinterpret_cast<uint4*>(p + o.Cpad + j + 8) = l1;
+          }
         }
       }
     } else {

@@ -23,6 +23,7 @@ int launch_latent(const float* params, const float* eps, unsigned long long seed
 int launch_prelu_vec(const float* z, const float* alpha, long long n, int C, float* out, cudaStream_t st);
 int launch_cast_f64_f32(const double* in, float* out, long long n, cudaStream_t st);
 int launch_act_to_f32(const OutSpec& o, long long B, float* out, cudaStream_t st);
+int launch_im2col_conv1(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st);
 
 // ---- tcgen05 implicit-GEMM convolution (tc_conv.cu) ------------------------------------------------
 // One k-block = one (tap, channel chunk[, hi/lo pairing]) : an A box of the activation tensor and a
@@ -79,7 +80,8 @@ struct HaloLayer {
   TcClass cls[TC_MAX_CLS];
   int n_cls;
   int W, H;          // tile-space extents (valid outputs sx < W, sy < H)
-  int R, WP;         // output rows per band, W + 2
+  int R, WP;         // output rows per band, W + 2*pad
+  int pad;           // halo width: 1 for 3x3 taps, 0 for a 1-tap layer (conv1 after im2col)
   int ntiles;        // ceil(R * WP / 128)
   int n_regions;     // planes * channel chunks
   int region_coff[8];
@@ -87,8 +89,11 @@ struct HaloLayer {
   int a_box_bytes;   // (R+2) * WP * ROWB
   int n_wblk, w_rows_per_blk, w_bytes;
   int nbuf;          // halo buffers in the ring (1 or 2)
+  int wide;          // bf16x3: accumulator tile = [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo] (2*NT columns, summed by the epilogue);
+                     // kb[].dy == 1 marks the k-blocks issued with N = 2*NT over the adjacent (hi, lo) weight blocks
   int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)
   int smem_bytes;
+  int dbg_skip;      // timing ablations only (env DBV_HALO_SKIP): bit0 skip the MMAs, bit1 skip the epilogue body
   int bands_per_img;
   long long B, total_bands;
   OutSpec o;

@@ -159,6 +159,47 @@ __global__ void __launch_bounds__(256) act_to_f32_kernel(OutSpec o, long long B,
   }
 }
 
+// BatchNorm + im2col for encoder conv1 (model/model.py:79-82): out[b][y][x][k], k = (ky*3+kx)*6 + band
+// (k >= 54 zero), value = BN(x[b][y+ky-1][x+kx-1][band]) inside the image and 0 outside (TF pads
+// AFTER the BatchNorm), stored bf16 hi[/lo].  One thread = one pixel x 8 consecutive k (one 16-byte store
+// per plane); 8 threads write a pixel's 128 contiguous bytes.
+__global__ void __launch_bounds__(256) im2col_conv1_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                           const float* __restrict__ sh, long long B, OutSpec o) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)(gid & 7);
+  const long long pix = gid >> 3;
+  if (pix >= B * S_ * S_) return;
+  const int xx = (int)(pix % S_), yy = (int)((pix / S_) % S_);
+  const long long b = pix / (S_ * S_);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = j * 8 + e;
+    const int tap = k / 6, ch = k - tap * 6;
+    const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+    float t = 0.f;
+    if (k < 54 && iy >= 0 && iy < S_ && ix >= 0 && ix < S_)
+      t = fmaf(__ldg(x + ((b * S_ + iy) * S_ + ix) * CB_ + ch), __ldg(sc + ch), __ldg(sh + ch));
+    v[e] = t;
+  }
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + pix * (long long)(o.planes * o.Cpad) + j * 8;
+  uint4 q, l;
+  split_bf16x2(v[0], v[1], q.x, l.x);
+  split_bf16x2(v[2], v[3], q.y, l.y);
+  split_bf16x2(v[4], v[5], q.z, l.z);
+  split_bf16x2(v[6], v[7], q.w, l.w);
+  *reinterpret_cast<uint4*>(p) = q;
+  if (o.planes == 2) *reinterpret_cast<uint4*>(p + o.Cpad) = l;
+}
+
+int launch_im2col_conv1(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st) {
+  const long long threads = B * S_ * S_ * 8;
+  if (threads == 0) return DBV_OK;
+  im2col_conv1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, bn_scale, bn_shift, B, o);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
 int launch_simt_conv(const SimtConv& p, cudaStream_t st) {
   const long long threads = (long long)p.B * p.Hout * p.Wout * (p.CoutP >> 2);
   if (threads == 0) return DBV_OK;

@@ -23,7 +23,8 @@
 
 namespace dbv {
 
-constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_EPI_SUBGROUPS = 1;  // epilogue groups (of 4 warps) per accumulator buffer; 2 was measured slower (L1-bound, spills)
+constexpr int TC_THREADS = 64 + 2 * TC_EPI_SUBGROUPS * 128;  // TMA warp, MMA warp, epilogue warps
 
 template <int CBK, int NT>
 struct TcCfg {
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_SUBGROUPS);
     }
     fence_barrier_init();
   }
@@ -132,9 +133,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
     }
   } else {
-    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains accumulator
-    // buffer g (every other tile), so two tiles are in the epilogue at once.
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    // 16 epilogue warps = 4 groups of 4 (one warp per TMEM lane quadrant in each group).  Groups 0,1 drain
+    // accumulator buffer 0 (even tiles), groups 2,3 buffer 1; the two groups of a buffer take alternate
+    // 32-channel chunks.  4 resident epilogue warps per scheduler hide the dependent-issue latency.
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
+    const int half = grp / TC_EPI_SUBGROUPS, sub = grp % TC_EPI_SUBGROUPS;
     const int row = quad * 32 + lane;
     const int rows_img = L.TW * L.TH;
     const int tb = row / rows_img;
@@ -166,22 +169,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           boff = nt * NT;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * NT);
-        ActRegs<NV> rc;
-        act_prefetch<NV>(L.o, ok, oy, ox, cbase, boff, rc);
+        ActRegs<NV> ra;
+        if (sub < NCHK) act_prefetch<NV>(L.o, ok, oy, ox, cbase + sub * NV, boff, ra);
         mbar_wait(bar_tfull + 8 * as, aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int q = 0; q < NCHK; ++q) {
-          ActRegs<NV> rn;
-          rn.fast = false;
-          if (q + 1 < NCHK) act_prefetch<NV>(L.o, ok, oy, ox, cbase + (q + 1) * NV, boff, rn);
+        for (int q = sub; q < NCHK; q += TC_EPI_SUBGROUPS) {
+          if (q != sub) act_prefetch<NV>(L.o, ok, oy, ox, cbase + q * NV, boff, ra);
           float v[NV];
           tmem_ld<NV>(taddr + q * NV, v);
           if (ok) {
-            act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, rc, v);
+            act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, ra, v);
             store_act<NV>(L.o, b, oy, ox, cbase + q * NV, v);
           }
-          rc = rn;
         }
         tc_fence_before();
         __syncwarp();

@@ -20,13 +20,15 @@
 
 namespace dbv {
 
-constexpr int HALO_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI_SUBGROUPS = 1;  // epilogue groups (of 4 warps) per accumulator buffer; 2 was measured slower (L1-bound, spills)
+constexpr int HALO_THREADS = 64 + 2 * EPI_SUBGROUPS * 128;  // TMA warp, MMA warp, epilogue warps
 constexpr int HALO_TBUF_COLS = 256;  // TMEM columns per accumulator buffer (2 buffers)
 
 template <int CBK, int NT>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = CBK * 2;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;                              // resident weights: n_wblk blocks of NT x ROWB
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, 4 * EPI_SUBGROUPS);
     }
     fence_barrier_init();
   }
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(L.n_regions * L.a_box_bytes));
         for (int r = 0; r < L.n_regions; ++r)
-          tma_load_5d(sA + (stage * L.n_regions + r) * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -1, y0 - 1, 0, (int)b);
+          tma_load_5d(sA + (stage * L.n_regions + r) * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, 0, (int)b);
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
       }
     }
@@ -88,18 +90,20 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
         const uint32_t a16 = kSmemDescLoConst | ((sA + stage * L.n_regions * L.region_bytes) >> 4);
-        for (int c = 0; c < L.n_cls; ++c) {
+        for (int c = 0; c < ((L.dbg_skip & 1) ? 0 : L.n_cls); ++c) {
           const int kb0 = L.cls[c].kb_begin, nkb = L.cls[c].nkb;
-          const uint32_t d0 = tmem_base + (uint32_t)(tb * HALO_TBUF_COLS + c * L.ntiles * NT);
+          const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per tile
+          const uint32_t d0 = tmem_base + (uint32_t)(tb * HALO_TBUF_COLS) + (uint32_t)(c * L.ntiles) * DW;
           // k-block outer, tile inner: the per-k-block table lookup is amortised over ntiles * CBK/16 MMAs
           for (int kb = 0; kb < nkb; ++kb) {
             const TcKBlock K = L.kb[kb0 + kb];
             uint32_t alo = a16 + (uint32_t)(uint16_t)K.c_off;
             const uint32_t blo = w16 + (uint32_t)K.b_row;
+            const uint32_t idesc = K.dy ? IDESC2 : IDESC;
             uint32_t d = d0;
-            for (int m = 0; m < L.ntiles; ++m, alo += MSTEP, d += NT) {
+            for (int m = 0; m < L.ntiles; ++m, alo += MSTEP, d += DW) {
 #pragma unroll
-              for (int k = 0; k < CBK / 16; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HI, blo + 2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < CBK / 16; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HI, blo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
         }
@@ -111,13 +115,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       }
     }
   } else {
-    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains accumulator
-    // buffer g, so two bands are in the epilogue at once and their global-load latencies overlap.
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    // 16 epilogue warps = 4 groups of 4 (one warp per TMEM lane quadrant in each group).  Groups 0,1 drain
+    // accumulator buffer 0, groups 2,3 buffer 1; within a band the two groups take alternate items
+    // (tile, 32-channel chunk).  The epilogue is dependent-issue bound (ncu: ~0.2 IPC per warp), so it is
+    // the number of resident warps per scheduler — 4 — that hides its latency.
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
+    const int half = grp / EPI_SUBGROUPS, sub = grp % EPI_SUBGROUPS;
     const int row = quad * 32 + lane;
     constexpr int NV = (NT % 32 == 0) ? 32 : 16;
     constexpr int NCHK = NT / NV;
     const int n_items = L.n_cls * L.ntiles * NCHK;
+    const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);
     int tb = 0;
     uint32_t tphase = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
@@ -125,43 +133,30 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         const long long b = t / L.bands_per_img;
         const int y0 = (int)(t - b * L.bands_per_img) * L.R;
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * HALO_TBUF_COLS);
-        auto decode = [&](int q, bool& ok, int& oy, int& ox, int& c0, uint32_t& ta) {
-          const int chunk = q % NCHK, tm = q / NCHK;
-          const int c = tm / L.ntiles, m = tm - c * L.ntiles;
-          const int p = 128 * m + row;
-          const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
-          ok = ly < L.R && sx < L.W && sy < L.H;
-          oy = L.cls[c].oy0 + L.cls[c].osy * sy;
-          ox = L.cls[c].ox0 + L.cls[c].osx * sx;
-          c0 = chunk * NV;
-          ta = tbase + (uint32_t)(tm * NT + c0);
-        };
-        ActRegs<NV> rc;
-        bool okc;
-        int oyc, oxc, c0c;
-        uint32_t tac;
-        decode(0, okc, oyc, oxc, c0c, tac);
-        act_prefetch<NV>(L.o, okc, oyc, oxc, c0c, 0, rc);
         mbar_wait(bar_tfull + 8 * tb, tphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int q = 0; q < n_items; ++q) {
-          ActRegs<NV> rn;
-          bool okn = false;
-          int oyn = 0, oxn = 0, c0n = 0;
-          uint32_t tan = 0;
-          rn.fast = false;
-          if (q + 1 < n_items) {
-            decode(q + 1, okn, oyn, oxn, c0n, tan);
-            act_prefetch<NV>(L.o, okn, oyn, oxn, c0n, 0, rn);
-          }
+        for (int q = sub; q < ((L.dbg_skip & 2) ? 0 : n_items); q += EPI_SUBGROUPS) {
+          const int tm = q / NCHK, c0 = (q - tm * NCHK) * NV;
+          const int c = tm / L.ntiles, m = tm - c * L.ntiles;
+          const int p = 128 * m + row;
+          const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
+          const bool ok = ly < L.R && sx < L.W && sy < L.H;
+          const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
+          ActRegs<NV> ra;
+          act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);
           float v[NV];
-          tmem_ld<NV>(tac, v);
-          if (okc) {
-            act_apply<NV>(L.o, oyc, oxc, c0c, 0, rc, v);
-            store_act<NV>(L.o, b, oyc, oxc, c0c, v);
+          tmem_ld<NV>(tbase + (uint32_t)tm * DW + (uint32_t)c0, v);
+          if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the tile's columns
+            float w[NV];
+            tmem_ld<NV>(tbase + (uint32_t)tm * DW + (uint32_t)(NT + c0), w);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] += w[j];
           }
-          rc = rn; okc = okn; oyc = oyn; oxc = oxn; c0c = c0n; tac = tan;
+          if (ok) {
+            act_apply<NV>(L.o, oy, ox, c0, 0, ra, v);
+            store_act<NV>(L.o, b, oy, ox, c0, v);
+          }
         }
         tc_fence_before();
         __syncwarp();
