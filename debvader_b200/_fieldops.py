@@ -113,21 +113,32 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
     n = len(plan["ok"])
     F_ = field_dev.shape[1]
     Cf = field_dev.shape[3]
-    out = torch.zeros((n, S, S, nb_of_bands), device=field_dev.device, dtype=out_dtype)
     ok = plan["ok"]
+    dev = field_dev.device
+    shape = (n, S, S, nb_of_bands)
     if Cf != nb_of_bands:
         if Cf != 1:  # numpy cannot broadcast (.., Cf) into (.., nb): every stamp raises ValueError in the reference
-            return out, []
+            return torch.zeros(shape, device=dev, dtype=out_dtype), []
         field_dev = field_dev.expand(1, F_, F_, nb_of_bands).contiguous()
     idx = np.nonzero(ok)[0]
+    # rejected stamps stay zero like the reference's np.zeros; when all are accepted skip the memset
+    out = torch.empty(shape, device=dev, dtype=out_dtype) if idx.size == n else torch.zeros(shape, device=dev, dtype=out_dtype)
     if idx.size == 0:
         return out, []
-    flags = ((plan["lx"][idx] == 1) & (S != 1)).astype(np.uint8) | (((plan["ly"][idx] == 1) & (S != 1)).astype(np.uint8) << 1)
-    dev = field_dev.device
-    sx = torch.from_numpy(plan["sx"][idx].astype(np.int32)).to(dev)
-    sy = torch.from_numpy(plan["sy"][idx].astype(np.int32)).to(dev)
-    fl = torch.from_numpy(flags).to(dev)
-    slot = torch.from_numpy(idx.astype(np.int64)).to(dev)
+    # one packed upload of the plan (cached on the plan: repeated extractions reuse the device copy)
+    cache = plan.get("_dev")
+    if cache is None or cache[0] != str(dev):
+        m = idx.size
+        flags = ((plan["lx"][idx] == 1) & (S != 1)).astype(np.uint8) | (((plan["ly"][idx] == 1) & (S != 1)).astype(np.uint8) << 1)
+        buf = np.zeros(4 * m + (m + 3) // 4, dtype=np.int32)
+        buf[:m] = plan["sx"][idx]
+        buf[m : 2 * m] = plan["sy"][idx]
+        buf[2 * m : 4 * m] = idx.astype(np.int64).view(np.int32)
+        buf[4 * m :].view(np.uint8)[:m] = flags
+        t = torch.from_numpy(buf).to(dev)
+        cache = (str(dev), t[:m], t[m : 2 * m], t[4 * m :].view(torch.uint8), t[2 * m : 4 * m].view(torch.int64))
+        plan["_dev"] = cache
+    _, sx, sy, fl, slot = cache
     with torch.cuda.device(dev):
         _ffi.check(
             _ffi.lib().dbv_extract(_ffi.ptr(field_dev), _DT[field_dev.dtype], F_, nb_of_bands, _ffi.ptr(sx), _ffi.ptr(sy), _ffi.ptr(fl),

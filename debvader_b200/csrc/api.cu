@@ -389,18 +389,14 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   return DBV_OK;
 }
 
-// Resident-halo plan for the stride-1 Conv2D / Conv2DTranspose layers (and stride-2 transposed convs as 4
-// classes over one halo) whose packed weights fit in shared memory next to the halo ring.
-static int build_halo_layer(dbv_ctx* c, int li) {
+// Fill T with the plan for R output rows per band and nbuf halo buffers.  Returns 1 if the plan is valid
+// (fits shared memory / TMEM / descriptor fields), 0 if not, < 0 on error.
+static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  if (getenv("DBV_NO_HALO")) return DBV_OK;
-  if (!R.has_tc || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
-  if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
-  if (in.mode != OUT_BF16_NHWC) return DBV_OK;
   const bool x3 = c->precision == DBV_PREC_BF16X3;
   const int ROWB = G.CBK * 2;
   std::vector<Tap> taps = make_taps(L);
@@ -414,26 +410,14 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
   const int w_bytes = ((n_wblk * G.NT * ROWB + 1023) / 1024) * 1024;
   const int n_regions = in.planes * nchunk;
-  if (n_regions > 8) return DBV_OK;
+  if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
   const int tail_pad = ((129 * ROWB + 1023) / 1024) * 1024;
-  int bestR = 0, bestBuf = 0;
-  double best = 0.0;
-  for (int nbuf = 2; nbuf >= 1; --nbuf)
-    for (int r = 1; r <= H; ++r) {
-      const int ntiles = (r * WP + 127) / 128;
-      if (ncls * ntiles * G.NT * (x3 ? 2 : 1) > 256) continue;
-      if (r + 2 * pad > 256 || WP > 256) continue;
-      const long long region = (((long long)(r + 2 * pad) * WP * ROWB + 1023) / 1024) * 1024;
-      const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 128;
-      if (smem > HALO_MAX_SMEM) continue;
-      const int bands = (H + r - 1) / r;
-      double eff = (double)H * W / ((double)bands * ntiles * 128.0);
-      eff *= (double)r / (r + 2.0 * pad) * 0.15 + 0.85;  // mild preference for a smaller halo overhead
-      if (nbuf == 1) eff *= 0.85;                  // exposed TMA latency per band
-      if (eff > best + 1e-9) { best = eff; bestR = r; bestBuf = nbuf; }
-    }
-  if (!bestR) return DBV_OK;
-  HaloLayer& T = R.halo;
+  const int ntiles = (bandR * WP + 127) / 128;
+  if (ncls * ntiles * G.NT * (x3 ? 2 : 1) > 256) return 0;
+  if (bandR + 2 * pad > 256 || WP > 256) return 0;
+  const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + 1023) / 1024) * 1024;
+  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 128;
+  if (smem > HALO_MAX_SMEM) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
   int nkb = 0;
@@ -445,13 +429,15 @@ static int build_halo_layer(dbv_ctx* c, int li) {
         // bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of N = 2*NT (the hi and lo weight blocks are adjacent in
         // shared memory) + (A_lo x B_hi): the A_hi window is fetched once instead of twice
         for (int pr = 0; pr < (x3 ? 2 : 1); ++pr) {
-          if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: halo k-block table overflow", L.name);
+          if (nkb >= TC_MAX_KB) return 0;
           const int a_lo = (pr == 1);
           TcKBlock& K = T.kb[nkb++];
           K.dy = (int16_t)((x3 && pr == 0) ? 1 : 0);  // wide MMA
-          K.plane = (int16_t)(a_lo * nchunk + ch);
-          K.dx = (int16_t)((taps[ti].dy + pad) * WP + taps[ti].dx + pad);  // row offset of the tap in the halo tile
-          K.b_row = (int32_t)((ti * nchunk + ch) * parts_w);             // weight block index (patched below)
+          const long long a_off = (long long)(a_lo * nchunk + ch) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB;
+          const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * ROWB;
+          if ((a_off >> 4) > 0x7fff || (b_off >> 4) > 0x3fff) return 0;
+          K.c_off = (int16_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
+          K.b_row = (int32_t)(b_off >> 4);
         }
     }
     T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
@@ -459,45 +445,106 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     T.cls[cl].ox0 = ncls == 4 ? (cl & 1) : 0;
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
-  T.W = W; T.H = H; T.R = bestR; T.WP = WP; T.pad = pad;
-  T.ntiles = (bestR * WP + 127) / 128;
+  T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
+  T.ntiles = ntiles;
   T.n_regions = n_regions;
   for (int r = 0; r < n_regions; ++r) T.region_coff[r] = (r / nchunk) * in.Cpad + (r % nchunk) * G.CBK;
-  T.a_box_bytes = (bestR + 2 * pad) * WP * ROWB;
-  T.region_bytes = ((T.a_box_bytes + 1023) / 1024) * 1024;
+  T.a_box_bytes = (bandR + 2 * pad) * WP * ROWB;
+  T.region_bytes = (int)region;
   T.n_wblk = n_wblk;
   T.w_rows_per_blk = G.NT;  // conv layers are not N-tiled: Ntot == NT
   T.w_bytes = w_bytes;
-  T.nbuf = bestBuf;
+  T.nbuf = nbuf;
   T.dbg_skip = getenv("DBV_HALO_SKIP") ? atoi(getenv("DBV_HALO_SKIP")) : 0;
   T.wide = x3 ? 1 : 0;
   T.tail_pad = tail_pad;
-  T.smem_bytes = 1024 + w_bytes + bestBuf * n_regions * T.region_bytes + tail_pad + 128;
-  T.bands_per_img = (H + bestR - 1) / bestR;
-  // descriptor offsets in 16-byte units, ready to be added to the low descriptor word by the MMA issuer
-  for (int i = 0; i < nkb; ++i) {
-    TcKBlock& K = T.kb[i];
-    const long long a_off = (long long)K.plane * T.region_bytes + (long long)K.dx * ROWB;
-    const long long b_off = (long long)K.b_row * G.NT * ROWB;
-    if ((a_off >> 4) > 0x7fff || (b_off >> 4) > 0x3fff) return fail(DBV_ERR_UNSUPPORTED, "%s: halo descriptor offset overflow", L.name);
-    K.c_off = (int16_t)(a_off >> 4);
-    K.b_row = (int32_t)(b_off >> 4);
+  T.smem_bytes = (int)smem;
+  T.bands_per_img = (H + bandR - 1) / bandR;
+  const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
+  uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
+  uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
+  uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
+  int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, ROWB);
+  if (r) return r;
+  T.tmB = R.tc.tmB;
+  return 1;
+}
+
+// Resident-halo plan for the stride-1 Conv2D / Conv2DTranspose layers (and stride-2 transposed convs as 4
+// classes over one halo) whose packed weights fit in shared memory next to the halo ring.  The band height
+// and ring depth are AUTOTUNED on the device at finalize time: analytic models of the MMA / epilogue /
+// barrier overlap mispredicted the best plan by up to 30 % ("halo plan autotune").
+static int build_halo_layer(dbv_ctx* c, int li) {
+  const LayerDesc& L = kLayers[li];
+  const TcGeom& G = kTc[li];
+  LayerRt& R = c->rt[li];
+  if (getenv("DBV_NO_HALO")) return DBV_OK;
+  if (!R.has_tc || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
+  if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
+  const OutSpec& in = ((li == I_CONV1) ? c->im2col : c->rt[li - 1]).ospec;
+  if (in.mode != OUT_BF16_NHWC) return DBV_OK;
+  const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
+  const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 0 : 2);
+  // candidates: the tallest band for each tile count (R*WP just below a multiple of 128), both ring depths
+  std::vector<std::pair<int, int>> cand;
+  for (int nt = 1; nt <= 16; ++nt) {
+    int r = std::min(H, nt * 128 / WP);
+    if (r < 1) continue;
+    for (int nbuf = 2; nbuf >= 1; --nbuf)
+      if (std::find(cand.begin(), cand.end(), std::make_pair(r, nbuf)) == cand.end()) cand.push_back({r, nbuf});
   }
-  {
-    const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
-    uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
-    uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
-    uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bestR + 2 * pad), 1u, 1u};
-    int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, ROWB);
-    if (r) return r;
-    T.tmB = R.tc.tmB;
+  const long long Bt = std::min<long long>(c->chunk, 296);
+  cudaEvent_t e0, e1;
+  DBV_CUDA(cudaEventCreate(&e0));
+  DBV_CUDA(cudaEventCreate(&e1));
+  float best_ms = 1e30f;
+  HaloLayer best{};
+  bool found = false;
+  OutSpec o = R.ospec;
+  std::vector<float> scratch_out;
+  float *hm = nullptr, *hs = nullptr;
+  if (li == I_HEAD) {  // the head writes the caller's buffers: give the tuner scratch ones
+    DBV_CUDA(cudaMalloc(&hm, (size_t)Bt * STAMP_ELTS * 4));
+    DBV_CUDA(cudaMalloc(&hs, (size_t)Bt * STAMP_ELTS * 4));
+    o.out = hm;
+    o.out2 = hs;
   }
-  if (getenv("DBV_VERBOSE"))
-    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d ntiles=%d regions=%d wblk=%d smem=%d eff=%.3f\n", L.name, bestR, bestBuf, T.ntiles,
-            n_regions, n_wblk, T.smem_bytes, best);
+  for (auto [r, nbuf] : cand) {
+    HaloLayer T;
+    int ok = halo_plan(c, li, r, nbuf, T);
+    if (ok < 0) return ok;
+    if (!ok) continue;
+    T.B = Bt;
+    T.o = o;
+    T.total_bands = Bt * T.bands_per_img;
+    float ms = 0.f;
+    for (int it = 0; it < 3; ++it) {  // 1 warm-up + best of 2
+      DBV_CUDA(cudaEventRecord(e0, 0));
+      int rr = launch_halo_layer(T, G.CBK, G.NT, kNumSMs, 0);
+      if (rr) return rr;
+      DBV_CUDA(cudaEventRecord(e1, 0));
+      DBV_CUDA(cudaEventSynchronize(e1));
+      float t;
+      DBV_CUDA(cudaEventElapsedTime(&t, e0, e1));
+      ms = (it == 1) ? t : (it == 2 ? std::min(ms, t) : ms);
+    }
+    if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate R=%d nbuf=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, r, nbuf, T.ntiles, T.smem_bytes, ms, Bt);
+    if (ms < best_ms) { best_ms = ms; best = T; found = true; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (hm) cudaFree(hm);
+  if (hs) cudaFree(hs);
+  if (!found) return DBV_OK;
+  R.halo = best;
   R.has_halo = true;
+  if (getenv("DBV_VERBOSE"))
+    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d ntiles=%d regions=%d smem=%d (%.3f ms / %lld stamps)\n", L.name, best.R, best.nbuf, best.ntiles,
+            best.n_regions, best.smem_bytes, best_ms, Bt);
   return DBV_OK;
 }
+
+static void prof_mark(dbv_ctx* c, const char* name, cudaStream_t st);
 
 static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, float* head_mean, float* head_std, float* params_out,
                      cudaStream_t st) {
@@ -509,6 +556,7 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
   if (li == I_CONV1 && R.has_tc) {
     int r = launch_im2col_conv1((const float*)input_f32, c->bn_scale, c->bn_shift, B, c->im2col.ospec, st);
     if (r) return r;
+    prof_mark(c, "enc_im2col", st);
   }
   if (R.has_halo) {
     HaloLayer T = R.halo;
@@ -634,7 +682,7 @@ extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chun
   dbv_ctx* c = new dbv_ctx();
   c->device = device;
   c->precision = precision;
-  c->chunk = chunk > 0 ? chunk : 512;
+  c->chunk = chunk > 0 ? chunk : 1024;
   *out = c;
   return DBV_OK;
 }

@@ -7,6 +7,7 @@
 //   dbv_center_mse   <- deblend/field_deblender.py:323-332
 //   dbv_mse          <- training/metrics.py:4-12
 #include "common.cuh"
+#include <cstdlib>
 
 namespace dbv {
 
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) extract_kernel(const Tin* __restrict__ fi
 // ascending stamp index) the stamps that overlap it, and applies them to each of its pixels in
 // that order.  No atomics; one rounding per addition; bit-identical to the sequential host loop.
 // ---------------------------------------------------------------------------------------------
-constexpr int AX_TR = 16, AX_TC = 64, AX_CAP = 768, AX_THREADS = 256;
+constexpr int AX_TR = 32, AX_TC = 64, AX_CAP = 768, AX_THREADS = 256;
 
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
@@ -156,7 +157,38 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
       if (!fits) break;
     }
     const int cnt = s_count;
-    if (cnt > 0 || first) {
+    if ((cnt > 0 || first) && (C & 1) == 0) {
+      // vector path: 2 bands per thread (16-byte field accesses for f64, 8-byte stamp reads); a pixel's C
+      // values start at an even element index, so the pairs never straddle pixels
+      using V2 = typename Vec2<T>::type;
+      const int rowv = AX_TC * C / 2;  // vectors per tile row
+      const int nvec = AX_TR * rowv;
+      for (int e = threadIdx.x; e < nvec; e += AX_THREADS) {
+        const int pr = e / rowv;
+        const int rem = e - pr * rowv;
+        const int X = tr0 + pr;
+        const int Y = tc0 + (2 * rem) / C;
+        const int ch = 2 * rem - ((2 * rem) / C) * C;
+        if (X >= F || Y >= F) continue;
+        const long long idx = ((long long)X * F + Y) * C + ch;
+        V2 acc;
+        if (first) {
+          if (in) acc = *reinterpret_cast<const V2*>(in + idx);
+          else { acc.x = (T)0; acc.y = (T)0; }
+        } else {
+          acc = *reinterpret_cast<const V2*>(out + idx);
+        }
+        for (int k = 0; k < cnt; ++k) {
+          const int dx = X - s_x[k], dy = Y - s_y[k];
+          if ((unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch));
+            acc.x = add_rn<T>(acc.x, mul_rn<T>(alpha, (T)v.x));
+            acc.y = add_rn<T>(acc.y, mul_rn<T>(alpha, (T)v.y));
+          }
+        }
+        *reinterpret_cast<V2*>(out + idx) = acc;
+      }
+    } else if (cnt > 0 || first) {
       for (int e = threadIdx.x; e < nelt; e += AX_THREADS) {
         const int ch = e % C;
         const int pc = (e / C) % AX_TC;
@@ -259,6 +291,7 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   int per = 2;
   if (N < 2048) per = 4;
   if (N < 256) per = 8;
+  if (const char* e = getenv("DBV_EXTRACT_PER")) per = atoi(e) > 0 ? atoi(e) : per;  // tuning knob
   dim3 grid((unsigned)N, per), block(256);
   if (field_dtype == DBV_F64 && out_dtype == DBV_F64)
     extract_kernel<double, double><<<grid, block, 0, st>>>((const double*)field, F, C, sx, sy, flags, slot, S, (double*)out);
