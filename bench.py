@@ -142,7 +142,8 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batched deblend() of synthetic 59x59x6 stamps (BASELINE cfg 2), CPU", "sample_per_step": sample},
+        "config": {"workload": "batched deblend() of 4096 synthetic 59x59x6 stamps per GPU (BASELINE cfg 2), random-init DC2 weights",
+                   "stamps_per_gpu_per_step": BATCH, "precision": "fp32 (CPU)", "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} stamps per step in one batch; torch-CPU restatement of the reference model (stand-in, not TensorFlow: TF 2.13 is not installable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

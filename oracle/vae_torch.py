@@ -41,8 +41,7 @@ class TorchOracle:
         n = 1
         while (E % (n, "kernel")) in w and w[E % (n, "kernel")].ndim == 4:
             for j, s in ((n, 1), (n + 2, 2)):
-                # conv1 (j == 1) runs in fp32 on the GPU in every mode: never rounded
-                k = (w[E % (j, "kernel")] if j == 1 else _q(w[E % (j, "kernel")], emulate)).permute(3, 2, 0, 1).contiguous()  # HWIO -> OIHW
+                k = _q(w[E % (j, "kernel")], emulate).permute(3, 2, 0, 1).contiguous()  # HWIO -> OIHW
                 a = w[E % (j + 1, "alpha")].permute(2, 0, 1).contiguous()  # HWC -> CHW
                 self.enc_convs.append((k, w[E % (j, "bias")], a, s))
             n += 4
@@ -66,7 +65,7 @@ class TorchOracle:
         g, b = w[E % (0, "gamma")], w[E % (0, "beta")]
         m, v = w[E % (0, "moving_mean")], w[E % (0, "moving_variance")]
         h = g * (x - m) / torch.sqrt(v + BN_EPS) + b
-        h = h.permute(0, 3, 1, 2)  # NCHW
+        h = _q(h, em).permute(0, 3, 1, 2)  # NCHW (the BatchNorm output is what conv1's im2col stores in 16 bits)
         last = len(self.enc_convs) - 1
         for i, (k, bias, alpha, s) in enumerate(self.enc_convs):
             _, pt, pb = same_pad(h.shape[2], k.shape[2], s)
