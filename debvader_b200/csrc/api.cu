@@ -73,7 +73,7 @@ struct TcGeom {
   int tc;  // 0: runs on the SIMT kernel even in tensor-core modes
 };
 static const TcGeom kTc[kNumLayers] = {
-    {64, 32, 59, 2, 1, 1},   // enc_conv1: BN + im2col (K = 9 taps x 6 bands = 54 -> 64) by a SIMT pre-kernel, then a 1-tap GEMM
+    {16, 32, 59, 2, 1, 1},   // enc_conv1: BN + 8-channel bf16 packing by a SIMT pre-kernel, then the no-swizzle halo kernel
     {32, 32, 30, 4, 1, 1},   // enc_conv2
     {32, 64, 30, 4, 1, 1},   // enc_conv3
     {64, 64, 15, 8, 1, 1},   // enc_conv4
@@ -133,7 +133,8 @@ struct dbv_ctx {
   float* params = nullptr;  // [chunk][560]
   float* z = nullptr;       // [chunk][32]
   float* zp = nullptr;      // [chunk][32]
-  LayerRt im2col;           // tensor-core modes: conv1's operand, bf16 [chunk][59][59][planes*64]
+  LayerRt im2col;           // tensor-core modes: conv1's operand, BN'd input as bf16 [chunk][59][59][planes*8]
+  __nv_bfloat16* conv1_wimg = nullptr;  // conv1 weights as a ready-made shared-memory image (no-swizzle core matrices)
   std::vector<void*> allocs;
   long long launches = 0;
   // host-buffer pipeline
@@ -398,17 +399,21 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
   const bool x3 = c->precision == DBV_PREC_BF16X3;
-  const int ROWB = G.CBK * 2;
+  const bool c1 = (li == I_CONV1);  // no-swizzle mode: 16-byte pixel rows, K=16 = two adjacent pixels
+  const int ROWB = c1 ? 16 : G.CBK * 2;
   std::vector<Tap> taps = make_taps(L);
-  if (li == I_CONV1) taps.assign(1, Tap{0, 0, 0, 0, 0, 0});  // taps already unrolled along K by the im2col pre-kernel
-  const int pad = (li == I_CONV1) ? 0 : 1;
-  const int cin = (li == I_CONV1) ? 64 : L.Cin;
-  const int nchunk = (cin + G.CBK - 1) / G.CBK;
+  if (c1) {  // per kernel row ky: pixel pairs (x-1, x) and (x+1, x+2); Tap.kx = pair index, dx = first pixel of the pair
+    taps.clear();
+    for (int ky = 0; ky < 3; ++ky)
+      for (int pr = 0; pr < 2; ++pr) taps.push_back(Tap{ky, pr, ky - 1, 2 * pr - 1, 0, 0});
+  }
+  const int pad = 1;
+  const int nchunk = c1 ? 1 : (L.Cin + G.CBK - 1) / G.CBK;
   const int parts_w = x3 ? 2 : 1;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
-  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2 * pad;
+  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2 * pad + (c1 ? 1 : 0);  // conv1: the pair (x+1, x+2) reads one more column
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
-  const int w_bytes = ((n_wblk * G.NT * ROWB + 1023) / 1024) * 1024;
+  const int w_bytes = ((n_wblk * G.NT * (c1 ? 32 : ROWB) + 1023) / 1024) * 1024;
   const int n_regions = in.planes * nchunk;
   if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
   const int tail_pad = ((129 * ROWB + 1023) / 1024) * 1024;
@@ -434,7 +439,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
           TcKBlock& K = T.kb[nkb++];
           K.dy = (int16_t)((x3 && pr == 0) ? 1 : 0);  // wide MMA
           const long long a_off = (long long)(a_lo * nchunk + ch) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB;
-          const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * ROWB;
+          const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * (c1 ? 32 : ROWB);
           if ((a_off >> 4) > 0x7fff || (b_off >> 4) > 0x3fff) return 0;
           K.c_off = (int16_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
           K.b_row = (int32_t)(b_off >> 4);
@@ -449,6 +454,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   T.ntiles = ntiles;
   T.n_regions = n_regions;
   for (int r = 0; r < n_regions; ++r) T.region_coff[r] = (r / nchunk) * in.Cpad + (r % nchunk) * G.CBK;
+  T.w_img = c1 ? (const void*)c->conv1_wimg : nullptr;
   T.a_box_bytes = (bandR + 2 * pad) * WP * ROWB;
   T.region_bytes = (int)region;
   T.n_wblk = n_wblk;
@@ -463,10 +469,10 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
   uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
   uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
-  uint32_t box[5] = {(uint32_t)G.CBK, (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
-  int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, ROWB);
+  uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
+  int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, c1 ? 0 : ROWB);
   if (r) return r;
-  T.tmB = R.tc.tmB;
+  if (!c1) T.tmB = R.tc.tmB;
   return 1;
 }
 
@@ -478,13 +484,13 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  if (getenv("DBV_NO_HALO")) return DBV_OK;
-  if (!R.has_tc || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
+  if (getenv("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
+  if ((!R.has_tc && li != I_CONV1) || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
   const OutSpec& in = ((li == I_CONV1) ? c->im2col : c->rt[li - 1]).ospec;
   if (in.mode != OUT_BF16_NHWC) return DBV_OK;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
-  const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 0 : 2);
+  const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 3 : 2);
   // candidates: the tallest band for each tile count (R*WP just below a multiple of 128), both ring depths
   std::vector<std::pair<int, int>> cand;
   for (int nt = 1; nt <= 16; ++nt) {
@@ -535,6 +541,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   cudaEventDestroy(e1);
   if (hm) cudaFree(hm);
   if (hs) cudaFree(hs);
+  if (!found && li == I_CONV1) return fail(DBV_ERR_STATE, "enc_conv1: no valid halo plan (the tensor-core modes have no other conv1 kernel)");
   if (!found) return DBV_OK;
   R.halo = best;
   R.has_halo = true;
@@ -553,10 +560,10 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
   OutSpec o = R.ospec;
   if (li == I_HEAD) { o.out = head_mean; o.out2 = head_std; }
   if (li == I_ENC_DENSE && params_out) o.out = params_out;
-  if (li == I_CONV1 && R.has_tc) {
-    int r = launch_im2col_conv1((const float*)input_f32, c->bn_scale, c->bn_shift, B, c->im2col.ospec, st);
+  if (li == I_CONV1 && R.has_halo) {
+    int r = launch_bn_pack8((const float*)input_f32, c->bn_scale, c->bn_shift, B, c->im2col.ospec, st);
     if (r) return r;
-    prof_mark(c, "enc_im2col", st);
+    prof_mark(c, "enc_bn_pack", st);
   }
   if (R.has_halo) {
     HaloLayer T = R.halo;
@@ -818,14 +825,35 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     o.mode = OUT_BF16_NHWC;
     o.planes = planes;
     o.OH = o.OW = S_;
-    o.Cout = o.Cpad = 64;
-    if ((r = dev_alloc(c, &c->im2col.out, (size_t)c->chunk * S_ * S_ * planes * 64 * 2, true))) return r;
+    o.Cout = o.Cpad = 8;
+    if ((r = dev_alloc(c, &c->im2col.out, (size_t)c->chunk * S_ * S_ * planes * 8 * 2, true))) return r;
     o.out = c->im2col.out;
+    // conv1 weights as the shared-memory image of the no-swizzle K-major B operand: block (ky, pair)[hi|lo] of
+    // 32 rows x 16 k; element (n, k) at (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes; k<8: kx = 2*pair,
+    // k>=8: kx = 2*pair+1 (zero when kx > 2), band = k%8 (zero for the two padding channels)
+    const HostTensor* W1 = find_w(c, wkey(1, 1, "kernel"));
+    const int parts = planes;
+    std::vector<uint16_t> img((size_t)6 * parts * 32 * 16, 0);
+    for (int ky = 0; ky < 3; ++ky)
+      for (int pr = 0; pr < 2; ++pr)
+        for (int n = 0; n < 32; ++n)
+          for (int k = 0; k < 16; ++k) {
+            const int kx = 2 * pr + (k >> 3), ch = k & 7;
+            const float w = (kx <= 2 && ch < 6) ? W1->data[(((size_t)ky * 3 + kx) * 6 + ch) * 32 + n] : 0.f;
+            const uint16_t hi = f2bf(w);
+            const size_t blk = (size_t)(ky * 2 + pr) * parts;
+            const size_t e = (size_t)(n / 8) * 128 + (size_t)(k / 8) * 64 + (size_t)(n % 8) * 8 + (k % 8);  // in bf16 elements
+            img[blk * 512 + e] = hi;
+            if (parts == 2) img[(blk + 1) * 512 + e] = f2bf(w - bf2f(hi));
+          }
+    std::vector<__nv_bfloat16> tmp(img.size());
+    memcpy(tmp.data(), img.data(), img.size() * 2);
+    if ((r = upload(c, &c->conv1_wimg, tmp))) return r;
   }
   // ---- tensor-core plans ------------------------------------------------------------------------
   if (!fp32)
     for (int li = 0; li < kNumLayers; ++li)
-      if (kTc[li].tc && ((r = build_tc_layer(c, li)) || (r = build_halo_layer(c, li)))) return r;
+      if (kTc[li].tc && ((li != I_CONV1 && (r = build_tc_layer(c, li))) || (r = build_halo_layer(c, li)))) return r;
   DBV_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
   c->host_w.clear();

@@ -23,7 +23,7 @@ int launch_latent(const float* params, const float* eps, unsigned long long seed
 int launch_prelu_vec(const float* z, const float* alpha, long long n, int C, float* out, cudaStream_t st);
 int launch_cast_f64_f32(const double* in, float* out, long long n, cudaStream_t st);
 int launch_act_to_f32(const OutSpec& o, long long B, float* out, cudaStream_t st);
-int launch_im2col_conv1(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st);
+int launch_bn_pack8(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st);
 
 // ---- tcgen05 implicit-GEMM convolution (tc_conv.cu) ------------------------------------------------
 // One k-block = one (tap, channel chunk[, hi/lo pairing]) : an A box of the activation tensor and a
@@ -88,6 +88,7 @@ struct HaloLayer {
   int region_bytes;  // (R+2) * WP * ROWB rounded up to 1024
   int a_box_bytes;   // (R+2) * WP * ROWB
   int n_wblk, w_rows_per_blk, w_bytes;
+  const void* w_img;  // no-swizzle mode (conv1): the resident weights as one ready-made shared-memory image (bulk copy)
   int nbuf;          // halo buffers in the ring (1 or 2)
   int wide;          // bf16x3: accumulator tile = [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo] (2*NT columns, summed by the epilogue);
                      // kb[].dy == 1 marks the k-blocks issued with N = 2*NT over the adjacent (hi, lo) weight blocks

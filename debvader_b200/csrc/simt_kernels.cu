@@ -159,50 +159,32 @@ __global__ void __launch_bounds__(256) act_to_f32_kernel(OutSpec o, long long B,
   }
 }
 
-// BatchNorm + im2col for encoder conv1 (model/model.py:79-82): out[b][y][x][k], k = (ky*3+kx)*6 + band
-// (k >= 54 zero), value = BN(x[b][y+ky-1][x+kx-1][band]) inside the image and 0 outside (TF pads
-// AFTER the BatchNorm), stored bf16 hi[/lo].  One thread = one pixel x 8 consecutive k (one 16-byte store
-// per plane); 8 threads write a pixel's 128 contiguous bytes.
-__global__ void __launch_bounds__(480) im2col_conv1_kernel(const float* __restrict__ x, const float* __restrict__ sc,
-                                                           const float* __restrict__ sh, long long B, OutSpec o) {
-  // one CTA = one image row: the three input rows it needs are staged in shared memory with the
-  // BatchNorm applied and the zero border in place, so each of the 59 x 8 (pixel, 8-k chunk) threads
-  // only does 8 conflict-light LDS + one 16-byte store per plane (8 lanes = one pixel's 128 bytes).
-  __shared__ float s_in[3][S_ + 2][CB_];
-  const long long rowid = blockIdx.x;  // b * 59 + y
-  const int yy = (int)(rowid % S_);
-  const long long b = rowid / S_;
-  for (int i = threadIdx.x; i < 3 * (S_ + 2) * CB_; i += blockDim.x) {
-    const int ch = i % CB_, px = (i / CB_) % (S_ + 2), r = i / (CB_ * (S_ + 2));
-    const int iy = yy + r - 1, ix = px - 1;
-    float t = 0.f;
-    if (iy >= 0 && iy < S_ && ix >= 0 && ix < S_) t = fmaf(__ldg(x + ((b * S_ + iy) * S_ + ix) * CB_ + ch), __ldg(sc + ch), __ldg(sh + ch));
-    s_in[r][px][ch] = t;
-  }
-  __syncthreads();
-  const int j = threadIdx.x & 7, xx = threadIdx.x >> 3;
-  if (xx >= S_) return;
-  float v[8];
+// BatchNorm of the input stamp (model/model.py:79; TF pads AFTER the BN, so it cannot be folded into conv1's
+// bias) and conversion to the tensor-core operand of conv1: bf16 hi[/lo], 6 bands padded to 8 channels =
+// one 16-byte row per pixel and plane.  One thread per pixel.
+__global__ void __launch_bounds__(256) bn_pack8_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                       const float* __restrict__ sh, long long npix, OutSpec o) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const float2* xp = reinterpret_cast<const float2*>(x + pix * CB_);  // 24-byte pixels: 8-byte aligned
+  const float2 a = __ldg(xp), b = __ldg(xp + 1), c = __ldg(xp + 2);
+  float v[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = j * 8 + e;
-    const int tap = k / 6, ch = k - tap * 6;  // k < 64: small-constant divisions on a 3-bit j
-    v[e] = k < 54 ? s_in[tap / 3][xx + tap % 3][ch] : 0.f;
-  }
-  const long long pix = rowid * S_ + xx;
-  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + pix * (long long)(o.planes * o.Cpad) + j * 8;
+  for (int ch = 0; ch < 6; ++ch) v[ch] = fmaf(v[ch], __ldg(sc + ch), __ldg(sh + ch));
   uint4 q, l;
   split_bf16x2(v[0], v[1], q.x, l.x);
   split_bf16x2(v[2], v[3], q.y, l.y);
   split_bf16x2(v[4], v[5], q.z, l.z);
-  split_bf16x2(v[6], v[7], q.w, l.w);
+  q.w = l.w = 0u;
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + pix * (long long)(o.planes * o.Cpad);
   *reinterpret_cast<uint4*>(p) = q;
   if (o.planes == 2) *reinterpret_cast<uint4*>(p + o.Cpad) = l;
 }
 
-int launch_im2col_conv1(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st) {
-  if (B == 0) return DBV_OK;
-  im2col_conv1_kernel<<<(unsigned)(B * S_), 480, 0, st>>>(x, bn_scale, bn_shift, B, o);
+int launch_bn_pack8(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st) {
+  const long long npix = B * S_ * S_;
+  if (npix == 0) return DBV_OK;
+  bn_pack8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, bn_scale, bn_shift, npix, o);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -24,9 +24,14 @@ constexpr int EPI_SUBGROUPS = 1;  // epilogue groups (of 4 warps) per accumulato
 constexpr int HALO_THREADS = 64 + 2 * EPI_SUBGROUPS * 128;  // TMA warp, MMA warp, epilogue warps
 constexpr int HALO_TBUF_COLS = 256;  // TMEM columns per accumulator buffer (2 buffers)
 
-template <int CBK, int NT>
+// NOSWZ (encoder conv1, Cin = 6 padded to 8): one 16-byte row per pixel, no swizzle.  A K=16 MMA operand is
+// then TWO ADJACENT PIXELS: core-matrix stride along K (LBO) = 16 bytes = the pixel pitch, so the 3x3x8
+// im2col never exists anywhere — the (kx, channel) axis of each kernel row is read as overlapping
+// windows of the halo tile.  Per kernel row ky: pixels (x-1, x) and (x+1, x+2[zero weights]).
+template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
-  constexpr int ROWB = CBK * 2;
+  constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
+  constexpr int KSTEPS = NOSWZ ? 1 : CBK / 16;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.tmA);
-    tma_prefetch_desc(&L.tmB);
+    if (!NOSWZ) tma_prefetch_desc(&L.tmB);
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
@@ -61,8 +66,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(bar_w, (uint32_t)(L.n_wblk * NT * ROWB));
-      for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB), &L.tmB, bar_w, 0, blk * L.w_rows_per_blk);
+      if constexpr (NOSWZ) {
+        mbar_expect_tx(bar_w, (uint32_t)L.w_bytes);
+        bulk_load(sW, L.w_img, (uint32_t)L.w_bytes, bar_w);
+      } else {
+        mbar_expect_tx(bar_w, (uint32_t)(L.n_wblk * NT * ROWB));
+        for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB), &L.tmB, bar_w, 0, blk * L.w_rows_per_blk);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < total; t += gridDim.x) {
@@ -82,9 +92,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       uint32_t phase = 0;
       int tb = 0;
       uint32_t tphase = 0;
-      constexpr uint32_t HI = smem_desc_hi<ROWB>();
+      // descriptor words: swizzled K-major rows, or (NOSWZ) interleaved 8x16-byte core matrices with
+      // A: SBO 128 B (8 pixels), LBO 16 B (next pixel);  B: SBO 256 B, LBO 128 B (host-packed image)
+      constexpr uint32_t HI = NOSWZ ? ((128u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
+      constexpr uint32_t HIB = NOSWZ ? ((256u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
+      constexpr uint32_t LOB = NOSWZ ? ((128u >> 4) << 16) : kSmemDescLoConst;
       constexpr uint32_t MSTEP = (128 * ROWB) >> 4;
-      const uint32_t w16 = kSmemDescLoConst | (sW >> 4);
+      const uint32_t w16 = LOB | (sW >> 4);
       for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         mbar_wait(bar_tempty + 8 * tb, tphase ^ 1u);
         mbar_wait(bar_afull + 8 * stage, phase);
@@ -103,7 +117,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
             uint32_t d = d0;
             for (int m = 0; m < L.ntiles; ++m, alo += MSTEP, d += DW) {
 #pragma unroll
-              for (int k = 0; k < CBK / 16; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HI, blo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HIB, blo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
         }
@@ -174,23 +188,24 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   }
 }
 
-template <int CBK, int NT>
+template <int CBK, int NT, bool NOSWZ = false>
 static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_halo_kernel<CBK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_MAX_SMEM);
+    attr_err = cudaFuncSetAttribute(tc_halo_kernel<CBK, NT, NOSWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_MAX_SMEM);
   });
   if (attr_err != cudaSuccess)
     return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_halo_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
   const long long grid = L.total_bands < max_ctas ? L.total_bands : max_ctas;
   if (grid <= 0) return DBV_OK;
-  tc_halo_kernel<CBK, NT><<<(unsigned)grid, HALO_THREADS, L.smem_bytes, st>>>(L);
+  tc_halo_kernel<CBK, NT, NOSWZ><<<(unsigned)grid, HALO_THREADS, L.smem_bytes, st>>>(L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
 
 bool halo_layer_supported(int CBK, int NT) {
+  if (CBK == 16) return NT == 32;  // encoder conv1, no-swizzle mode
   if (CBK == 32) return NT == 16 || NT == 32 || NT == 64;
   if (CBK == 64) return NT == 32 || NT == 64 || NT == 128;
   return false;
@@ -199,6 +214,7 @@ bool halo_layer_supported(int CBK, int NT) {
 int launch_halo_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
 #define DBV_HALO_CASE(cb, nt) \
   if (CBK == cb && NT == nt) return launch_halo_one<cb, nt>(L, max_ctas, st);
+  if (CBK == 16 && NT == 32) return launch_halo_one<16, 32, true>(L, max_ctas, st);
   DBV_HALO_CASE(32, 16)
   DBV_HALO_CASE(32, 32)
   DBV_HALO_CASE(32, 64)
