@@ -40,6 +40,7 @@ UNIT = "stamps/s"
 BATCH = 4096
 CFG = ("dc2", (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3])
 STAMP_ELTS = 59 * 59 * 6
+HALO_LAYERS = {"enc_conv1", "enc_conv3", "enc_conv5", "dec_convT5", "dec_convT6", "dec_convT7", "dec_convT8", "dec_head"}
 
 
 def peaks():
@@ -262,11 +263,13 @@ def main():
         clocks.start()
     l0 = _ffi.lib().dbv_global_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` then sees only the timed region (not the plan autotuner)
     e0.record()
     for _ in range(args.steps):
         net.deblend_into(x, mean, std)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = int(_ffi.lib().dbv_global_launch_count() - l0)
     clk = clocks.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -311,8 +314,17 @@ def main():
     top = max(tc_lay, key=lambda l: l["ms"]) if tc_lay else {"layer": None, "tflops": 0.0, "ms": 0.0}
     sum_ms = sum(l["ms"] for l in lay) or 1.0
     net_tf = value / world * spec.FLOP_PER_STAMP / 1e12
-    roofline = {"bound": "tensor", "kernel": f"tc_conv_kernel[{top['layer']}]", "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(top["tflops"] / peak_tf, 4), "traffic": None, "share_of_step": round(top["ms"] / sum_ms, 4),
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this layer's kernel, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(args.precision, {}).get(top["layer"])
+        if ent:
+            traffic = {"bytes_per_launch": ent["dram_bytes"], "stamps_per_launch": ent["stamps"], "source": tj.get("source")}
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": f"{top['layer']} ({'tc_halo_kernel' if top['layer'] in HALO_LAYERS else 'tc_conv_kernel'}, tcgen05)",
+                "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(top["tflops"] / peak_tf, 4), "traffic": traffic, "share_of_step": round(top["ms"] / sum_ms, 4),
                 "peak_source": pk["source"] + " bf16 sustained", "flops": "algorithmic (nominal 2*MACs of the layer; bf16x3 executes 3x that on the tensor pipe)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
