@@ -418,10 +418,10 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
   const int tail_pad = ((129 * ROWB + 1023) / 1024) * 1024;
   const int ntiles = (bandR * WP + 127) / 128;
-  if (ncls * ntiles * G.NT * (x3 ? 2 : 1) > 256) return 0;
+  if (G.NT * (x3 ? 2 : 1) > 256) return 0;  // one unit (tile of one class) must fit a TMEM slot; the ring has 512 / width slots
   if (bandR + 2 * pad > 256 || WP > 256) return 0;
   const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + 1023) / 1024) * 1024;
-  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 128;
+  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 2048;  // + barriers and the k-block table
   if (smem > HALO_MAX_SMEM) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
@@ -773,8 +773,6 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     }
     if (L.a2n >= 0 && (r = check_shape(c, wkey(L.enc, L.a2n, "alpha"), {(int64_t)L.Hout * L.Hout * L.Cout}, &A2))) return r;
     if ((r = upload(c, &R.bias, Bv->data))) return r;
-    if (A && (r = upload(c, &R.alpha, A->data))) return r;
-    if (A2 && (r = upload(c, &R.alpha2, A2->data))) return r;
     R.CoutP = (L.Cout + 3) & ~3;
     const bool simt = fp32 || !kTc[li].tc;
     if (simt) {
@@ -802,6 +800,18 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     } else {
       tc_out_layout(li, planes, &o);
     }
+    // PReLU slopes: checkpoint layout (h,w,c) of the map THIS OutSpec describes -> [c/4][h*w][4] (epilogue.cuh:alpha_index)
+    auto regroup = [&](const HostTensor* t) {
+      const long long npix = (long long)o.OH * o.OW;
+      std::vector<float> g(t->data.size());
+      for (long long pix = 0; pix < npix; ++pix)
+        for (int ch = 0; ch < o.Cout; ++ch) g[alpha_index(npix, pix, ch)] = t->data[pix * o.Cout + ch];
+      return g;
+    };
+    if ((A || A2) && (o.Cout % 4 != 0 || (size_t)o.OH * o.OW * o.Cout != (A ? A : A2)->data.size()))
+      return fail(DBV_ERR_UNSUPPORTED, "%s: PReLU slopes do not match the output map", L.name);
+    if (A && (r = upload(c, &R.alpha, regroup(A)))) return r;
+    if (A2 && (r = upload(c, &R.alpha2, regroup(A2)))) return r;
     o.bias = R.bias;
     o.alpha = R.alpha;
     o.alpha2 = R.alpha2;

@@ -27,12 +27,20 @@ struct OutSpec {
   int Cpad;            // channels per plane as stored (>= Cout)
   int PH, PW;          // OUT_BF16_PARITY plane extents
   const float* bias;   // [Cout]
-  const float* alpha;  // [OH][OW][Cout] or null
-  const float* alpha2; // second PReLU (encoder Flatten PReLU, model/model.py:95) or null
+  const float* alpha;  // PReLU slopes of the (OH,OW,Cout) map in the library's layout [Cout/4][OH*OW][4] (see alpha_index), or null
+  const float* alpha2; // second PReLU (encoder Flatten PReLU, model/model.py:95), same layout, or null
   int relu;
 };
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
+
+// PReLU slopes are stored channel-group-major: element (pixel, c) at ((c/4) * npix + pixel) * 4 + c%4.  In the
+// tensor-core epilogues lane = pixel, so a warp's 16-byte load of four channels covers 512 contiguous bytes
+// (4 L1 wavefronts) instead of 32 separate lines; the L1 data path is shared with the MMA operand fetch from
+// shared memory, which is what bounds the few-channel layers.  Cout % 4 == 0 everywhere.
+__host__ __device__ __forceinline__ long long alpha_index(long long npix, long long pix, int c) {
+  return ((long long)(c >> 2) * npix + pix) * 4 + (c & 3);
+}
 
 // 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
 __device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
@@ -60,21 +68,21 @@ __device__ __forceinline__ long long pixel_offset(const OutSpec& o, long long b,
 // bias_off shifts the bias index only (Dense -> Reshape layers whose N tile is a pixel).
 template <int NV>
 __device__ __forceinline__ void apply_act(const OutSpec& o, int y, int x, int c, float (&v)[NV], int bias_off = 0) {
-  const long long pix = (long long)y * o.OW + x;
+  const long long pix = (long long)y * o.OW + x, npix = (long long)o.OH * o.OW;
   if (c + NV <= o.Cout && (o.Cout & 3) == 0) {  // fast path: 16-byte loads (c is a multiple of 4)
     const float4* bp = reinterpret_cast<const float4*>(o.bias + bias_off + c);
-    const float4* ap = o.alpha ? reinterpret_cast<const float4*>(o.alpha + pix * o.Cout + c) : nullptr;
-    const float4* a2p = o.alpha2 ? reinterpret_cast<const float4*>(o.alpha2 + pix * o.Cout + c) : nullptr;
+    const float4* ap = o.alpha ? reinterpret_cast<const float4*>(o.alpha) + (long long)(c >> 2) * npix + pix : nullptr;
+    const float4* a2p = o.alpha2 ? reinterpret_cast<const float4*>(o.alpha2) + (long long)(c >> 2) * npix + pix : nullptr;
 #pragma unroll
     for (int j = 0; j < NV; j += 4) {
       const float4 bb = __ldg(bp + (j >> 2));
       v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
       if (ap) {
-        const float4 a = __ldg(ap + (j >> 2));
+        const float4 a = __ldg(ap + (long long)(j >> 2) * npix);
         v[j] = prelu_f(v[j], a.x); v[j + 1] = prelu_f(v[j + 1], a.y); v[j + 2] = prelu_f(v[j + 2], a.z); v[j + 3] = prelu_f(v[j + 3], a.w);
       }
       if (a2p) {
-        const float4 a = __ldg(a2p + (j >> 2));
+        const float4 a = __ldg(a2p + (long long)(j >> 2) * npix);
         v[j] = prelu_f(v[j], a.x); v[j + 1] = prelu_f(v[j + 1], a.y); v[j + 2] = prelu_f(v[j + 2], a.z); v[j + 3] = prelu_f(v[j + 3], a.w);
       }
       if (o.relu) {
@@ -87,8 +95,8 @@ __device__ __forceinline__ void apply_act(const OutSpec& o, int y, int x, int c,
   for (int j = 0; j < NV; ++j) {
     if (c + j < o.Cout) {
       float t = v[j] + __ldg(o.bias + bias_off + c + j);
-      if (o.alpha) t = prelu_f(t, __ldg(o.alpha + pix * o.Cout + c + j));
-      if (o.alpha2) t = prelu_f(t, __ldg(o.alpha2 + pix * o.Cout + c + j));
+      if (o.alpha) t = prelu_f(t, __ldg(o.alpha + alpha_index(npix, pix, c + j)));
+      if (o.alpha2) t = prelu_f(t, __ldg(o.alpha2 + alpha_index(npix, pix, c + j)));
       if (o.relu) t = fmaxf(t, 0.f);
       v[j] = t;
     } else {
@@ -109,17 +117,10 @@ template <int NV>
 __device__ __forceinline__ void act_prefetch(const OutSpec& o, bool ok, int y, int x, int c, int bias_off, ActRegs<NV>& r) {
   r.fast = ok && (c + NV <= o.Cout) && ((o.Cout & 3) == 0) && o.alpha != nullptr;
   if (r.fast) {
-    const long long pix = (long long)y * o.OW + x;
-    const float* ap = o.alpha + pix * o.Cout + c;
-    if constexpr (NV % 8 == 0) {
-      if ((o.Cout & 7) == 0) {  // 32-byte aligned: 256-bit loads halve the L1 wavefronts of this per-lane-line pattern
+    const long long npix = (long long)o.OH * o.OW;
+    const float4* ap = reinterpret_cast<const float4*>(o.alpha) + (long long)(c >> 2) * npix + ((long long)y * o.OW + x);
 #pragma unroll
-        for (int j = 0; j < NV / 8; ++j) ldg256(ap + 8 * j, r.a[2 * j], r.a[2 * j + 1]);
-        return;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NV / 4; ++j) r.a[j] = __ldg(reinterpret_cast<const float4*>(ap) + j);
+    for (int j = 0; j < NV / 4; ++j) r.a[j] = __ldg(ap + (long long)j * npix);
   }
 }
 
@@ -139,10 +140,11 @@ __device__ __forceinline__ void act_apply(const OutSpec& o, int y, int x, int c,
     v[4 * j + 3] = prelu_f(v[4 * j + 3] + bb.w, r.a[j].w);
   }
   if (o.alpha2) {
-    const float4* a2p = reinterpret_cast<const float4*>(o.alpha2 + ((long long)y * o.OW + x) * o.Cout + c);
+    const long long npix = (long long)o.OH * o.OW;
+    const float4* a2p = reinterpret_cast<const float4*>(o.alpha2) + (long long)(c >> 2) * npix + ((long long)y * o.OW + x);
 #pragma unroll
     for (int j = 0; j < NV / 4; ++j) {
-      const float4 a = __ldg(a2p + j);
+      const float4 a = __ldg(a2p + (long long)j * npix);
       v[4 * j + 0] = prelu_f(v[4 * j + 0], a.x);
       v[4 * j + 1] = prelu_f(v[4 * j + 1], a.y);
       v[4 * j + 2] = prelu_f(v[4 * j + 2], a.z);

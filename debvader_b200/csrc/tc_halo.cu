@@ -20,31 +20,44 @@
 
 namespace dbv {
 
-constexpr int EPI_SUBGROUPS = 1;  // epilogue groups (of 4 warps) per accumulator buffer; 2 was measured slower (L1-bound, spills)
-constexpr int HALO_THREADS = 64 + 2 * EPI_SUBGROUPS * 128;  // TMA warp, MMA warp, epilogue warps
-constexpr int HALO_TBUF_COLS = 256;  // TMEM columns per accumulator buffer (2 buffers)
+constexpr int HALO_THREADS = 64 + 2 * 128;  // TMA warp, MMA warp, two epilogue groups of 4 warps
+constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring (512 columns / slot width, capped)
 
 // NOSWZ (encoder conv1, Cin = 6 padded to 8): one 16-byte row per pixel, no swizzle.  A K=16 MMA operand is
 // then TWO ADJACENT PIXELS: core-matrix stride along K (LBO) = 16 bytes = the pixel pitch, so the 3x3x8
 // im2col never exists anywhere — the (kx, channel) axis of each kernel row is read as overlapping
 // windows of the halo tile.  Per kernel row ky: pixels (x-1, x) and (x+1, x+2[zero weights]).
+//
+// Work decomposition: item g in [0, B * bands_per_img) is band  g / B  of stamp  g % B  (band-major), and CTA i
+// owns the contiguous range [total*i/grid, total*(i+1)/grid): a CTA stays on ONE band row for (almost) its whole
+// life, so the PReLU alpha slice of that band (tens of KB, the same for every stamp) stays L1-resident.
+//
+// Accumulators: TMEM is a ring of `nslot` slots of DW columns; a "unit" = one 128-position tile of one
+// output-parity class.  The MMA warp issues all k-blocks of a unit into the next free slot and commits it;
+// the two epilogue groups drain alternate units.  The MMA warp can therefore run up to nslot units ahead of
+// the epilogue and neither side idles while the other works on "its" buffer (the previous two-buffer-per-band
+// scheme serialised MMA(band i+2) behind epilogue(band i): measured 1.6 ms where max(MMA, epilogue) was 1.1).
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
   constexpr int KSTEPS = NOSWZ ? 1 : CBK / 16;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;                              // resident weights: n_wblk blocks of NT x ROWB
   const uint32_t sA = base + L.w_bytes;                  // nbuf x n_regions x region_bytes
   const uint32_t sBar = sA + L.nbuf * L.n_regions * L.region_bytes + L.tail_pad;
-  const uint32_t bar_w = sBar, bar_afull = sBar + 8, bar_aempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 56;
-  const uint32_t s_tmem = sBar + 72;
+  const uint32_t bar_w = sBar, bar_afull = sBar + 8, bar_aempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 104;
+  const uint32_t s_tmem = sBar + 168, sTbl = sBar + 192;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (s_tmem - base));
+  uint2* tbl = reinterpret_cast<uint2*>(gen_base + (sTbl - base));  // per k-block: {A window offset >> 4, B block offset >> 4 | wide << 31}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per unit
+  const uint32_t nslot = (512u / DW) < (uint32_t)HALO_NSLOT_MAX ? (512u / DW) : (uint32_t)HALO_NSLOT_MAX;  // power of two
+  const uint32_t slot_shift = 31u - (uint32_t)__clz((int)nslot);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.tmA);
     if (!NOSWZ) tma_prefetch_desc(&L.tmB);
@@ -52,10 +65,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int s = 0; s < HALO_NSLOT_MAX; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4 * EPI_SUBGROUPS);
+      mbar_init(bar_tempty + 8 * s, 4);
     }
     fence_barrier_init();
+  }
+  {
+    const int nkb_total = L.cls[L.n_cls - 1].kb_begin + L.cls[L.n_cls - 1].nkb;
+    for (int i = threadIdx.x; i <= nkb_total; i += HALO_THREADS) {
+      const TcKBlock K = L.kb[i < nkb_total ? i : 0];
+      tbl[i] = make_uint2((uint32_t)(uint16_t)K.c_off, (uint32_t)K.b_row | (K.dy ? 0x80000000u : 0u));
+    }
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
@@ -63,6 +85,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long total = L.total_bands;
+  const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
+  const long long yb0 = g0 / L.B;
+  const int b_first = (int)(g0 - yb0 * L.B);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -75,14 +100,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        const long long b = t / L.bands_per_img;
-        const int y0 = (int)(t - b * L.bands_per_img) * L.R;
+      int b = b_first, y0 = (int)yb0 * L.R;
+      for (long long g = g0; g < g1; ++g) {
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(L.n_regions * L.a_box_bytes));
         for (int r = 0; r < L.n_regions; ++r)
-          tma_load_5d(sA + (stage * L.n_regions + r) * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, 0, (int)b);
+          tma_load_5d(sA + (stage * L.n_regions + r) * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, 0, b);
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
+        if (++b == (int)L.B) { b = 0; y0 += L.R; }
       }
     }
   } else if (warp == 1) {
@@ -90,8 +115,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       mbar_wait(bar_w, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int tb = 0;
-      uint32_t tphase = 0;
+      uint32_t u = 0;  // running unit counter (slot = u % nslot)
       // descriptor words: swizzled K-major rows, or (NOSWZ) interleaved 8x16-byte core matrices with
       // A: SBO 128 B (8 pixels), LBO 16 B (next pixel);  B: SBO 256 B, LBO 128 B (host-packed image)
       constexpr uint32_t HI = NOSWZ ? ((128u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
@@ -99,85 +123,89 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       constexpr uint32_t LOB = NOSWZ ? ((128u >> 4) << 16) : kSmemDescLoConst;
       constexpr uint32_t MSTEP = (128 * ROWB) >> 4;
       const uint32_t w16 = LOB | (sW >> 4);
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * tb, tphase ^ 1u);
+      const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;
+      for (long long g = g0; g < g1; ++g) {
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
         const uint32_t a16 = kSmemDescLoConst | ((sA + stage * L.n_regions * L.region_bytes) >> 4);
-        for (int c = 0; c < ((L.dbg_skip & 1) ? 0 : L.n_cls); ++c) {
+        for (int c = 0; c < ncls; ++c) {
           const int kb0 = L.cls[c].kb_begin, nkb = L.cls[c].nkb;
-          const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per tile
-          const uint32_t d0 = tmem_base + (uint32_t)(tb * HALO_TBUF_COLS) + (uint32_t)(c * L.ntiles) * DW;
-          // k-block outer, tile inner: the per-k-block table lookup is amortised over ntiles * CBK/16 MMAs
-          for (int kb = 0; kb < nkb; ++kb) {
-            const TcKBlock K = L.kb[kb0 + kb];
-            uint32_t alo = a16 + (uint32_t)(uint16_t)K.c_off;
-            const uint32_t blo = w16 + (uint32_t)K.b_row;
-            const uint32_t idesc = K.dy ? IDESC2 : IDESC;
-            uint32_t d = d0;
-            for (int m = 0; m < L.ntiles; ++m, alo += MSTEP, d += DW) {
+          uint32_t am = a16;
+          for (int m = 0; m < L.ntiles; ++m, am += MSTEP, ++u) {
+            const uint32_t slot = u & (nslot - 1);
+            mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + slot * DW;
+            uint2 K = tbl[kb0];
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint2 Kn = tbl[kb0 + kb + 1];  // software prefetch of the next entry (the table has one spare)
+              const uint32_t alo = am + K.x, blo = w16 + (K.y & 0x7fffffffu);
+              const uint32_t idesc = (K.y >> 31) ? IDESC2 : IDESC;
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HIB, blo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              K = Kn;
             }
+            umma_commit(bar_tfull + 8 * slot);
           }
         }
         umma_commit(bar_aempty + 8 * stage);
-        umma_commit(bar_tfull + 8 * tb);
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
-        tb ^= 1;
-        if (tb == 0) tphase ^= 1u;
       }
     }
   } else {
-    // 16 epilogue warps = 4 groups of 4 (one warp per TMEM lane quadrant in each group).  Groups 0,1 drain
-    // accumulator buffer 0, groups 2,3 buffer 1; within a band the two groups take alternate items
-    // (tile, 32-channel chunk).  The epilogue is dependent-issue bound (ncu: ~0.2 IPC per warp), so it is
-    // the number of resident warps per scheduler — 4 — that hides its latency.
+    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains units u with (u & 1) == g.
     const int quad = warp & 3, grp = (warp - 2) >> 2;
-    const int half = grp / EPI_SUBGROUPS, sub = grp % EPI_SUBGROUPS;
     const int row = quad * 32 + lane;
     constexpr int NV = (NT % 32 == 0) ? 32 : 16;
     constexpr int NCHK = NT / NV;
-    const int n_items = L.n_cls * L.ntiles * NCHK;
-    const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);
-    int tb = 0;
-    uint32_t tphase = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      if (tb == half) {
-        const long long b = t / L.bands_per_img;
-        const int y0 = (int)(t - b * L.bands_per_img) * L.R;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * HALO_TBUF_COLS);
-        mbar_wait(bar_tfull + 8 * tb, tphase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int q = sub; q < ((L.dbg_skip & 2) ? 0 : n_items); q += EPI_SUBGROUPS) {
-          const int tm = q / NCHK, c0 = (q - tm * NCHK) * NV;
-          const int c = tm / L.ntiles, m = tm - c * L.ntiles;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
+    uint32_t u = 0;
+    int b = b_first, y0 = (int)yb0 * L.R;
+    for (long long g = g0; g < g1; ++g) {
+      for (int c = 0; c < ncls; ++c) {
+        for (int m = 0; m < L.ntiles; ++m, ++u) {
+          if ((int)(u & 1u) != grp) continue;
+          const uint32_t slot = u & (nslot - 1);
           const int p = 128 * m + row;
           const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
-          const bool ok = ly < L.R && sx < L.W && sy < L.H;
+          const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
           const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
           ActRegs<NV> ra;
-          act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);
-          float v[NV];
-          tmem_ld<NV>(tbase + (uint32_t)tm * DW + (uint32_t)c0, v);
-          if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the tile's columns
-            float w[NV];
-            tmem_ld<NV>(tbase + (uint32_t)tm * DW + (uint32_t)(NT + c0), w);
+          ra.fast = false;
+          if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, 0, 0, ra);
+          mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+          tc_fence_after();
+          const uint32_t tcol = lane_base + slot * DW;
+#pragma unroll 1
+          for (int q = 0; q < NCHK; ++q) {
+            const int c0 = q * NV;
+            if (q && !(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);
+            float v[NV];
+            if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the unit's columns
+              float w[NV];
+              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+              tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
+              tmem_ld_wait<NV>(v);
+              tmem_ld_wait<NV>(w);
 #pragma unroll
-            for (int j = 0; j < NV; ++j) v[j] += w[j];
+              for (int j = 0; j < NV; ++j) v[j] += w[j];
+            } else {
+              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+              tmem_ld_wait<NV>(v);
+            }
+            if (ok) {
+              if (!(L.dbg_skip & 4)) act_apply<NV>(L.o, oy, ox, c0, 0, ra, v);
+              if (!(L.dbg_skip & 8)) store_act<NV>(L.o, b, oy, ox, c0, v);
+              else if (v[0] == 123.456f) store_act<NV>(L.o, b, oy, ox, c0, v);  // keep the loads / math alive
+            }
           }
-          if (ok) {
-            act_apply<NV>(L.o, oy, ox, c0, 0, ra, v);
-            store_act<NV>(L.o, b, oy, ox, c0, v);
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * tb);
       }
-      tb ^= 1;
-      if (tb == 0) tphase ^= 1u;
+      if (++b == (int)L.B) { b = 0; y0 += L.R; }
     }
   }
   tc_fence_before();

@@ -3,6 +3,10 @@
 #pragma once
 #include "kernels.h"
 
+#ifndef DBV_MMA_AB_FMT
+#define DBV_MMA_AB_FMT 1  // tcgen05 instruction-descriptor A/B format: 0 = F16, 1 = BF16
+#endif
+
 namespace dbv {
 
 // ---------------------------------------------------------------------------------------------
@@ -124,6 +128,52 @@ template <int NV>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NV]) {
   if constexpr (NV == 32) tmem_ld_x32(taddr, v);
   else tmem_ld_x16(taddr, v);
+}
+
+// ---- split issue / wait: several tcgen05.ld in flight before one wait --------------------------------
+// tmem_ld_wait takes the destination registers as read-write operands, so the compiler cannot schedule a
+// use of them above the wait.
+template <int NV>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[NV]) {
+  if constexpr (NV == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    static_assert(NV == 16, "tmem_ld_issue: NV must be 16 or 32");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+template <int NV>
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[NV]) {
+  if constexpr (NV == 32) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]),
+                   "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]),
+                   "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+  }
 }
 
 // smem matrix descriptor, K-major operand, rows of ROWB bytes packed densely, 8-row swizzle atoms.

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for skip in 0 1 2 3; do
+for skip in ${SKIPS:-0 1 2 3}; do
   DBV_HALO_SKIP=$skip timeout 300 python bench.py --steps 3 --warmup 3 --no-extras > gpurun_out/abl_$skip.json 2>gpurun_out/abl_$skip.err
   python - $skip <<'PY'
 import json,sys
