@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdebvader_b200.so")
-SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_halo.cu", "tc_probe.cu"]
+SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_halo.cu", "tc_probe.cu"]
 HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "debvader_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -110,6 +110,8 @@ struct LayerRt {
   // tcgen05 plan
   TcLayer tc{};
   bool has_tc = false;
+  TcLayer tcp{};  // CTA-pair plan (many-channel layers)
+  bool has_pair = false;
   // resident-halo plan (preferred when it exists)
   HaloLayer halo{};
   bool has_halo = false;
@@ -335,19 +337,16 @@ static int build_tc_layer(dbv_ctx* c, int li) {
     for (size_t ti = 0; ti < taps.size(); ++ti) {
       if (taps[ti].cls != cl) continue;
       for (int ch = 0; ch < nchunk; ++ch) {
-        // pairings: (a_hi, w_hi) [, (a_hi, w_lo), (a_lo, w_hi)]
-        const int npair = x3 ? 3 : 1;
-        for (int pr = 0; pr < npair; ++pr) {
-          if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: k-block table overflow", L.name);
-          const int a_lo = (pr == 2), w_lo = (pr == 1);
-          if (a_lo && in_planes < 2) return fail(DBV_ERR_STATE, "%s: input has no lo plane", L.name);
-          TcKBlock& K = T.kb[nkb++];
-          K.dx = (int16_t)taps[ti].dx;
-          K.dy = (int16_t)taps[ti].dy;
-          K.plane = (int16_t)taps[ti].plane;
-          K.c_off = (int16_t)(ch * G.CBK + (a_lo ? in_cpad : 0));
-          K.b_row = (int32_t)(((ti * nchunk + ch) * parts_w + w_lo) * Ntot);
-        }
+        // one k-block per (tap, chunk); in the hi/lo split precisions the kernel loads the lo activation plane
+        // (channel offset + lo_coff) and the lo weight block (row offset + lo_brow) into the same stage
+        if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: k-block table overflow", L.name);
+        if (x3 && in_planes < 2) return fail(DBV_ERR_STATE, "%s: input has no lo plane", L.name);
+        TcKBlock& K = T.kb[nkb++];
+        K.dx = (int16_t)taps[ti].dx;
+        K.dy = (int16_t)taps[ti].dy;
+        K.plane = (int16_t)taps[ti].plane;
+        K.c_off = (int16_t)(ch * G.CBK);
+        K.b_row = (int32_t)(((ti * nchunk + ch) * parts_w) * Ntot);
       }
     }
     T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
@@ -366,6 +365,10 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   T.nt_pixel_mode = (li == I_DENSE2);
   T.a_bytes = G.CBK * 2 * G.TW * G.TH * G.TB;
   T.b_bytes = G.NT * G.CBK * 2;
+  T.x3 = x3 ? 1 : 0;
+  T.lo_coff = in_cpad;
+  T.lo_brow = Ntot;
+  tc_stage_plan(T, G.CBK, G.NT);
   // ---- tensor maps ----------------------------------------------------------------------------------
   {
     // input viewed as (C, W, H, P, B)
@@ -387,6 +390,16 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   }
   if (!tc_layer_supported(G.CBK, G.NT)) return fail(DBV_ERR_UNSUPPORTED, "%s: no kernel for CBK=%d NT=%d", L.name, G.CBK, G.NT);
   R.has_tc = true;
+  if (tc_pair_supported(G.CBK, G.NT) && Ntot % G.NT == 0 && !getenv("DBV_NO_PAIR")) {
+    R.tcp = T;
+    uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};
+    uint64_t bs[1] = {(uint64_t)G.CBK * 2};
+    uint32_t bb[2] = {(uint32_t)G.CBK, (uint32_t)(G.NT / 2)};
+    int r = encode_tmap(&R.tcp.tmB, R.w_packed, 2, bd, bs, bb, G.CBK * 2);
+    if (r) return r;
+    tc_pair_stage_plan(R.tcp, G.CBK, G.NT);
+    R.has_pair = true;
+  }
   return DBV_OK;
 }
 
@@ -571,6 +584,14 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
     T.o = o;
     T.total_bands = B * T.bands_per_img;
     return launch_halo_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
+  }
+  if (R.has_pair) {
+    TcLayer T = R.tcp;
+    T.B = B;
+    T.o = o;
+    const long long mt = ((B + T.TB - 1) / T.TB) * T.tiles_x * T.tiles_y;
+    T.pair_items = (long long)T.n_cls * ((mt + 1) / 2) * T.n_tiles_n;
+    return launch_tc_pair(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
   }
   if (R.has_tc) {
     TcLayer T = R.tc;

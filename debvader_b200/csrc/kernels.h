@@ -26,8 +26,8 @@ int launch_act_to_f32(const OutSpec& o, long long B, float* out, cudaStream_t st
 int launch_bn_pack8(const float* x, const float* bn_scale, const float* bn_shift, long long B, const OutSpec& o, cudaStream_t st);
 
 // ---- tcgen05 implicit-GEMM convolution (tc_conv.cu) ------------------------------------------------
-// One k-block = one (tap, channel chunk[, hi/lo pairing]) : an A box of the activation tensor and a
-// B box of the packed weights, multiplied by CB/16 tcgen05.mma of K=16.
+// One k-block = one (tap, channel chunk): the A box(es) of the activation tensor (hi[, lo] plane) and the
+// B box(es) of the packed weights (hi[, lo] part), multiplied by CBK/16 x {1, 2 or 3} tcgen05.mma of K=16.
 struct TcKBlock {
   int16_t dx, dy;     // offset of the A box relative to the output tile origin (pixels)
   int16_t plane;      // parity plane of the input tensor (0 for plain tensors)
@@ -58,7 +58,13 @@ struct TcLayer {
   long long B;        // stamps in this launch
   long long tiles_per_cls;
   long long total_tiles;
-  int a_bytes, b_bytes;  // expect_tx per k-block
+  int a_bytes, b_bytes;  // bytes of one activation box / one weight box (expect_tx = parts * (a_bytes + b_bytes))
+  int x3;                // hi/lo split precision: a k-block loads A_hi, A_lo, B_hi, B_lo once and issues all three pairings
+  int lo_coff;           // channel offset of the lo plane in the activation tensor (input Cpad)
+  int lo_brow;           // row offset of the lo weight block relative to the hi block (Ntot)
+  int wide;              // A_hi x [B_hi | B_lo] as one MMA of N = 2*NT (set by tc_stage_plan when 2*NT <= 256)
+  int stages, stage_bytes;
+  long long pair_items;  // CTA-pair kernel: n_cls x ceil(m tiles / 2) x n_tiles_n cluster work items
   int dbg_shift_rows;    // probe only: A box loaded dbg_shift_rows batch rows early, descriptor start advanced to compensate
   int dbg_base_mode;     // probe only: 0 = base_offset field 0, 1 = (start_addr >> 7) & 7
   OutSpec o;
@@ -67,6 +73,13 @@ struct TcLayer {
 // CBK: K elements per k-block (32 -> 64-byte rows / SWIZZLE_64B, 64 -> 128-byte rows / SWIZZLE_128B)
 // NT : MMA N (multiple of 16, 16..256)
 int launch_tc_layer(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+void tc_stage_plan(TcLayer& L, int CBK, int NT);  // call after x3 is set
+
+// ---- the same GEMM on CTA pairs (tc_pair.cu): cta_group::2, M = 256, each CTA holds half of every weight box ----
+// TcLayer.tmB must have a box of NT/2 rows.
+int launch_tc_pair(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+bool tc_pair_supported(int CBK, int NT);
+void tc_pair_stage_plan(TcLayer& L, int CBK, int NT);
 bool tc_layer_supported(int CBK, int NT);
 
 // ---- tcgen05 convolution with a resident halo tile (tc_halo.cu) ----------------------------------------

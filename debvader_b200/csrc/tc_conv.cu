@@ -23,39 +23,49 @@
 
 namespace dbv {
 
-constexpr int TC_EPI_SUBGROUPS = 1;  // epilogue groups (of 4 warps) per accumulator buffer; 2 was measured slower (L1-bound, spills)
-constexpr int TC_THREADS = 64 + 2 * TC_EPI_SUBGROUPS * 128;  // TMA warp, MMA warp, epilogue warps
+constexpr int TC_THREADS = 64 + 2 * 128;  // TMA warp, MMA warp, two epilogue groups of 4 warps
+constexpr int TC_NSLOT_MAX = 4;            // accumulator slots in the TMEM ring
 
 template <int CBK, int NT>
 struct TcCfg {
   static constexpr int ROWB = CBK * 2;
-  static constexpr int A_STAGE = 128 * ROWB;
-  static constexpr int B_STAGE = NT * ROWB;
-  static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int STAGES = (196608 / STAGE) > 8 ? 8 : (196608 / STAGE);
-  static constexpr int TMEM_COLS = tmem_cols_for(2 * NT);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
-  // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=BF16 [7,10)/[10,13),
+  static constexpr int A_BYTES = 128 * ROWB;  // one activation box (one plane)
+  static constexpr int B_BYTES = NT * ROWB;   // one weight box (one part)
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b format [7,10)/[10,13),
   // K-major both, N>>3 [17,23), M>>4 [24,29)
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC =
+      (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC2 =
+      (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(((2 * NT) & 0x1ff) >> 3) << 17) | ((128u >> 4) << 24);
 };
 
+// smem stage of one k-block = (tap, channel chunk):  [A_hi | A_lo | B_hi | B_lo]  (the lo boxes only in the hi/lo split
+// precisions).  Every box is loaded ONCE and used by all pairings:
+//   wide (2*NT <= 256):  D[:, 0:2NT] += A_hi x [B_hi | B_lo]   (one MMA of N = 2*NT: B_hi, B_lo are adjacent)
+//                        D[:, 0:NT ] += A_lo x B_hi            (the epilogue adds the two halves)
+//   else              :  D += A_hi x B_hi;  D += A_hi x B_lo;  D += A_lo x B_hi
+// Shared-memory bandwidth (TMA fill + MMA operand fetch) is what bounds these layers, so not re-loading A_hi and
+// B_hi per pairing is worth 1.5x on the fill side.
 template <int CBK, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcLayer L) {
   using Cfg = TcCfg<CBK, NT>;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;
-  const uint32_t sB = base + STAGES * Cfg::A_STAGE;
-  const uint32_t sBar = sB + STAGES * Cfg::B_STAGE;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES;
-  const uint32_t bar_tfull = sBar + 16 * STAGES, bar_tempty = bar_tfull + 16;
-  const uint32_t s_tmem = bar_tempty + 16;
+  const int STAGES = L.stages;
+  const uint32_t stage_bytes = (uint32_t)L.stage_bytes;
+  const uint32_t offB = (uint32_t)(L.x3 ? 2 : 1) * Cfg::A_BYTES;  // B_hi inside a stage; A_lo at A_BYTES, B_lo at offB + B_BYTES
+  const uint32_t sBar = base + (uint32_t)STAGES * stage_bytes;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 64;
+  const uint32_t bar_tfull = sBar + 128, bar_tempty = bar_tfull + 8 * TC_NSLOT_MAX;
+  const uint32_t s_tmem = bar_tempty + 8 * TC_NSLOT_MAX;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t SLOTW = (uint32_t)tmem_cols_for(NT);  // slot pitch in columns (power of two >= NT)
+  const uint32_t slot_pitch = L.wide ? 2 * SLOTW : SLOTW;
+  const uint32_t nslot = (512u / slot_pitch) < (uint32_t)TC_NSLOT_MAX ? (512u / slot_pitch) : (uint32_t)TC_NSLOT_MAX;  // 2 or 4
+  const uint32_t slot_shift = 31u - (uint32_t)__clz((int)nslot);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.tmA);
@@ -64,13 +74,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TC_NSLOT_MAX; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_SUBGROUPS);
+      mbar_init(bar_tempty + 8 * s, 4);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+  if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,6 +93,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)((L.x3 ? 2 : 1) * (L.a_bytes + L.b_bytes));
       for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         const int c = (int)(t / L.tiles_per_cls);
         long long r = t - (long long)c * L.tiles_per_cls;
@@ -94,10 +105,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const TcClass cl = L.cls[c];
         for (int kb = 0; kb < cl.nkb; ++kb) {
           const TcKBlock K = L.kb[cl.kb_begin + kb];
+          const uint32_t sS = base + (uint32_t)stage * stage_bytes, bar = bar_full + 8 * stage;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(L.a_bytes + L.b_bytes));
-          tma_load_5d(sA + stage * Cfg::A_STAGE, &L.tmA, bar_full + 8 * stage, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
-          tma_load_2d(sB + stage * Cfg::B_STAGE, &L.tmB, bar_full + 8 * stage, 0, K.b_row + nt * NT);
+          mbar_expect_tx(bar, tx);
+          tma_load_5d(sS, &L.tmA, bar, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
+          tma_load_2d(sS + offB, &L.tmB, bar, 0, K.b_row + nt * NT);
+          if (L.x3) {
+            tma_load_5d(sS + Cfg::A_BYTES, &L.tmA, bar, K.c_off + L.lo_coff, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
+            tma_load_2d(sS + offB + Cfg::B_BYTES, &L.tmB, bar, 0, K.b_row + L.lo_brow + nt * NT);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -106,38 +122,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      uint32_t u = 0;
+      constexpr uint32_t HI = smem_desc_hi<Cfg::ROWB>();
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
         const int c = (int)(t / L.tiles_per_cls);
         const int nkb = L.cls[c].nkb;
-        mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);
+        const uint32_t slot = u & (nslot - 1);
+        mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * NT);
+        const uint32_t d_tmem = tmem_base + slot * slot_pitch;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          uint64_t adesc = make_smem_desc<Cfg::ROWB>(sA + stage * Cfg::A_STAGE + L.dbg_shift_rows * Cfg::ROWB);
-          if (L.dbg_base_mode == 1)
-            adesc |= (uint64_t)(((sA + stage * Cfg::A_STAGE + L.dbg_shift_rows * Cfg::ROWB) >> 7) & 7u) << 49;
-          const uint64_t bdesc = make_smem_desc<Cfg::ROWB>(sB + stage * Cfg::B_STAGE);
+          const uint32_t sS = base + (uint32_t)stage * stage_bytes;
+          uint32_t a_addr = sS + L.dbg_shift_rows * Cfg::ROWB;
+          uint32_t ahi = kSmemDescLoConst | ((a_addr & 0x3FFFFu) >> 4);
+          uint32_t HIA = HI;
+          if (L.dbg_base_mode == 1) HIA |= ((a_addr >> 7) & 7u) << 17;  // base_offset field (bits 49-51 of the descriptor)
+          const uint32_t alo = ahi + (Cfg::A_BYTES >> 4);
+          const uint32_t bhi = kSmemDescLoConst | (((sS + offB) & 0x3FFFFu) >> 4);
+          const uint32_t blo = bhi + (Cfg::B_BYTES >> 4);
+          if (L.wide) {
 #pragma unroll
-          for (int k = 0; k < CBK / 16; ++k)
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < CBK / 16; ++k) {
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC2, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, 1u);
+            }
+          } else if (L.x3) {
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k) {
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, blo + 2 * k), Cfg::IDESC, 1u);
+              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k)
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_tfull + 8 * as);
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
+        umma_commit(bar_tfull + 8 * slot);
       }
     }
   } else {
-    // 16 epilogue warps = 4 groups of 4 (one warp per TMEM lane quadrant in each group).  Groups 0,1 drain
-    // accumulator buffer 0 (even tiles), groups 2,3 buffer 1; the two groups of a buffer take alternate
-    // 32-channel chunks.  4 resident epilogue warps per scheduler hide the dependent-issue latency.
+    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains this CTA's tiles u with (u & 1) == g
     const int quad = warp & 3, grp = (warp - 2) >> 2;
-    const int half = grp / TC_EPI_SUBGROUPS, sub = grp % TC_EPI_SUBGROUPS;
     const int row = quad * 32 + lane;
     const int rows_img = L.TW * L.TH;
     const int tb = row / rows_img;
@@ -146,49 +177,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const bool row_ok = tb < L.TB;
     constexpr int NV = (NT % 32 == 0) ? 32 : 16;
     constexpr int NCHK = NT / NV;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      if (as == half) {
-        const int c = (int)(t / L.tiles_per_cls);
-        long long r = t - (long long)c * L.tiles_per_cls;
-        const int nt = (int)(r % L.n_tiles_n);
-        r /= L.n_tiles_n;
-        const int ti = (int)(r % tiles_img);
-        const int bt = (int)(r / tiles_img);
-        const int sx = (ti % L.tiles_x) * L.TW + tx, sy = (ti / L.tiles_x) * L.TH + ty;
-        const long long b = (long long)bt * L.TB + tb;
-        const TcClass cl = L.cls[c];
-        const bool ok = row_ok && b < L.B && sx < L.SW && sy < L.SH;
-        int oy = cl.oy0 + cl.osy * sy, ox = cl.ox0 + cl.osx * sx;
-        int cbase = nt * NT, boff = 0;
-        if (L.nt_pixel_mode) {
-          oy = nt / L.o.OW;
-          ox = nt - oy * L.o.OW;
-          cbase = 0;
-          boff = nt * NT;
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * NT);
-        ActRegs<NV> ra;
-        if (sub < NCHK) act_prefetch<NV>(L.o, ok, oy, ox, cbase + sub * NV, boff, ra);
-        mbar_wait(bar_tfull + 8 * as, aphase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int q = sub; q < NCHK; q += TC_EPI_SUBGROUPS) {
-          if (q != sub) act_prefetch<NV>(L.o, ok, oy, ox, cbase + q * NV, boff, ra);
-          float v[NV];
-          tmem_ld<NV>(taddr + q * NV, v);
-          if (ok) {
-            act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, ra, v);
-            store_act<NV>(L.o, b, oy, ox, cbase + q * NV, v);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t u = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
+      if ((int)(u & 1u) != grp) continue;
+      const int c = (int)(t / L.tiles_per_cls);
+      long long r = t - (long long)c * L.tiles_per_cls;
+      const int nt = (int)(r % L.n_tiles_n);
+      r /= L.n_tiles_n;
+      const int ti = (int)(r % tiles_img);
+      const int bt = (int)(r / tiles_img);
+      const int sx = (ti % L.tiles_x) * L.TW + tx, sy = (ti / L.tiles_x) * L.TH + ty;
+      const long long b = (long long)bt * L.TB + tb;
+      const TcClass cl = L.cls[c];
+      const bool ok = row_ok && b < L.B && sx < L.SW && sy < L.SH;
+      int oy = cl.oy0 + cl.osy * sy, ox = cl.ox0 + cl.osx * sx;
+      int cbase = nt * NT, boff = 0;
+      if (L.nt_pixel_mode) {
+        oy = nt / L.o.OW;
+        ox = nt - oy * L.o.OW;
+        cbase = 0;
+        boff = nt * NT;
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
+      const uint32_t slot = u & (nslot - 1);
+      const uint32_t tcol = lane_base + slot * slot_pitch;
+      ActRegs<NV> ra;
+      act_prefetch<NV>(L.o, ok, oy, ox, cbase, boff, ra);
+      mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < NCHK; ++q) {
+        if (q) act_prefetch<NV>(L.o, ok, oy, ox, cbase + q * NV, boff, ra);
+        float v[NV];
+        if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the tile's columns
+          float w[NV];
+          tmem_ld_issue<NV>(tcol + (uint32_t)(q * NV), v);
+          tmem_ld_issue<NV>(tcol + (uint32_t)(NT + q * NV), w);
+          tmem_ld_wait<NV>(v);
+          tmem_ld_wait<NV>(w);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) v[j] += w[j];
+        } else {
+          tmem_ld_issue<NV>(tcol + (uint32_t)(q * NV), v);
+          tmem_ld_wait<NV>(v);
+        }
+        if (ok) {
+          act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, ra, v);
+          store_act<NV>(L.o, b, oy, ox, cbase + q * NV, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
     }
   }
 
@@ -196,30 +236,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
+constexpr int TC_MAX_SMEM = 232448;  // 227 KB
+
 template <int CBK, int NT>
 static int launch_one(const TcLayer& L, int max_ctas, cudaStream_t st) {
-  using Cfg = TcCfg<CBK, NT>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_conv_kernel<CBK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel<CBK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM);
   });
   if (attr_err != cudaSuccess)
-    return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_conv_kernel<%d,%d>, smem=%d): %s", CBK, NT, Cfg::SMEM,
-                cudaGetErrorString(attr_err));
+    return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_conv_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
   long long grid = L.total_tiles < max_ctas ? L.total_tiles : max_ctas;
   if (grid <= 0) return DBV_OK;
-  tc_conv_kernel<CBK, NT><<<(unsigned)grid, TC_THREADS, Cfg::SMEM, st>>>(L);
+  const int smem = L.stages * L.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  if (L.stages < 2 || L.stages > 8 || smem > TC_MAX_SMEM) return fail(DBV_ERR_STATE, "tc_conv_kernel<%d,%d>: bad stage plan (%d x %d B)", CBK, NT, L.stages, L.stage_bytes);
+  tc_conv_kernel<CBK, NT><<<(unsigned)grid, TC_THREADS, smem, st>>>(L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
 
+// fills stages / stage_bytes / wide from x3, CBK, NT
+void tc_stage_plan(TcLayer& L, int CBK, int NT) {
+  const int parts = L.x3 ? 2 : 1;
+  L.stage_bytes = parts * (128 * CBK * 2 + NT * CBK * 2);
+  int st = (TC_MAX_SMEM - 1536) / L.stage_bytes;
+  L.stages = st > 8 ? 8 : st;
+  L.wide = (L.x3 && 2 * NT <= 256) ? 1 : 0;
+}
+
 bool tc_layer_supported(int CBK, int NT) {
-  if (CBK == 32) return NT == 16 || NT == 32 || NT == 64;
+  if (CBK == 32) return NT == 16 || NT == 32 || NT == 64 || NT == 256;
   if (CBK == 64) return NT == 32 || NT == 64 || NT == 112 || NT == 128 || NT == 256;
   return false;
 }
@@ -230,6 +281,7 @@ int launch_tc_layer(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_
   DBV_TC_CASE(32, 16)
   DBV_TC_CASE(32, 32)
   DBV_TC_CASE(32, 64)
+  DBV_TC_CASE(32, 256)
   DBV_TC_CASE(64, 32)
   DBV_TC_CASE(64, 64)
   DBV_TC_CASE(64, 112)

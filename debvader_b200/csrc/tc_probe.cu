@@ -53,6 +53,7 @@ extern "C" int dbv_probe(int which, const void* a_dev, const void* b_dev, float*
   T.total_tiles = T.tiles_per_cls;
   T.a_bytes = CBK * 2 * 128;
   T.b_bytes = N * CBK * 2;
+  tc_stage_plan(T, CBK, N);
   T.dbg_shift_rows = shift;
   T.dbg_base_mode = base_mode;
   OutSpec& o = T.o;
