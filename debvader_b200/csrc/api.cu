@@ -443,20 +443,20 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
     T.cls[cl].kb_begin = nkb;
     for (size_t ti = 0; ti < taps.size(); ++ti) {
       if (taps[ti].cls != cl) continue;
+      // one entry per MMA: (tap, channel chunk, pairing, k-step).  bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of
+      // N = 2*NT (the hi and lo weight blocks are adjacent in shared memory) + (A_lo x B_hi): A_hi is fetched once
       for (int ch = 0; ch < nchunk; ++ch)
-        // bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of N = 2*NT (the hi and lo weight blocks are adjacent in
-        // shared memory) + (A_lo x B_hi): the A_hi window is fetched once instead of twice
-        for (int pr = 0; pr < (x3 ? 2 : 1); ++pr) {
-          if (nkb >= TC_MAX_KB) return 0;
-          const int a_lo = (pr == 1);
-          TcKBlock& K = T.kb[nkb++];
-          K.dy = (int16_t)((x3 && pr == 0) ? 1 : 0);  // wide MMA
-          const long long a_off = (long long)(a_lo * nchunk + ch) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB;
-          const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * (c1 ? 32 : ROWB);
-          if ((a_off >> 4) > 0x7fff || (b_off >> 4) > 0x3fff) return 0;
-          K.c_off = (int16_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
-          K.b_row = (int32_t)(b_off >> 4);
-        }
+        for (int pr = 0; pr < (x3 ? 2 : 1); ++pr)
+          for (int k = 0; k < (c1 ? 1 : G.CBK / 16); ++k) {
+            if (nkb >= TC_MAX_KB) return 0;
+            const int a_lo = (pr == 1);
+            const long long a_off = (long long)(a_lo * nchunk + ch) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
+            const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * (c1 ? 32 : ROWB) + 32 * k;
+            if ((a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return 0;
+            T.mma[nkb].a = (uint32_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
+            T.mma[nkb].b = (uint32_t)(b_off >> 4) | ((x3 && pr == 0) ? 0x80000000u : 0u);
+            ++nkb;
+          }
     }
     T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
     T.cls[cl].oy0 = ncls == 4 ? (cl >> 1) : 0;

@@ -83,13 +83,16 @@ void tc_pair_stage_plan(TcLayer& L, int CBK, int NT);
 bool tc_layer_supported(int CBK, int NT);
 
 // ---- tcgen05 convolution with a resident halo tile (tc_halo.cu) ----------------------------------------
-// kb[] entries are repurposed: c_off = byte offset >> 4 of the tap's window inside one halo buffer
-// (region * region_bytes + ((dy+1)*(W+2) + dx+1) * ROWB), b_row = byte offset >> 4 of the resident weight block.
 constexpr int HALO_MAX_SMEM = 232448;  // 227 KB
+struct HaloMma {  // one tcgen05.mma (K = 16) of a unit: descriptor start offsets (bytes >> 4) and the N selector
+  uint32_t a;     // A window inside one halo buffer: region of the (plane, channel chunk) + tap shift + k-step
+  uint32_t b;     // resident weight block + k-step; bit 31: wide (N = 2*NT over the adjacent hi|lo blocks)
+};
 struct HaloLayer {
   CUtensorMap tmA;  // 5D (C, W, H, 1, B) bf16, box (CBK, W+2, R+2, 1, 1)
   CUtensorMap tmB;  // packed weights, box (CBK, NT)
-  TcKBlock kb[TC_MAX_KB];
+  HaloMma mma[TC_MAX_KB];  // flat MMA list per class (cls[c].kb_begin / nkb index it): taps x chunks x pairings x k-steps,
+                           // precomputed on the host so that the single issuing thread does nothing but issue
   TcClass cls[TC_MAX_CLS];
   int n_cls;
   int W, H;          // tile-space extents (valid outputs sx < W, sy < H)

@@ -40,7 +40,6 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
-  constexpr int KSTEPS = NOSWZ ? 1 : CBK / 16;
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
@@ -49,10 +48,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   const uint32_t sA = base + L.w_bytes;                  // nbuf x n_regions x region_bytes
   const uint32_t sBar = sA + L.nbuf * L.n_regions * L.region_bytes + L.tail_pad;
   const uint32_t bar_w = sBar, bar_afull = sBar + 8, bar_aempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 104;
-  const uint32_t s_tmem = sBar + 168, sTbl = sBar + 192;
+  const uint32_t s_tmem = sBar + 168;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (s_tmem - base));
-  uint2* tbl = reinterpret_cast<uint2*>(gen_base + (sTbl - base));  // per k-block: {A window offset >> 4, B block offset >> 4 | wide << 31}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per unit
@@ -71,13 +69,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       mbar_init(bar_tempty + 8 * s, 4);
     }
     fence_barrier_init();
-  }
-  {
-    const int nkb_total = L.cls[L.n_cls - 1].kb_begin + L.cls[L.n_cls - 1].nkb;
-    for (int i = threadIdx.x; i <= nkb_total; i += HALO_THREADS) {
-      const TcKBlock K = L.kb[i < nkb_total ? i : 0];
-      tbl[i] = make_uint2((uint32_t)(uint16_t)K.c_off, (uint32_t)K.b_row | (K.dy ? 0x80000000u : 0u));
-    }
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
@@ -136,14 +127,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
             mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d = tmem_base + slot * DW;
-            uint2 K = tbl[kb0];
-            for (int kb = 0; kb < nkb; ++kb) {
-              const uint2 Kn = tbl[kb0 + kb + 1];  // software prefetch of the next entry (the table has one spare)
-              const uint32_t alo = am + K.x, blo = w16 + (K.y & 0x7fffffffu);
-              const uint32_t idesc = (K.y >> 31) ? IDESC2 : IDESC;
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) umma_f16(d, desc64(HI, alo + 2 * k), desc64(HIB, blo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-              K = Kn;
+            // flat list, one entry per MMA (read with uniform constant loads): the loop is pure issue
+#pragma unroll 4
+            for (int i = 0; i < nkb; ++i) {
+              const HaloMma e = L.mma[kb0 + i];
+              umma_f16(d, desc64(HI, am + e.a), desc64(HIB, w16 + (e.b & 0x7fffffffu)), (e.b >> 31) ? IDESC2 : IDESC, i != 0 ? 1u : 0u);
             }
             umma_commit(bar_tfull + 8 * slot);
           }
