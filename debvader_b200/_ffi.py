@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdebvader_b200.so")
 
-PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3}
 F32, F64 = 0, 1
 
 _lib = None
@@ -39,7 +39,7 @@ def _declare(lib):
         "dbv_latent": (C.c_int, [c_vp, c_vp, c_vp, C.c_uint64, C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
         "dbv_decode": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
         "dbv_deblend": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
-        "dbv_deblend_host": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp]),
+        "dbv_deblend_host": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "dbv_extract": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
         "dbv_window_axpy": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
         "dbv_center_mse": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),

@@ -8,6 +8,7 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cuda_fp16.h>
 
 namespace dbv {
 
@@ -250,6 +251,20 @@ static inline float bf2f(uint16_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
+// 16-bit storage format of a context's weights / activations: bf16, or fp16 for DBV_PREC_FP16X3
+static inline uint16_t f2h16(int f16, float f) {
+  if (!f16) return f2bf(f);
+  const __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+static inline float h162f(int f16, uint16_t u) {
+  if (!f16) return bf2f(u);
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
 
 // describe how layer li's OUTPUT is stored in the tensor-core modes
 static void tc_out_layout(int li, int planes, OutSpec* o) {
@@ -282,7 +297,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  const bool x3 = c->precision == DBV_PREC_BF16X3;
+  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
   const HostTensor* W = find_w(c, wkey(L.enc, L.wn, "kernel"));
   // ---- input tensor (previous layer's output buffer) -------------------------------------------
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
@@ -315,10 +330,11 @@ static int build_tc_layer(dbv_ctx* c, int li) {
           if (li == I_ENC_DENSE) w = W->data[((size_t)taps[ti].ky * 256 + ci) * L.Cout + n];  // flat (h,w,c) index
           else if (li == I_CONV1) w = ci < 54 ? W->data[(size_t)ci * L.Cout + n] : 0.f;  // HWIO flattened: k = (ky*3+kx)*6 + band
           else w = w_at(L, *W, taps[ti].ky, taps[ti].kx, ci, n);
-          const uint16_t hi = f2bf(w);
+          const int f16 = c->precision == DBV_PREC_FP16X3;
+          const uint16_t hi = f2h16(f16, w);
           const size_t b0 = ((ti * nchunk + ch) * parts_w) * blk_elems + (size_t)n * G.CBK + k;
           packed[b0] = hi;
-          if (x3) packed[b0 + blk_elems] = f2bf(w - bf2f(hi));
+          if (x3) packed[b0 + blk_elems] = f2h16(f16, w - h162f(f16, hi));
         }
   {
     std::vector<__nv_bfloat16> tmp(packed.size());
@@ -411,7 +427,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   LayerRt& R = c->rt[li];
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
-  const bool x3 = c->precision == DBV_PREC_BF16X3;
+  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
   const bool c1 = (li == I_CONV1);  // no-swizzle mode: 16-byte pixel rows, K=16 = two adjacent pixels
   const int ROWB = c1 ? 16 : G.CBK * 2;
   std::vector<Tap> taps = make_taps(L);
@@ -424,17 +440,22 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const int nchunk = c1 ? 1 : (L.Cin + G.CBK - 1) / G.CBK;
   const int parts_w = x3 ? 2 : 1;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
-  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = W + 2 * pad + (c1 ? 1 : 0);  // conv1: the pair (x+1, x+2) reads one more column
+  // Row pitch of the halo tile: W + 1 — ONE shared zero column per row (slot 0 = x = -1): the right neighbour of x = W-1 is
+  // the next row's slot 0, and the slot after the last row is zeroed slack.  conv1's pair trick (x+1, x+2) keeps W + 3.
+  const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = c1 ? W + 3 : W + 1;
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
   const int w_bytes = ((n_wblk * G.NT * (c1 ? 32 : ROWB) + 1023) / 1024) * 1024;
   const int n_regions = in.planes * nchunk;
   if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
-  const int tail_pad = ((129 * ROWB + 1023) / 1024) * 1024;
   const int ntiles = (bandR * WP + 127) / 128;
   if (G.NT * (x3 ? 2 : 1) > 256) return 0;  // one unit (tile of one class) must fit a TMEM slot; the ring has 512 / width slots
   if (bandR + 2 * pad > 256 || WP > 256) return 0;
-  const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + 1023) / 1024) * 1024;
-  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 2048;  // + barriers and the k-block table
+  const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + ROWB + 1023) / 1024) * 1024;  // >= one zeroed slack slot after the box
+  // layout: [halo ring][weights][barriers].  The last tile of a band over-reads < 131 garbage rows past its region: into the
+  // next region, or (last region of the last buffer) into the weights — readable memory, results dropped by the epilogue.
+  const int overread = 131 * ROWB;
+  const int tail_pad = w_bytes >= overread ? 0 : ((overread - w_bytes + 1023) / 1024) * 1024;
+  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 2048;  // + barriers
   if (smem > HALO_MAX_SMEM) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
@@ -694,7 +715,7 @@ extern "C" int64_t dbv_launch_count(const dbv_ctx* c) { return c ? c->launches :
 
 extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chunk) {
   DBV_REQUIRE(out, "dbv_create: null out");
-  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_BF16X3, "dbv_create: bad precision %d", precision);
+  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_FP16X3, "dbv_create: bad precision %d", precision);
   DBV_REQUIRE(chunk >= 0 && chunk <= (1 << 20), "dbv_create: bad chunk %lld", (long long)chunk);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -757,7 +778,8 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   if (c->finalized) return fail(DBV_ERR_STATE, "dbv_finalize_weights: already finalized");
   DBV_CUDA(cudaSetDevice(c->device));
   const bool fp32 = c->precision == DBV_PREC_FP32;
-  const int planes = c->precision == DBV_PREC_BF16X3 ? 2 : 1;
+  const int planes = (c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3) ? 2 : 1;
+  const int f16 = c->precision == DBV_PREC_FP16X3 ? 1 : 0;
   int r;
   // ---- BatchNorm (model/model.py:79; Keras eps 1e-3) folded to scale/shift -----------------------
   {
@@ -837,6 +859,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     o.alpha = R.alpha;
     o.alpha2 = R.alpha2;
     o.relu = L.relu_head;
+    o.f16 = f16;
     const size_t el = out_elems_per_stamp(o);
     const size_t esz = (o.mode == OUT_F32_NHWC) ? 4 : 2;
     R.out_bytes_per_stamp = el * esz;
@@ -855,6 +878,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     memset(&o, 0, sizeof o);
     o.mode = OUT_BF16_NHWC;
     o.planes = planes;
+    o.f16 = f16;
     o.OH = o.OW = S_;
     o.Cout = o.Cpad = 8;
     if ((r = dev_alloc(c, &c->im2col.out, (size_t)c->chunk * S_ * S_ * planes * 8 * 2, true))) return r;
@@ -871,11 +895,11 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
           for (int k = 0; k < 16; ++k) {
             const int kx = 2 * pr + (k >> 3), ch = k & 7;
             const float w = (kx <= 2 && ch < 6) ? W1->data[(((size_t)ky * 3 + kx) * 6 + ch) * 32 + n] : 0.f;
-            const uint16_t hi = f2bf(w);
+            const uint16_t hi = f2h16(f16, w);
             const size_t blk = (size_t)(ky * 2 + pr) * parts;
             const size_t e = (size_t)(n / 8) * 128 + (size_t)(k / 8) * 64 + (size_t)(n % 8) * 8 + (k % 8);  // in bf16 elements
             img[blk * 512 + e] = hi;
-            if (parts == 2) img[(blk + 1) * 512 + e] = f2bf(w - bf2f(hi));
+            if (parts == 2) img[(blk + 1) * 512 + e] = f2h16(f16, w - h162f(f16, hi));
           }
     std::vector<__nv_bfloat16> tmp(img.size());
     memcpy(tmp.data(), img.data(), img.size() * 2);
@@ -959,7 +983,8 @@ static int ensure_pipe(dbv_ctx* c) {
 }
 
 extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int64_t B, const float* eps_host, uint64_t seed,
-                                int sample, float* mean_host, float* stddev_host, float* z_host) {
+                                int sample, float* mean_host, float* stddev_host, float* z_host, float* mean_dev,
+                                float* stddev_dev) {
   int r = check_ready(c, "dbv_deblend_host");
   if (r) return r;
   DBV_REQUIRE(x_host && mean_host, "dbv_deblend_host: null buffer");
@@ -986,14 +1011,17 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
     DBV_CUDA(cudaEventRecord(c->ev_in[s], c->s_h2d));
     DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[s], 0));
     if (x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return r;
+    // outputs: the caller's resident device buffers when given, else the double-buffered staging slots
+    float* d_mean = mean_dev ? mean_dev + (size_t)b0 * STAMP_ELTS : c->stage_mean[s];
+    float* d_std = stddev_dev ? stddev_dev + (size_t)b0 * STAMP_ELTS : (stddev_host ? c->stage_std[s] : nullptr);
     r = run_chunk(c, c->stage_x[s], nb, eps_host ? c->stage_eps[s] : nullptr, seed, sample, b0, nullptr, c->stage_z[s], nullptr,
-                  nullptr, c->stage_mean[s], stddev_host ? c->stage_std[s] : nullptr, true, true, true, c->s_comp);
+                  nullptr, d_mean, d_std, true, true, true, c->s_comp);
     if (r) return r;
     DBV_CUDA(cudaEventRecord(c->ev_comp[s], c->s_comp));
     DBV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
-    DBV_CUDA(cudaMemcpyAsync(mean_host + (size_t)b0 * STAMP_ELTS, c->stage_mean[s], n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    DBV_CUDA(cudaMemcpyAsync(mean_host + (size_t)b0 * STAMP_ELTS, d_mean, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     if (stddev_host)
-      DBV_CUDA(cudaMemcpyAsync(stddev_host + (size_t)b0 * STAMP_ELTS, c->stage_std[s], n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      DBV_CUDA(cudaMemcpyAsync(stddev_host + (size_t)b0 * STAMP_ELTS, d_std, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     if (z_host) DBV_CUDA(cudaMemcpyAsync(z_host + b0 * LAT, c->stage_z[s], (size_t)nb * LAT * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     DBV_CUDA(cudaEventRecord(c->ev_out[s], c->s_d2h));
   }

@@ -12,6 +12,7 @@
 // planes = 2 stores a hi/lo bf16 split (v ~= hi + lo) at channel offsets [0,Cpad) and [Cpad,2Cpad).
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace dbv {
 
@@ -21,7 +22,8 @@ struct OutSpec {
   void* out;
   void* out2;          // OUT_HEAD: stddev
   int mode;
-  int planes;          // bf16 modes: 1 or 2
+  int planes;          // 16-bit modes: 1 or 2
+  int f16;             // 16-bit modes: 0 = bf16, 1 = fp16 storage (DBV_PREC_FP16X3)
   int OH, OW;          // full output image extents (addressing + alpha indexing)
   int Cout;            // real channels
   int Cpad;            // channels per plane as stored (>= Cout)
@@ -161,12 +163,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 hi/lo split; values saturate at the fp16 range so that hi never becomes inf (lo = v - hi would be NaN)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  lo = pack_f16x2(a - hf.x, b - hf.y);
+}
+// format-dispatching versions (f16 is warp-uniform)
+__device__ __forceinline__ uint32_t pack16x2(int f16, float a, float b) { return f16 ? pack_f16x2(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f)) : pack_bf16x2(a, b); }
+__device__ __forceinline__ float round16(int f16, float a) { return f16 ? __half2float(__float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f))) : __bfloat162float(__float2bfloat16_rn(a)); }
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 // hi = bf16x2(a,b); lo = bf16x2(a - hi.a, b - hi.b): 6 instructions per pair
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16x2(a, b);
   const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
   lo = pack_bf16x2(a - ha, b - hb);
+}
+
+__device__ __forceinline__ void split16x2(int f16, float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (f16) split_f16x2(a, b, hi, lo);
+  else split_bf16x2(a, b, hi, lo);
 }
 
 // store NV (multiple of 4, c multiple of 4) activated channels of pixel (b,y,x)
@@ -207,23 +230,23 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
       for (int j = 0; j < NV; j += 16) {
         uint4 q0, q1, l0, l1;
         if (o.planes == 2) {
-          split_bf16x2(v[j], v[j + 1], q0.x, l0.x);
-          split_bf16x2(v[j + 2], v[j + 3], q0.y, l0.y);
-          split_bf16x2(v[j + 4], v[j + 5], q0.z, l0.z);
-          split_bf16x2(v[j + 6], v[j + 7], q0.w, l0.w);
-          split_bf16x2(v[j + 8], v[j + 9], q1.x, l1.x);
-          split_bf16x2(v[j + 10], v[j + 11], q1.y, l1.y);
-          split_bf16x2(v[j + 12], v[j + 13], q1.z, l1.z);
-          split_bf16x2(v[j + 14], v[j + 15], q1.w, l1.w);
+          split16x2(o.f16, v[j], v[j + 1], q0.x, l0.x);
+          split16x2(o.f16, v[j + 2], v[j + 3], q0.y, l0.y);
+          split16x2(o.f16, v[j + 4], v[j + 5], q0.z, l0.z);
+          split16x2(o.f16, v[j + 6], v[j + 7], q0.w, l0.w);
+          split16x2(o.f16, v[j + 8], v[j + 9], q1.x, l1.x);
+          split16x2(o.f16, v[j + 10], v[j + 11], q1.y, l1.y);
+          split16x2(o.f16, v[j + 12], v[j + 13], q1.z, l1.z);
+          split16x2(o.f16, v[j + 14], v[j + 15], q1.w, l1.w);
         } else {
-          q0.x = pack_bf16x2(v[j], v[j + 1]);
-          q0.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          q0.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          q0.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          q1.x = pack_bf16x2(v[j + 8], v[j + 9]);
-          q1.y = pack_bf16x2(v[j + 10], v[j + 11]);
-          q1.z = pack_bf16x2(v[j + 12], v[j + 13]);
-          q1.w = pack_bf16x2(v[j + 14], v[j + 15]);
+          q0.x = pack16x2(o.f16, v[j], v[j + 1]);
+          q0.y = pack16x2(o.f16, v[j + 2], v[j + 3]);
+          q0.z = pack16x2(o.f16, v[j + 4], v[j + 5]);
+          q0.w = pack16x2(o.f16, v[j + 6], v[j + 7]);
+          q1.x = pack16x2(o.f16, v[j + 8], v[j + 9]);
+          q1.y = pack16x2(o.f16, v[j + 10], v[j + 11]);
+          q1.z = pack16x2(o.f16, v[j + 12], v[j + 13]);
+          q1.w = pack16x2(o.f16, v[j + 14], v[j + 15]);
           l0 = l1 = make_uint4(0u, 0u, 0u, 0u);
         }
         if (a32) {
@@ -242,13 +265,13 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
 #pragma unroll
       for (int j = 0; j < NV; j += 4) {
         uint2 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]);
-        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.x = pack16x2(o.f16, v[j], v[j + 1]);
+        q.y = pack16x2(o.f16, v[j + 2], v[j + 3]);
         *reinterpret_cast<uint2*>(p + j) = q;
         if (o.planes == 2) {
           uint2 r;
-          r.x = pack_bf16x2(v[j] - bf16_round(v[j]), v[j + 1] - bf16_round(v[j + 1]));
-          r.y = pack_bf16x2(v[j + 2] - bf16_round(v[j + 2]), v[j + 3] - bf16_round(v[j + 3]));
+          r.x = pack16x2(o.f16, v[j] - round16(o.f16, v[j]), v[j + 1] - round16(o.f16, v[j + 1]));
+          r.y = pack16x2(o.f16, v[j + 2] - round16(o.f16, v[j + 2]), v[j + 3] - round16(o.f16, v[j + 3]));
           *reinterpret_cast<uint2*>(p + o.Cpad + j) = r;
         }
       }
@@ -257,9 +280,10 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (c + j < o.Cpad) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-        p[j] = h;
-        if (o.planes == 2) p[o.Cpad + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+        const float hv = round16(o.f16, v[j]);
+        const uint32_t hb = pack16x2(o.f16, hv, 0.f), lb = pack16x2(o.f16, v[j] - hv, 0.f);
+        reinterpret_cast<uint16_t*>(p)[j] = (uint16_t)hb;
+        if (o.planes == 2) reinterpret_cast<uint16_t*>(p)[o.Cpad + j] = (uint16_t)lb;
       }
     }
   }

@@ -152,9 +152,16 @@ __global__ void __launch_bounds__(256) act_to_f32_kernel(OutSpec o, long long B,
   if (o.mode == OUT_F32_NHWC) {
     out[gid] = reinterpret_cast<const float*>(o.out)[off];
   } else {
-    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(o.out);
-    float v = __bfloat162float(p[off]);
-    if (o.planes == 2) v += __bfloat162float(p[off + o.Cpad]);
+    float v;
+    if (o.f16) {
+      const __half* p = reinterpret_cast<const __half*>(o.out);
+      v = __half2float(p[off]);
+      if (o.planes == 2) v += __half2float(p[off + o.Cpad]);
+    } else {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(o.out);
+      v = __bfloat162float(p[off]);
+      if (o.planes == 2) v += __bfloat162float(p[off + o.Cpad]);
+    }
     out[gid] = v;
   }
 }
@@ -172,9 +179,9 @@ __global__ void __launch_bounds__(256) bn_pack8_kernel(const float* __restrict__
 #pragma unroll
   for (int ch = 0; ch < 6; ++ch) v[ch] = fmaf(v[ch], __ldg(sc + ch), __ldg(sh + ch));
   uint4 q, l;
-  split_bf16x2(v[0], v[1], q.x, l.x);
-  split_bf16x2(v[2], v[3], q.y, l.y);
-  split_bf16x2(v[4], v[5], q.z, l.z);
+  split16x2(o.f16, v[0], v[1], q.x, l.x);
+  split16x2(o.f16, v[2], v[3], q.y, l.y);
+  split16x2(o.f16, v[4], v[5], q.z, l.z);
   q.w = l.w = 0u;
   __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.out) + pix * (long long)(o.planes * o.Cpad);
   *reinterpret_cast<uint4*>(p) = q;

@@ -34,9 +34,9 @@ struct TcCfg {
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b format [7,10)/[10,13),
   // K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t IDESC =
-      (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);  // + idesc_ab_fmt()
   static constexpr uint32_t IDESC2 =
-      (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(((2 * NT) & 0x1ff) >> 3) << 17) | ((128u >> 4) << 24);
+      (1u << 4) | ((uint32_t)(((2 * NT) & 0x1ff) >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 // smem stage of one k-block = (tap, channel chunk):  [A_hi | A_lo | B_hi | B_lo]  (the lo boxes only in the hi/lo split
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       uint32_t phase = 0;
       uint32_t u = 0;
       constexpr uint32_t HI = smem_desc_hi<Cfg::ROWB>();
+      const uint32_t IDESC = Cfg::IDESC | idesc_ab_fmt(L.o.f16), IDESC2 = Cfg::IDESC2 | idesc_ab_fmt(L.o.f16);
       for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
         const int c = (int)(t / L.tiles_per_cls);
         const int nkb = L.cls[c].nkb;
@@ -145,20 +146,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           if (L.wide) {
 #pragma unroll
             for (int k = 0; k < CBK / 16; ++k) {
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC2, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, 1u);
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC2, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
             }
           } else if (L.x3) {
 #pragma unroll
             for (int k = 0; k < CBK / 16; ++k) {
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, blo + 2 * k), Cfg::IDESC, 1u);
-              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, 1u);
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, blo + 2 * k), IDESC, 1u);
+              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < CBK / 16; ++k)
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }

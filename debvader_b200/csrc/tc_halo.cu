@@ -20,7 +20,11 @@
 
 namespace dbv {
 
-constexpr int HALO_THREADS = 64 + 2 * 128;  // TMA warp, MMA warp, two epilogue groups of 4 warps
+#ifndef DBV_HALO_EPI_GROUPS
+#define DBV_HALO_EPI_GROUPS 2
+#endif
+constexpr int HALO_EPI_GROUPS = DBV_HALO_EPI_GROUPS;  // epilogue groups of 4 warps (one warp per TMEM lane quadrant); the epilogue is latency bound
+constexpr int HALO_THREADS = 64 + HALO_EPI_GROUPS * 128;  // TMA warp, MMA warp, epilogue groups
 constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring (512 columns / slot width, capped)
 
 // NOSWZ (encoder conv1, Cin = 6 padded to 8): one 16-byte row per pixel, no swizzle.  A K=16 MMA operand is
@@ -40,13 +44,13 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)DBV_MMA_AB_FMT << 7) | ((uint32_t)DBV_MMA_AB_FMT << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t IDESC2 = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sW = base;                              // resident weights: n_wblk blocks of NT x ROWB
-  const uint32_t sA = base + L.w_bytes;                  // nbuf x n_regions x region_bytes
-  const uint32_t sBar = sA + L.nbuf * L.n_regions * L.region_bytes + L.tail_pad;
+  const uint32_t sA = base;                              // nbuf x n_regions x region_bytes
+  const uint32_t sW = sA + L.nbuf * L.n_regions * L.region_bytes;  // resident weights: n_wblk blocks of NT x ROWB
+  const uint32_t sBar = sW + L.w_bytes + L.tail_pad;
   const uint32_t bar_w = sBar, bar_afull = sBar + 8, bar_aempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 104;
   const uint32_t s_tmem = sBar + 168;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -70,6 +74,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     }
     fence_barrier_init();
   }
+  // zero the slack after every region's TMA box once: with the W+1 pitch the slot after the last halo row is the right
+  // neighbour of its last pixel and must read as zero padding (TMA never writes there)
+  for (int r = 0; r < L.nbuf * L.n_regions; ++r)
+    for (int i = L.a_box_bytes + 16 * (int)threadIdx.x; i < L.region_bytes; i += 16 * HALO_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + r * L.region_bytes + i), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
   __syncthreads();
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     for (long long g = g0; g < g1; ++g) {
       for (int c = 0; c < ncls; ++c) {
         for (int m = 0; m < L.ntiles; ++m, ++u) {
-          if ((int)(u & 1u) != grp) continue;
+          if ((int)(u % (uint32_t)HALO_EPI_GROUPS) != grp) continue;
           const uint32_t slot = u & (nslot - 1);
           const int p = 128 * m + row;
           const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;

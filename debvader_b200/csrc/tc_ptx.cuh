@@ -3,9 +3,6 @@
 #pragma once
 #include "kernels.h"
 
-#ifndef DBV_MMA_AB_FMT
-#define DBV_MMA_AB_FMT 1  // tcgen05 instruction-descriptor A/B format: 0 = F16, 1 = BF16
-#endif
 
 namespace dbv {
 
@@ -194,6 +191,9 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 }
 constexpr uint32_t kSmemDescLoConst = 1u << 16;
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// tcgen05 instruction-descriptor A/B format bits ([7,10) and [10,13)): 0 = F16, 1 = BF16
+__device__ __forceinline__ uint32_t idesc_ab_fmt(int f16) { return f16 ? 0u : ((1u << 7) | (1u << 10)); }
 
 constexpr int tmem_cols_for(int n2) { return n2 <= 32 ? 32 : n2 <= 64 ? 64 : n2 <= 128 ? 128 : n2 <= 256 ? 256 : 512; }
 

@@ -27,8 +27,10 @@ def deblend(net, images, normalise=False, **kw):
             dist = net(images, **kw)
             mean = dist.mean().numpy()
         else:
-            mean, std = net.deblend_host(images, **kw)
-            dist = NormalOutput(torch.from_numpy(mean), torch.from_numpy(std))
+            # only the mean crosses PCIe eagerly (the reference returns outimg.mean().numpy() plus the distribution
+            # object, deblender.py:24); the distribution stays on the device and .stddev().numpy() fetches on demand
+            mean, mean_dev, std_dev = net.deblend_host(images, resident=True, **kw)
+            dist = NormalOutput(mean_dev, std_dev)
     else:  # a foreign model object: call it the way the reference does (deblender.py:18)
         dist = net(np.asarray(images, dtype=np.float32))
         mean = dist.mean().numpy()

@@ -158,9 +158,13 @@ class Deblender:
         )
 
     # ---- host buffers: the end-to-end call ---------------------------------------------------------
-    def deblend_host(self, images, eps=None, sample=True, seed=None, want_stddev=True, out_mean=None, out_stddev=None):
+    def deblend_host(self, images, eps=None, sample=True, seed=None, want_stddev=True, out_mean=None, out_stddev=None, resident=False):
         """Host ndarray in, host ndarrays out, H2D / compute / D2H pipelined inside the C-ABI
-        (dbv_deblend_host).  float64 input is cast on the device.  Returns (mean, stddev|None)."""
+        (dbv_deblend_host).  float64 input is cast on the device.  Returns (mean, stddev|None).
+
+        resident=True keeps both outputs on the device as well and copies only the MEAN back
+        (``deblend()`` returns the mean ndarray plus a distribution whose stddev is fetched on demand);
+        it returns (mean ndarray, mean CUDA tensor, stddev CUDA tensor)."""
         a = images if isinstance(images, np.ndarray) else np.asarray(images)
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float32)
@@ -171,7 +175,14 @@ class Deblender:
         # D2H copies of the pipeline are asynchronous DMA transfers
         new = lambda: torch.empty((B, S, S, NB), dtype=torch.float32, pin_memory=True).numpy()
         mean = out_mean if out_mean is not None else new()
-        std = (out_stddev if out_stddev is not None else new()) if want_stddev else None
+        std = (out_stddev if out_stddev is not None else new()) if (want_stddev and not resident) else None
+        mean_dev = std_dev = None
+        if resident:
+            with torch.cuda.device(self.device):
+                mean_dev = torch.empty((B, S, S, NB), device=self.device, dtype=torch.float32)
+                std_dev = torch.empty_like(mean_dev)
+                # the library runs on its own streams: make sure nothing queued on torch's stream still uses these blocks
+                torch.cuda.current_stream().synchronize()
         e = None
         if eps is not None:
             e = np.ascontiguousarray(np.asarray(eps, dtype=np.float32))
@@ -180,8 +191,11 @@ class Deblender:
         vp = lambda arr: None if arr is None else arr.ctypes.data_as(C.c_void_p)
         _ffi.check(
             _ffi.lib().dbv_deblend_host(self._ctx, vp(a), _ffi.F64 if a.dtype == np.float64 else _ffi.F32, B, vp(e),
-                                        self._next_seed(seed), int(bool(sample)), vp(mean), vp(std), None)
+                                        self._next_seed(seed), int(bool(sample)), vp(mean), vp(std), None,
+                                        _ffi.ptr(mean_dev), _ffi.ptr(std_dev))
         )
+        if resident:
+            return mean, mean_dev, std_dev
         return mean, std
 
     # ---- diagnostics ------------------------------------------------------------------------------

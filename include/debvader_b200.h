@@ -43,8 +43,11 @@ typedef enum {
 typedef enum {
   DBV_PREC_FP32 = 0,   /* fp32 SIMT kernels: <=1e-5 of peak flux vs the fp64 oracle        */
   DBV_PREC_BF16 = 1,   /* tcgen05 bf16 x bf16 -> fp32, activations stored once in bf16      */
-  DBV_PREC_BF16X3 = 2  /* tcgen05, hi/lo bf16 split of activations and weights (3 MMAs per
+  DBV_PREC_BF16X3 = 2, /* tcgen05, hi/lo bf16 split of activations and weights (3 MMAs per
                           product, ~16-bit mantissa): <=1e-3 of peak flux                   */
+  DBV_PREC_FP16X3 = 3  /* tcgen05, hi/lo fp16 split (~22-bit mantissa), same cost as BF16X3:
+                          meets the fp32 bound (<=1e-5 of peak flux); activations saturate
+                          at +-65504 (fp16 range)                                           */
 } dbv_precision;
 
 typedef enum { DBV_F32 = 0, DBV_F64 = 1 } dbv_dtype;
@@ -92,9 +95,13 @@ int dbv_deblend(dbv_ctx* ctx, const float* x_dev, int64_t B, const float* eps_de
 /* deblend_cutout/deblender.py:6-24 including tf.cast(images, tf.float32) (x_dtype = DBV_F32 or
  * DBV_F64; the cast is done on the device) and outimg.mean().numpy().  Chunks are pipelined:
  * H2D of chunk k+1, compute of chunk k and D2H of chunk k-1 overlap on three streams.
- * stddev_host / z_host / eps_host may be NULL.  Synchronous. */
+ * stddev_host / z_host / eps_host may be NULL.  mean_dev / stddev_dev (device, (B,59,59,6) fp32, may be
+ * NULL) keep the outputs resident: the decoder then writes them directly, and a NULL stddev_host
+ * skips that device-to-host copy — the distribution object deblend() returns fetches the stddev
+ * only when a caller asks for it (the reference's callers mostly use the mean).  Synchronous. */
 int dbv_deblend_host(dbv_ctx* ctx, const void* x_host, int x_dtype, int64_t B, const float* eps_host,
-                     uint64_t seed, int sample, float* mean_host, float* stddev_host, float* z_host);
+                     uint64_t seed, int sample, float* mean_host, float* stddev_host, float* z_host,
+                     float* mean_dev, float* stddev_dev);
 
 /* ---- field operators: device buffers -------------------------------------------------------- */
 /* extract_cutouts: extract/extraction.py:21-36.  For k in [0,N): copies the window of `field`
