@@ -151,59 +151,97 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       }
     }
   } else {
-    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains units u with (u & 1) == g.
+    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains units u with u % 2 == g, one
+    // "item" = (unit, chunk of NV channels) at a time.  The epilogue is a latency chain (PReLU slopes from L2 -> accumulator
+    // wait -> tcgen05.ld -> math -> stores), so the slopes of the NEXT item are requested before the current one is processed.
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     constexpr int NV = (NT % 32 == 0) ? 32 : 16;
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
-    uint32_t u = 0;
-    int b = b_first, y0 = (int)yb0 * L.R;
-    for (long long g = g0; g < g1; ++g) {
-      for (int c = 0; c < ncls; ++c) {
-        for (int m = 0; m < L.ntiles; ++m, ++u) {
-          if ((int)(u % (uint32_t)HALO_EPI_GROUPS) != grp) continue;
-          const uint32_t slot = u & (nslot - 1);
-          const int p = 128 * m + row;
-          const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
-          const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
-          const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
-          ActRegs<NV> ra;
-          ra.fast = false;
-          if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, 0, 0, ra);
-          mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
-          tc_fence_after();
-          const uint32_t tcol = lane_base + slot * DW;
-#pragma unroll 1
-          for (int q = 0; q < NCHK; ++q) {
-            const int c0 = q * NV;
-            if (q && !(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);
-            float v[NV];
-            if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the unit's columns
-              float w[NV];
-              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-              tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
-              tmem_ld_wait<NV>(v);
-              tmem_ld_wait<NV>(w);
-#pragma unroll
-              for (int j = 0; j < NV; ++j) v[j] += w[j];
-            } else {
-              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-              tmem_ld_wait<NV>(v);
-            }
-            if (ok) {
-              if (!(L.dbg_skip & 4)) act_apply<NV>(L.o, oy, ox, c0, 0, ra, v);
-              if (!(L.dbg_skip & 8)) store_act<NV>(L.o, b, oy, ox, c0, v);
-              else if (v[0] == 123.456f) store_act<NV>(L.o, b, oy, ox, c0, v);  // keep the loads / math alive
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+    struct Item {
+      long long g;
+      int c, m, q, b, y0, oy, ox;
+      uint32_t u;
+      bool ok;
+    };
+    auto next_unit = [&](Item& it) {  // advance by one unit
+      ++it.u;
+      if (++it.m == L.ntiles) {
+        it.m = 0;
+        if (++it.c == ncls) {
+          it.c = 0;
+          ++it.g;
+          if (++it.b == (int)L.B) { it.b = 0; it.y0 += L.R; }
         }
       }
-      if (++b == (int)L.B) { b = 0; y0 += L.R; }
+    };
+    auto locate = [&](Item& it) {  // output pixel of this thread's accumulator row
+      const int p = 128 * it.m + row;
+      const int ly = p / L.WP, sx = p - ly * L.WP, sy = it.y0 + ly;
+      it.ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
+      it.oy = L.cls[it.c].oy0 + L.cls[it.c].osy * sy;
+      it.ox = L.cls[it.c].ox0 + L.cls[it.c].osx * sx;
+    };
+    Item cur{g0, 0, 0, 0, b_first, (int)yb0 * L.R, 0, 0, 0u, false};
+    bool live = ncls > 0 && g0 < g1;
+    if (live)
+      for (int k = 0; k < grp; ++k) next_unit(cur);
+    live = live && cur.g < g1;
+    ActRegs<NV> ra;
+    ra.fast = false;
+    if (live) {
+      locate(cur);
+      if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, cur.ok, cur.oy, cur.ox, 0, 0, ra);
+    }
+    while (live) {
+      Item nxt = cur;
+      if (++nxt.q == NCHK) {
+        nxt.q = 0;
+#pragma unroll
+        for (int k = 0; k < HALO_EPI_GROUPS; ++k) next_unit(nxt);
+      }
+      const bool nlive = nxt.g < g1;
+      ActRegs<NV> rn;
+      rn.fast = false;
+      if (nlive) {
+        if (nxt.q == 0) locate(nxt);
+        if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, nxt.ok, nxt.oy, nxt.ox, nxt.q * NV, 0, rn);
+      }
+      const uint32_t slot = cur.u & (nslot - 1);
+      if (cur.q == 0) {
+        mbar_wait(bar_tfull + 8 * slot, (cur.u >> slot_shift) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t tcol = lane_base + slot * DW;
+      const int c0 = cur.q * NV;
+      float v[NV];
+      if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the unit's columns
+        float w[NV];
+        tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+        tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
+        tmem_ld_wait<NV>(v);
+        tmem_ld_wait<NV>(w);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] += w[j];
+      } else {
+        tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+        tmem_ld_wait<NV>(v);
+      }
+      if (cur.q == NCHK - 1) {  // the accumulator is in registers: hand the slot back before the math and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+      }
+      if (cur.ok) {
+        if (!(L.dbg_skip & 4)) act_apply<NV>(L.o, cur.oy, cur.ox, c0, 0, ra, v);
+        if (!(L.dbg_skip & 8)) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);
+        else if (v[0] == 123.456f) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);  // keep the loads / math alive
+      }
+      cur = nxt;
+      ra = rn;
+      live = nlive;
     }
   }
   tc_fence_before();
