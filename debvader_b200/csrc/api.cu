@@ -445,7 +445,9 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = c1 ? W + 3 : W + 1;
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
   const int w_bytes = ((n_wblk * G.NT * (c1 ? 32 : ROWB) + 1023) / 1024) * 1024;
-  const int n_regions = in.planes * nchunk;
+  // stride-2 Conv2D: the input is stored as 4 parity planes (OUT_BF16_PARITY); every (plane, hi/lo, chunk) is its own region
+  const int npar = (in.mode == OUT_BF16_PARITY) ? 4 : 1;
+  const int n_regions = in.planes * nchunk * npar;
   if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
   const int ntiles = (bandR * WP + 127) / 128;
   if (G.NT * (x3 ? 2 : 1) > 256) return 0;  // one unit (tile of one class) must fit a TMEM slot; the ring has 512 / width slots
@@ -471,7 +473,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
           for (int k = 0; k < (c1 ? 1 : G.CBK / 16); ++k) {
             if (nkb >= TC_MAX_KB) return 0;
             const int a_lo = (pr == 1);
-            const long long a_off = (long long)(a_lo * nchunk + ch) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
+            const long long a_off = (long long)((a_lo * nchunk + ch) * npar + taps[ti].plane) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
             const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * (c1 ? 32 : ROWB) + 32 * k;
             if ((a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return 0;
             T.mma[nkb].a = (uint32_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
@@ -487,7 +489,11 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
   T.ntiles = ntiles;
   T.n_regions = n_regions;
-  for (int r = 0; r < n_regions; ++r) T.region_coff[r] = (r / nchunk) * in.Cpad + (r % nchunk) * G.CBK;
+  for (int r = 0; r < n_regions; ++r) {  // r = ((plane_hi_lo * nchunk + chunk) * npar + parity plane)
+    const int pc = r / npar;
+    T.region_coff[r] = (pc / nchunk) * in.Cpad + (pc % nchunk) * G.CBK;
+    T.region_c3[r] = r % npar;
+  }
   T.w_img = c1 ? (const void*)c->conv1_wimg : nullptr;
   T.a_box_bytes = (bandR + 2 * pad) * WP * ROWB;
   T.region_bytes = (int)region;
@@ -501,8 +507,9 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   T.smem_bytes = (int)smem;
   T.bands_per_img = (H + bandR - 1) / bandR;
   const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
-  uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)in.OH, 1, (uint64_t)c->chunk};
-  uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW * in.OH};
+  const uint64_t Wd = npar == 4 ? in.PW : in.OW, Hd = npar == 4 ? in.PH : in.OH;
+  uint64_t dims[5] = {Ct, Wd, Hd, (uint64_t)npar, (uint64_t)c->chunk};
+  uint64_t str[4] = {Ct * 2, Ct * 2 * Wd, Ct * 2 * Wd * Hd, Ct * 2 * Wd * Hd * npar};
   uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
   int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, c1 ? 0 : ROWB);
   if (r) return r;
@@ -519,12 +526,15 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   if (getenv("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
-  if ((!R.has_tc && li != I_CONV1) || L.kind == L_DENSE || (L.kind == L_CONV && L.stride != 1)) return DBV_OK;
+  if ((!R.has_tc && li != I_CONV1) || L.kind == L_DENSE) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
   const OutSpec& in = ((li == I_CONV1) ? c->im2col : c->rt[li - 1]).ospec;
-  if (in.mode != OUT_BF16_NHWC) return DBV_OK;
+  if (in.mode != OUT_BF16_NHWC && in.mode != OUT_BF16_PARITY) return DBV_OK;
+  if ((L.kind == L_CONV && L.stride == 2) != (in.mode == OUT_BF16_PARITY)) return DBV_OK;
+  // resident weights must leave room for a useful halo band (else the streaming kernels are the better plan)
+  if (in.mode == OUT_BF16_PARITY && (long long)9 * L.Cin * G.NT * 2 * (c->precision == DBV_PREC_BF16 ? 1 : 2) > 64 * 1024) return DBV_OK;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
-  const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 3 : 2);
+  const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 3 : 1);
   // candidates: the tallest band for each tile count (R*WP just below a multiple of 128), both ring depths
   std::vector<std::pair<int, int>> cand;
   for (int nt = 1; nt <= 16; ++nt) {

@@ -100,7 +100,8 @@ struct HaloLayer {
   int pad;           // halo width: 1 for 3x3 taps, 0 for a 1-tap layer (conv1 after im2col)
   int ntiles;        // ceil(R * WP / 128)
   int n_regions;     // planes * channel chunks
-  int region_coff[8];
+  int region_coff[8];  // TMA coordinate 0 (first channel) of each region
+  int region_c3[8];    // TMA coordinate 3: parity plane of a stride-2 Conv2D's input, else 0
   int region_bytes;  // (R+2) * WP * ROWB rounded up to 1024
   int a_box_bytes;   // (R+2) * WP * ROWB
   int n_wblk, w_rows_per_blk, w_bytes;
