@@ -741,7 +741,8 @@ extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chun
   dbv_ctx* c = new dbv_ctx();
   c->device = device;
   c->precision = precision;
-  c->chunk = chunk > 0 ? chunk : 1024;
+  c->chunk = chunk > 0 ? chunk : 2048;  // stamps per pass of the layer sequence: large enough that a launch of the small-image
+                                        // layers (one pass over the layer's weights per SM, ~50 us) is amortised
   *out = c;
   return DBV_OK;
 }
@@ -1003,10 +1004,27 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
   if ((r = ensure_pipe(c))) return r;
   const long long before = g_launches.load();
   const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
-  int k = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += c->chunk, ++k) {
+  // chunk schedule: a short first chunk (its H2D copy cannot overlap anything) and a short tail (neither can the last
+  // D2H copy), full chunks in between
+  std::vector<std::pair<int64_t, long long>> sched;
+  {
+    int64_t b0 = 0;
+    const long long piece = std::min<long long>(c->chunk, 1024);  // pipeline granularity (transfers overlap compute piece by piece)
+    const long long q = std::max<long long>(piece / 4, 1);
+    if (B > 2 * piece) { sched.push_back({0, q}); b0 = q; }
+    while (B - b0 > piece + q) { sched.push_back({b0, piece}); b0 += piece; }
+    while (b0 < B) {
+      long long rem = B - b0, nb = rem;
+      if (B > 2 * piece && rem > q) nb = std::max<long long>((rem + 1) / 2, q);
+      nb = std::min<long long>(nb, piece);
+      sched.push_back({b0, nb});
+      b0 += nb;
+    }
+  }
+  for (int k = 0; k < (int)sched.size(); ++k) {
     const int s = k & 1;
-    const long long nb = std::min<long long>(c->chunk, B - b0);
+    const int64_t b0 = sched[k].first;
+    const long long nb = sched[k].second;
     const size_t n = (size_t)nb * STAMP_ELTS;
     // slot s is free for new input once the compute that used it (chunk k-2) is done, and its
     // outputs are free once the D2H of chunk k-2 is done
