@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdebvader_b200.so")
-SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_halo.cu", "tc_probe.cu"]
-HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "debvader_b200.h")]
+SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "tc_probe.cu"]
+HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", "tc_pair_ptx.cuh", os.path.join("..", "..", "include", "debvader_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -54,6 +54,7 @@ static const LayerDesc kLayers[] = {
     {"dec_head", L_CONV, 1, 64, 32, 64, 12, 0, 21, -1, -1, 1},
 };
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+constexpr int PH_SMEM_BUDGET = 232448 - 1024 - 512 - 2048;
 enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_HEAD = 19 };
 
 static std::string wkey(int enc, int n, const char* nm) {
@@ -113,6 +114,8 @@ struct LayerRt {
   bool has_tc = false;
   TcLayer tcp{};  // CTA-pair plan (many-channel layers)
   bool has_pair = false;
+  PairHLayer ph{};  // CTA-pair plan with a per-chunk halo box (8x8 .. 16x16 stride-1 / transposed layers)
+  bool has_pairh = false;
   // resident-halo plan (preferred when it exists)
   HaloLayer halo{};
   bool has_halo = false;
@@ -419,6 +422,67 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   return DBV_OK;
 }
 
+// CTA-pair plan with a per-chunk halo box (tc_pairh.cu) for the stride-1 Conv2D / Conv2DTranspose layers (and stride-2
+// transposed convs over their input grid) on 8..16-pixel maps with N = 128 / 256 in the hi/lo split precisions.
+static int build_pairh_layer(dbv_ctx* c, int li) {
+  const LayerDesc& L = kLayers[li];
+  const TcGeom& G = kTc[li];
+  LayerRt& R = c->rt[li];
+  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
+  if (!x3 || !R.has_pair || getenv("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
+  if (L.kind == L_CONV && L.stride != 1) return DBV_OK;
+  const OutSpec& in = c->rt[li - 1].ospec;
+  const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
+  const int space = (ncls == 4) ? L.Hin : L.Hout;  // tile space = the input grid
+  if (in.mode != OUT_BF16_NHWC || in.planes != 2 || in.OW != space || space < 8 || space > 16 || L.Cin % 64 != 0 || ncls * G.NT > 256) return DBV_OK;  // (accumulators double-buffered: 2 x n_cls x NT <= 512)
+  PairHLayer& P = R.ph;
+  memset(&P, 0, sizeof P);
+  const int TB = space <= 8 ? 2 : 1;
+  const int HB = space + 2;
+  const std::vector<Tap> taps = make_taps(L);
+  if (taps.size() > 16) return DBV_OK;
+  const int nchunk = L.Cin / 64, parts = 2;
+  const int Ntot = G.NT;  // conv layers are not N-tiled
+  P.n_cls = ncls;
+  int nt = 0;
+  std::vector<int> order;
+  for (int cl = 0; cl < ncls; ++cl) {
+    P.cls_begin[cl] = nt;
+    for (size_t ti = 0; ti < taps.size(); ++ti) {
+      if (taps[ti].cls != cl) continue;
+      P.tap_aoff[nt] = ((taps[ti].dy + 1) * TB * 10 + taps[ti].dx + 1) * 128;
+      P.tap_brow[nt] = (int)(ti * nchunk * parts) * Ntot;
+      ++nt;
+    }
+    P.cls[cl] = R.tc.cls[cl];
+  }
+  P.cls_begin[ncls] = nt;
+  P.nchunk = nchunk;
+  P.chunk_brow = parts * Ntot;
+  P.lo_brow = Ntot;
+  P.lo_coff = in.Cpad;
+  P.TB = TB;
+  P.tiles_x = (space + 7) / 8;
+  P.SW = P.SH = space;
+  P.abox_tx = 64 * 2 * 10 * TB * HB;
+  P.abox_bytes = ((P.abox_tx + 1023) / 1024) * 1024;
+  const int bh = (G.NT / 2) * 128;
+  P.a_stages = 2;
+  P.b_stages = std::min(8, (PH_SMEM_BUDGET - P.a_stages * 2 * P.abox_bytes) / (2 * bh));
+  if (P.b_stages < 2) return DBV_OK;
+  P.tail_pad = 2048;  // the last 8-row group of a 15-row map reads a few rows past its box
+  P.smem_bytes = 1024 + P.a_stages * 2 * P.abox_bytes + P.b_stages * 2 * bh + P.tail_pad + 512;
+  const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
+  uint64_t dims[5] = {Ct, (uint64_t)in.OW, (uint64_t)c->chunk, (uint64_t)in.OH, 1};
+  uint64_t str[4] = {Ct * 2, Ct * 2 * in.OW * in.OH, Ct * 2 * in.OW, Ct * 2 * in.OW * in.OH * (uint64_t)c->chunk};
+  uint32_t box[5] = {64u, 10u, (uint32_t)TB, (uint32_t)HB, 1u};
+  int r = encode_tmap(&P.tmA, c->rt[li - 1].out, 5, dims, str, box, 128);
+  if (r) return r;
+  P.tmB = R.tcp.tmB;  // box (64, NT/2)
+  R.has_pairh = true;
+  return DBV_OK;
+}
+
 // Fill T with the plan for R output rows per band and nbuf halo buffers.  Returns 1 if the plan is valid
 // (fits shared memory / TMEM / descriptor fields), 0 if not, < 0 on error.
 static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
@@ -615,6 +679,14 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
     T.o = o;
     T.total_bands = B * T.bands_per_img;
     return launch_halo_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
+  }
+  if (R.has_pairh) {
+    PairHLayer T = R.ph;
+    T.B = B;
+    T.o = o;
+    const long long mt = ((B + T.TB - 1) / T.TB) * T.tiles_x;
+    T.pair_items = (mt + 1) / 2;
+    return launch_tc_pairh(T, kTc[li].NT, kNumSMs, st);
   }
   if (R.has_pair) {
     TcLayer T = R.tcp;
@@ -919,7 +991,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   // ---- tensor-core plans ------------------------------------------------------------------------
   if (!fp32)
     for (int li = 0; li < kNumLayers; ++li)
-      if (kTc[li].tc && ((li != I_CONV1 && (r = build_tc_layer(c, li))) || (r = build_halo_layer(c, li)))) return r;
+      if (kTc[li].tc && ((li != I_CONV1 && (r = build_tc_layer(c, li))) || (li != I_CONV1 && (r = build_pairh_layer(c, li))) || (r = build_halo_layer(c, li)))) return r;
   DBV_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
   c->host_w.clear();

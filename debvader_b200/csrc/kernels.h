@@ -82,6 +82,26 @@ bool tc_pair_supported(int CBK, int NT);
 void tc_pair_stage_plan(TcLayer& L, int CBK, int NT);
 bool tc_layer_supported(int CBK, int NT);
 
+// ---- CTA-pair GEMM with a per-chunk halo box (tc_pairh.cu): 8x8 .. 16x16 maps, N = 128 / 256 -----------------------------
+struct PairHLayer {
+  CUtensorMap tmA;   // (C, W, B, H, 1) bf16, box (64, 10, TB, HB, 1), SWIZZLE_128B: shared memory [row][stamp][10 px][64 ch]
+  CUtensorMap tmB;   // packed weights, box (64, NT/2)
+  TcClass cls[TC_MAX_CLS];
+  int n_cls;
+  int cls_begin[TC_MAX_CLS + 1];  // taps of class c: [cls_begin[c], cls_begin[c+1])
+  int tap_aoff[16];  // byte offset of the tap's window in the halo box: ((dy+1) * TB * 10 + dx+1) * 128
+  int tap_brow[16];  // first weight row of the tap's hi block for chunk 0
+  int nchunk, chunk_brow, lo_brow, lo_coff;
+  int TB, tiles_x, SW, SH;
+  int abox_bytes;    // one halo box rounded up to 1024
+  int abox_tx;       // bytes one box load delivers
+  int a_stages, b_stages, tail_pad, smem_bytes;
+  long long B, pair_items;
+  OutSpec o;
+};
+int launch_tc_pairh(const PairHLayer& L, int NT, int max_ctas, cudaStream_t st);
+bool tc_pairh_supported(int NT);
+
 // ---- tcgen05 convolution with a resident halo tile (tc_halo.cu) ----------------------------------------
 constexpr int HALO_MAX_SMEM = 232448;  // 227 KB
 struct HaloMma {  // one tcgen05.mma (K = 16) of a unit: descriptor start offsets (bytes >> 4) and the N selector
