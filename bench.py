@@ -219,7 +219,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["mixed", "bf16x3", "fp16x3", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / field / alternative-precision extras")
@@ -351,7 +351,7 @@ def main():
     if not args.no_extras:
         try:
             alt = {}
-            for prec in [p for p in ("bf16", "bf16x3", "fp16x3") if p != args.precision]:
+            for prec in [p for p in ("bf16", "bf16x3", "fp16x3", "mixed") if p != args.precision]:
                 n2 = load_deblender(*CFG, weights="random:1234", precision=prec, chunk=args.chunk)
                 for _ in range(3):
                     n2.deblend_into(x, mean, std)

@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdebvader_b200.so")
 
-PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3}
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4}
 F32, F64 = 0, 1
 
 _lib = None

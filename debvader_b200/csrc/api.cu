@@ -55,7 +55,7 @@ static const LayerDesc kLayers[] = {
 };
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 constexpr int PH_SMEM_BUDGET = 232448 - 1024 - 512 - 2048;
-enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_HEAD = 19 };
+enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_T6 = 16, I_HEAD = 19 };
 
 static std::string wkey(int enc, int n, const char* nm) {
   char buf[128];
@@ -269,10 +269,21 @@ static inline float h162f(int f16, uint16_t u) {
   return __half2float(h);
 }
 
+// Storage of the activations ENTERING layer li (and the format of its weights) in the tensor-core modes.
+// DBV_PREC_MIXED: the four large-image decoder layers read single-plane fp16 activations with fp16 hi/lo weights.
+static bool mixed_tail(int precision, int li) { return precision == DBV_PREC_MIXED && li >= I_T6 && li <= I_HEAD; }
+static int layer_f16(int precision, int li) { return (precision == DBV_PREC_FP16X3 || mixed_tail(precision, li)) ? 1 : 0; }
+static int layer_in_planes(int precision, int li) {
+  if (precision == DBV_PREC_BF16) return 1;
+  return mixed_tail(precision, li) ? 1 : 2;
+}
+static bool prec_x3(int precision) { return precision == DBV_PREC_BF16X3 || precision == DBV_PREC_FP16X3 || precision == DBV_PREC_MIXED; }
+
 // describe how layer li's OUTPUT is stored in the tensor-core modes
-static void tc_out_layout(int li, int planes, OutSpec* o) {
+static void tc_out_layout(int li, int precision, OutSpec* o) {
   const LayerDesc& L = kLayers[li];
-  o->planes = planes;
+  o->planes = li + 1 < kNumLayers ? layer_in_planes(precision, li + 1) : 1;
+  o->f16 = li + 1 < kNumLayers ? layer_f16(precision, li + 1) : 0;
   o->OH = L.Hout;
   o->OW = L.Hout;
   o->Cout = L.Cout;
@@ -300,7 +311,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
+  const bool x3 = prec_x3(c->precision);
   const HostTensor* W = find_w(c, wkey(L.enc, L.wn, "kernel"));
   // ---- input tensor (previous layer's output buffer) -------------------------------------------
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
@@ -333,7 +344,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
           if (li == I_ENC_DENSE) w = W->data[((size_t)taps[ti].ky * 256 + ci) * L.Cout + n];  // flat (h,w,c) index
           else if (li == I_CONV1) w = ci < 54 ? W->data[(size_t)ci * L.Cout + n] : 0.f;  // HWIO flattened: k = (ky*3+kx)*6 + band
           else w = w_at(L, *W, taps[ti].ky, taps[ti].kx, ci, n);
-          const int f16 = c->precision == DBV_PREC_FP16X3;
+          const int f16 = layer_f16(c->precision, li);
           const uint16_t hi = f2h16(f16, w);
           const size_t b0 = ((ti * nchunk + ch) * parts_w) * blk_elems + (size_t)n * G.CBK + k;
           packed[b0] = hi;
@@ -348,6 +359,12 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   // ---- k-block table ------------------------------------------------------------------------------
   TcLayer& T = R.tc;
   memset(&T, 0, sizeof T);
+  if (x3 && in_planes < 2) {  // single-plane input (DBV_PREC_MIXED tail): only the resident-halo kernel runs this layer;
+    uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};  // it needs the packed weights' tensor map
+    uint64_t bs[1] = {(uint64_t)G.CBK * 2};
+    uint32_t bb[2] = {(uint32_t)G.CBK, (uint32_t)G.NT};
+    return encode_tmap(&T.tmB, R.w_packed, 2, bd, bs, bb, G.CBK * 2);
+  }
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
   T.n_cls = ncls;
   int nkb = 0;
@@ -359,7 +376,6 @@ static int build_tc_layer(dbv_ctx* c, int li) {
         // one k-block per (tap, chunk); in the hi/lo split precisions the kernel loads the lo activation plane
         // (channel offset + lo_coff) and the lo weight block (row offset + lo_brow) into the same stage
         if (nkb >= TC_MAX_KB) return fail(DBV_ERR_UNSUPPORTED, "%s: k-block table overflow", L.name);
-        if (x3 && in_planes < 2) return fail(DBV_ERR_STATE, "%s: input has no lo plane", L.name);
         TcKBlock& K = T.kb[nkb++];
         K.dx = (int16_t)taps[ti].dx;
         K.dy = (int16_t)taps[ti].dy;
@@ -385,6 +401,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   T.a_bytes = G.CBK * 2 * G.TW * G.TH * G.TB;
   T.b_bytes = G.NT * G.CBK * 2;
   T.x3 = x3 ? 1 : 0;
+  T.ab_f16 = layer_f16(c->precision, li);
   T.lo_coff = in_cpad;
   T.lo_brow = Ntot;
   tc_stage_plan(T, G.CBK, G.NT);
@@ -428,7 +445,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
+  const bool x3 = prec_x3(c->precision);
   if (!x3 || !R.has_pair || getenv("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
   if (L.kind == L_CONV && L.stride != 1) return DBV_OK;
   const OutSpec& in = c->rt[li - 1].ospec;
@@ -444,6 +461,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const int nchunk = L.Cin / 64, parts = 2;
   const int Ntot = G.NT;  // conv layers are not N-tiled
   P.n_cls = ncls;
+  P.ab_f16 = layer_f16(c->precision, li);
   int nt = 0;
   std::vector<int> order;
   for (int cl = 0; cl < ncls; ++cl) {
@@ -491,7 +509,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   LayerRt& R = c->rt[li];
   const LayerRt& P = (li == I_CONV1) ? c->im2col : c->rt[li - 1];
   const OutSpec& in = P.ospec;
-  const bool x3 = c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3;
+  const bool x3 = prec_x3(c->precision);
   const bool c1 = (li == I_CONV1);  // no-swizzle mode: 16-byte pixel rows, K=16 = two adjacent pixels
   const int ROWB = c1 ? 16 : G.CBK * 2;
   std::vector<Tap> taps = make_taps(L);
@@ -533,7 +551,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
       // one entry per MMA: (tap, channel chunk, pairing, k-step).  bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of
       // N = 2*NT (the hi and lo weight blocks are adjacent in shared memory) + (A_lo x B_hi): A_hi is fetched once
       for (int ch = 0; ch < nchunk; ++ch)
-        for (int pr = 0; pr < (x3 ? 2 : 1); ++pr)
+        for (int pr = 0; pr < in.planes; ++pr)  // pr = 1: the lo activation plane (absent for single-plane inputs)
           for (int k = 0; k < (c1 ? 1 : G.CBK / 16); ++k) {
             if (nkb >= TC_MAX_KB) return 0;
             const int a_lo = (pr == 1);
@@ -550,6 +568,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
     T.cls[cl].ox0 = ncls == 4 ? (cl & 1) : 0;
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
+  T.ab_f16 = layer_f16(c->precision, li);
   T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
   T.ntiles = ntiles;
   T.n_regions = n_regions;
@@ -590,7 +609,8 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   if (getenv("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
-  if ((!R.has_tc && li != I_CONV1) || L.kind == L_DENSE) return DBV_OK;
+  const bool must = li == I_CONV1 || mixed_tail(c->precision, li);  // these layers have no other tensor-core kernel
+  if ((!R.has_tc && !must) || L.kind == L_DENSE) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
   const OutSpec& in = ((li == I_CONV1) ? c->im2col : c->rt[li - 1]).ospec;
   if (in.mode != OUT_BF16_NHWC && in.mode != OUT_BF16_PARITY) return DBV_OK;
@@ -649,7 +669,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   cudaEventDestroy(e1);
   if (hm) cudaFree(hm);
   if (hs) cudaFree(hs);
-  if (!found && li == I_CONV1) return fail(DBV_ERR_STATE, "enc_conv1: no valid halo plan (the tensor-core modes have no other conv1 kernel)");
+  if (!found && must) return fail(DBV_ERR_STATE, "%s: no valid halo plan (there is no other tensor-core kernel for this layer in this precision)", L.name);
   if (!found) return DBV_OK;
   R.halo = best;
   R.has_halo = true;
@@ -797,7 +817,7 @@ extern "C" int64_t dbv_launch_count(const dbv_ctx* c) { return c ? c->launches :
 
 extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chunk) {
   DBV_REQUIRE(out, "dbv_create: null out");
-  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_FP16X3, "dbv_create: bad precision %d", precision);
+  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_MIXED, "dbv_create: bad precision %d", precision);
   DBV_REQUIRE(chunk >= 0 && chunk <= (1 << 20), "dbv_create: bad chunk %lld", (long long)chunk);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -861,7 +881,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   if (c->finalized) return fail(DBV_ERR_STATE, "dbv_finalize_weights: already finalized");
   DBV_CUDA(cudaSetDevice(c->device));
   const bool fp32 = c->precision == DBV_PREC_FP32;
-  const int planes = (c->precision == DBV_PREC_BF16X3 || c->precision == DBV_PREC_FP16X3) ? 2 : 1;
+  const int planes = prec_x3(c->precision) ? 2 : 1;  // conv1's operand (and every layer outside the mixed tail)
   const int f16 = c->precision == DBV_PREC_FP16X3 ? 1 : 0;
   int r;
   // ---- BatchNorm (model/model.py:79; Keras eps 1e-3) folded to scale/shift -----------------------
@@ -924,7 +944,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
       o.OH = o.OW = L.Hout;
       o.Cout = o.Cpad = L.Cout;
     } else {
-      tc_out_layout(li, planes, &o);
+      tc_out_layout(li, c->precision, &o);
     }
     // PReLU slopes: checkpoint layout (h,w,c) of the map THIS OutSpec describes -> [c/4][h*w][4] (epilogue.cuh:alpha_index)
     auto regroup = [&](const HostTensor* t) {
@@ -942,7 +962,6 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     o.alpha = R.alpha;
     o.alpha2 = R.alpha2;
     o.relu = L.relu_head;
-    o.f16 = f16;
     const size_t el = out_elems_per_stamp(o);
     const size_t esz = (o.mode == OUT_F32_NHWC) ? 4 : 2;
     R.out_bytes_per_stamp = el * esz;

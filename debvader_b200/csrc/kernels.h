@@ -59,6 +59,7 @@ struct TcLayer {
   long long tiles_per_cls;
   long long total_tiles;
   int a_bytes, b_bytes;  // bytes of one activation box / one weight box (expect_tx = parts * (a_bytes + b_bytes))
+  int ab_f16;            // operand format of this layer's activations and weights: 0 = bf16, 1 = fp16
   int x3;                // hi/lo split precision: a k-block loads A_hi, A_lo, B_hi, B_lo once and issues all three pairings
   int lo_coff;           // channel offset of the lo plane in the activation tensor (input Cpad)
   int lo_brow;           // row offset of the lo weight block relative to the hi block (Ntot)
@@ -88,6 +89,7 @@ struct PairHLayer {
   CUtensorMap tmB;   // packed weights, box (64, NT/2)
   TcClass cls[TC_MAX_CLS];
   int n_cls;
+  int ab_f16;        // operand format: 0 = bf16, 1 = fp16
   int cls_begin[TC_MAX_CLS + 1];  // taps of class c: [cls_begin[c], cls_begin[c+1])
   int tap_aoff[16];  // byte offset of the tap's window in the halo box: ((dy+1) * TB * 10 + dx+1) * 128
   int tap_brow[16];  // first weight row of the tap's hi block for chunk 0
@@ -115,6 +117,7 @@ struct HaloLayer {
                            // precomputed on the host so that the single issuing thread does nothing but issue
   TcClass cls[TC_MAX_CLS];
   int n_cls;
+  int ab_f16;        // operand format of this layer's activations and weights: 0 = bf16, 1 = fp16
   int W, H;          // tile-space extents (valid outputs sx < W, sy < H)
   int R, WP;         // output rows per band, W + 2*pad
   int pad;           // halo width: 1 for 3x3 taps, 0 for a 1-tap layer (conv1 after im2col)

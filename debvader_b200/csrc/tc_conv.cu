@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       uint32_t phase = 0;
       uint32_t u = 0;
       constexpr uint32_t HI = smem_desc_hi<Cfg::ROWB>();
-      const uint32_t IDESC = Cfg::IDESC | idesc_ab_fmt(L.o.f16), IDESC2 = Cfg::IDESC2 | idesc_ab_fmt(L.o.f16);
+      const uint32_t IDESC = Cfg::IDESC | idesc_ab_fmt(L.ab_f16), IDESC2 = Cfg::IDESC2 | idesc_ab_fmt(L.ab_f16);
       for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
         const int c = (int)(t / L.tiles_per_cls);
         const int nkb = L.cls[c].nkb;

@@ -44,8 +44,8 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
-  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t IDESC2 = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t IDESC2 = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                              // nbuf x n_regions x region_bytes

@@ -29,7 +29,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1) tc_pa
   constexpr int A_BYTES = 128 * ROWB;
   constexpr int BH_BYTES = (NT / 2) * ROWB;  // this CTA's half of one weight box
   // M = 256 (both CTAs), N = NT
-  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
+  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int STAGES = L.stages;

@@ -111,7 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
     if (rank == 0 && elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, u = 0;
-      const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.o.f16) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
       // A: 128B-swizzled K-major rows, 8-row groups 10 pixel rows (1280 B) apart;  B: dense groups (1024 B)
       constexpr uint32_t HIA = (uint32_t)(1280 >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t HIB = smem_desc_hi<ROWB>();

@@ -45,9 +45,13 @@ typedef enum {
   DBV_PREC_BF16 = 1,   /* tcgen05 bf16 x bf16 -> fp32, activations stored once in bf16      */
   DBV_PREC_BF16X3 = 2, /* tcgen05, hi/lo bf16 split of activations and weights (3 MMAs per
                           product, ~16-bit mantissa): <=1e-3 of peak flux                   */
-  DBV_PREC_FP16X3 = 3  /* tcgen05, hi/lo fp16 split (~22-bit mantissa), same cost as BF16X3:
-                          meets the fp32 bound (<=1e-5 of peak flux); activations saturate
+  DBV_PREC_FP16X3 = 3, /* tcgen05, hi/lo fp16 split, same cost as BF16X3; activations saturate
                           at +-65504 (fp16 range)                                           */
+  DBV_PREC_MIXED = 4   /* BF16X3, except that the activations entering the four large-image
+                          decoder layers (convT6, convT7, convT8, head: 55 % of the step) are
+                          stored ONCE in fp16 (11-bit mantissa, saturating at +-65504) and
+                          multiplied by fp16 hi/lo weights: 2 MMAs per product instead of 3
+                          and half the activation traffic there; ~5e-4 of peak flux         */
 } dbv_precision;
 
 typedef enum { DBV_F32 = 0, DBV_F64 = 1 } dbv_dtype;
