@@ -21,7 +21,10 @@ from .._dist import MVNTriLOutput, NormalOutput, Value
 from . import ckpt, spec
 
 S, NB, LAT, NPAR = 59, 6, 32, 560
-DEFAULT_PRECISION = os.environ.get("DEBVADER_B200_PRECISION", "bf16x3")
+# "mixed" = bf16 hi/lo split everywhere except single-plane fp16 activations into the four large-image decoder layers:
+# ~5e-4 of peak flux (north_star tolerance for the tensor-core path: 1e-3), fp16 range (+-65504) on those activations.
+# "bf16x3" (~5e-5, full fp32 range) and "fp32" (SIMT, <= 1e-5) are the tighter choices.
+DEFAULT_PRECISION = os.environ.get("DEBVADER_B200_PRECISION", "mixed")
 
 
 def _as_device_f32(x, device):
@@ -308,7 +311,7 @@ def create_model_vae(input_shape, latent_dim, filters, kernels, conv_activation=
 def load_deblender(survey, input_shape, latent_dim, filters, kernels, return_encoder_decoder_z=False, for_onnx=False,
                    *, weights=None, precision=None, device=None, chunk=0, seed=0):
     """Reference signature model/model.py:221-229.  Extension kwargs are keyword-only:
-    weights (dict | .npz | checkpoint dir | 'random[:seed]'), precision ('fp32'|'bf16'|'bf16x3'), device, chunk, seed."""
+    weights (dict | .npz | checkpoint dir | 'random[:seed]'), precision ('mixed'|'bf16x3'|'fp16x3'|'bf16'|'fp32'), device, chunk, seed."""
     if not spec.is_dc2(input_shape, latent_dim, filters, kernels):
         raise NotImplementedError("debvader_b200 implements the DC2 deblender architecture only (no fallback)")
     net = Deblender(_resolve_weights(survey, weights), precision=precision, device=device, chunk=chunk, seed=seed)

@@ -37,7 +37,8 @@ keep = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__pipe_tc_cycles_
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic"]
 body = raw[2:2 + len(names)]
-traffic = {"source": f"profiles/{tag}_full_raw_summary.csv (ncu --set full --clock-control none, one chunk of 1024 stamps, bf16x3)", "bf16x3": {}}
+prec = bench["config"]["precision"]
+traffic = {"source": f"profiles/{tag}_full_raw_summary.csv (ncu --set full --clock-control none, one launch of 1024 stamps, precision {prec})", prec: {}}
 with open(os.path.join(P, f"{tag}_full_raw_summary.csv"), "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["layer", "kernel"] + keep)
@@ -50,7 +51,7 @@ with open(os.path.join(P, f"{tag}_full_raw_summary.csv"), "w", newline="") as f:
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
             u = raw[1]
             db = tobytes(col(r, "dram__bytes_read.sum"), u[h.index("dram__bytes_read.sum")]) + tobytes(col(r, "dram__bytes_write.sum"), u[h.index("dram__bytes_write.sum")])
-            traffic["bf16x3"][nm] = {"dram_bytes": int(db), "stamps": 1024, "kernel": kn}
+            traffic[prec][nm] = {"dram_bytes": int(db), "stamps": 1024, "kernel": kn}
         except Exception:
             pass
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
@@ -79,6 +80,6 @@ with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
     f.write("## one chunk under `ncu --set full` (see the _full_raw_summary.csv next to this file)\n\n| layer | kernel | us | tensor pipe active % | TC smem wavefronts % | LSU wavefronts % | L2 % | DRAM % | DRAM MB |\n|---|---|---|---|---|---|---|---|---|\n")
     for nm, r in zip(names, body):
         kn = col(r, "Kernel Name").split("(")[0].replace("void ", "")
-        db = traffic["bf16x3"].get(nm, {}).get("dram_bytes", 0) / 1e6
+        db = traffic[prec].get(nm, {}).get("dram_bytes", 0) / 1e6
         f.write(f"| {nm} | `{kn}` | {col(r, keep[0])} | {col(r, keep[2])[:5]} | {col(r, keep[3])[:5]} | {col(r, keep[4])[:5]} | {col(r, keep[5])[:5]} | {col(r, keep[6])[:5]} | {db:.0f} |\n")
 print("wrote profiles/%s_*" % tag)
