@@ -102,6 +102,7 @@ struct LayerRt {
   float* w_gather = nullptr;       // SIMT gather form [taps][Cin][CoutP]
   __nv_bfloat16* w_packed = nullptr;  // tcgen05 packed blocks [nblk][Ntot][CBK]
   float* bias = nullptr;
+  std::vector<float> bias_host;
   float* alpha = nullptr;
   float* alpha2 = nullptr;
   int CoutP = 0;
@@ -569,6 +570,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
   T.ab_f16 = layer_f16(c->precision, li);
+  for (int i = 0; i < 64; ++i) T.bias_c[i] = i < L.Cout ? R.bias_host[i] : 0.f;
   T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
   T.ntiles = ntiles;
   T.n_regions = n_regions;
@@ -919,6 +921,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     }
     if (L.a2n >= 0 && (r = check_shape(c, wkey(L.enc, L.a2n, "alpha"), {(int64_t)L.Hout * L.Hout * L.Cout}, &A2))) return r;
     if ((r = upload(c, &R.bias, Bv->data))) return r;
+    R.bias_host = Bv->data;
     R.CoutP = (L.Cout + 3) & ~3;
     const bool simt = fp32 || !kTc[li].tc;
     if (simt) {

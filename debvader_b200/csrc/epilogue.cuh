@@ -126,16 +126,27 @@ __device__ __forceinline__ void act_prefetch(const OutSpec& o, bool ok, int y, i
   }
 }
 
-template <int NV>
+// BIASED: the caller has already added the bias (from the kernel's constant bank) — only valid with r.fast or the head
+template <int NV, bool BIASED = false>
 __device__ __forceinline__ void act_apply(const OutSpec& o, int y, int x, int c, int bias_off, const ActRegs<NV>& r, float (&v)[NV]) {
   if (!r.fast) {
+    if constexpr (BIASED) {
+      if (o.mode == OUT_HEAD) {  // decoder head: bias already in, no PReLU, ReLU on every channel (model/model.py:137)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c + j < o.Cout) v[j] -= __ldg(o.bias + bias_off + c + j);  // generic path re-adds it
+    }
     apply_act<NV>(o, y, x, c, v, bias_off);
     return;
   }
   const float4* bp = reinterpret_cast<const float4*>(o.bias + bias_off + c);
 #pragma unroll
   for (int j = 0; j < NV / 4; ++j) {
-    const float4 bb = __ldg(bp + j);
+    const float4 bb = BIASED ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bp + j);
     v[4 * j + 0] = prelu_f(v[4 * j + 0] + bb.x, r.a[j].x);
     v[4 * j + 1] = prelu_f(v[4 * j + 1] + bb.y, r.a[j].y);
     v[4 * j + 2] = prelu_f(v[4 * j + 2] + bb.z, r.a[j].z);
@@ -163,22 +174,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp16 conversions SATURATE at +-65504 (one F2FP.SATFINITE), so that a large activation never becomes inf
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // a -> low half, b -> high half
+  return r;
 }
-// fp16 hi/lo split; values saturate at the fp16 range so that hi never becomes inf (lo = v - hi would be NaN)
+// fp16 hi/lo split (hi saturates, lo = v - hi stays finite)
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float2 hf = __half22float2(h);
+  hi = pack_f16x2(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = pack_f16x2(a - hf.x, b - hf.y);
 }
 // format-dispatching versions (f16 is warp-uniform)
-__device__ __forceinline__ uint32_t pack16x2(int f16, float a, float b) { return f16 ? pack_f16x2(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f)) : pack_bf16x2(a, b); }
-__device__ __forceinline__ float round16(int f16, float a) { return f16 ? __half2float(__float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f))) : __bfloat162float(__float2bfloat16_rn(a)); }
+__device__ __forceinline__ uint32_t pack16x2(int f16, float a, float b) { return f16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
+__device__ __forceinline__ float round16(int f16, float a) {
+  if (!f16) return __bfloat162float(__float2bfloat16_rn(a));
+  const uint32_t h = pack_f16x2(a, 0.f);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 // hi = bf16x2(a,b); lo = bf16x2(a - hi.a, b - hi.b): 6 instructions per pair
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -198,6 +212,21 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
   if (o.mode == OUT_HEAD) {
     if (y < 2 || y >= 61 || x < 2 || x >= 61) return;
     const long long base = ((b * 59 + (y - 2)) * 59 + (x - 2)) * 6;
+    if constexpr (NV >= 12) {
+      if (c == 0) {  // 24-byte pixels: three 8-byte stores per output
+        float2* pm = reinterpret_cast<float2*>(reinterpret_cast<float*>(o.out) + base);
+        pm[0] = make_float2(v[0], v[1]);
+        pm[1] = make_float2(v[2], v[3]);
+        pm[2] = make_float2(v[4], v[5]);
+        if (o.out2) {
+          float2* ps = reinterpret_cast<float2*>(reinterpret_cast<float*>(o.out2) + base);
+          ps[0] = make_float2(1e-4f + v[6], 1e-4f + v[7]);
+          ps[1] = make_float2(1e-4f + v[8], 1e-4f + v[9]);
+          ps[2] = make_float2(1e-4f + v[10], 1e-4f + v[11]);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int cc = c + j;

@@ -113,6 +113,7 @@ struct HaloMma {  // one tcgen05.mma (K = 16) of a unit: descriptor start offset
 struct HaloLayer {
   CUtensorMap tmA;  // 5D (C, W, H, 1, B) bf16, box (CBK, W+2, R+2, 1, 1)
   CUtensorMap tmB;  // packed weights, box (CBK, NT)
+  float bias_c[64];        // the layer's bias (zero padded to NT) in the kernel's constant bank: added without a load
   HaloMma mma[TC_MAX_KB];  // flat MMA list per class (cls[c].kb_begin / nkb index it): taps x chunks x pairings x k-steps,
                            // precomputed on the host so that the single issuing thread does nothing but issue
   TcClass cls[TC_MAX_CLS];

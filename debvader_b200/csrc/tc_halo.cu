@@ -21,7 +21,7 @@
 namespace dbv {
 
 #ifndef DBV_HALO_EPI_GROUPS
-#define DBV_HALO_EPI_GROUPS 2
+#define DBV_HALO_EPI_GROUPS 4
 #endif
 constexpr int HALO_EPI_GROUPS = DBV_HALO_EPI_GROUPS;  // epilogue groups of 4 warps (one warp per TMEM lane quadrant); the epilogue is latency bound
 constexpr int HALO_THREADS = 64 + HALO_EPI_GROUPS * 128;  // TMA warp, MMA warp, epilogue groups
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     // wait -> tcgen05.ld -> math -> stores), so the slopes of the NEXT item are requested before the current one is processed.
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    constexpr int NV = (NT % 32 == 0) ? 32 : 16;
+    constexpr int NV = (HALO_EPI_GROUPS > 2 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
       }
       if (cur.ok) {
-        if (!(L.dbg_skip & 4)) act_apply<NV>(L.o, cur.oy, cur.ox, c0, 0, ra, v);
+        if (!(L.dbg_skip & 4)) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];
+          act_apply<NV, true>(L.o, cur.oy, cur.ox, c0, 0, ra, v);
+        }
         if (!(L.dbg_skip & 8)) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);
         else if (v[0] == 123.456f) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);  // keep the loads / math alive
       }
