@@ -447,7 +447,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   const bool x3 = prec_x3(c->precision);
-  if (!x3 || !R.has_pair || getenv("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
+  if (!x3 || !R.has_tc || getenv("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
   if (L.kind == L_CONV && L.stride != 1) return DBV_OK;
   const OutSpec& in = c->rt[li - 1].ospec;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
@@ -497,7 +497,13 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   uint32_t box[5] = {64u, 10u, (uint32_t)TB, (uint32_t)HB, 1u};
   int r = encode_tmap(&P.tmA, c->rt[li - 1].out, 5, dims, str, box, 128);
   if (r) return r;
-  P.tmB = R.tcp.tmB;  // box (64, NT/2)
+  {  // packed weights, box (64, NT/2): each CTA of the pair loads its half of a block
+    const size_t nblk = taps.size() * nchunk * parts;
+    uint64_t bd[2] = {64, (uint64_t)(nblk * Ntot)};
+    uint64_t bs[1] = {128};
+    uint32_t bb[2] = {64u, (uint32_t)(G.NT / 2)};
+    if ((r = encode_tmap(&P.tmB, R.w_packed, 2, bd, bs, bb, 128))) return r;
+  }
   R.has_pairh = true;
   return DBV_OK;
 }

@@ -225,9 +225,10 @@ static int launch_pairh_one(const PairHLayer& L, int max_ctas, cudaStream_t st) 
   return DBV_OK;
 }
 
-bool tc_pairh_supported(int NT) { return NT == 128 || NT == 256; }
+bool tc_pairh_supported(int NT) { return NT == 64 || NT == 128 || NT == 256; }
 
 int launch_tc_pairh(const PairHLayer& L, int NT, int max_ctas, cudaStream_t st) {
+  if (NT == 64) return launch_pairh_one<64>(L, max_ctas, st);
   if (NT == 128) return launch_pairh_one<128>(L, max_ctas, st);
   if (NT == 256) return launch_pairh_one<256>(L, max_ctas, st);
   return fail(DBV_ERR_UNSUPPORTED, "no halo CTA-pair kernel instance for NT=%d", NT);
