@@ -841,7 +841,7 @@ extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chun
   dbv_ctx* c = new dbv_ctx();
   c->device = device;
   c->precision = precision;
-  c->chunk = chunk > 0 ? chunk : 2048;  // stamps per pass of the layer sequence: large enough that a launch of the small-image
+  c->chunk = chunk > 0 ? chunk : 4096;  // stamps per pass of the layer sequence: large enough that a launch of the small-image
                                         // layers (one pass over the layer's weights per SM, ~50 us) is amortised
   *out = c;
   return DBV_OK;
