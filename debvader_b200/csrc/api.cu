@@ -510,7 +510,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
 
 // Fill T with the plan for R output rows per band and nbuf halo buffers.  Returns 1 if the plan is valid
 // (fits shared memory / TMEM / descriptor fields), 0 if not, < 0 on error.
-static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
+static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& T) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
@@ -539,7 +539,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   const int n_regions = in.planes * nchunk * npar;
   if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
   const int ntiles = (bandR * WP + 127) / 128;
-  if (G.NT * (x3 ? 2 : 1) > 256) return 0;  // one unit (tile of one class) must fit a TMEM slot; the ring has 512 / width slots
+  if (U * G.NT * (x3 ? 2 : 1) > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
   if (bandR + 2 * pad > 256 || WP > 256) return 0;
   const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + ROWB + 1023) / 1024) * 1024;  // >= one zeroed slack slot after the box
   // layout: [halo ring][weights][barriers].  The last tile of a band over-reads < 131 garbage rows past its region: into the
@@ -592,6 +592,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, HaloLayer& T) {
   T.w_rows_per_blk = G.NT;  // conv layers are not N-tiled: Ntot == NT
   T.w_bytes = w_bytes;
   T.nbuf = nbuf;
+  T.U = U;
   T.dbg_skip = getenv("DBV_HALO_SKIP") ? atoi(getenv("DBV_HALO_SKIP")) : 0;
   T.wide = x3 ? 1 : 0;
   T.tail_pad = tail_pad;
@@ -628,14 +629,20 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
   const int H = (ncls == 4) ? L.Hin : L.Hout, WP = H + (li == I_CONV1 ? 3 : 1);
   // candidates: the tallest band for each tile count (R*WP just below a multiple of 128), both ring depths
-  std::vector<std::pair<int, int>> cand;
+  struct Cand { int r, nbuf, U; };
+  std::vector<Cand> cand;
   for (int nt = 1; nt <= 16; ++nt) {
     int r = std::min(H, nt * 128 / WP);
     if (r < 1) continue;
     for (int nbuf = 2; nbuf >= 1; --nbuf)
-      if (std::find(cand.begin(), cand.end(), std::make_pair(r, nbuf)) == cand.end()) cand.push_back({r, nbuf});
+      for (int U = 1; U <= 4; U *= 2) {
+        if (U > ncls * nt && U > 1) continue;  // no band has that many sub-units
+        bool dup = false;
+        for (const Cand& q : cand) dup = dup || (q.r == r && q.nbuf == nbuf && q.U == U);
+        if (!dup) cand.push_back({r, nbuf, U});
+      }
   }
-  const long long Bt = std::min<long long>(c->chunk, 296);
+  const long long Bt = std::min<long long>(c->chunk, 592);  // 4 stamps per SM: enough bands per CTA for a stable ranking
   cudaEvent_t e0, e1;
   DBV_CUDA(cudaEventCreate(&e0));
   DBV_CUDA(cudaEventCreate(&e1));
@@ -651,16 +658,17 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     o.out = hm;
     o.out2 = hs;
   }
-  for (auto [r, nbuf] : cand) {
+  for (const Cand& cd : cand) {
+    const int r = cd.r, nbuf = cd.nbuf;
     HaloLayer T;
-    int ok = halo_plan(c, li, r, nbuf, T);
+    int ok = halo_plan(c, li, r, nbuf, cd.U, T);
     if (ok < 0) return ok;
     if (!ok) continue;
     T.B = Bt;
     T.o = o;
     T.total_bands = Bt * T.bands_per_img;
     float ms = 0.f;
-    for (int it = 0; it < 3; ++it) {  // 1 warm-up + best of 2
+    for (int it = 0; it < 4; ++it) {  // 1 warm-up + best of 3
       DBV_CUDA(cudaEventRecord(e0, 0));
       int rr = launch_halo_layer(T, G.CBK, G.NT, kNumSMs, 0);
       if (rr) return rr;
@@ -668,9 +676,9 @@ static int build_halo_layer(dbv_ctx* c, int li) {
       DBV_CUDA(cudaEventSynchronize(e1));
       float t;
       DBV_CUDA(cudaEventElapsedTime(&t, e0, e1));
-      ms = (it == 1) ? t : (it == 2 ? std::min(ms, t) : ms);
+      ms = (it == 1) ? t : (it >= 2 ? std::min(ms, t) : ms);
     }
-    if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate R=%d nbuf=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, r, nbuf, T.ntiles, T.smem_bytes, ms, Bt);
+    if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate R=%d nbuf=%d U=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, r, nbuf, cd.U, T.ntiles, T.smem_bytes, ms, Bt);
     if (ms < best_ms) { best_ms = ms; best = T; found = true; }
   }
   cudaEventDestroy(e0);
@@ -682,8 +690,8 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   R.halo = best;
   R.has_halo = true;
   if (getenv("DBV_VERBOSE"))
-    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d ntiles=%d regions=%d smem=%d (%.3f ms / %lld stamps)\n", L.name, best.R, best.nbuf, best.ntiles,
-            best.n_regions, best.smem_bytes, best_ms, Bt);
+    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d U=%d ntiles=%d regions=%d smem=%d (%.3f ms / %lld stamps)\n", L.name, best.R, best.nbuf, best.U,
+            best.ntiles, best.n_regions, best.smem_bytes, best_ms, Bt);
   return DBV_OK;
 }
 

@@ -131,6 +131,7 @@ struct HaloLayer {
   int n_wblk, w_rows_per_blk, w_bytes;
   const void* w_img;  // no-swizzle mode (conv1): the resident weights as one ready-made shared-memory image (bulk copy)
   int nbuf;          // halo buffers in the ring (1 or 2)
+  int U;             // sub-units (tile x class) per accumulator slot / commit: 1, 2 or 4 with U * accumulator width <= 256 columns
   int wide;          // bf16x3: accumulator tile = [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo] (2*NT columns, summed by the epilogue);
                      // kb[].dy == 1 marks the k-blocks issued with N = 2*NT over the adjacent (hi, lo) weight blocks
   int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)

@@ -36,11 +36,9 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 // owns the contiguous range [total*i/grid, total*(i+1)/grid): a CTA stays on ONE band row for (almost) its whole
 // life, so the PReLU alpha slice of that band (tens of KB, the same for every stamp) stays L1-resident.
 //
-// Accumulators: TMEM is a ring of `nslot` slots of DW columns; a "unit" = one 128-position tile of one
-// output-parity class.  The MMA warp issues all k-blocks of a unit into the next free slot and commits it;
-// the two epilogue groups drain alternate units.  The MMA warp can therefore run up to nslot units ahead of
-// the epilogue and neither side idles while the other works on "its" buffer (the previous two-buffer-per-band
-// scheme serialised MMA(band i+2) behind epilogue(band i): measured 1.6 ms where max(MMA, epilogue) was 1.1).
+// Accumulators: TMEM is two slots of 256 columns; a "unit" = up to 256 / DW consecutive sub-units (one 128-position
+// tile of one output-parity class each) of a band.  The MMA warp issues all MMAs of a unit into the free slot and
+// commits it once; the epilogue groups split the unit's sub-units; the MMA warp runs one unit ahead of the epilogue.
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
@@ -57,9 +55,16 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per unit
-  const uint32_t nslot = (512u / DW) < (uint32_t)HALO_NSLOT_MAX ? (512u / DW) : (uint32_t)HALO_NSLOT_MAX;  // power of two
+  const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per sub-unit (one tile of one class)
+  // A "unit" = up to U consecutive sub-units of a band sharing ONE accumulator slot, one tempty wait and one commit: the
+  // issuing thread pays its per-unit overhead (barrier wait ~100 cycles, commit, loop set-up: ~300 cycles measured, which
+  // showed up 1:1 as tensor-pipe idle time) once per 256 accumulator columns instead of once per 128-row tile.
+  const uint32_t U = (uint32_t)L.U;                    // sub-units per unit (U * DW <= 256; autotuned with the band plan)
+  const uint32_t SW = U * DW;                          // slot width
+  const uint32_t nslot = (512u / SW) < (uint32_t)HALO_NSLOT_MAX ? (512u / SW) : (uint32_t)HALO_NSLOT_MAX;  // power of two
   const uint32_t slot_shift = 31u - (uint32_t)__clz((int)nslot);
+  const int nsub = L.n_cls * L.ntiles;                 // sub-units per band, class-major
+  const int units_per_band = (nsub + (int)U - 1) / (int)U;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.tmA);
     if (!NOSWZ) tma_prefetch_desc(&L.tmB);
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     }
     for (int s = 0; s < HALO_NSLOT_MAX; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, 4 * HALO_EPI_GROUPS);  // every epilogue warp releases every unit
     }
     fence_barrier_init();
   }
@@ -129,123 +134,96 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
         const uint32_t a16 = kSmemDescLoConst | ((sA + stage * L.n_regions * L.region_bytes) >> 4);
-        for (int c = 0; c < ncls; ++c) {
-          const int kb0 = L.cls[c].kb_begin, nkb = L.cls[c].nkb;
-          uint32_t am = a16;
-          for (int m = 0; m < L.ntiles; ++m, am += MSTEP, ++u) {
-            const uint32_t slot = u & (nslot - 1);
-            mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t d = tmem_base + slot * DW;
+        for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
+          const uint32_t slot = u & (nslot - 1);
+          mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
+          tc_fence_after();
+          const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
+          uint32_t d = tmem_base + slot * SW;
+          for (int sidx = s0; sidx < s1; ++sidx, d += DW) {
+            const int c = sidx / L.ntiles, m = sidx - c * L.ntiles;
+            const int kb0 = L.cls[c].kb_begin, nkb = L.cls[c].nkb;
+            const uint32_t am = a16 + (uint32_t)m * MSTEP;
             // flat list, one entry per MMA (read with uniform constant loads): the loop is pure issue
 #pragma unroll 4
             for (int i = 0; i < nkb; ++i) {
               const HaloMma e = L.mma[kb0 + i];
               umma_f16(d, desc64(HI, am + e.a), desc64(HIB, w16 + (e.b & 0x7fffffffu)), (e.b >> 31) ? IDESC2 : IDESC, i != 0 ? 1u : 0u);
             }
-            umma_commit(bar_tfull + 8 * slot);
           }
+          umma_commit(bar_tfull + 8 * slot);
         }
         umma_commit(bar_aempty + 8 * stage);
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
-    // 8 epilogue warps = 2 groups of 4 (one warp per TMEM lane quadrant); group g drains units u with u % 2 == g, one
-    // "item" = (unit, chunk of NV channels) at a time.  The epilogue is a latency chain (PReLU slopes from L2 -> accumulator
-    // wait -> tcgen05.ld -> math -> stores), so the slopes of the NEXT item are requested before the current one is processed.
+    // Epilogue: HALO_EPI_GROUPS groups of 4 warps (one warp per TMEM lane quadrant).  Every group walks every unit and
+    // takes every G-th item (sub-unit x NV-channel chunk) of it; all 4*G warps release the slot.
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     constexpr int NV = (HALO_EPI_GROUPS > 2 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
-    struct Item {
-      long long g;
-      int c, m, q, b, y0, oy, ox;
-      uint32_t u;
-      bool ok;
-    };
-    auto next_unit = [&](Item& it) {  // advance by one unit
-      ++it.u;
-      if (++it.m == L.ntiles) {
-        it.m = 0;
-        if (++it.c == ncls) {
-          it.c = 0;
-          ++it.g;
-          if (++it.b == (int)L.B) { it.b = 0; it.y0 += L.R; }
+    uint32_t u = 0;
+    int b = b_first, y0 = (int)yb0 * L.R;
+    for (long long g = g0; g < g1; ++g) {
+      for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
+        const uint32_t slot = u & (nslot - 1);
+        const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
+        bool waited = false;
+        const int nitems = (s1 - s0) * NCHK;  // items of this unit: (sub-unit, NV-channel chunk); group g takes items g, g + G, ...
+#pragma unroll 1
+        for (int item = grp; item < nitems; item += HALO_EPI_GROUPS) {
+          const int sidx = s0 + item / NCHK, q = item % NCHK;
+          const int c = sidx / L.ntiles, m = sidx - c * L.ntiles;
+          const int p = 128 * m + row;
+          const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
+          const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
+          const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
+          const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
+          const int c0 = q * NV;
+          ActRegs<NV> ra;
+          ra.fast = false;
+          if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);  // requested before the accumulator wait
+          if (!waited) {
+            mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+            tc_fence_after();
+            waited = true;
+          }
+          float v[NV];
+          if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the sub-unit's columns
+            float w[NV];
+            tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+            tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
+            tmem_ld_wait<NV>(v);
+            tmem_ld_wait<NV>(w);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] += w[j];
+          } else {
+            tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+            tmem_ld_wait<NV>(v);
+          }
+          if (ok) {
+            if (!(L.dbg_skip & 4)) {
+#pragma unroll
+              for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];
+              act_apply<NV, true>(L.o, oy, ox, c0, 0, ra, v);
+            }
+            if (!(L.dbg_skip & 8)) store_act<NV>(L.o, b, oy, ox, c0, v);
+            else if (v[0] == 123.456f) store_act<NV>(L.o, b, oy, ox, c0, v);  // keep the loads / math alive
+          }
         }
-      }
-    };
-    auto locate = [&](Item& it) {  // output pixel of this thread's accumulator row
-      const int p = 128 * it.m + row;
-      const int ly = p / L.WP, sx = p - ly * L.WP, sy = it.y0 + ly;
-      it.ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
-      it.oy = L.cls[it.c].oy0 + L.cls[it.c].osy * sy;
-      it.ox = L.cls[it.c].ox0 + L.cls[it.c].osx * sx;
-    };
-    Item cur{g0, 0, 0, 0, b_first, (int)yb0 * L.R, 0, 0, 0u, false};
-    bool live = ncls > 0 && g0 < g1;
-    if (live)
-      for (int k = 0; k < grp; ++k) next_unit(cur);
-    live = live && cur.g < g1;
-    ActRegs<NV> ra;
-    ra.fast = false;
-    if (live) {
-      locate(cur);
-      if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, cur.ok, cur.oy, cur.ox, 0, 0, ra);
-    }
-    while (live) {
-      Item nxt = cur;
-      if (++nxt.q == NCHK) {
-        nxt.q = 0;
-#pragma unroll
-        for (int k = 0; k < HALO_EPI_GROUPS; ++k) next_unit(nxt);
-      }
-      const bool nlive = nxt.g < g1;
-      ActRegs<NV> rn;
-      rn.fast = false;
-      if (nlive) {
-        if (nxt.q == 0) locate(nxt);
-        if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, nxt.ok, nxt.oy, nxt.ox, nxt.q * NV, 0, rn);
-      }
-      const uint32_t slot = cur.u & (nslot - 1);
-      if (cur.q == 0) {
-        mbar_wait(bar_tfull + 8 * slot, (cur.u >> slot_shift) & 1u);
-        tc_fence_after();
-      }
-      const uint32_t tcol = lane_base + slot * DW;
-      const int c0 = cur.q * NV;
-      float v[NV];
-      if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the unit's columns
-        float w[NV];
-        tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-        tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
-        tmem_ld_wait<NV>(v);
-        tmem_ld_wait<NV>(w);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) v[j] += w[j];
-      } else {
-        tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-        tmem_ld_wait<NV>(v);
-      }
-      if (cur.q == NCHK - 1) {  // the accumulator is in registers: hand the slot back before the math and the stores
+        if (!waited) {  // a group without a sub-unit in this unit still takes part in the hand-over, in phase order
+          mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+          tc_fence_after();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
       }
-      if (cur.ok) {
-        if (!(L.dbg_skip & 4)) {
-#pragma unroll
-          for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];
-          act_apply<NV, true>(L.o, cur.oy, cur.ox, c0, 0, ra, v);
-        }
-        if (!(L.dbg_skip & 8)) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);
-        else if (v[0] == 123.456f) store_act<NV>(L.o, cur.b, cur.oy, cur.ox, c0, v);  // keep the loads / math alive
-      }
-      cur = nxt;
-      ra = rn;
-      live = nlive;
+      if (++b == (int)L.B) { b = 0; y0 += L.R; }
     }
   }
   tc_fence_before();
