@@ -1056,26 +1056,26 @@ static int chunked(dbv_ctx* c, const char* fn, const float* x, int64_t B, const 
 }
 
 extern "C" int dbv_encode(dbv_ctx* c, const float* x, int64_t B, float* params, void* stream) {
-  DBV_REQUIRE(x && params, "dbv_encode: null buffer");
+  DBV_REQUIRE(B == 0 || (x && params), "dbv_encode: null buffer");
   return chunked(c, "dbv_encode", x, B, nullptr, 0, 0, 0, params, nullptr, nullptr, nullptr, nullptr, nullptr, true, false, false, stream);
 }
 
 extern "C" int dbv_latent(dbv_ctx* c, const float* params, const float* eps, uint64_t seed, int sample, int64_t first_stamp,
                           int64_t B, float* z, float* loc, float* zstd, void* stream) {
-  DBV_REQUIRE(params && z, "dbv_latent: null buffer");
+  DBV_REQUIRE(B == 0 || (params && z), "dbv_latent: null buffer");
   return chunked(c, "dbv_latent", nullptr, B, eps, seed, sample, first_stamp, const_cast<float*>(params), z, loc, zstd, nullptr,
                  nullptr, false, true, false, stream);
 }
 
 extern "C" int dbv_decode(dbv_ctx* c, const float* z, int64_t B, float* mean, float* stddev, void* stream) {
-  DBV_REQUIRE(z && mean, "dbv_decode: null buffer");
+  DBV_REQUIRE(B == 0 || (z && mean), "dbv_decode: null buffer");
   return chunked(c, "dbv_decode", nullptr, B, nullptr, 0, 0, 0, nullptr, const_cast<float*>(z), nullptr, nullptr, mean, stddev,
                  false, false, true, stream);
 }
 
 extern "C" int dbv_deblend(dbv_ctx* c, const float* x, int64_t B, const float* eps, uint64_t seed, int sample, float* mean,
                            float* stddev, float* z, void* stream) {
-  DBV_REQUIRE(x && mean, "dbv_deblend: null buffer");
+  DBV_REQUIRE(B == 0 || (x && mean), "dbv_deblend: null buffer");
   return chunked(c, "dbv_deblend", x, B, eps, seed, sample, 0, nullptr, z, nullptr, nullptr, mean, stddev, true, true, true, stream);
 }
 
@@ -1106,7 +1106,7 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
                                 float* stddev_dev) {
   int r = check_ready(c, "dbv_deblend_host");
   if (r) return r;
-  DBV_REQUIRE(x_host && mean_host, "dbv_deblend_host: null buffer");
+  DBV_REQUIRE(B == 0 || (x_host && mean_host), "dbv_deblend_host: null buffer");
   DBV_REQUIRE(x_dtype == DBV_F32 || x_dtype == DBV_F64, "dbv_deblend_host: bad dtype %d", x_dtype);
   DBV_REQUIRE(B >= 0, "dbv_deblend_host: negative B");
   if ((r = ensure_pipe(c))) return r;

@@ -241,6 +241,21 @@ def test_cfg2_batch_4096_properties(wts, precision):
     net.close()
 
 
+@pytest.mark.parametrize("precision", ["mixed", "bf16x3"])
+def test_ragged_batch_sizes(wts, precision):
+    """Every kernel family (halo bands, CTA pairs with an odd tile count, two-stamp tiles, 128-row dense tiles) must give
+    each stamp the same result whatever the batch around it: empty, 1, odd, and non-multiple-of-128 batches."""
+    x = torch.from_numpy(ow.synthetic_stamps(301, seed=5)).cuda()
+    net = _net(wts, precision)
+    full = net(x, sample=False)
+    fm, fs = full.mean().tensor, full.stddev().tensor
+    assert net(x[:0], sample=False).mean().tensor.shape == (0, 59, 59, 6)
+    for lo, hi in ((0, 1), (0, 2), (5, 8), (0, 129), (40, 297), (300, 301)):
+        d = net(x[lo:hi].contiguous(), sample=False)
+        assert torch.equal(d.mean().tensor, fm[lo:hi]) and torch.equal(d.stddev().tensor, fs[lo:hi]), (precision, lo, hi)
+    net.close()
+
+
 @pytest.mark.parametrize("which", [0, 1])
 def test_probe_descriptor_row_shift(which):
     """Records (does not assert) how tcgen05 treats an operand whose start address is not aligned to the
