@@ -122,3 +122,42 @@ def exchange_halo_stamps(local_stamps, local_ids, owner, touches, group=None):
     stamps = recv.reshape((-1,) + tuple(local_stamps.shape[1:]))
     order = np.argsort(ids, kind="stable")
     return stamps[torch.as_tensor(order, dtype=torch.long, device=stamps.device)], ids[order]
+
+
+def deblend_field_tiled(net, field_image, galaxy_distances_to_center, group=None, cutout_size=59, nb_of_bands=6, sample=False, seed=None):
+    """One deblending pass over a field split into owner tiles, one rank per GPU (BASELINE config 4).
+
+    Every rank holds the field, deblends the sources whose centre lies in ITS tile (extract -> net), then the predicted
+    stamps whose 59x59 window reaches into another rank's tile are exchanged (``exchange_halo_stamps``: one
+    all_to_all_single over NCCL/NVLink) and each rank subtracts, in ascending global source index, every stamp that
+    touches its tile (deblend/field_deblender.py:46-97 restricted to the tile).  Returns
+    ``(residual_tile (r1-r0, c1-c0, C) CUDA tensor, (r0, r1, c0, c1), accepted source indices)``; the tiles of all ranks
+    together are bit-identical to the single-GPU residual field.  ``sample=False`` (z = loc) makes the pass
+    deterministic; sampling uses the stamp's global index as Philox offset only through ``seed``."""
+    from . import _fieldops
+
+    rank, world = _world(group)
+    field_dev = _fieldops.to_device_field(field_image)
+    F_, S = field_dev.shape[1], int(cutout_size)
+    centres = np.asarray(galaxy_distances_to_center, dtype=np.float64).reshape(-1, 2)
+    plan = _fieldops.plan_windows(centres, S, F_)
+    idx = np.nonzero(plan["ok"])[0]  # accepted sources, in detection order (the order contract)
+    off = _fieldops.subtract_offset(F_, S)
+    x0 = off + _fieldops.integer_positions(centres[idx, 0], np.zeros(len(idx)), "x positions")
+    y0 = off + _fieldops.integer_positions(centres[idx, 1], np.zeros(len(idx)), "y positions")
+    owner = assign_owners(np.trunc(centres[idx, 0]) + F_ // 2, np.trunc(centres[idx, 1]) + F_ // 2, F_, world)
+    touches = overlap_matrix(x0, y0, S, F_, world)
+    mine = np.nonzero(owner == rank)[0]  # positions in idx
+    sub = {k: plan[k][idx[mine]] for k in ("sx", "sy", "lx", "ly", "ok")}
+    cut, _ = _fieldops.extract(field_dev, sub, S, nb_of_bands, out_dtype=torch.float32)
+    if len(mine):
+        mean = net(cut, sample=sample, seed=seed).mean().tensor
+    else:
+        mean = torch.empty((0, S, S, nb_of_bands), device=field_dev.device, dtype=torch.float32)
+    stamps, ids = exchange_halo_stamps(mean.contiguous(), mine, owner, touches, group)
+    r0, r1, c0, c1 = tile_bounds(F_, world)[rank]
+    if len(ids):
+        res = _fieldops.window_axpy(field_dev, stamps.contiguous(), x0[ids], y0[ids], -1.0)
+    else:
+        res = field_dev.clone()
+    return res[0, r0:r1, c0:c1], (r0, r1, c0, c1), [int(i) for i in idx]

@@ -81,3 +81,21 @@ def test_iterative_deblending_on_device(wts):
     want = fo.residual_field(field, means, np.array(list(rec["galaxy_distances_to_center_x"])), np.array(list(rec["galaxy_distances_to_center_y"])))
     np.testing.assert_array_equal(res, want)
     net.close()
+
+
+def test_field_tiled_over_two_gpus_is_bit_identical():
+    """BASELINE config 4 protocol on real GPUs: owner tiles + one NCCL all_to_all of overlapping stamps (skipped on a
+    one-GPU box; the exchange logic itself is also covered on CPU by tests/test_parallel_gloo.py)."""
+    import json
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "field_tiled_nccl.py"), "1025", "300"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["tiles_bit_identical_to_single_gpu"] is True and line["n_gpus"] == 2
