@@ -54,6 +54,9 @@ static const LayerDesc kLayers[] = {
     {"dec_head", L_CONV, 1, 64, 32, 64, 12, 0, 21, -1, -1, 1},
 };
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+#ifndef DBV_CG8_FIRST
+#define DBV_CG8_FIRST 19  // first layer of the decoder tail that reads CG8 (19 = head only ... 17 = convT7, convT8, head)
+#endif
 constexpr int PH_SMEM_BUDGET = 232448 - 1024 - 512 - 2048;
 enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_T6 = 16, I_HEAD = 19 };
 
@@ -74,7 +77,7 @@ struct TcGeom {
   int CBK, NT, TW, TH, TB;
   int tc;  // 0: runs on the SIMT kernel even in tensor-core modes
 };
-static const TcGeom kTc[kNumLayers] = {
+static const TcGeom kTcBase[kNumLayers] = {
     {16, 32, 59, 2, 1, 1},   // enc_conv1: BN + 8-channel bf16 packing by a SIMT pre-kernel, then the no-swizzle halo kernel
     {32, 32, 30, 4, 1, 1},   // enc_conv2
     {32, 64, 30, 4, 1, 1},   // enc_conv3
@@ -96,6 +99,19 @@ static const TcGeom kTc[kNumLayers] = {
     {32, 32, 64, 2, 1, 1},   // dec_convT8
     {32, 16, 64, 2, 1, 1},   // dec_head
 };
+
+// geometry actually used: layers reading a channel-group-planar input take K = 16 chunks (two 8-channel groups per MMA)
+struct TcTable {
+  TcGeom g[kNumLayers];
+  TcTable() {
+    for (int i = 0; i < kNumLayers; ++i) {
+      g[i] = kTcBase[i];
+      if (i >= DBV_CG8_FIRST && i <= 19) g[i].CBK = 16;
+    }
+  }
+  const TcGeom& operator[](int i) const { return g[i]; }
+};
+static const TcTable kTc;
 
 struct LayerRt {
   // device weights
@@ -270,6 +286,9 @@ static inline float h162f(int f16, uint16_t u) {
   return __half2float(h);
 }
 
+// Layers that read a channel-group-planar (OUT_BF16_CG8) input: they exist only as resident-halo kernels.
+static bool consumes_cg8(int li) { return li >= DBV_CG8_FIRST && li <= I_HEAD; }
+
 // Storage of the activations ENTERING layer li (and the format of its weights) in the tensor-core modes.
 // DBV_PREC_MIXED: the four large-image decoder layers read single-plane fp16 activations with fp16 hi/lo weights.
 static bool mixed_tail(int precision, int li) { return precision == DBV_PREC_MIXED && li >= I_T6 && li <= I_HEAD; }
@@ -296,6 +315,7 @@ static void tc_out_layout(int li, int precision, OutSpec* o) {
     o->mode = OUT_BF16_PARITY;
     o->PH = o->PW = (L.Hout + 1) / 2;
   }
+  if (li + 1 < kNumLayers && consumes_cg8(li + 1)) o->mode = OUT_BF16_CG8;
   if (li == I_ENC_DENSE) { o->mode = OUT_F32_NHWC; o->planes = 1; }
   if (li == I_DENSE1) o->Cpad = 576;                    // K of dec_dense2 padded to 9 x 64
   if (li == I_DENSE2) { o->OH = o->OW = 4; o->Cout = o->Cpad = 256; }  // Reshape(4,4,256), model/model.py:119
@@ -360,7 +380,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   // ---- k-block table ------------------------------------------------------------------------------
   TcLayer& T = R.tc;
   memset(&T, 0, sizeof T);
-  if (x3 && in_planes < 2) {  // single-plane input (DBV_PREC_MIXED tail): only the resident-halo kernel runs this layer;
+  if ((x3 && in_planes < 2) || in.mode == OUT_BF16_CG8) {  // single-plane / channel-group-planar input: only the resident-halo kernel runs this layer;
     uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};  // it needs the packed weights' tensor map
     uint64_t bs[1] = {(uint64_t)G.CBK * 2};
     uint32_t bb[2] = {(uint32_t)G.CBK, (uint32_t)G.NT};
@@ -518,7 +538,10 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   const OutSpec& in = P.ospec;
   const bool x3 = prec_x3(c->precision);
   const bool c1 = (li == I_CONV1);  // no-swizzle mode: 16-byte pixel rows, K=16 = two adjacent pixels
-  const int ROWB = c1 ? 16 : G.CBK * 2;
+  const bool cg8 = in.mode == OUT_BF16_CG8;       // channel-group-planar input: 16-byte pixel rows, K = 16 = two group planes
+  const int ROWB = (c1 || cg8) ? 16 : G.CBK * 2;  // activation row pitch in shared memory
+  const int ROWB_W = c1 ? 32 : G.CBK * 2;         // bytes of one weight row
+  if (cg8 && (G.CBK != 16 || in.Cpad != L.Cin || L.Cin % 16 != 0)) return fail(DBV_ERR_STATE, "%s: channel-group-planar input needs K = 16 chunks", L.name);
   std::vector<Tap> taps = make_taps(L);
   if (c1) {  // per kernel row ky: pixel pairs (x-1, x) and (x+1, x+2); Tap.kx = pair index, dx = first pixel of the pair
     taps.clear();
@@ -533,20 +556,22 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   // the next row's slot 0, and the slot after the last row is zeroed slack.  conv1's pair trick (x+1, x+2) keeps W + 3.
   const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = c1 ? W + 3 : W + 1;
   const int n_wblk = (int)taps.size() * nchunk * parts_w;
-  const int w_bytes = ((n_wblk * G.NT * (c1 ? 32 : ROWB) + 1023) / 1024) * 1024;
+  const int w_bytes = ((n_wblk * G.NT * ROWB_W + 1023) / 1024) * 1024;
   // stride-2 Conv2D: the input is stored as 4 parity planes (OUT_BF16_PARITY); every (plane, hi/lo, chunk) is its own region
   const int npar = (in.mode == OUT_BF16_PARITY) ? 4 : 1;
-  const int n_regions = in.planes * nchunk * npar;
-  if (n_regions > 8 || bandR < 1 || bandR > H) return 0;
+  const int n_regions = in.planes * nchunk * npar * (cg8 ? 2 : 1);  // CG8: two 8-channel group planes per K = 16 chunk
+  if ((!cg8 && n_regions > 8) || bandR < 1 || bandR > H) return 0;
   const int ntiles = (bandR * WP + 127) / 128;
   if (U * G.NT * (x3 ? 2 : 1) > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
   if (bandR + 2 * pad > 256 || WP > 256) return 0;
-  const long long region = (((long long)(bandR + 2 * pad) * WP * ROWB + ROWB + 1023) / 1024) * 1024;  // >= one zeroed slack slot after the box
+  // >= one zeroed slack slot after the box; CG8: the regions of a buffer are ONE contiguous TMA box, the slack follows the buffer
+  const long long region = cg8 ? (long long)(bandR + 2 * pad) * WP * ROWB : (((long long)(bandR + 2 * pad) * WP * ROWB + ROWB + 1023) / 1024) * 1024;
+  const long long buf = cg8 ? ((n_regions * region + 16 + 1023) / 1024) * 1024 : n_regions * region;
   // layout: [halo ring][weights][barriers].  The last tile of a band over-reads < 131 garbage rows past its region: into the
   // next region, or (last region of the last buffer) into the weights — readable memory, results dropped by the epilogue.
   const int overread = 131 * ROWB;
   const int tail_pad = w_bytes >= overread ? 0 : ((overread - w_bytes + 1023) / 1024) * 1024;
-  const long long smem = 1024 + w_bytes + (long long)nbuf * n_regions * region + tail_pad + 2048;  // + barriers
+  const long long smem = 1024 + w_bytes + (long long)nbuf * buf + tail_pad + 2048;  // + barriers
   if (smem > HALO_MAX_SMEM) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
@@ -562,8 +587,9 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
           for (int k = 0; k < (c1 ? 1 : G.CBK / 16); ++k) {
             if (nkb >= TC_MAX_KB) return 0;
             const int a_lo = (pr == 1);
-            const long long a_off = (long long)((a_lo * nchunk + ch) * npar + taps[ti].plane) * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
-            const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * (c1 ? 32 : ROWB) + 32 * k;
+            const long long areg = cg8 ? (a_lo * nchunk + ch) * 2 : (a_lo * nchunk + ch) * npar + taps[ti].plane;
+            const long long a_off = areg * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
+            const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * ROWB_W + 32 * k;
             if ((a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return 0;
             T.mma[nkb].a = (uint32_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
             T.mma[nkb].b = (uint32_t)(b_off >> 4) | ((x3 && pr == 0) ? 0x80000000u : 0u);
@@ -579,6 +605,8 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   for (int i = 0; i < 64; ++i) T.bias_c[i] = i < L.Cout ? R.bias_host[i] : 0.f;
   T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
   T.ntiles = ntiles;
+  T.magic_wp = (uint32_t)(((1ull << 32) + WP - 1) / WP);
+  T.magic_nt = (uint32_t)(((1ull << 32) + ntiles - 1) / ntiles);
   T.n_regions = n_regions;
   for (int r = 0; r < n_regions; ++r) {  // r = ((plane_hi_lo * nchunk + chunk) * npar + parity plane)
     const int pc = r / npar;
@@ -588,6 +616,8 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   T.w_img = c1 ? (const void*)c->conv1_wimg : nullptr;
   T.a_box_bytes = (bandR + 2 * pad) * WP * ROWB;
   T.region_bytes = (int)region;
+  T.buf_bytes = (int)buf;
+  T.cg8 = cg8 ? 1 : 0;
   T.n_wblk = n_wblk;
   T.w_rows_per_blk = G.NT;  // conv layers are not N-tiled: Ntot == NT
   T.w_bytes = w_bytes;
@@ -599,11 +629,21 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   T.smem_bytes = (int)smem;
   T.bands_per_img = (H + bandR - 1) / bandR;
   const uint64_t Ct = (uint64_t)in.planes * in.Cpad;
-  const uint64_t Wd = npar == 4 ? in.PW : in.OW, Hd = npar == 4 ? in.PH : in.OH;
-  uint64_t dims[5] = {Ct, Wd, Hd, (uint64_t)npar, (uint64_t)c->chunk};
-  uint64_t str[4] = {Ct * 2, Ct * 2 * Wd, Ct * 2 * Wd * Hd, Ct * 2 * Wd * Hd * npar};
-  uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
-  int r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, c1 ? 0 : ROWB);
+  int r;
+  if (cg8) {  // u64 elements: (2W, H, planes * Cin/8, B, 1); ONE box = whole rows of 16-byte pixels of every channel-group plane
+    const uint64_t ng = Ct / 8;
+    uint64_t dims[5] = {2ull * in.OW, (uint64_t)in.OH, ng, (uint64_t)c->chunk, 1};
+    uint64_t str[4] = {16ull * in.OW, 16ull * in.OW * in.OH, 16ull * in.OW * in.OH * ng, 16ull * in.OW * in.OH * ng * c->chunk};
+    uint32_t bx[5] = {(uint32_t)(2 * WP), (uint32_t)(bandR + 2 * pad), (uint32_t)ng, 1u, 1u};
+    if (2 * WP > 256 || ng > 256) return 0;
+    r = encode_tmap(&T.tmA, P.out, 5, dims, str, bx, 0, 8);
+  } else {
+    const uint64_t Wd = npar == 4 ? in.PW : in.OW, Hd = npar == 4 ? in.PH : in.OH;
+    uint64_t dims[5] = {Ct, Wd, Hd, (uint64_t)npar, (uint64_t)c->chunk};
+    uint64_t str[4] = {Ct * 2, Ct * 2 * Wd, Ct * 2 * Wd * Hd, Ct * 2 * Wd * Hd * npar};
+    uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
+    r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, c1 ? 0 : ROWB);
+  }
   if (r) return r;
   if (!c1) T.tmB = R.tc.tmB;
   return 1;
@@ -618,11 +658,11 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   if (getenv("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
-  const bool must = li == I_CONV1 || mixed_tail(c->precision, li);  // these layers have no other tensor-core kernel
+  const bool must = li == I_CONV1 || mixed_tail(c->precision, li) || consumes_cg8(li);  // these layers have no other tensor-core kernel
   if ((!R.has_tc && !must) || L.kind == L_DENSE) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
   const OutSpec& in = ((li == I_CONV1) ? c->im2col : c->rt[li - 1]).ospec;
-  if (in.mode != OUT_BF16_NHWC && in.mode != OUT_BF16_PARITY) return DBV_OK;
+  if (in.mode != OUT_BF16_NHWC && in.mode != OUT_BF16_PARITY && in.mode != OUT_BF16_CG8) return DBV_OK;
   if ((L.kind == L_CONV && L.stride == 2) != (in.mode == OUT_BF16_PARITY)) return DBV_OK;
   // resident weights must leave room for a useful halo band (else the streaming kernels are the better plan)
   if (in.mode == OUT_BF16_PARITY && (long long)9 * L.Cin * G.NT * 2 * (c->precision == DBV_PREC_BF16 ? 1 : 2) > 64 * 1024) return DBV_OK;

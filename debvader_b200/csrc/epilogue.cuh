@@ -9,6 +9,13 @@
 //                    TF "SAME" padding; rows/cols a plane lacks stay zero from allocation)
 //   OUT_HEAD         decoder head (model/model.py:137-159): ReLU, crop [2:61]^2 of the 64x64 map,
 //                    channels 0-5 -> mean, 6-11 -> 1e-4 + v -> stddev, both fp32 (B,59,59,6)
+//   OUT_BF16_CG8     16-bit [B][planes][Cpad/8][OH][OW][8]: channel groups of 8 are PLANAR (the consumer is a resident-halo
+//                    layer).  One pixel of one group is 16 bytes and eight consecutive pixels are one 128-byte tcgen05 core
+//                    matrix, so (a) the consumer loads whole image rows of all groups with ONE un-swizzled TMA box and reads
+//                    a K=16 operand as two groups one region apart (descriptor LBO), and (b) in the producer's epilogue,
+//                    where lane = pixel, a warp's 128-bit store covers 512 CONTIGUOUS bytes: 4 L1 wavefronts instead of the
+//                    32 of a pixel-major layout (measured: the pixel-major stores saturate the L1 data pipe, which is shared
+//                    with the MMA's operand fetch from shared memory — tools/ + DESIGN.md section 4).
 // planes = 2 stores a hi/lo bf16 split (v ~= hi + lo) at channel offsets [0,Cpad) and [Cpad,2Cpad).
 #pragma once
 #include "common.cuh"
@@ -16,7 +23,7 @@
 
 namespace dbv {
 
-enum OutMode { OUT_F32_NHWC = 0, OUT_BF16_NHWC = 1, OUT_BF16_PARITY = 2, OUT_HEAD = 3 };
+enum OutMode { OUT_F32_NHWC = 0, OUT_BF16_NHWC = 1, OUT_BF16_PARITY = 2, OUT_HEAD = 3, OUT_BF16_CG8 = 4 };
 
 struct OutSpec {
   void* out;
@@ -59,6 +66,8 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
 // element offset of channel 0 of pixel (b,y,x); OUT_HEAD handled by the callers
 __device__ __forceinline__ long long pixel_offset(const OutSpec& o, long long b, int y, int x) {
   const int cs = o.planes * o.Cpad;
+  if (o.mode == OUT_BF16_CG8)  // offset of (plane 0, group 0); + (plane * Cpad/8 + group) * OH*OW*8 for the others
+    return b * cs * o.OH * o.OW + ((long long)y * o.OW + x) * 8;
   if (o.mode == OUT_BF16_PARITY) {
     const long long plane = b * 4 + ((y & 1) * 2 + (x & 1));
     return ((plane * o.PH + (y >> 1)) * o.PW + (x >> 1)) * cs;
@@ -245,6 +254,32 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
 #pragma unroll
       for (int j = 0; j < NV; ++j)
         if (c + j < o.Cout) p[j] = v[j];
+    }
+    return;
+  }
+  if (o.mode == OUT_BF16_CG8) {
+    if constexpr (NV % 8 == 0) {
+      const long long gstride = (long long)o.OH * o.OW * 8;  // elements between channel groups (and, x Cpad/8, between planes)
+      uint16_t* p = reinterpret_cast<uint16_t*>(o.out) + off + (long long)(c >> 3) * gstride;
+      const long long pstride = (long long)(o.Cpad >> 3) * gstride;
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        if (c + j >= o.Cpad) break;
+        uint4 q, l;
+        if (o.planes == 2) {
+          split16x2(o.f16, v[j], v[j + 1], q.x, l.x);
+          split16x2(o.f16, v[j + 2], v[j + 3], q.y, l.y);
+          split16x2(o.f16, v[j + 4], v[j + 5], q.z, l.z);
+          split16x2(o.f16, v[j + 6], v[j + 7], q.w, l.w);
+        } else {
+          q.x = pack16x2(o.f16, v[j], v[j + 1]);
+          q.y = pack16x2(o.f16, v[j + 2], v[j + 3]);
+          q.z = pack16x2(o.f16, v[j + 4], v[j + 5]);
+          q.w = pack16x2(o.f16, v[j + 6], v[j + 7]);
+        }
+        *reinterpret_cast<uint4*>(p + (long long)(j >> 3) * gstride) = q;
+        if (o.planes == 2) *reinterpret_cast<uint4*>(p + pstride + (long long)(j >> 3) * gstride) = l;
+      }
     }
     return;
   }

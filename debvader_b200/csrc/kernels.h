@@ -126,10 +126,14 @@ struct HaloLayer {
   int n_regions;     // planes * channel chunks
   int region_coff[8];  // TMA coordinate 0 (first channel) of each region
   int region_c3[8];    // TMA coordinate 3: parity plane of a stride-2 Conv2D's input, else 0
-  int region_bytes;  // (R+2) * WP * ROWB rounded up to 1024
+  int region_bytes;  // (R+2) * WP * ROWB rounded up to 1024 (CG8: exact, the regions of a buffer are one contiguous TMA box)
+  int buf_bytes;     // stride between halo buffers: n_regions * region_bytes (CG8: rounded up, with >= 16 zeroed bytes of slack)
   int a_box_bytes;   // (R+2) * WP * ROWB
   int n_wblk, w_rows_per_blk, w_bytes;
   const void* w_img;  // no-swizzle mode (conv1): the resident weights as one ready-made shared-memory image (bulk copy)
+  uint32_t magic_wp, magic_nt;  // ceil(2^32 / WP), ceil(2^32 / ntiles): n / d == __umulhi(n, magic) for n, d < 2^16 (epilogue coordinates)
+  int cg8;           // the input is OUT_BF16_CG8: ONE un-swizzled TMA box (u64 tensor map (2W, H, planes*Cin/8, B, 1)) fills all
+                     // group-plane regions; the A operand is un-swizzled with LBO = region_bytes (K=16 = two groups)
   int nbuf;          // halo buffers in the ring (1 or 2)
   int U;             // sub-units (tile x class) per accumulator slot / commit: 1, 2 or 4 with U * accumulator width <= 256 columns
   int wide;          // bf16x3: accumulator tile = [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo] (2*NT columns, summed by the epilogue);
@@ -146,6 +150,6 @@ bool halo_layer_supported(int CBK, int NT);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, int swizzle_bytes);
+                const uint32_t* box, int swizzle_bytes, int elem_bytes = 2);
 
 }  // namespace dbv

@@ -148,6 +148,21 @@ __global__ void __launch_bounds__(256) act_to_f32_kernel(OutSpec o, long long B,
   const long long pix = gid / o.Cout;
   const int x = (int)(pix % o.OW), y = (int)((pix / o.OW) % o.OH);
   const long long b = pix / ((long long)o.OW * o.OH);
+  if (o.mode == OUT_BF16_CG8) {
+    const long long gstride = (long long)o.OH * o.OW * 8;
+    const long long e = pixel_offset(o, b, y, x) + (long long)(c >> 3) * gstride + (c & 7);
+    const long long pl = (long long)(o.Cpad >> 3) * gstride;
+    float v;
+    if (o.f16) {
+      const __half* p = reinterpret_cast<const __half*>(o.out);
+      v = __half2float(p[e]) + (o.planes == 2 ? __half2float(p[e + pl]) : 0.f);
+    } else {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(o.out);
+      v = __bfloat162float(p[e]) + (o.planes == 2 ? __bfloat162float(p[e + pl]) : 0.f);
+    }
+    out[gid] = v;
+    return;
+  }
   const long long off = pixel_offset(o, b, y, x) + c;
   if (o.mode == OUT_F32_NHWC) {
     out[gid] = reinterpret_cast<const float*>(o.out)[off];

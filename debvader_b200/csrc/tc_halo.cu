@@ -41,13 +41,15 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 // commits it once; the epilogue groups split the unit's sub-units; the MMA warp runs one unit ahead of the epilogue.
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
-  constexpr int ROWB = NOSWZ ? 16 : CBK * 2;
+  constexpr bool CG8 = !NOSWZ && CBK == 16;             // channel-group-planar input: 16-byte pixel rows, K=16 = two groups one region apart
+  constexpr int ROWB = (NOSWZ || CG8) ? 16 : CBK * 2;   // activation row pitch in shared memory
+  constexpr int ROWB_W = NOSWZ ? 16 : CBK * 2;          // weight rows (K-major, swizzled; conv1: host-packed core matrices)
   const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t IDESC2 = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                              // nbuf x n_regions x region_bytes
-  const uint32_t sW = sA + L.nbuf * L.n_regions * L.region_bytes;  // resident weights: n_wblk blocks of NT x ROWB
+  const uint32_t sW = sA + L.nbuf * L.buf_bytes;  // resident weights: n_wblk blocks of NT x ROWB
   const uint32_t sBar = sW + L.w_bytes + L.tail_pad;
   const uint32_t bar_w = sBar, bar_afull = sBar + 8, bar_aempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 104;
   const uint32_t s_tmem = sBar + 168;
@@ -83,7 +85,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   // neighbour of its last pixel and must read as zero padding (TMA never writes there)
   for (int r = 0; r < L.nbuf * L.n_regions; ++r)
     for (int i = L.a_box_bytes + 16 * (int)threadIdx.x; i < L.region_bytes; i += 16 * HALO_THREADS)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + r * L.region_bytes + i), "r"(0) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + (r / L.n_regions) * L.buf_bytes + (r % L.n_regions) * L.region_bytes + i), "r"(0) : "memory");
+  for (int r = 0; r < L.nbuf; ++r)  // ... and the slack after each buffer (CG8: the regions themselves are packed)
+    for (int i = L.n_regions * L.region_bytes + 16 * (int)threadIdx.x; i < L.buf_bytes; i += 16 * HALO_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + r * L.buf_bytes + i), "r"(0) : "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
@@ -101,8 +106,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         mbar_expect_tx(bar_w, (uint32_t)L.w_bytes);
         bulk_load(sW, L.w_img, (uint32_t)L.w_bytes, bar_w);
       } else {
-        mbar_expect_tx(bar_w, (uint32_t)(L.n_wblk * NT * ROWB));
-        for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB), &L.tmB, bar_w, 0, blk * L.w_rows_per_blk);
+        mbar_expect_tx(bar_w, (uint32_t)(L.n_wblk * NT * ROWB_W));
+        for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB_W), &L.tmB, bar_w, 0, blk * L.w_rows_per_blk);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -110,8 +115,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       for (long long g = g0; g < g1; ++g) {
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(L.n_regions * L.a_box_bytes));
-        for (int r = 0; r < L.n_regions; ++r)
-          tma_load_5d(sA + (stage * L.n_regions + r) * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, L.region_c3[r], b);
+        if constexpr (CG8) {  // one box: all channel-group planes, whole rows of 16-byte pixels (x in u64 units)
+          tma_load_5d(sA + stage * L.buf_bytes, &L.tmA, bar_afull + 8 * stage, -2 * L.pad, y0 - L.pad, 0, b, 0);
+        } else {
+          for (int r = 0; r < L.n_regions; ++r)
+            tma_load_5d(sA + stage * L.buf_bytes + r * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, L.region_c3[r], b);
+        }
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
         if (++b == (int)L.B) { b = 0; y0 += L.R; }
       }
@@ -124,16 +133,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       uint32_t u = 0;  // running unit counter (slot = u % nslot)
       // descriptor words: swizzled K-major rows, or (NOSWZ) interleaved 8x16-byte core matrices with
       // A: SBO 128 B (8 pixels), LBO 16 B (next pixel);  B: SBO 256 B, LBO 128 B (host-packed image)
-      constexpr uint32_t HI = NOSWZ ? ((128u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
-      constexpr uint32_t HIB = NOSWZ ? ((256u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
+      constexpr uint32_t HI = (NOSWZ || CG8) ? ((128u >> 4) | (1u << 14)) : smem_desc_hi<ROWB>();
+      constexpr uint32_t HIB = NOSWZ ? ((256u >> 4) | (1u << 14)) : smem_desc_hi<ROWB_W>();
       constexpr uint32_t LOB = NOSWZ ? ((128u >> 4) << 16) : kSmemDescLoConst;
+      // A low word: LBO = distance (>>4) between the two K-halves of a K=16 operand: 16 B = the next pixel (conv1), one region =
+      // the next channel group (CG8); unused (1) for swizzled rows
+      const uint32_t LOA = CG8 ? ((uint32_t)(L.region_bytes >> 4) << 16) : kSmemDescLoConst;
       constexpr uint32_t MSTEP = (128 * ROWB) >> 4;
       const uint32_t w16 = LOB | (sW >> 4);
       const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;
       for (long long g = g0; g < g1; ++g) {
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t a16 = kSmemDescLoConst | ((sA + stage * L.n_regions * L.region_bytes) >> 4);
+        const uint32_t a16 = LOA | ((sA + stage * L.buf_bytes) >> 4);
         for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
           const uint32_t slot = u & (nslot - 1);
           mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
@@ -166,6 +178,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
+    const bool has_alpha = L.o.alpha != nullptr && !(L.dbg_skip & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
+    const float4* alpha4 = reinterpret_cast<const float4*>(L.o.alpha);
+    const uint32_t npix = (uint32_t)(L.o.OH * L.o.OW);
     uint32_t u = 0;
     int b = b_first, y0 = (int)yb0 * L.R;
     for (long long g = g0; g < g1; ++g) {
@@ -177,16 +192,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
 #pragma unroll 1
         for (int item = grp; item < nitems; item += HALO_EPI_GROUPS) {
           const int sidx = s0 + item / NCHK, q = item % NCHK;
-          const int c = sidx / L.ntiles, m = sidx - c * L.ntiles;
+          // (class, tile) of the sub-unit and this thread's output pixel: divisions by multiply-high with host-made magics
+          const int c = L.ntiles == 1 ? sidx : (int)__umulhi((uint32_t)sidx, L.magic_nt), m = sidx - c * L.ntiles;  // (2^32 / 1 does not fit)
           const int p = 128 * m + row;
-          const int ly = p / L.WP, sx = p - ly * L.WP, sy = y0 + ly;
+          const int ly = (int)__umulhi((uint32_t)p, L.magic_wp), sx = p - ly * L.WP, sy = y0 + ly;
           const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
           const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
           const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
           const int c0 = q * NV;
-          ActRegs<NV> ra;
-          ra.fast = false;
-          if (!(L.dbg_skip & 4)) act_prefetch<NV>(L.o, ok, oy, ox, c0, 0, ra);  // requested before the accumulator wait
+          // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
+          // requested before the accumulator wait
+          float4 al[NV / 4];
+          if (has_alpha && ok) {
+            const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
+#pragma unroll
+            for (int j = 0; j < NV / 4; ++j) al[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
+          }
           if (!waited) {
             mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
             tc_fence_after();
@@ -208,8 +229,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
           if (ok) {
             if (!(L.dbg_skip & 4)) {
 #pragma unroll
-              for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];
-              act_apply<NV, true>(L.o, oy, ox, c0, 0, ra, v);
+              for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];  // bias from the constant bank
+              if (has_alpha) {
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                  v[4 * j + 0] = prelu_f(v[4 * j + 0], al[j].x);
+                  v[4 * j + 1] = prelu_f(v[4 * j + 1], al[j].y);
+                  v[4 * j + 2] = prelu_f(v[4 * j + 2], al[j].z);
+                  v[4 * j + 3] = prelu_f(v[4 * j + 3], al[j].w);
+                }
+              } else if (L.o.relu) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
             }
             if (!(L.dbg_skip & 8)) store_act<NV>(L.o, b, oy, ox, c0, v);
             else if (v[0] == 123.456f) store_act<NV>(L.o, b, oy, ox, c0, v);  // keep the loads / math alive
@@ -251,7 +283,7 @@ static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
 }
 
 bool halo_layer_supported(int CBK, int NT) {
-  if (CBK == 16) return NT == 32;  // encoder conv1, no-swizzle mode
+  if (CBK == 16) return NT == 16 || NT == 32 || NT == 64;  // conv1 (no-swizzle pair trick, NT = 32) / channel-group-planar inputs
   if (CBK == 32) return NT == 16 || NT == 32 || NT == 64;
   if (CBK == 64) return NT == 32 || NT == 64 || NT == 128;
   return false;
@@ -260,6 +292,11 @@ bool halo_layer_supported(int CBK, int NT) {
 int launch_halo_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
 #define DBV_HALO_CASE(cb, nt) \
   if (CBK == cb && NT == nt) return launch_halo_one<cb, nt>(L, max_ctas, st);
+  if (CBK == 16 && L.cg8) {
+    if (NT == 16) return launch_halo_one<16, 16>(L, max_ctas, st);
+    if (NT == 32) return launch_halo_one<16, 32>(L, max_ctas, st);
+    if (NT == 64) return launch_halo_one<16, 64>(L, max_ctas, st);
+  }
   if (CBK == 16 && NT == 32) return launch_halo_one<16, 32, true>(L, max_ctas, st);
   DBV_HALO_CASE(32, 16)
   DBV_HALO_CASE(32, 32)
