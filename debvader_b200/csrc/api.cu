@@ -54,9 +54,11 @@ static const LayerDesc kLayers[] = {
     {"dec_head", L_CONV, 1, 64, 32, 64, 12, 0, 21, -1, -1, 1},
 };
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
-#ifndef DBV_CG8_FIRST
-#define DBV_CG8_FIRST 19  // first layer of the decoder tail that reads CG8 (19 = head only ... 17 = convT7, convT8, head)
-#endif
+// first layer of the decoder tail that reads a channel-group-planar input (19 = head only ... 17 = convT7, convT8, head; 20 = none)
+static int cg8_first() {
+  static const int v = getenv("DBV_CG8_FIRST") ? atoi(getenv("DBV_CG8_FIRST")) : 20;
+  return v;
+}
 constexpr int PH_SMEM_BUDGET = 232448 - 1024 - 512 - 2048;
 enum { I_CONV1 = 0, I_CONV8 = 7, I_ENC_DENSE = 8, I_DENSE1 = 9, I_DENSE2 = 10, I_T1 = 11, I_T6 = 16, I_HEAD = 19 };
 
@@ -106,7 +108,7 @@ struct TcTable {
   TcTable() {
     for (int i = 0; i < kNumLayers; ++i) {
       g[i] = kTcBase[i];
-      if (i >= DBV_CG8_FIRST && i <= 19) g[i].CBK = 16;
+      if (i >= cg8_first() && i <= 19) g[i].CBK = 16;
     }
   }
   const TcGeom& operator[](int i) const { return g[i]; }
@@ -287,7 +289,7 @@ static inline float h162f(int f16, uint16_t u) {
 }
 
 // Layers that read a channel-group-planar (OUT_BF16_CG8) input: they exist only as resident-halo kernels.
-static bool consumes_cg8(int li) { return li >= DBV_CG8_FIRST && li <= I_HEAD; }
+static bool consumes_cg8(int li) { return li >= cg8_first() && li <= I_HEAD; }
 
 // Storage of the activations ENTERING layer li (and the format of its weights) in the tensor-core modes.
 // DBV_PREC_MIXED: the four large-image decoder layers read single-plane fp16 activations with fp16 hi/lo weights.

@@ -21,7 +21,7 @@
 namespace dbv {
 
 #ifndef DBV_HALO_EPI_GROUPS
-#define DBV_HALO_EPI_GROUPS 4
+#define DBV_HALO_EPI_GROUPS 2
 #endif
 constexpr int HALO_EPI_GROUPS = DBV_HALO_EPI_GROUPS;  // epilogue groups of 4 warps (one warp per TMEM lane quadrant); the epilogue is latency bound
 constexpr int HALO_THREADS = 64 + HALO_EPI_GROUPS * 128;  // TMA warp, MMA warp, epilogue groups
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     // takes every G-th item (sub-unit x NV-channel chunk) of it; all 4*G warps release the slot.
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    constexpr int NV = (HALO_EPI_GROUPS > 2 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
+    constexpr int NV = (HALO_EPI_GROUPS > 3 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them

@@ -280,3 +280,31 @@ def test_probe_descriptor_row_shift(which):
             res[(shift, mode)] = e / float(want.abs().max())
     print(f"ROWSHIFT CBK={CBK}: " + " ".join(f"s{s}m{m}={'OK' if v < 1e-4 else 'BAD(%.2g)' % v}" for (s, m), v in res.items()))
     assert res[(0, 0)] < 1e-4 and res[(8, 0)] < 1e-4
+
+
+def test_channel_group_planar_tail_matches(wts, data):
+    """The optional channel-group-planar (CG8) layout of the decoder tail (env DBV_CG8_FIRST; measured neutral, off by
+    default) must give the same numbers as the default pixel-major layout: run it in a subprocess (the switch is read once)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import weights as ow\n"
+        "from debvader_b200.model.model import load_deblender\n"
+        "w = ow.make_random_weights(seed=1234); x = ow.synthetic_stamps(40, seed=11)\n"
+        "net = load_deblender('dc2', (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights=w, precision='mixed')\n"
+        "d = net(x, sample=False); np.save(sys.argv[1], d.mean().numpy())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+
+    outs = []
+    for first in ("20", "18"):
+        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
+            path = f.name
+        r = subprocess.run([sys.executable, "-c", code, path], env={**os.environ, "DBV_CG8_FIRST": first}, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+        os.unlink(path)
+    np.testing.assert_array_equal(outs[0], outs[1])
