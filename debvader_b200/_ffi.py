@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdebvader_b200.so")
+LIB_PATH = os.environ.get("DEBVADER_B200_LIB") or os.path.join(_HERE, "libdebvader_b200.so")  # env override: A/B builds of the same source
 
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4}
 F32, F64 = 0, 1

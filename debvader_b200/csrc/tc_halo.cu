@@ -17,6 +17,7 @@
 //   warps 2-9 epilogue, two groups of 4 (shared with tc_conv.cu: bias, PReLU(h,w,c), ReLU/crop/split, bf16 hi/lo)
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <type_traits>
 
 namespace dbv {
 
@@ -181,82 +182,100 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     const bool has_alpha = L.o.alpha != nullptr && !(L.dbg_skip & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
     const float4* alpha4 = reinterpret_cast<const float4*>(L.o.alpha);
     const uint32_t npix = (uint32_t)(L.o.OH * L.o.OW);
-    uint32_t u = 0;
-    int b = b_first, y0 = (int)yb0 * L.R;
-    for (long long g = g0; g < g1; ++g) {
-      for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
-        const uint32_t slot = u & (nslot - 1);
-        const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
-        bool waited = false;
-        const int nitems = (s1 - s0) * NCHK;  // items of this unit: (sub-unit, NV-channel chunk); group g takes items g, g + G, ...
-#pragma unroll 1
-        for (int item = grp; item < nitems; item += HALO_EPI_GROUPS) {
-          const int sidx = s0 + item / NCHK, q = item % NCHK;
-          // (class, tile) of the sub-unit and this thread's output pixel: divisions by multiply-high with host-made magics
-          const int c = L.ntiles == 1 ? sidx : (int)__umulhi((uint32_t)sidx, L.magic_nt), m = sidx - c * L.ntiles;  // (2^32 / 1 does not fit)
-          const int p = 128 * m + row;
-          const int ly = (int)__umulhi((uint32_t)p, L.magic_wp), sx = p - ly * L.WP, sy = y0 + ly;
-          const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
-          const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
-          const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
-          const int c0 = q * NV;
-          // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
-          // requested before the accumulator wait
-          float4 al[NV / 4];
-          if (has_alpha && ok) {
-            const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
-#pragma unroll
-            for (int j = 0; j < NV / 4; ++j) al[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
+    // The output layout (mode / planes / 16-bit format) is constant for a launch: the loops are instantiated once per
+    // layout actually used, with those OutSpec fields as compile-time constants, so that store_act's dispatch folds away
+    // (the epilogue is instruction-issue bound: ~250 instructions per 32-channel item).
+    auto run = [&](auto MODE, auto PLANES, auto F16) {
+      OutSpec o = L.o;
+      if constexpr (decltype(MODE)::value >= 0) {
+        o.mode = decltype(MODE)::value;
+        o.planes = decltype(PLANES)::value;
+        o.f16 = decltype(F16)::value;
+      }
+      uint32_t u = 0;
+      int b = b_first, y0 = (int)yb0 * L.R;
+      for (long long g = g0; g < g1; ++g) {
+        for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
+          const uint32_t slot = u & (nslot - 1);
+          const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
+          bool waited = false;
+          const int nitems = (s1 - s0) * NCHK;  // items of this unit: (sub-unit, NV-channel chunk); group g takes items g, g + G, ...
+  #pragma unroll 1
+          for (int item = grp; item < nitems; item += HALO_EPI_GROUPS) {
+            const int sidx = s0 + item / NCHK, q = item % NCHK;
+            // (class, tile) of the sub-unit and this thread's output pixel: divisions by multiply-high with host-made magics
+            const int c = L.ntiles == 1 ? sidx : (int)__umulhi((uint32_t)sidx, L.magic_nt), m = sidx - c * L.ntiles;  // (2^32 / 1 does not fit)
+            const int p = 128 * m + row;
+            const int ly = (int)__umulhi((uint32_t)p, L.magic_wp), sx = p - ly * L.WP, sy = y0 + ly;
+            const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
+            const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
+            const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
+            const int c0 = q * NV;
+            // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
+            // requested before the accumulator wait
+            float4 al[NV / 4];
+            if (has_alpha && ok) {
+              const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
+  #pragma unroll
+              for (int j = 0; j < NV / 4; ++j) al[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
+            }
+            if (!waited) {
+              mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+              tc_fence_after();
+              waited = true;
+            }
+            float v[NV];
+            if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the sub-unit's columns
+              float w[NV];
+              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+              tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
+              tmem_ld_wait<NV>(v);
+              tmem_ld_wait<NV>(w);
+  #pragma unroll
+              for (int j = 0; j < NV; ++j) v[j] += w[j];
+            } else {
+              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+              tmem_ld_wait<NV>(v);
+            }
+            if (ok) {
+              if (!(L.dbg_skip & 4)) {
+  #pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];  // bias from the constant bank
+                if (has_alpha) {
+  #pragma unroll
+                  for (int j = 0; j < NV / 4; ++j) {
+                    v[4 * j + 0] = prelu_f(v[4 * j + 0], al[j].x);
+                    v[4 * j + 1] = prelu_f(v[4 * j + 1], al[j].y);
+                    v[4 * j + 2] = prelu_f(v[4 * j + 2], al[j].z);
+                    v[4 * j + 3] = prelu_f(v[4 * j + 3], al[j].w);
+                  }
+                } else if (L.o.relu) {
+  #pragma unroll
+                  for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+              }
+              if (!(L.dbg_skip & 8)) store_act<NV>(o, b, oy, ox, c0, v);
+              else if (v[0] == 123.456f) store_act<NV>(o, b, oy, ox, c0, v);  // keep the loads / math alive
+            }
           }
-          if (!waited) {
+          if (!waited) {  // a group without a sub-unit in this unit still takes part in the hand-over, in phase order
             mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
             tc_fence_after();
-            waited = true;
           }
-          float v[NV];
-          if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the sub-unit's columns
-            float w[NV];
-            tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-            tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
-            tmem_ld_wait<NV>(v);
-            tmem_ld_wait<NV>(w);
-#pragma unroll
-            for (int j = 0; j < NV; ++j) v[j] += w[j];
-          } else {
-            tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-            tmem_ld_wait<NV>(v);
-          }
-          if (ok) {
-            if (!(L.dbg_skip & 4)) {
-#pragma unroll
-              for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];  // bias from the constant bank
-              if (has_alpha) {
-#pragma unroll
-                for (int j = 0; j < NV / 4; ++j) {
-                  v[4 * j + 0] = prelu_f(v[4 * j + 0], al[j].x);
-                  v[4 * j + 1] = prelu_f(v[4 * j + 1], al[j].y);
-                  v[4 * j + 2] = prelu_f(v[4 * j + 2], al[j].z);
-                  v[4 * j + 3] = prelu_f(v[4 * j + 3], al[j].w);
-                }
-              } else if (L.o.relu) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-            }
-            if (!(L.dbg_skip & 8)) store_act<NV>(L.o, b, oy, ox, c0, v);
-            else if (v[0] == 123.456f) store_act<NV>(L.o, b, oy, ox, c0, v);  // keep the loads / math alive
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
         }
-        if (!waited) {  // a group without a sub-unit in this unit still takes part in the hand-over, in phase order
-          mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
-          tc_fence_after();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+        if (++b == (int)L.B) { b = 0; y0 += L.R; }
       }
-      if (++b == (int)L.B) { b = 0; y0 += L.R; }
-    }
+    };
+    using std::integral_constant;
+    const int om = L.o.mode, op = L.o.planes, of = L.o.f16;
+    if (om == OUT_BF16_NHWC && op == 2 && of == 0) run(integral_constant<int, OUT_BF16_NHWC>{}, integral_constant<int, 2>{}, integral_constant<int, 0>{});
+    else if (om == OUT_BF16_NHWC && op == 1 && of == 1) run(integral_constant<int, OUT_BF16_NHWC>{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
+    else if (om == OUT_BF16_PARITY && op == 2 && of == 0) run(integral_constant<int, OUT_BF16_PARITY>{}, integral_constant<int, 2>{}, integral_constant<int, 0>{});
+    else if (om == OUT_HEAD) run(integral_constant<int, OUT_HEAD>{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
+    else run(integral_constant<int, -1>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});  // any other layout: runtime dispatch
   }
   tc_fence_before();
   __syncthreads();
