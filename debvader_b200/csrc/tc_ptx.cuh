@@ -192,6 +192,13 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 constexpr uint32_t kSmemDescLoConst = 1u << 16;
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
+// packed fp32 add (sm_100 FADD2): (a0, a1) += (b0, b1) in one instruction — the epilogues are instruction-issue bound
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; add.rn.f32x2 ra, ra, rb; mov.b64 {%0, %1}, ra; }"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
 // tcgen05 instruction-descriptor A/B format bits ([7,10) and [10,13)): 0 = F16, 1 = BF16
 __device__ __forceinline__ uint32_t idesc_ab_fmt(int f16) { return f16 ? 0u : ((1u << 7) | (1u << 10)); }
 
