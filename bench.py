@@ -58,7 +58,12 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The sampler is started before the warm-up steps (nvidia-smi needs ~0.2 s to start) and every sample carries its wall-clock
+    time; stop(t0, t1) keeps the samples taken inside the timed region [t0, t1].  A short timed region (10 steps of ~9 ms) can
+    fall between two samples: the caller then keeps the SAME step running untimed for a moment (t1 is extended) so that the
+    clocks are still read under exactly this load, and the window is named in the result."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -66,6 +71,39 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        # NVML (what nvidia-smi reads) polled from a thread every ~4 ms when the binding is importable: a 10-step timed region
+        # of ~90 ms then holds ~20 samples; else an `nvidia-smi -lms` child as in the profiling recipe
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._stop = False
+            R = pynvml
+            bits = [("hw_slowdown", R.nvmlClocksEventReasonHwSlowdown if hasattr(R, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                    ("hw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                    ("sw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                    ("sw_power_cap", getattr(R, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+            get_reasons = getattr(R, "nvmlDeviceGetCurrentClocksEventReasons", None) or R.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = R.nvmlDeviceGetMaxClockInfo(h, R.NVML_CLOCK_SM)
+
+            def poll():
+                while not self._stop:
+                    try:
+                        m = get_reasons(h)
+                        row = [str(R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM)), str(mx), str(R.nvmlDeviceGetPowerUsage(h) / 1000.0)] + \
+                              ["Active" if (m & b) else "Not Active" for _, b in bits]
+                        self.rows.append((time.time(), row))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.proc = "nvml"
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,20 +114,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0, t1):
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
+
+    def stop(self, t0=None, t1=None, window="timed region"):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        time.sleep(0.05)
+        if self.proc == "nvml":
+            self._stop = True
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -100,7 +147,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window, "source": "NVML polled every ~4 ms" if self.proc == "nvml" else "nvidia-smi -lms 20"}
 
 
 def synthetic_stamps_device(n, seed, device):
@@ -260,13 +307,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)  # nvidia-smi start-up
+    torch.cuda.synchronize()
+    t_warm0 = time.time()
     for _ in range(args.warmup):
         net.deblend_into(x, mean, std)
     net.set_profiling(True)
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
+    t_wall0 = time.time()
     l0 = _ffi.lib().dbv_global_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` then sees only the timed region (not the plan autotuner)
@@ -277,7 +328,25 @@ def main():
     barrier()
     torch.cuda.profiler.stop()
     launches = int(_ffi.lib().dbv_global_launch_count() - l0)
-    clk = clocks.stop() if rank == 0 else None
+    t_wall1 = time.time()
+    clk = None
+    if rank == 0:
+        window = "timed region"
+        if clocks.proc is not None and clocks.count(t_wall0, t_wall1) < 3 and clocks.count(t_warm0, t_wall1) >= 3:
+            t_wall0, window = t_warm0, "warm-up steps + timed region (the same step, back to back; the timed region alone is shorter than three sampling periods)"
+        elif clocks.proc is not None and clocks.count(t_wall0, t_wall1) < 3:
+            # too short for the sampler: keep the identical step running (untimed, profiling off) until it has read the clocks
+            net.set_profiling(False)
+            t_end = time.time() + 0.6
+            while time.time() < t_end:
+                net.deblend_into(x, mean, std)
+                torch.cuda.synchronize()
+            t_wall1 = time.time()
+            window = "timed region + 0.6 s of the same step repeated right after it (the timed region is shorter than the sampling period)"
+            net.set_profiling(True)
+            net.deblend_into(x, mean, std)  # per-layer event times of one more step for the layer table
+            torch.cuda.synchronize()
+        clk = clocks.stop(t_wall0, t_wall1, window)
     ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
