@@ -130,16 +130,21 @@ class DeblendField:
 
         n = len(list_idx)
         if self.epistemic_uncertainty_estimation:
-            # field_deblender.py:303-316: std over 100 stochastic passes of each stamp
-            epistemic = []
-            norm = []
-            for i in range(n):
-                rep = sel[i : i + 1].expand(100, S, S, C).contiguous()
-                m100 = self.net(rep).mean().tensor if isinstance(self.net, Deblender) else torch.as_tensor(deblend(self.net, rep.cpu().numpy(), normalise=self.normalise)[0]).to(dev)
-                e = m100.double().std(dim=0, unbiased=False)
-                epistemic.append(e.cpu().numpy())
-                norm.append(float(e[:, :, 2].sum() / mean_dev[i, :, :, 2].double().sum()))
-            epistemic_norm = np.array(norm)
+            # field_deblender.py:303-316: std over 100 stochastic passes of each stamp, normalised by the r-band flux
+            if isinstance(self.net, Deblender) and not self.normalise:
+                e_dev = self.net.epistemic_std(sel, 100)  # batched: encoder once, 100 latent draws + decoder passes per stamp
+                norm_dev = e_dev[:, :, :, 2].sum(dim=(1, 2)) / mean_dev[:, :, :, 2].double().sum(dim=(1, 2))
+                epistemic = list(e_dev.cpu().numpy())
+                epistemic_norm = norm_dev.cpu().numpy()
+            else:
+                epistemic, norm = [], []
+                for i in range(n):
+                    rep = sel[i : i + 1].expand(100, S, S, C).contiguous()
+                    m100 = torch.as_tensor(deblend(self.net, rep.cpu().numpy(), normalise=self.normalise)[0]).to(dev)
+                    e = m100.double().std(dim=0, unbiased=False)
+                    epistemic.append(e.cpu().numpy())
+                    norm.append(float(e[:, :, 2].sum() / mean_dev[i, :, :, 2].double().sum()))
+                epistemic_norm = np.array(norm)
         else:
             epistemic = list(np.zeros((n, S, S, C)))
             epistemic_norm = np.zeros(n)

@@ -153,6 +153,23 @@ class Deblender:
         out = NormalOutput(mean, std)
         return (out, z) if return_z else out
 
+    def epistemic_std(self, x, n: int = 100, seed=None) -> torch.Tensor:
+        """Per-pixel std of the predicted mean over `n` latent draws per stamp — the epistemic uncertainty of
+        deblend/field_deblender.py:303-316 (np.std(deblend(net, [cutout] * 100)[0], axis=0)), batched: the encoder is
+        deterministic, so it runs ONCE per stamp; only the latent sampling and the decoder run n times.
+        (B,59,59,6) -> (B,59,59,6) float64 CUDA tensor (ddof = 0 like np.std)."""
+        params = self.encode(x)
+        B = params.shape[0]
+        out = torch.empty((B, S, S, NB), device=self.device, dtype=torch.float64)
+        per = max(1, 4096 // int(n))  # stamps per decoder call (n draws each)
+        for s in range(0, B, per):
+            e = min(B, s + per)
+            p = params[s:e].repeat_interleave(int(n), dim=0).contiguous()
+            z, _, _ = self.latent(p, sample=True, seed=None if seed is None else int(seed) + s)
+            m = self.decode(z).mean().tensor.view(e - s, int(n), S, S, NB)
+            out[s:e] = m.double().std(dim=1, unbiased=False)
+        return out
+
     def deblend_into(self, x, mean, stddev=None, z=None, eps=None, sample=True, seed=None):
         """net(x) into caller-provided CUDA tensors (no allocation; what bench.py times)."""
         _ffi.check(
