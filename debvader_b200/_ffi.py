@@ -11,6 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEBVADER_B200_LIB") or os.path.join(_HERE, "libdebvader_b200.so")  # env override: A/B builds of the same source
 
+ABI_VERSION = 2  # must equal DBV_ABI_VERSION in include/debvader_b200.h
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4}
 F32, F64 = 0, 1
 
@@ -75,7 +76,7 @@ def lib():
                     )
                 l = C.CDLL(LIB_PATH)
                 EXPORTS = _declare(l)
-                if l.dbv_abi_version() != 1:
+                if l.dbv_abi_version() != ABI_VERSION:
                     raise ImportError("libdebvader_b200.so ABI version mismatch; rebuild it")
                 _lib = l
     return _lib

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DBV_ABI_VERSION 1
+#define DBV_ABI_VERSION 2  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED */
 
 typedef enum {
   DBV_OK = 0,
