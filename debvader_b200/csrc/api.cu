@@ -1159,7 +1159,7 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
   std::vector<std::pair<int64_t, long long>> sched;
   {
     int64_t b0 = 0;
-    const long long piece = std::min<long long>(c->chunk, 1024);  // pipeline granularity (transfers overlap compute piece by piece)
+    const long long piece = std::min<long long>(c->chunk, getenv("DBV_HOST_PIECE") ? atoll(getenv("DBV_HOST_PIECE")) : 1024);  // pipeline granularity (transfers overlap compute piece by piece)
     const long long q = std::max<long long>(piece / 4, 1);
     if (B > 2 * piece) { sched.push_back({0, q}); b0 = q; }
     while (B - b0 > piece + q) { sched.push_back({b0, piece}); b0 += piece; }
