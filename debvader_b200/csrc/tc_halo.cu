@@ -1,20 +1,19 @@
 // tcgen05 implicit-GEMM convolution with a RESIDENT HALO TILE (sm_100a).
 //
-// tc_conv.cu re-reads the activation tile from L2 once per 3x3 tap (and, in the bf16x3 split, once
-// per hi/lo pairing): 27 x 10 KB per 128 output pixels for a 32-channel layer, which made the
-// large-image / few-channel layers L2-bandwidth bound (profiles/r01_v1_summary.md).  Here a CTA loads
-// a band of R+2 input rows x (W+2) columns ONCE per plane (TMA, out-of-bounds zero fill = TF "SAME"
-// padding) and all taps, all output-parity classes of a stride-2 transposed conv and all hi/lo
-// pairings read it as *row-shifted windows of the same shared-memory tile*: output position
-// p = y*(W+2)+x of the band, tap (dy,dx) -> smem row p + (dy+1)*(W+2) + (dx+1).  That works because
-// tcgen05 applies the 64B/128B swizzle to absolute shared-memory address bits, so a descriptor
-// whose start is shifted by whole rows stays consistent with what TMA wrote (measured:
-// tests/test_gpu_network.py::test_probe_descriptor_row_shift).  Weights are loaded once per CTA and
-// stay resident.  Two columns per row (x = W, W+1) compute garbage that the epilogue drops.
+// A streaming kernel re-reads the activation tile from L2 once per 3x3 tap (and, in the hi/lo split precisions, once
+// per plane), which made the large-image / few-channel layers L2-bandwidth bound (profiles/r01_v1_summary.md).  Here a
+// CTA loads a band of R+2 input rows ONCE per plane (TMA, out-of-bounds zero fill = TF "SAME" padding) and all taps,
+// all output-parity classes of a stride-2 transposed conv, all parity planes of a stride-2 conv and all hi/lo pairings
+// read it as *row-shifted windows of the same shared-memory tile*: with row pitch WP = W + 1 (slot 0 of a row is x = -1,
+// shared as the right neighbour of the previous row's last pixel) output position p = y*WP + x of the band reads, for
+// tap (dy, dx), shared-memory row p + (dy+1)*WP + (dx+1).  That works because tcgen05 applies the 64B/128B swizzle to
+// absolute shared-memory address bits, so a descriptor whose start is shifted by whole rows stays consistent with what
+// TMA wrote (tests/test_gpu_network.py::test_probe_descriptor_row_shift).  Weights are loaded once per CTA and stay
+// resident.  One position per row (x = W) computes garbage that the epilogue drops.
 //
 //   warp 0    TMA producer (weights once; one halo band per work item, ring of nbuf buffers)
-//   warp 1    MMA issuer: for class, for 128-position tile, for (tap, chunk, pairing), CBK/16 MMAs
-//   warps 2-9 epilogue, two groups of 4 (shared with tc_conv.cu: bias, PReLU(h,w,c), ReLU/crop/split, bf16 hi/lo)
+//   warp 1    MMA issuer: per unit (several (class, tile) sub-units sharing one TMEM slot) a flat, host-made list of MMAs
+//   warps 2-9 epilogue, two groups of 4: hi/lo accumulator sum, bias, PReLU(h,w,c) / ReLU, 16-bit hi[/lo] conversion, stores
 #include "tc_ptx.cuh"
 #include <mutex>
 #include <type_traits>
@@ -24,7 +23,7 @@ namespace dbv {
 #ifndef DBV_HALO_EPI_GROUPS
 #define DBV_HALO_EPI_GROUPS 2
 #endif
-constexpr int HALO_EPI_GROUPS = DBV_HALO_EPI_GROUPS;  // epilogue groups of 4 warps (one warp per TMEM lane quadrant); the epilogue is latency bound
+constexpr int HALO_EPI_GROUPS = DBV_HALO_EPI_GROUPS;  // epilogue groups of 4 warps (one warp per TMEM lane quadrant); 2 x 32-channel items measured best
 constexpr int HALO_THREADS = 64 + HALO_EPI_GROUPS * 128;  // TMA warp, MMA warp, epilogue groups
 constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring (512 columns / slot width, capped)
 
@@ -37,9 +36,9 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 // owns the contiguous range [total*i/grid, total*(i+1)/grid): a CTA stays on ONE band row for (almost) its whole
 // life, so the PReLU alpha slice of that band (tens of KB, the same for every stamp) stays L1-resident.
 //
-// Accumulators: TMEM is two slots of 256 columns; a "unit" = up to 256 / DW consecutive sub-units (one 128-position
-// tile of one output-parity class each) of a band.  The MMA warp issues all MMAs of a unit into the free slot and
-// commits it once; the epilogue groups split the unit's sub-units; the MMA warp runs one unit ahead of the epilogue.
+// Accumulators: TMEM is a ring of 512 / (U*DW) slots; a "unit" = up to U consecutive sub-units (one 128-position tile of
+// one output-parity class each) of a band.  The MMA warp issues all MMAs of a unit into the next free slot and commits
+// it once; the epilogue groups split the unit's (sub-unit, channel chunk) items and all release the slot.
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   constexpr bool CG8 = !NOSWZ && CBK == 16;             // channel-group-planar input: 16-byte pixel rows, K=16 = two groups one region apart
