@@ -290,6 +290,18 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU path)"
     torch.cuda.set_device(local)
+    numa = "unchanged"
+    if world > 1:
+        # one process per GPU: run it (and first-touch its pinned host buffers) on the CPUs / NUMA node next to its GPU, so that
+        # the host<->device copies of the end-to-end path do not all cross the socket interconnect
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = f"cpu affinity set to GPU {local}'s local CPUs ({len(os.sched_getaffinity(0))} of {os.cpu_count()})"
+        except Exception as e:  # the measurement still stands, only slower copies
+            numa = f"not set ({type(e).__name__})"
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -410,7 +422,8 @@ def main():
                    "parallelism": f"dp{world} (stamps sharded, no data-path collective)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * STAMP_ELTS * 4, "d2h_bytes_per_step": B * STAMP_ELTS * 4,
                 "api": "debvader_b200.deblend_cutout.deblender.deblend(net, host ndarray) -> dbv_deblend_host", "timing": "wall clock, max over ranks",
-                "note": "returns the mean ndarray (device->host copy inside the timed region) and the distribution object, whose stddev stays on the device until a caller asks for it"},
+                "note": "returns the mean ndarray (device->host copy inside the timed region) and the distribution object, whose stddev stays on the device until a caller asks for it",
+                "host_affinity": numa},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
