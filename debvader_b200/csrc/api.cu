@@ -550,7 +550,13 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
     for (int ky = 0; ky < 3; ++ky)
       for (int pr = 0; pr < 2; ++pr) taps.push_back(Tap{ky, pr, ky - 1, 2 * pr - 1, 0, 0});
   }
-  const int pad = 1;
+  const int pad = 1;  // left zero column (slot 0 of every row is x = -1)
+  int pad_top = 0, pad_bot = 0;  // halo rows above / below the band: what the taps actually reach (a stride-2 transposed conv
+  for (const Tap& t : taps) {    // and a stride-2 conv look only one way)
+    pad_top = std::max(pad_top, -t.dy);
+    pad_bot = std::max(pad_bot, t.dy);
+  }
+  const int hrows = bandR + pad_top + pad_bot;
   const int nchunk = c1 ? 1 : (L.Cin + G.CBK - 1) / G.CBK;
   const int parts_w = x3 ? 2 : 1;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
@@ -565,9 +571,9 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   if ((!cg8 && n_regions > 8) || bandR < 1 || bandR > H) return 0;
   const int ntiles = (bandR * WP + 127) / 128;
   if (U * G.NT * (x3 ? 2 : 1) > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
-  if (bandR + 2 * pad > 256 || WP > 256) return 0;
+  if (hrows > 256 || WP > 256) return 0;
   // >= one zeroed slack slot after the box; CG8: the regions of a buffer are ONE contiguous TMA box, the slack follows the buffer
-  const long long region = cg8 ? (long long)(bandR + 2 * pad) * WP * ROWB : (((long long)(bandR + 2 * pad) * WP * ROWB + ROWB + 1023) / 1024) * 1024;
+  const long long region = cg8 ? (long long)hrows * WP * ROWB : (((long long)hrows * WP * ROWB + ROWB + 1023) / 1024) * 1024;
   const long long buf = cg8 ? ((n_regions * region + 16 + 1023) / 1024) * 1024 : n_regions * region;
   // layout: [halo ring][weights][barriers].  The last tile of a band over-reads < 131 garbage rows past its region: into the
   // next region, or (last region of the last buffer) into the weights — readable memory, results dropped by the epilogue.
@@ -590,7 +596,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
             if (nkb >= TC_MAX_KB) return 0;
             const int a_lo = (pr == 1);
             const long long areg = cg8 ? (a_lo * nchunk + ch) * 2 : (a_lo * nchunk + ch) * npar + taps[ti].plane;
-            const long long a_off = areg * region + (long long)((taps[ti].dy + pad) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
+            const long long a_off = areg * region + (long long)((taps[ti].dy + pad_top) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
             const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * ROWB_W + 32 * k;
             if ((a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return 0;
             T.mma[nkb].a = (uint32_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
@@ -605,7 +611,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   }
   T.ab_f16 = layer_f16(c->precision, li);
   for (int i = 0; i < 64; ++i) T.bias_c[i] = i < L.Cout ? R.bias_host[i] : 0.f;
-  T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad;
+  T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad; T.pad_top = pad_top;
   T.ntiles = ntiles;
   T.magic_wp = (uint32_t)(((1ull << 32) + WP - 1) / WP);
   T.magic_nt = (uint32_t)(((1ull << 32) + ntiles - 1) / ntiles);
@@ -616,7 +622,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
     T.region_c3[r] = r % npar;
   }
   T.w_img = c1 ? (const void*)c->conv1_wimg : nullptr;
-  T.a_box_bytes = (bandR + 2 * pad) * WP * ROWB;
+  T.a_box_bytes = hrows * WP * ROWB;
   T.region_bytes = (int)region;
   T.buf_bytes = (int)buf;
   T.cg8 = cg8 ? 1 : 0;
@@ -636,14 +642,14 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
     const uint64_t ng = Ct / 8;
     uint64_t dims[5] = {2ull * in.OW, (uint64_t)in.OH, ng, (uint64_t)c->chunk, 1};
     uint64_t str[4] = {16ull * in.OW, 16ull * in.OW * in.OH, 16ull * in.OW * in.OH * ng, 16ull * in.OW * in.OH * ng * c->chunk};
-    uint32_t bx[5] = {(uint32_t)(2 * WP), (uint32_t)(bandR + 2 * pad), (uint32_t)ng, 1u, 1u};
+    uint32_t bx[5] = {(uint32_t)(2 * WP), (uint32_t)hrows, (uint32_t)ng, 1u, 1u};
     if (2 * WP > 256 || ng > 256) return 0;
     r = encode_tmap(&T.tmA, P.out, 5, dims, str, bx, 0, 8);
   } else {
     const uint64_t Wd = npar == 4 ? in.PW : in.OW, Hd = npar == 4 ? in.PH : in.OH;
     uint64_t dims[5] = {Ct, Wd, Hd, (uint64_t)npar, (uint64_t)c->chunk};
     uint64_t str[4] = {Ct * 2, Ct * 2 * Wd, Ct * 2 * Wd * Hd, Ct * 2 * Wd * Hd * npar};
-    uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)(bandR + 2 * pad), 1u, 1u};
+    uint32_t box[5] = {(uint32_t)(c1 ? 8 : G.CBK), (uint32_t)WP, (uint32_t)hrows, 1u, 1u};
     r = encode_tmap(&T.tmA, P.out, 5, dims, str, box, c1 ? 0 : ROWB);
   }
   if (r) return r;

@@ -121,7 +121,8 @@ struct HaloLayer {
   int ab_f16;        // operand format of this layer's activations and weights: 0 = bf16, 1 = fp16
   int W, H;          // tile-space extents (valid outputs sx < W, sy < H)
   int R, WP;         // output rows per band, W + 2*pad
-  int pad;           // halo width: 1 for 3x3 taps, 0 for a 1-tap layer (conv1 after im2col)
+  int pad;           // zero columns left of a row (slot 0 = x = -1)
+  int pad_top;       // halo rows above the band (0 or 1: what the taps reach); the box holds R + pad_top + pad_bottom rows
   int ntiles;        // ceil(R * WP / 128)
   int n_regions;     // planes * channel chunks
   int region_coff[8];  // TMA coordinate 0 (first channel) of each region

@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(L.n_regions * L.a_box_bytes));
         if constexpr (CG8) {  // one box: all channel-group planes, whole rows of 16-byte pixels (x in u64 units)
-          tma_load_5d(sA + stage * L.buf_bytes, &L.tmA, bar_afull + 8 * stage, -2 * L.pad, y0 - L.pad, 0, b, 0);
+          tma_load_5d(sA + stage * L.buf_bytes, &L.tmA, bar_afull + 8 * stage, -2 * L.pad, y0 - L.pad_top, 0, b, 0);
         } else {
           for (int r = 0; r < L.n_regions; ++r)
-            tma_load_5d(sA + stage * L.buf_bytes + r * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad, L.region_c3[r], b);
+            tma_load_5d(sA + stage * L.buf_bytes + r * L.region_bytes, &L.tmA, bar_afull + 8 * stage, L.region_coff[r], -L.pad, y0 - L.pad_top, L.region_c3[r], b);
         }
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
         if (++b == (int)L.B) { b = 0; y0 += L.R; }
