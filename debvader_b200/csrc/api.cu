@@ -474,7 +474,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const OutSpec& in = c->rt[li - 1].ospec;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
   const int space = (ncls == 4) ? L.Hin : L.Hout;  // tile space = the input grid
-  if (in.mode != OUT_BF16_NHWC || in.planes != 2 || in.OW != space || space < 8 || space > 16 || L.Cin % 64 != 0 || ncls * G.NT > 256) return DBV_OK;  // (accumulators double-buffered: 2 x n_cls x NT <= 512)
+  if (in.mode != OUT_BF16_NHWC || in.planes != 2 || in.OW != space || space < 8 || space > 16 || L.Cin % 64 != 0 || ncls * G.NT > 512) return DBV_OK;
   PairHLayer& P = R.ph;
   memset(&P, 0, sizeof P);
   const int TB = space <= 8 ? 2 : 1;
@@ -484,6 +484,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const int nchunk = L.Cin / 64, parts = 2;
   const int Ntot = G.NT;  // conv layers are not N-tiled
   P.n_cls = ncls;
+  P.cls_groups = (ncls * G.NT > 256) ? 2 : 1;  // keep the accumulators of a work item within 256 columns (double buffered)
   P.ab_f16 = layer_f16(c->precision, li);
   int nt = 0;
   std::vector<int> order;

@@ -91,6 +91,8 @@ struct PairHLayer {
   int n_cls;
   int ab_f16;        // operand format: 0 = bf16, 1 = fp16
   int cls_begin[TC_MAX_CLS + 1];  // taps of class c: [cls_begin[c], cls_begin[c+1])
+  int cls_groups;    // 1, or 2 when the accumulators of all classes do not fit 256 TMEM columns: a work item then covers one
+                     // half of the classes (the halo boxes are loaded once per half) and the accumulators stay double buffered
   int tap_aoff[16];  // byte offset of the tap's window in the halo box: ((dy+1) * TB * 10 + dx+1) * 128
   int tap_brow[16];  // first weight row of the tap's hi block for chunk 0
   int nchunk, chunk_brow, lo_brow, lo_coff;

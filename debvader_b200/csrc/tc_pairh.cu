@@ -45,7 +45,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t acc_cols = (uint32_t)(L.n_cls * NT);                      // accumulator columns of one item
+  const int gs = L.n_cls / L.cls_groups;                                   // classes per work item
+  const uint32_t acc_cols = (uint32_t)(gs * NT);                           // accumulator columns of one item
   const uint32_t nslot = acc_cols <= 256 ? 2u : 1u;                        // accumulator double buffering when it fits
 
   if (warp == 0 && lane == 0) {
@@ -72,10 +73,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long items = L.pair_items;
+  const long long items = L.pair_items * L.cls_groups;  // (tile pair, class group)
   const uint32_t cid = cluster_id_x(), ncl = nclusters_x();
   const int tiles_img = L.tiles_x;  // one strip row of 8-pixel-wide tiles per image group
-  const int ntaps = L.cls_begin[L.n_cls];
 
   if (warp == 0) {
     if (elect_one()) {
@@ -84,7 +84,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
       const uint32_t atx = 2u * 2u * (uint32_t)L.abox_tx, btx = 2u * 2u * (uint32_t)BH_BYTES;  // both CTAs, hi + lo
       const uint32_t afull0 = map_to_rank(bar_afull, 0), bfull0 = map_to_rank(bar_bfull, 0);
       for (long long w = cid; w < items; w += ncl) {
-        const long long m = 2 * w + rank;  // this CTA's tile (may be one past the end: all-zero loads, masked stores)
+        const long long m = 2 * (w / L.cls_groups) + rank;  // this CTA's tile (may be one past the end: all-zero loads, masked stores)
+        const int cg = (int)(w % L.cls_groups);
+        const int t0 = L.cls_begin[cg * gs], t1 = L.cls_begin[(cg + 1) * gs];
         const int ti = (int)(m % tiles_img);
         const int b0 = (int)(m / tiles_img) * L.TB;
         const int x0 = ti * 8 - 1;
@@ -95,7 +97,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
           tma2_load_5d(dA, &L.tmA, afull0 + 8 * as, ch * 64, x0, b0, -1, 0);
           tma2_load_5d(dA + (uint32_t)L.abox_bytes, &L.tmA, afull0 + 8 * as, L.lo_coff + ch * 64, x0, b0, -1, 0);
           if (++as == L.a_stages) { as = 0; aph ^= 1u; }
-          for (int t = 0; t < ntaps; ++t) {
+          for (int t = t0; t < t1; ++t) {
             mbar_wait_cluster(bar_bempty + 8 * bs, bph ^ 1u);
             if (rank == 0) mbar_expect_tx(bar_bfull + 8 * bs, btx);
             const uint32_t dB = sB + (uint32_t)bs * b_stage;
@@ -121,12 +123,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
         mbar_wait_cluster(bar_tempty + 8 * slot, tph ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + slot * 256u;
+        const int c_first = (int)(w % L.cls_groups) * gs;
         for (int ch = 0; ch < L.nchunk; ++ch) {
           mbar_wait_cluster(bar_afull + 8 * as, aph);
           tc_fence_after();
           const uint32_t aBase = sA + (uint32_t)as * a_stage;
-          for (int c = 0; c < L.n_cls; ++c) {
-            const uint32_t d = d0 + (uint32_t)c * NT;
+          for (int c = c_first; c < c_first + gs; ++c) {
+            const uint32_t d = d0 + (uint32_t)(c - c_first) * NT;
             for (int t = L.cls_begin[c]; t < L.cls_begin[c + 1]; ++t) {
               mbar_wait_cluster(bar_bfull + 8 * bs, bph);
               tc_fence_after();
@@ -163,7 +166,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
     const uint32_t tempty0 = map_to_rank(bar_tempty, 0);
     uint32_t u = 0;
     for (long long w = cid; w < items; w += ncl, ++u) {
-      const long long m = 2 * w + rank;
+      const long long m = 2 * (w / L.cls_groups) + rank;
+      const int c_first = (int)(w % L.cls_groups) * gs;
       const int ti = (int)(m % tiles_img);
       const long long b = (m / tiles_img) * L.TB + tb;
       const int sx = ti * 8 + tx, sy = ty;
@@ -171,9 +175,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
       const uint32_t slot = nslot == 2 ? (u & 1u) : 0u;
       const uint32_t tph = nslot == 2 ? ((u >> 1) & 1u) : (u & 1u);
       bool waited = false;
-      for (int c = 0; c < L.n_cls; ++c) {
+      for (int c = c_first; c < c_first + gs; ++c) {
         const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
-        const uint32_t tcol = lane_base + slot * 256u + (uint32_t)c * NT;
+        const uint32_t tcol = lane_base + slot * 256u + (uint32_t)(c - c_first) * NT;
 #pragma unroll 1
         for (int q = grp; q < NCHK; q += 2) {  // the two groups split the 32-channel chunks
           ActRegs<NV> ra;
