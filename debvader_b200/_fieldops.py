@@ -67,17 +67,23 @@ def subtract_offset(field_size: int, cutout_size: int) -> int:
     return int((int(field_size) - int(cutout_size)) / 2)
 
 
-def integer_positions(dist, shifts, what="positions"):
-    """x_pos = distance + shift (field_deblender.py:83-90) as int64; raises for sub-pixel values."""
+def positions(dist, shifts):
+    """x_pos = distance + shift (field_deblender.py:83-90) as float64, and whether all are integer-valued."""
     p = np.asarray(dist, dtype=np.float64) + np.asarray(shifts, dtype=np.float64)
-    r = np.rint(p)
-    if not np.array_equal(r, p):
-        raise NotImplementedError(
-            f"{what} are not integer-valued: the sub-pixel cubic-spline placement of the reference "
-            "(scipy.ndimage.shift) is not part of the B200 hot path; round the centres first "
-            "(detect_objects already does)"
-        )
-    return r.astype(np.int64)
+    if not np.isfinite(p).all():
+        raise ValueError("positions must be finite")
+    return p, bool(np.array_equal(np.rint(p), p))
+
+
+def integer_positions(dist, shifts, what="positions"):
+    """positions() as int64 for the callers that only take whole pixels (the tiled multi-GPU pass)."""
+    p, integer = positions(dist, shifts)
+    if not integer:
+        raise NotImplementedError(f"{what} are not integer-valued: this path places stamps on whole pixels only")
+    return np.rint(p).astype(np.int64)
+
+
+SPLINE_MARGIN = 28  # pixels kept around the stamp by the sub-pixel placement (prefilter response 0.268^28 = 1e-16)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -150,8 +156,6 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
 def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64):
     """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy)."""
     _require_cuda(stamps, "stamps")
-    if stamps.dtype != torch.float32:
-        raise TypeError("stamps must be float32 (the network's output dtype)")
     dev = stamps.device
     if field_in is not None:
         _require_cuda(field_in, "field")
@@ -166,9 +170,72 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
     ys = torch.from_numpy(np.asarray(y0, dtype=np.int32)).to(dev)
     with torch.cuda.device(dev):
         _ffi.check(
-            _ffi.lib().dbv_window_axpy(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _ffi.ptr(xs), _ffi.ptr(ys),
-                                       n, S, float(alpha), _ffi.stream_ptr())
+            _ffi.lib().dbv_window_axpy_ex(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _DT[stamps.dtype],
+                                          _ffi.ptr(xs), _ffi.ptr(ys), n, S, float(alpha), _ffi.stream_ptr())
         )
+    return out
+
+
+def spline_extent(size: int, margin: int = SPLINE_MARGIN) -> int:
+    """side of the window dbv_spline_place writes for a data block of `size` samples per axis."""
+    try:
+        return _ffi.check(_ffi.lib().dbv_spline_extent(int(size), int(margin)))
+    except _ffi.DbvError as e:
+        raise NotImplementedError(f"sub-pixel placement: {e}") from None
+
+
+def _anchor(origin, pos, margin):
+    lim = 2**30
+    return (np.asarray(origin, dtype=np.int64) - margin - 1 + np.clip(np.floor(pos), -lim, lim).astype(np.int64)).astype(np.int32)
+
+
+def spline_place(data, pos_x, pos_y, field_size: int, margin: int = SPLINE_MARGIN, origin_x=None, origin_y=None):
+    """scipy.ndimage.shift of a zero canvas holding `data` (field_deblender.py:66-95), on the window that matters.
+
+    data (N,S,S,C) CUDA f32/f64, sample 0 at canvas (origin_x[k], origin_y[k]) — default int((F-S)/2), the padded
+    stamp of the reference; pos = the shift (float).  Returns (placed (N,E,E,C) f64, ax, ay): window k covers
+    field rows ax[k]..ax[k]+E, cols ay[k]..ay[k]+E.
+    """
+    _require_cuda(data, "data")
+    dev = data.device
+    n, S, _, Cc = data.shape
+    E = spline_extent(S, margin)
+    px = np.ascontiguousarray(pos_x, dtype=np.float64)
+    py = np.ascontiguousarray(pos_y, dtype=np.float64)
+    off = subtract_offset(field_size, S)
+    ox = np.full(n, off, dtype=np.int64) if origin_x is None else np.asarray(origin_x, dtype=np.int64)
+    oy = np.full(n, off, dtype=np.int64) if origin_y is None else np.asarray(origin_y, dtype=np.int64)
+    ax, ay = _anchor(ox, px, margin), _anchor(oy, py, margin)
+    pos = torch.from_numpy(np.stack([px, py])).to(dev)
+    ints = torch.from_numpy(np.stack([ax, ay, ox.astype(np.int32), oy.astype(np.int32)])).to(dev)
+    scratch = torch.empty((n, E, S, Cc), device=dev, dtype=torch.float64)
+    placed = torch.empty((n, E, E, Cc), device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        _ffi.check(
+            _ffi.lib().dbv_spline_place(_ffi.ptr(data), _DT[data.dtype], n, S, Cc, int(field_size), int(off), _ffi.ptr(ints[2]), _ffi.ptr(ints[3]),
+                                        _ffi.ptr(pos[0]), _ffi.ptr(pos[1]), _ffi.ptr(ints[0]), _ffi.ptr(ints[1]), int(margin),
+                                        _ffi.ptr(scratch), _ffi.ptr(placed), _ffi.stream_ptr())
+        )
+    return placed, ax, ay
+
+
+def spline_window_axpy(field_in, stamps, pos_x, pos_y, alpha: float, field_shape=None, dtype=torch.float64, batch: int = 512,
+                       margin: int = SPLINE_MARGIN):
+    """out = field_in + alpha * sum_k ndimage.shift(padded stamps[k], (pos_x[k], pos_y[k])), stamps applied in ascending k
+    (batches of `batch` stamps keep the placed windows, 0.66 MB each for DC2, bounded)."""
+    _require_cuda(stamps, "stamps")
+    if field_in is not None:
+        shape, dtype = tuple(field_in.shape), field_in.dtype
+    else:
+        shape = tuple(field_shape)
+    F_ = shape[-3]
+    n = stamps.shape[0]
+    out = None
+    for b0 in range(0, max(n, 1), batch):
+        sl = slice(b0, min(b0 + batch, n))
+        placed, ax, ay = spline_place(stamps[sl], pos_x[sl], pos_y[sl], F_, margin)
+        src = field_in if out is None else out
+        out = window_axpy(src, placed, ax, ay, alpha, out=out, field_shape=shape, dtype=dtype)
     return out
 
 

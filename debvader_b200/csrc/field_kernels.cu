@@ -7,6 +7,7 @@
 //   dbv_center_mse   <- deblend/field_deblender.py:323-332
 //   dbv_mse          <- training/metrics.py:4-12
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cstdlib>
 
 namespace dbv {
@@ -89,11 +90,89 @@ __global__ void __launch_bounds__(256) extract_kernel(const Tin* __restrict__ fi
 }
 
 // ---------------------------------------------------------------------------------------------
+// extraction through shared memory with bulk asynchronous copies (the default when alignment allows):
+// a CTA takes `rows_per_cta` rows of one stamp; every row is one cp.async.bulk global -> shared
+// (row = S*C contiguous elements of the field, 2832 B for DC2/f64, 16-byte aligned because a pixel is
+// 48 B), completion on one mbarrier.  Same-type output leaves as ONE bulk copy shared -> global (the
+// rows are contiguous in the stamp); the fused f64 -> f32 cast reads the staged rows and stores
+// 8-byte pairs.  No per-element address arithmetic, ~42 KB in flight per CTA, 5 CTAs per SM.
+// ---------------------------------------------------------------------------------------------
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(128) extract_bulk_kernel(const Tin* __restrict__ field, long long F, int C,
+                                                           const int32_t* __restrict__ sx, const int32_t* __restrict__ sy,
+                                                           const uint8_t* __restrict__ flags, const int64_t* __restrict__ slot,
+                                                           int S, Tout* __restrict__ out, int rows_per_cta) {
+  extern __shared__ __align__(128) unsigned char ex_smem[];
+  __shared__ __align__(8) uint64_t ex_bar;
+  const long long k = blockIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int nr = min(rows_per_cta, S - r0);
+  const int fl = flags ? flags[k] : 0;
+  const int x0 = sx[k], y0 = sy[k];
+  const long long dst = slot ? slot[k] : k;
+  const int L = S * C;
+  Tout* __restrict__ o = out + (dst * S + r0) * (long long)L;
+  if (fl != 0) {
+    // a length-1 source axis broadcast over the stamp (numpy assignment): rare, element-wise
+    const int bx = fl & 1, by = (fl >> 1) & 1;
+    for (int idx = threadIdx.x; idx < nr * L; idx += blockDim.x) {
+      const int r = idx / L;
+      const int rem = idx - r * L;
+      const int c = rem / C, ch = rem - c * C;
+      const long long xr = x0 + (bx ? 0 : r0 + r), yc = y0 + (by ? 0 : c);
+      o[idx] = cvt<Tout, Tin>(__ldg(field + (xr * F + yc) * C + ch));
+    }
+    return;
+  }
+  const uint32_t bar = smem_u32(&ex_bar);
+  const uint32_t row_bytes = (uint32_t)L * sizeof(Tin);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)nr * row_bytes);
+    __syncwarp();
+    const Tin* base = field + ((long long)(x0 + r0) * F + y0) * C;
+    for (int r = threadIdx.x; r < nr; r += 32)
+      bulk_load(smem_u32(ex_smem) + (uint32_t)r * row_bytes, base + (long long)r * F * C, row_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  if constexpr (sizeof(Tin) == sizeof(Tout)) {
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o), "r"(smem_u32(ex_smem)),
+                   "r"((uint32_t)nr * row_bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+    }
+  } else {
+    using VI = typename Vec2<Tin>::type;
+    using VO = typename Vec2<Tout>::type;
+    const VI* __restrict__ sv = reinterpret_cast<const VI*>(ex_smem);
+    VO* __restrict__ ov = reinterpret_cast<VO*>(o);
+    const int total = nr * (L >> 1);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const VI v = sv[i];
+      VO w;
+      w.x = cvt<Tout, Tin>(v.x);
+      w.y = cvt<Tout, Tin>(v.y);
+      __stcs(ov + i, w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // windowed axpy, owner-computes: a CTA owns a TR x TC pixel tile of the field, collects (in
 // ascending stamp index) the stamps that overlap it, and applies them to each of its pixels in
-// that order.  No atomics; one rounding per addition; bit-identical to the sequential host loop.
+// that order.  No atomics on the data; one rounding per addition; bit-identical to the sequential
+// host loop.  The per-tile stamp lists come from a binning pass (one thread per stamp appends its
+// index to the <= AX_LCAP-entry list of every tile it touches; the tile CTA sorts its list, so the
+// order of the appends does not matter); a tile whose list overflowed scans all N stamps instead.
+// Field accesses are 16-byte vectors, 4 independent loads in flight per thread.
 // ---------------------------------------------------------------------------------------------
-constexpr int AX_TR = 32, AX_TC = 64, AX_CAP = 768, AX_THREADS = 256;
+constexpr int AX_TR = 32, AX_TC = 64, AX_CAP = 768, AX_THREADS = 256, AX_LCAP = 32, AX_U = 4;
 
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
@@ -102,11 +181,28 @@ template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
 
-template <typename T>
+__global__ void __launch_bounds__(256) axpy_bin_kernel(const int32_t* __restrict__ x0, const int32_t* __restrict__ y0, int N, int S,
+                                                       long long F, int tiles_c, int* __restrict__ cnt, int* __restrict__ list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const long long xi = x0[i], yi = y0[i];
+  if (xi + S <= 0 || xi >= F || yi + S <= 0 || yi >= F) return;
+  const int r_lo = (int)((xi > 0 ? xi : 0) / AX_TR), r_hi = (int)((xi + S - 1 < F - 1 ? xi + S - 1 : F - 1) / AX_TR);
+  const int c_lo = (int)((yi > 0 ? yi : 0) / AX_TC), c_hi = (int)((yi + S - 1 < F - 1 ? yi + S - 1 : F - 1) / AX_TC);
+  for (int r = r_lo; r <= r_hi; ++r)
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const int t = r * tiles_c + c;
+      const int p = atomicAdd(cnt + t, 1);
+      if (p < AX_LCAP) list[(long long)t * AX_LCAP + p] = i;
+    }
+}
+
+template <typename T, typename TS>
 __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T* out, long long F, int C,
-                                                                  const float* __restrict__ stamps,
+                                                                  const TS* __restrict__ stamps,
                                                                   const int32_t* __restrict__ x0, const int32_t* __restrict__ y0,
-                                                                  int N, int S, double alpha_d, int tiles_c) {
+                                                                  int N, int S, double alpha_d, int tiles_c,
+                                                                  const int* __restrict__ bin_cnt, const int* __restrict__ bin_list) {
   __shared__ int s_id[AX_CAP], s_x[AX_CAP], s_y[AX_CAP];
   __shared__ int s_wcnt[AX_THREADS / 32];
   __shared__ int s_count, s_next;
@@ -116,77 +212,116 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
   const T alpha = (T)alpha_d;
   const int nelt = AX_TR * AX_TC * C;
   const long long stamp_sz = (long long)S * S * C;
+  const int binned = bin_cnt ? bin_cnt[blockIdx.x] : -1;
   int start = 0;
   bool first = true;
   do {
-    if (threadIdx.x == 0) { s_count = 0; s_next = N; }
-    __syncthreads();
-    // ordered compaction of the overlapping stamps of [start, N)
-    for (int i0 = start; i0 < N; i0 += AX_THREADS) {
-      const int i = i0 + threadIdx.x;
-      int ov = 0, xi = 0, yi = 0;
-      if (i < N) {
-        xi = x0[i];
-        yi = y0[i];
-        ov = (xi < tr0 + AX_TR) && (xi + S > tr0) && (yi < tc0 + AX_TC) && (yi + S > tc0);
+    if (binned >= 0 && binned <= AX_LCAP) {
+      // sorted copy of the binned list (rank sort: the indices are distinct)
+      int mine = 0;
+      if ((int)threadIdx.x < binned) {
+        mine = bin_list[(long long)blockIdx.x * AX_LCAP + threadIdx.x];
+        s_id[AX_CAP - 1 - threadIdx.x] = mine;  // staging area at the far end of the list
       }
-      const unsigned m = __ballot_sync(0xffffffffu, ov);
-      if (lane == 0) s_wcnt[wid] = __popc(m);
       __syncthreads();
-      int before = 0, tot = 0;
+      int rank = 0;
+      if ((int)threadIdx.x < binned) {
+        for (int j = 0; j < binned; ++j) rank += s_id[AX_CAP - 1 - j] < mine;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < binned) {
+        s_id[rank] = mine;
+        s_x[rank] = x0[mine];
+        s_y[rank] = y0[mine];
+      }
+      if (threadIdx.x == 0) { s_count = binned; s_next = N; }
+      __syncthreads();
+    } else {
+      if (threadIdx.x == 0) { s_count = 0; s_next = N; }
+      __syncthreads();
+      // ordered compaction of the overlapping stamps of [start, N)
+      for (int i0 = start; i0 < N; i0 += AX_THREADS) {
+        const int i = i0 + threadIdx.x;
+        int ov = 0, xi = 0, yi = 0;
+        if (i < N) {
+          xi = x0[i];
+          yi = y0[i];
+          ov = (xi < tr0 + AX_TR) && (xi + S > tr0) && (yi < tc0 + AX_TC) && (yi + S > tc0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (lane == 0) s_wcnt[wid] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
 #pragma unroll
-      for (int w = 0; w < AX_THREADS / 32; ++w) {
-        const int c = s_wcnt[w];
-        if (w < wid) before += c;
-        tot += c;
+        for (int w = 0; w < AX_THREADS / 32; ++w) {
+          const int c = s_wcnt[w];
+          if (w < wid) before += c;
+          tot += c;
+        }
+        const int base = s_count;
+        const bool fits = base + tot <= AX_CAP;
+        if (fits && ov) {
+          const int p = base + before + __popc(m & ((1u << lane) - 1u));
+          s_id[p] = i;
+          s_x[p] = xi;
+          s_y[p] = yi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          if (fits) s_count = base + tot;
+          else s_next = i0;
+        }
+        __syncthreads();
+        if (!fits) break;
       }
-      const int base = s_count;
-      const bool fits = base + tot <= AX_CAP;
-      if (fits && ov) {
-        const int p = base + before + __popc(m & ((1u << lane) - 1u));
-        s_id[p] = i;
-        s_x[p] = xi;
-        s_y[p] = yi;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (fits) s_count = base + tot;
-        else s_next = i0;
-      }
-      __syncthreads();
-      if (!fits) break;
     }
     const int cnt = s_count;
     if ((cnt > 0 || first) && (C & 1) == 0) {
-      // vector path: 2 bands per thread (16-byte field accesses for f64, 8-byte stamp reads); a pixel's C
-      // values start at an even element index, so the pairs never straddle pixels
+      // vector path: 2 bands per thread (16-byte field accesses for f64); a pixel's C values start at an even
+      // element index, so the pairs never straddle pixels
       using V2 = typename Vec2<T>::type;
+      using VS = typename Vec2<TS>::type;
       const int rowv = AX_TC * C / 2;  // vectors per tile row
       const int nvec = AX_TR * rowv;
-      for (int e = threadIdx.x; e < nvec; e += AX_THREADS) {
-        const int pr = e / rowv;
-        const int rem = e - pr * rowv;
-        const int X = tr0 + pr;
-        const int Y = tc0 + (2 * rem) / C;
-        const int ch = 2 * rem - ((2 * rem) / C) * C;
-        if (X >= F || Y >= F) continue;
-        const long long idx = ((long long)X * F + Y) * C + ch;
-        V2 acc;
-        if (first) {
-          if (in) acc = *reinterpret_cast<const V2*>(in + idx);
-          else { acc.x = (T)0; acc.y = (T)0; }
-        } else {
-          acc = *reinterpret_cast<const V2*>(out + idx);
-        }
-        for (int k = 0; k < cnt; ++k) {
-          const int dx = X - s_x[k], dy = Y - s_y[k];
-          if ((unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch));
-            acc.x = add_rn<T>(acc.x, mul_rn<T>(alpha, (T)v.x));
-            acc.y = add_rn<T>(acc.y, mul_rn<T>(alpha, (T)v.y));
+      for (int e0 = threadIdx.x; e0 < nvec; e0 += AX_U * AX_THREADS) {
+        V2 acc[AX_U];
+        long long idx[AX_U];
+        int X[AX_U], Y[AX_U], ch[AX_U];
+        bool ok[AX_U];
+#pragma unroll
+        for (int j = 0; j < AX_U; ++j) {
+          const int e = e0 + j * AX_THREADS;
+          const int pr = e / rowv;
+          const int rem = e - pr * rowv;
+          X[j] = tr0 + pr;
+          Y[j] = tc0 + (2 * rem) / C;
+          ch[j] = 2 * rem - ((2 * rem) / C) * C;
+          ok[j] = e < nvec && X[j] < F && Y[j] < F;
+          idx[j] = ((long long)X[j] * F + Y[j]) * C + ch[j];
+          acc[j].x = (T)0;
+          acc[j].y = (T)0;
+          if (ok[j]) {
+            if (!first) acc[j] = *reinterpret_cast<const V2*>(out + idx[j]);
+            else if (in) acc[j] = *reinterpret_cast<const V2*>(in + idx[j]);
           }
         }
-        *reinterpret_cast<V2*>(out + idx) = acc;
+        if (cnt > 0) {
+#pragma unroll
+          for (int j = 0; j < AX_U; ++j) {
+            if (!ok[j]) continue;
+            for (int k = 0; k < cnt; ++k) {
+              const int dx = X[j] - s_x[k], dy = Y[j] - s_y[k];
+              if ((unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S) {
+                const VS v = __ldg(reinterpret_cast<const VS*>(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch[j]));
+                acc[j].x = add_rn<T>(acc[j].x, mul_rn<T>(alpha, (T)v.x));
+                acc[j].y = add_rn<T>(acc[j].y, mul_rn<T>(alpha, (T)v.y));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < AX_U; ++j)
+          if (ok[j]) *reinterpret_cast<V2*>(out + idx[j]) = acc[j];
       }
     } else if (cnt > 0 || first) {
       for (int e = threadIdx.x; e < nelt; e += AX_THREADS) {
@@ -200,7 +335,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
         for (int k = 0; k < cnt; ++k) {
           const int dx = X - s_x[k], dy = Y - s_y[k];
           if ((unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S) {
-            const float v = __ldg(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch);
+            const TS v = __ldg(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch);
             acc = add_rn<T>(acc, mul_rn<T>(alpha, (T)v));
           }
         }
@@ -287,6 +422,33 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   DBV_REQUIRE(N < (1ll << 31), "dbv_extract: N too large");
   if (N == 0) return DBV_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t isz = field_dtype == DBV_F64 ? 8 : 4, osz = out_dtype == DBV_F64 ? 8 : 4;
+  const size_t row_bytes = (size_t)S * C * isz;
+  // bulk-copy path: every source row and (same-type) destination block must be 16-byte aligned
+  bool bulk = ((size_t)C * isz) % 16 == 0 && ((uintptr_t)field % 16) == 0 && row_bytes <= 48 * 1024 && ((S * C) & 1) == 0;
+  if (isz == osz) bulk = bulk && ((uintptr_t)out % 16) == 0;  // S*S*C*size and r0*row_bytes are multiples of 16 given the row is
+  else bulk = bulk && ((uintptr_t)out % 8) == 0;
+  if (const char* e = getenv("DBV_EXTRACT_BULK")) bulk = bulk && atoi(e) != 0;  // tuning knob (0 = vector kernel)
+  if (bulk) {
+    int rows = (int)((44 * 1024) / row_bytes);  // <= 44 KB of shared memory per CTA: 5 CTAs per SM
+    if (rows > S) rows = S;
+    if (rows < 1) rows = 1;
+    if (const char* e = getenv("DBV_EXTRACT_ROWS")) rows = atoi(e) > 0 && (size_t)atoi(e) * row_bytes <= 48 * 1024 ? atoi(e) : rows;
+    dim3 grid((unsigned)N, (unsigned)((S + rows - 1) / rows)), block(128);
+    const size_t smem = (size_t)rows * row_bytes;
+    if (field_dtype == DBV_F64 && out_dtype == DBV_F64)
+      extract_bulk_kernel<double, double><<<grid, block, smem, st>>>((const double*)field, F, C, sx, sy, flags, slot, S, (double*)out, rows);
+    else if (field_dtype == DBV_F64 && out_dtype == DBV_F32)
+      extract_bulk_kernel<double, float><<<grid, block, smem, st>>>((const double*)field, F, C, sx, sy, flags, slot, S, (float*)out, rows);
+    else if (field_dtype == DBV_F32 && out_dtype == DBV_F32)
+      extract_bulk_kernel<float, float><<<grid, block, smem, st>>>((const float*)field, F, C, sx, sy, flags, slot, S, (float*)out, rows);
+    else if (field_dtype == DBV_F32 && out_dtype == DBV_F64)
+      extract_bulk_kernel<float, double><<<grid, block, smem, st>>>((const float*)field, F, C, sx, sy, flags, slot, S, (double*)out, rows);
+    else
+      return fail(DBV_ERR_INVALID, "dbv_extract: bad dtype %d -> %d", field_dtype, out_dtype);
+    DBV_LAUNCH_CHECK();
+    return DBV_OK;
+  }
   // enough CTAs per stamp to keep >= 4 waves of 148 SMs busy for small N, 1-2 for large N
   int per = 2;
   if (N < 2048) per = 4;
@@ -307,22 +469,46 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   return DBV_OK;
 }
 
-extern "C" int dbv_window_axpy(const void* in, void* out, int dtype, int64_t F, int C, const float* stamps,
-                               const int32_t* x0, const int32_t* y0, int64_t N, int S, double alpha, void* stream) {
+extern "C" int dbv_window_axpy_ex(const void* in, void* out, int dtype, int64_t F, int C, const void* stamps, int stamp_dtype,
+                                  const int32_t* x0, const int32_t* y0, int64_t N, int S, double alpha, void* stream) {
   DBV_REQUIRE(out, "dbv_window_axpy: null out");
   DBV_REQUIRE(N == 0 || (stamps && x0 && y0), "dbv_window_axpy: null stamp arrays");
   DBV_REQUIRE(F > 0 && C > 0 && S > 0 && N >= 0 && N < (1ll << 31), "dbv_window_axpy: bad sizes");
+  DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_window_axpy: bad dtype %d", dtype);
+  DBV_REQUIRE(stamp_dtype == DBV_F64 || stamp_dtype == DBV_F32, "dbv_window_axpy: bad stamp dtype %d", stamp_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles_r = (int)((F + AX_TR - 1) / AX_TR), tiles_c = (int)((F + AX_TC - 1) / AX_TC);
-  dim3 grid((unsigned)(tiles_r * tiles_c)), block(AX_THREADS);
-  if (dtype == DBV_F64)
-    window_axpy_kernel<double><<<grid, block, 0, st>>>((const double*)in, (double*)out, F, C, stamps, x0, y0, (int)N, S, alpha, tiles_c);
-  else if (dtype == DBV_F32)
-    window_axpy_kernel<float><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, stamps, x0, y0, (int)N, S, alpha, tiles_c);
+  const int ntiles = tiles_r * tiles_c;
+  // binning pass (stream-ordered scratch: tile counts + fixed-capacity lists)
+  int* bins = nullptr;
+  bool use_bins = N > 0;
+  if (const char* e = getenv("DBV_AXPY_BINS")) use_bins = use_bins && atoi(e) != 0;  // tuning knob (0 = every tile scans)
+  if (use_bins) {
+    const size_t bytes = (size_t)ntiles * (1 + AX_LCAP) * sizeof(int);
+    DBV_CUDA(cudaMallocAsync((void**)&bins, bytes, st));
+    DBV_CUDA(cudaMemsetAsync(bins, 0, (size_t)ntiles * sizeof(int), st));
+    axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, F, tiles_c, bins, bins + ntiles);
+    DBV_LAUNCH_CHECK();
+  }
+  const int* bc = bins;
+  const int* bl = bins ? bins + ntiles : nullptr;
+  dim3 grid((unsigned)ntiles), block(AX_THREADS);
+  if (dtype == DBV_F64 && stamp_dtype == DBV_F32)
+    window_axpy_kernel<double, float><<<grid, block, 0, st>>>((const double*)in, (double*)out, F, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);
+  else if (dtype == DBV_F32 && stamp_dtype == DBV_F32)
+    window_axpy_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);
+  else if (dtype == DBV_F64 && stamp_dtype == DBV_F64)
+    window_axpy_kernel<double, double><<<grid, block, 0, st>>>((const double*)in, (double*)out, F, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);
   else
-    return fail(DBV_ERR_INVALID, "dbv_window_axpy: bad dtype %d", dtype);
+    window_axpy_kernel<float, double><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);
   DBV_LAUNCH_CHECK();
+  if (bins) DBV_CUDA(cudaFreeAsync(bins, st));
   return DBV_OK;
+}
+
+extern "C" int dbv_window_axpy(const void* in, void* out, int dtype, int64_t F, int C, const float* stamps,
+                               const int32_t* x0, const int32_t* y0, int64_t N, int S, double alpha, void* stream) {
+  return dbv_window_axpy_ex(in, out, dtype, F, C, stamps, DBV_F32, x0, y0, N, S, alpha, stream);
 }
 
 extern "C" int dbv_center_mse(const void* cut, int cut_dtype, const float* mean, int64_t N, int S, int C, int lo, int hi,
@@ -361,5 +547,312 @@ extern "C" int dbv_mse(const void* a, const void* b, int dtype, int64_t n, doubl
   DBV_LAUNCH_CHECK();
   sqdiff_final_kernel<<<1, 256, 0, st>>>((const double*)scratch, nb, n, out);
   DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+namespace dbv {
+
+// ---------------------------------------------------------------------------------------------
+// Sub-pixel placement: scipy.ndimage.shift(canvas, (x_pos, y_pos)) of deblend/field_deblender.py:92-95
+// (order 3, mode 'constant', prefilter) restricted to the window where the result is not negligible.
+// The canvas is zero but for one block of data (the stamp), the cubic B-spline prefilter has one pole
+// z = sqrt(3)-2 and its response decays as |z|^d, so per axis only the line segment
+// [origin - P, origin + S + P) clipped to the canvas is filtered (P = 28: |z|^28 = 1e-16): zero causal
+// state before it, exact geometric tail after it, and scipy's mirror initialisation at an end that IS
+// the canvas edge — a canvas not larger than the segment is therefore filtered whole, exactly as scipy
+// does.  The 2-D operation is separable: pass X filters and interpolates every data column along the
+// rows, pass Y does the same along the columns.  One thread owns one line, which lives in its local
+// memory (all threads of a warp touch the same element index, so the accesses coalesce); fp64.
+// ---------------------------------------------------------------------------------------------
+struct SplineGeom {
+  long long F;  // canvas (field) size
+  int S;        // data samples per axis
+  int P;        // margin kept around the data
+  int origin;   // canvas coordinate of data sample 0 (when no per-stamp origin array is given)
+  int n_out;    // outputs per axis = S + 2P + 2, output a of stamp k <-> canvas index anchor[k] + a
+  // by-value parameters of a single item (used when the per-item arrays are NULL): the position fit
+  double pos_x1, pos_y1;
+  int origin_x1, origin_y1, ax1, ay1;
+};
+
+// the line segment of one (stamp, axis): canvas range [lo, hi), filtered in place
+struct SplineLine {
+  int lo, hi;
+};
+
+template <int LMAX>
+__device__ __forceinline__ void spline_prefilter_line(double* line, const SplineLine& sl, long long F) {
+  const double z = -0.26794919243112270647;  // sqrt(3) - 2
+  const int n = sl.hi - sl.lo;
+  if (n < 2) return;  // scipy leaves lines shorter than 2 untouched (n == F == 1)
+  if (sl.lo == 0) {
+    // ni_splines.c:_init_causal_mirror over the canvas line of length F (zero outside the segment)
+    const double z_n_1 = pow(z, (double)(F - 1));
+    const bool tail = sl.hi == F;  // canvas index F-1-i lies inside the segment only then
+    double c0 = line[0] + (tail ? z_n_1 * line[n - 1] : 0.0);
+    double z_i = z;
+    const int last = (long long)n - 1 < F - 2 ? n - 1 : (int)(F - 2);
+    for (int i = 1; i <= last; ++i) {
+      const long long j = F - 1 - i - sl.lo;
+      c0 = c0 + z_i * (line[i] + ((tail && j >= 0 && j < n) ? z_n_1 * line[j] : 0.0));
+      z_i *= z;
+    }
+    line[0] = c0 / (1.0 - z_n_1 * z_n_1);
+  }
+  for (int i = 1; i < n; ++i) line[i] += z * line[i - 1];
+  if (sl.hi == F) line[n - 1] = (z * line[n - 2] + line[n - 1]) * z / (z * z - 1.0);  // _init_anticausal_mirror
+  else line[n - 1] = line[n - 1] * (z / (z * z - 1.0));                                // infinite geometric tail
+  for (int i = n - 2; i >= 0; --i) line[i] = z * (line[i + 1] - line[i]);
+}
+
+__device__ __forceinline__ long long spline_mirror_index(long long idx, long long n) {
+  if (n <= 1) return 0;
+  const long long s2 = 2 * n - 2;
+  if (idx < 0) {
+    idx = s2 * (-idx / s2) + idx;
+    idx = idx <= 1 - n ? idx + s2 : -idx;
+  } else if (idx >= n) {
+    idx -= s2 * (idx / s2);
+    if (idx >= n) idx = s2 - idx;
+  }
+  return idx;
+}
+
+// value of the shifted line at canvas index i: source coordinate cc = i - pos (NI_ZoomShift)
+__device__ __forceinline__ double spline_eval(const double* line, const SplineLine& sl, long long F, long long i, double neg_pos) {
+  const double cc = (double)i + neg_pos;
+  if (cc < 0.0 || cc > (double)(F - 1)) return 0.0;  // mode='constant': outside the canvas -> cval
+  const double fl = floor(cc);
+  const double y = cc - fl, zc = 1.0 - y;
+  double w[4];
+  w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+  w[2] = (zc * zc * (zc - 2.0) * 3.0 + 4.0) / 6.0;
+  w[0] = zc * zc * zc / 6.0;
+  w[3] = 1.0 - w[0] - w[1] - w[2];
+  const long long start = (long long)fl - 1;
+  double t = 0.0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const long long idx = spline_mirror_index(start + l, F);
+    const double c = (idx >= sl.lo && idx < sl.hi) ? line[idx - sl.lo] : 0.0;  // beyond the segment: < |z|^P
+    t += c * w[l];
+  }
+  return t;
+}
+
+__device__ __forceinline__ SplineLine spline_segment(const SplineGeom& g, long long origin) {
+  SplineLine sl;
+  const long long lo = origin - g.P, hi = origin + g.S + g.P;
+  sl.lo = (int)(lo < 0 ? 0 : (lo > g.F ? g.F : lo));
+  sl.hi = (int)(hi > g.F ? g.F : (hi < 0 ? 0 : hi));
+  if (sl.hi < sl.lo) sl.hi = sl.lo;
+  return sl;
+}
+
+// pass X: one thread per (stamp, column s, band): data (N,S,S,C) -> U (N, n_out, S, C)
+template <typename TS, int LMAX>
+__global__ void __launch_bounds__(128) spline_pass_x_kernel(const TS* __restrict__ data, long long N, int C, SplineGeom g,
+                                                            const int32_t* __restrict__ origin_x, const double* __restrict__ pos_x,
+                                                            const int32_t* __restrict__ ax, double* __restrict__ U) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = g.S * C;
+  if (t >= N * per) return;
+  const long long k = t / per;
+  const int sc = (int)(t - k * per);  // s * C + ch
+  const long long origin = origin_x ? origin_x[k] : (pos_x ? g.origin : g.origin_x1);
+  const SplineLine sl = spline_segment(g, origin);
+  const int n = sl.hi - sl.lo;
+  double line[LMAX];
+  const double gain = 6.0;  // (1 - z)(1 - 1/z)
+  for (int i = 0; i < n; ++i) line[i] = 0.0;
+  const TS* __restrict__ src = data + k * (long long)g.S * per + sc;
+  for (int r = 0; r < g.S; ++r) {
+    const long long u = origin + r - sl.lo;  // data outside the canvas is dropped
+    if (u >= 0 && u < n) line[u] = gain * (double)__ldg(src + (long long)r * per);
+  }
+  spline_prefilter_line<LMAX>(line, sl, g.F);
+  const double neg_pos = pos_x ? -pos_x[k] : -g.pos_x1;
+  const long long anchor = pos_x ? ax[k] : g.ax1;
+  double* __restrict__ dst = U + k * (long long)g.n_out * per + sc;
+  for (int a = 0; a < g.n_out; ++a) dst[(long long)a * per] = spline_eval(line, sl, g.F, anchor + a, neg_pos);
+}
+
+// pass Y: one thread per (stamp, output row a, band): U (N, n_out, S, C) -> T (N, n_out, n_out, C)
+template <int LMAX>
+__global__ void __launch_bounds__(128) spline_pass_y_kernel(const double* __restrict__ U, long long N, int C, SplineGeom g,
+                                                            const int32_t* __restrict__ origin_y, const double* __restrict__ pos_y,
+                                                            const int32_t* __restrict__ ay, double* __restrict__ T) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = g.n_out * C;
+  if (t >= N * per) return;
+  const long long k = t / per;
+  const int ac = (int)(t - k * per);
+  const int a = ac / C, ch = ac - a * C;
+  const long long origin = origin_y ? origin_y[k] : (pos_y ? g.origin : g.origin_y1);
+  const SplineLine sl = spline_segment(g, origin);
+  const int n = sl.hi - sl.lo;
+  double line[LMAX];
+  const double gain = 6.0;
+  for (int i = 0; i < n; ++i) line[i] = 0.0;
+  const double* __restrict__ src = U + (k * g.n_out + a) * (long long)g.S * C + ch;
+  for (int s = 0; s < g.S; ++s) {
+    const long long u = origin + s - sl.lo;
+    if (u >= 0 && u < n) line[u] = gain * src[(long long)s * C];
+  }
+  spline_prefilter_line<LMAX>(line, sl, g.F);
+  const double neg_pos = pos_y ? -pos_y[k] : -g.pos_y1;
+  const long long anchor = pos_y ? ay[k] : g.ay1;
+  double* __restrict__ dst = T + (k * g.n_out + a) * (long long)g.n_out * C + ch;
+  for (int b = 0; b < g.n_out; ++b) dst[(long long)b * C] = spline_eval(line, sl, g.F, anchor + b, neg_pos);
+}
+
+// position fit objective (deblend_cutout/optimization.py:21-33): sum over a placed window T (E,E) of
+// T^2 - 2*img*T against one band of the field; with the field's own sum of squares this gives
+// mean((img - shifted)^2) over the whole canvas without touching the rest of it.  One CTA, fixed order.
+__global__ void __launch_bounds__(256) shift_objective_kernel(const double* __restrict__ field, long long F, int C, int band,
+                                                              const double* __restrict__ T, int E, int ax, int ay,
+                                                              double sumsq_field, double* __restrict__ out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < E * E; e += 256) {
+    const int a = e / E, b = e - a * E;
+    const long long X = (long long)ax + a, Y = (long long)ay + b;
+    if (X < 0 || X >= F || Y < 0 || Y >= F) continue;
+    const double t = T[e], v = field[(X * F + Y) * C + band];
+    acc += t * t - 2.0 * v * t;
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (sumsq_field + s[0]) / ((double)F * (double)F);
+}
+
+// sum of squares of one band of the field (two deterministic passes through `partial`)
+__global__ void __launch_bounds__(256) band_sumsq_kernel(const double* __restrict__ field, long long npix, int C, int band,
+                                                         double* __restrict__ partial) {
+  __shared__ double s[8];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const double v = field[i * C + band];
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) sum_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+constexpr int SPL_LMAX_SMALL = 128, SPL_LMAX_LARGE = 192;
+
+}  // namespace dbv
+using namespace dbv;
+
+extern "C" int dbv_spline_extent(int S, int P) {
+  if (S < 1 || P < 0 || S + 2 * P > SPL_LMAX_LARGE) return fail(DBV_ERR_UNSUPPORTED, "dbv_spline_extent: S + 2P = %d exceeds the %d-sample line buffer", S + 2 * P, SPL_LMAX_LARGE);
+  return S + 2 * P + 2;
+}
+
+extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int S, int C, int64_t F, int origin,
+                                const int32_t* origin_x, const int32_t* origin_y, const double* pos_x, const double* pos_y,
+                                const int32_t* ax, const int32_t* ay, int P, double* scratch, double* placed, void* stream) {
+  DBV_REQUIRE(N >= 0 && S > 0 && C > 0 && F > 0 && P >= 0, "dbv_spline_place: bad sizes");
+  if (N == 0) return DBV_OK;
+  DBV_REQUIRE(data && pos_x && pos_y && ax && ay && scratch && placed, "dbv_spline_place: null pointer");
+  DBV_REQUIRE((origin_x == nullptr) == (origin_y == nullptr), "dbv_spline_place: give both origin arrays or neither");
+  DBV_REQUIRE(data_dtype == DBV_F32 || data_dtype == DBV_F64, "dbv_spline_place: bad data dtype %d", data_dtype);
+  const int n_out = dbv_spline_extent(S, P);
+  if (n_out < 0) return n_out;
+  SplineGeom g = {};
+  g.F = F; g.S = S; g.P = P; g.origin = origin; g.n_out = n_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tx = N * (long long)S * C, ty = N * (long long)n_out * C;
+  const unsigned gx = (unsigned)((tx + 127) / 128), gy = (unsigned)((ty + 127) / 128);
+  const bool small = S + 2 * P <= SPL_LMAX_SMALL;
+  if (data_dtype == DBV_F32) {
+    if (small) spline_pass_x_kernel<float, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
+    else spline_pass_x_kernel<float, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
+  } else {
+    if (small) spline_pass_x_kernel<double, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
+    else spline_pass_x_kernel<double, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
+  }
+  DBV_LAUNCH_CHECK();
+  if (small) spline_pass_y_kernel<SPL_LMAX_SMALL><<<gy, 128, 0, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
+  else spline_pass_y_kernel<SPL_LMAX_LARGE><<<gy, 128, 0, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+extern "C" int dbv_band_sumsq(const double* field, int64_t F, int C, int band, double* out, void* scratch, int64_t scratch_bytes,
+                              void* stream) {
+  DBV_REQUIRE(field && out && scratch, "dbv_band_sumsq: null pointer");
+  DBV_REQUIRE(F > 0 && C > 0 && band >= 0 && band < C, "dbv_band_sumsq: bad sizes");
+  DBV_REQUIRE(scratch_bytes >= dbv_mse_scratch_bytes(), "dbv_band_sumsq: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long npix = (long long)F * F;
+  long long want = (npix + 1023) / 1024;
+  const int nb = (int)(want < MSE_BLOCKS ? (want < 1 ? 1 : want) : MSE_BLOCKS);
+  band_sumsq_kernel<<<nb, 256, 0, st>>>(field, npix, C, band, (double*)scratch);
+  DBV_LAUNCH_CHECK();
+  sum_final_kernel<<<1, 256, 0, st>>>((const double*)scratch, nb, out);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+extern "C" int dbv_shift_objective(const double* field, int64_t F, int C, int band, const double* placed, int E, int ax, int ay,
+                                   double sumsq_field, double* out, void* stream) {
+  DBV_REQUIRE(field && placed && out, "dbv_shift_objective: null pointer");
+  DBV_REQUIRE(F > 0 && C > 0 && band >= 0 && band < C && E > 0, "dbv_shift_objective: bad sizes");
+  shift_objective_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(field, F, C, band, placed, E, ax, ay, sumsq_field, out);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+extern "C" int dbv_position_objective(const double* field, int64_t F, int C, int band, const double* placed1, int E1, int a1x, int a1y,
+                                      double x0, double x1, int P, double sumsq_field, double* scratch, double* placed2,
+                                      double* out_dev, double* out_host, void* stream) {
+  DBV_REQUIRE(field && placed1 && scratch && placed2 && out_dev && out_host, "dbv_position_objective: null pointer");
+  DBV_REQUIRE(F > 0 && C > 0 && band >= 0 && band < C && E1 > 0 && P >= 0, "dbv_position_objective: bad sizes");
+  DBV_REQUIRE(x0 == x0 && x1 == x1 && fabs(x0) < 1e9 && fabs(x1) < 1e9, "dbv_position_objective: bad shift");
+  const int E2 = dbv_spline_extent(E1, P);
+  if (E2 < 0) return E2;
+  SplineGeom g = {};
+  g.F = F; g.S = E1; g.P = P; g.n_out = E2;
+  g.pos_x1 = x0; g.pos_y1 = x1;
+  g.origin_x1 = a1x; g.origin_y1 = a1y;
+  g.ax1 = a1x - P - 1 + (int)floor(x0);
+  g.ay1 = a1y - P - 1 + (int)floor(x1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool small = E1 + 2 * P <= SPL_LMAX_SMALL;
+  const unsigned gx = (unsigned)((E1 + 127) / 128), gy = (unsigned)((E2 + 127) / 128);
+  if (small) spline_pass_x_kernel<double, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
+  else spline_pass_x_kernel<double, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
+  DBV_LAUNCH_CHECK();
+  if (small) spline_pass_y_kernel<SPL_LMAX_SMALL><<<gy, 128, 0, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
+  else spline_pass_y_kernel<SPL_LMAX_LARGE><<<gy, 128, 0, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
+  DBV_LAUNCH_CHECK();
+  shift_objective_kernel<<<1, 256, 0, st>>>(field, F, C, band, placed2, E2, g.ax1, g.ay1, sumsq_field, out_dev);
+  DBV_LAUNCH_CHECK();
+  DBV_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  DBV_CUDA(cudaStreamSynchronize(st));
   return DBV_OK;
 }

@@ -3,9 +3,10 @@
 Same constructor, methods, attributes and record layout as the reference; the field lives on the
 device, extraction / network / centre-MSE / subtract-back are CUDA kernels, and only the record
 materialisation (a numpy recarray of per-stamp arrays, as the reference returns) touches the host.
-Not implemented (outside the B200 hot path): ``optimise_positions=True`` (scipy
-least-squares over sub-pixel shifts) and non-integer positions in get_residual_field /
-get_predicted_field (cubic-spline ndimage.shift); both raise NotImplementedError.
+Fractional positions in get_residual_field / get_predicted_field go through the cubic-spline placement kernels
+(the reference's ndimage.shift, evaluated only where it matters); ``optimise_positions=True`` runs the
+reference's own scipy least-squares call with the objective evaluated on the device
+(deblend_cutout/optimization.py).
 """
 import numpy as np
 import pandas as pd
@@ -39,13 +40,23 @@ class DeblendField:
 
     # ------------------------------------------------------------------------------------------
     def _positions(self, res_deblend):
+        """x_pos / y_pos of field_deblender.py:83-90 (float64) and whether every one is integer-valued."""
         dx = np.array([r["galaxy_distances_to_center_x"] for r in res_deblend], dtype=np.float64)
         dy = np.array([r["galaxy_distances_to_center_y"] for r in res_deblend], dtype=np.float64)
         sh = np.array([np.asarray(r["shifts"], dtype=np.float64) for r in res_deblend]).reshape(-1, 2)
-        off = _fieldops.subtract_offset(self.field_size, self.cutout_size)
-        x0 = off + _fieldops.integer_positions(dx, sh[:, 0], "x positions")
-        y0 = off + _fieldops.integer_positions(dy, sh[:, 1], "y positions")
-        return x0, y0
+        px, ix = _fieldops.positions(dx, sh[:, 0])
+        py, iy = _fieldops.positions(dy, sh[:, 1])
+        return px, py, ix and iy
+
+    def _paste(self, base, stamps, px, py, integer, alpha, shape=None):
+        """base + alpha * sum of the placed stamps: window copy for integer positions, cubic-spline
+        ndimage.shift placement (field_deblender.py:92-95) as soon as one position is fractional."""
+        if integer:
+            off = _fieldops.subtract_offset(self.field_size, self.cutout_size)
+            x0 = off + px.astype(np.int64)
+            y0 = off + py.astype(np.int64)
+            return _fieldops.window_axpy(base, stamps, x0, y0, alpha, field_shape=shape, dtype=torch.float64)
+        return _fieldops.spline_window_axpy(base, stamps, px, py, alpha, field_shape=shape, dtype=torch.float64)
 
     def _stamps_dev(self, res_deblend, column):
         c = self._dev_cache
@@ -62,8 +73,8 @@ class DeblendField:
         if res_deblend is None or len(res_deblend) == 0:
             out = base.clone()
         else:
-            x0, y0 = self._positions(res_deblend)
-            out = _fieldops.window_axpy(base, self._stamps_dev(res_deblend, "output_images_mean"), x0, y0, -1.0)
+            px, py, integer = self._positions(res_deblend)
+            out = self._paste(base, self._stamps_dev(res_deblend, "output_images_mean"), px, py, integer, -1.0)
         return out if as_tensor else out.cpu().numpy()
 
     def get_predicted_field(self, res_deblend=None, as_tensor=False):
@@ -79,8 +90,8 @@ class DeblendField:
             if res_deblend is None or len(res_deblend) == 0 or (col == "epistemic_uncertainty" and not self.epistemic_uncertainty_estimation):
                 f = torch.zeros((F_, F_, C), device=dev, dtype=torch.float64)
             else:
-                x0, y0 = self._positions(res_deblend)
-                f = _fieldops.window_axpy(None, self._stamps_dev(res_deblend, col), x0, y0, 1.0, field_shape=(F_, F_, C), dtype=torch.float64)
+                px, py, integer = self._positions(res_deblend)
+                f = self._paste(None, self._stamps_dev(res_deblend, col), px, py, integer, 1.0, shape=(F_, F_, C))
             out[name] = f if as_tensor else f.cpu().numpy()
         return out
 
@@ -94,8 +105,6 @@ class DeblendField:
     def deblend_field(self, galaxy_distances_to_center, cutout_images=None, optimise_positions=False, epistemic_criterion=100.0,
                       mse_criterion=100.0, field_image=None):
         """field_deblender.py:219-382."""
-        if optimise_positions:
-            raise NotImplementedError("optimise_positions=True (scipy sub-pixel position fit) is outside the B200 hot path")
         res_deblend = {"cutout_images": None, "output_images_mean": None, "output_images_stddev": None, "shifts": None, "list_idx": None}
         if field_image is None:
             field_dev = self._field_dev
@@ -155,7 +164,16 @@ class DeblendField:
 
         gx = [galaxy_distances_to_center[k][0] for k in list_idx]
         gy = [galaxy_distances_to_center[k][1] for k in list_idx]
-        shifts = [np.array([0, 0]) for _ in range(n)]
+        if optimise_positions:
+            # field_deblender.py:337-352: bounded least-squares fit of a sub-pixel shift per galaxy on the r band
+            # (the reference pads with self.field_size; it only works when field_image has that size too)
+            from ..deblend_cutout.optimization import FieldBand, fit_position
+
+            fb = FieldBand(field_dev)
+            r_band = mean_dev[:, :, :, 2].contiguous()
+            shifts = [np.array(fit_position(fb, r_band[i], galaxy_distances_to_center[k])) for i, k in enumerate(list_idx)]
+        else:
+            shifts = [np.array([0, 0]) for _ in range(n)]
 
         self.nb_of_detected_objects += [len(list(galaxy_distances_to_center))]
         self.nb_of_deblended_galaxies += [len(list_idx)]

@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define DBV_ABI_VERSION 2  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED */
+#define DBV_ABI_VERSION 3  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
+                              3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective */
 
 typedef enum {
   DBV_OK = 0,
@@ -125,6 +126,46 @@ int dbv_extract(const void* field_dev, int field_dtype, int64_t F, int C, const 
  * result is bit-identical to the sequential numpy loop.  stamps (N,S,S,C) f32. */
 int dbv_window_axpy(const void* in_dev, void* out_dev, int field_dtype, int64_t F, int C, const float* stamps_dev,
                     const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S, double alpha, void* stream);
+
+/* The same with f32 or f64 stamps (stamp_dtype): the sub-pixel path pastes f64 stamps. */
+int dbv_window_axpy_ex(const void* in_dev, void* out_dev, int field_dtype, int64_t F, int C, const void* stamps_dev,
+                       int stamp_dtype, const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S, double alpha,
+                       void* stream);
+
+/* Sub-pixel placement: scipy.ndimage.shift(padded_canvas, shift=(x_pos, y_pos)) of
+ * deblend/field_deblender.py:66-95, 121-182 and deblend_cutout/optimization.py:27-29, 41-44 (order 3,
+ * mode 'constant', prefilter=True; scipy==1.11.2, requirements.txt:7), evaluated on the window of the
+ * canvas where the result is not negligible: per axis the segment [origin-P, origin+S+P) clipped to
+ * the canvas is prefiltered (the prefilter's response decays as 0.268^d, P = 28 truncates at 1e-16 of
+ * the data's peak) with scipy's mirror initialisation wherever the segment ends on the canvas edge, so
+ * a canvas smaller than the segment is filtered whole, exactly as scipy does.
+ *   data (N,S,S,C) f32/f64: the block of non-zero canvas samples of each item; its sample 0 sits at
+ *   canvas row origin_x[k] / col origin_y[k] (both NULL: `origin` for all, i.e. int((F-S)/2) of
+ *   field_deblender.py:72).  pos = the shift.  Output window k has side E = dbv_spline_extent(S,P)
+ *   = S+2P+2 and starts at canvas row ax[k], col ay[k] (the caller passes origin - P - 1 + floor(pos));
+ *   placed (N,E,E,C) f64 is then pasted with dbv_window_axpy_ex(..., DBV_F64, ax, ay, N, E, ...).
+ *   scratch: N*E*S*C doubles.  S + 2P <= 192. */
+int dbv_spline_extent(int S, int P);
+int dbv_spline_place(const void* data_dev, int data_dtype, int64_t N, int S, int C, int64_t F, int origin,
+                     const int32_t* origin_x_dev, const int32_t* origin_y_dev, const double* pos_x_dev,
+                     const double* pos_y_dev, const int32_t* ax_dev, const int32_t* ay_dev, int P, double* scratch_dev,
+                     double* placed_dev, void* stream);
+
+/* Objective of position_optimization (deblend_cutout/optimization.py:21-33):
+ * out[0] = mean over the F x F canvas of (field[..., band] - shifted)^2 where `shifted` is zero but for
+ * the placed window (E,E) f64 at (ax, ay): (sumsq_field + sum_window(T^2 - 2 field T)) / F^2, with
+ * sumsq_field = sum field[..., band]^2 from dbv_band_sumsq (scratch as for dbv_mse). */
+int dbv_band_sumsq(const double* field_dev, int64_t F, int C, int band, double* out_dev, void* scratch_dev,
+                   int64_t scratch_bytes, void* stream);
+int dbv_shift_objective(const double* field_dev, int64_t F, int C, int band, const double* placed_dev, int E, int ax,
+                        int ay, double sumsq_field, double* out_dev, void* stream);
+/* One evaluation of `fun(x)` of optimization.py:21-33 for the already placed prediction placed1 (E1,E1) f64
+ * at (a1x, a1y) (= shift(r_band_prediction, galaxy_distance_to_center), optimization.py:41-44): a second
+ * placement by x = (x0, x1) into placed2 (E2 = dbv_spline_extent(E1,P) squared; scratch E2*E1 doubles), then
+ * dbv_shift_objective.  Synchronous: the value is written to out_host (and out_dev). */
+int dbv_position_objective(const double* field_dev, int64_t F, int C, int band, const double* placed1_dev, int E1, int a1x,
+                           int a1y, double x0, double x1, int P, double sumsq_field, double* scratch_dev,
+                           double* placed2_dev, double* out_dev, double* out_host, void* stream);
 
 /* mse of the centre window: deblend/field_deblender.py:323-332.  out[k] = mean over
  * [lo,hi)x[lo,hi)xC of (cutouts[k] - mean[k])^2 in fp64. */

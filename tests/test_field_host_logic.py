@@ -57,10 +57,34 @@ def test_precomputed_cutouts_branch(field_mod, golden_dir):
     np.testing.assert_array_equal(np.stack(list(rec["output_images_mean"])), g["mean"])
 
 
-def test_optimise_positions_is_refused(field_mod):
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_optimise_positions_has_no_cpu_fallback(field_mod):
+    """the position fit evaluates its objective on the device: without one it fails loudly"""
     obj = field_mod.DeblendField(fake_net, np.zeros((1, 80, 80, 6)))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError, match="CUDA"):
         obj.deblend_field(np.array([[0, 0]]), optimise_positions=True)
+
+
+def test_fractional_shifts_go_through_the_spline_placement(field_mod, golden_dir):
+    """records with fractional shifts: get_residual_field / get_predicted_field route to spline_window_axpy
+    (oracle-backed here) and reproduce the reference's outputs"""
+    import pandas as pd
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    name = "win_even"
+    field, means, stds, pos, sh = (g[f"{name}_{k}"] for k in ("field", "means", "stds", "pos", "shifts"))
+    rows = {
+        "output_images_mean": list(means),
+        "output_images_stddev": list(stds),
+        "epistemic_uncertainty": list(np.zeros_like(means)),
+        "shifts": [s for s in sh],
+        "galaxy_distances_to_center_x": list(pos[:, 0]),
+        "galaxy_distances_to_center_y": list(pos[:, 1]),
+    }
+    rec = pd.DataFrame(rows).to_records(index=False)
+    obj = field_mod.DeblendField(None, field, cutout_size=means.shape[1], nb_of_bands=field.shape[3])
+    np.testing.assert_allclose(obj.get_residual_field(rec), g[f"{name}_residual"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(obj.get_predicted_field(rec)["predicted_stddev_field"], g[f"{name}_pred_std"], rtol=0, atol=1e-12)
 
 
 def test_iterative_loop_control(monkeypatch):

@@ -153,3 +153,148 @@ def test_full_size_round_trip_property(ops):
     # scatter-add the stamps back: exact reconstruction of the windows
     back = ops.window_axpy(res, stamps, x0, y0, 1.0)
     assert torch.equal(back, field)
+
+
+# ---- sub-pixel placement (cubic-spline ndimage.shift of field_deblender.py:92-95) ---------------
+@pytest.mark.parametrize("name", ["win_odd", "win_even", "whole"])
+def test_subpixel_placement_matches_reference(ops, golden_dir, name):
+    """get_residual_field / get_predicted_field of the REFERENCE with fractional positions (tests/golden/subpixel.npz),
+    tolerance 1e-12 absolute (stamp peaks ~15): fp64 spline arithmetic in a different association order."""
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    field, means, stds = g[f"{name}_field"], g[f"{name}_means"], g[f"{name}_stds"]
+    pos = g[f"{name}_pos"] + g[f"{name}_shifts"]
+    F, C = field.shape[1], field.shape[3]
+    got = ops.spline_window_axpy(torch.from_numpy(field).cuda(), torch.from_numpy(means).cuda(), pos[:, 0], pos[:, 1], -1.0)
+    np.testing.assert_allclose(got.cpu().numpy(), g[f"{name}_residual"], rtol=0, atol=1e-12)
+    got = ops.spline_window_axpy(None, torch.from_numpy(stds).cuda(), pos[:, 0], pos[:, 1], 1.0, field_shape=(F, F, C), batch=2)
+    np.testing.assert_allclose(got.cpu().numpy(), g[f"{name}_pred_std"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("F", [200, 129, 128, 101])
+def test_subpixel_placement_vs_oracle(ops, F):
+    from oracle import spline_numpy as sp
+
+    S, C, N = 59, 6, 7
+    rng = np.random.default_rng(F)
+    field = rng.normal(size=(1, F, F, C))
+    means = (rng.random((N, S, S, C)) * 10).astype(np.float32)  # white noise: the harshest input for the spline
+    pos = rng.uniform(-F / 2 - 10, F / 2 + 10, size=(N, 2))  # some partly / fully off the canvas
+    pos[0] = (2.0, -3.0)  # integer positions go through the same path when any other is fractional
+    pos[1, 1] = 7.0
+    want = sp.residual_field_subpixel(field, means, pos[:, 0], pos[:, 1], S)
+    got = ops.spline_window_axpy(torch.from_numpy(field).cuda(), torch.from_numpy(means).cuda(), pos[:, 0], pos[:, 1], -1.0)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-12)
+
+
+def test_subpixel_drop_in_residual_and_predicted_fields(golden_dir):
+    """through DeblendField (reference import path): records with fractional shifts."""
+    import pandas as pd
+    from debvader.deblend.field_deblender import DeblendField
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    name = "win_odd"
+    field, means, stds, pos, sh = (g[f"{name}_{k}"] for k in ("field", "means", "stds", "pos", "shifts"))
+    rows = {
+        "output_images_mean": list(means),
+        "output_images_stddev": list(stds),
+        "epistemic_uncertainty": list(np.zeros_like(means)),
+        "shifts": [s for s in sh],
+        "galaxy_distances_to_center_x": list(pos[:, 0]),
+        "galaxy_distances_to_center_y": list(pos[:, 1]),
+    }
+    rec = pd.DataFrame(rows).to_records(index=False)
+    obj = DeblendField(None, field, cutout_size=means.shape[1], nb_of_bands=field.shape[3])
+    np.testing.assert_allclose(obj.get_residual_field(rec), g[f"{name}_residual"], rtol=0, atol=1e-12)
+    pf = obj.get_predicted_field(rec)
+    np.testing.assert_allclose(pf["predicted_mean_field"], g[f"{name}_pred_mean"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(pf["predicted_stddev_field"], g[f"{name}_pred_std"], rtol=0, atol=1e-12)
+
+
+def test_subpixel_full_size_properties(ops):
+    """BASELINE cfg 4 size (4096^2 x 6, 2000 sources) through the sub-pixel path: (i) with whole-pixel positions it
+    reproduces the window copy to 1e-12 (the reference's own spline-vs-slice difference is 5.7e-14), (ii) flux is
+    conserved for stamps inside the field (the cardinal spline sums to one), (iii) linearity in the stamps."""
+    F, S, C, N = 4096, 59, 6, 2000
+    rng = np.random.default_rng(4)
+    stamps = torch.from_numpy((rng.random((N, S, S, C)) * 5).astype(np.float32)).cuda()
+    ipos = rng.integers(-(F // 2 - 70), F // 2 - 70, size=(N, 2)).astype(np.float64)
+    off = ops.subtract_offset(F, S)
+    want = ops.window_axpy(None, stamps, off + ipos[:, 0].astype(np.int64), off + ipos[:, 1].astype(np.int64), 1.0, field_shape=(F, F, C))
+    got = ops.spline_window_axpy(None, stamps, ipos[:, 0], ipos[:, 1], 1.0, field_shape=(F, F, C))
+    assert float((got - want).abs().max()) < 1e-12 * 5 * 8  # up to ~8 overlapping stamps of peak 5
+    fpos = ipos + rng.uniform(-0.5, 0.5, size=(N, 2))
+    a = ops.spline_window_axpy(None, stamps, fpos[:, 0], fpos[:, 1], 1.0, field_shape=(F, F, C))
+    tot, ref = float(a.sum()), float(stamps.double().sum())
+    assert abs(tot - ref) < 1e-9 * ref
+    b = ops.spline_window_axpy(None, stamps * 2, fpos[:, 0], fpos[:, 1], 0.5, field_shape=(F, F, C))
+    assert float((a - b).abs().max()) < 1e-12 * 5 * 8
+
+
+# ---- position fit (deblend_cutout/optimization.py) ---------------------------------------------
+def test_position_objective_matches_the_reference_fun(golden_dir):
+    """fun(x) of optimization.py:21-33 (two successive full-canvas spline shifts + mean of squares, restated in
+    oracle/spline_numpy.py) vs the device evaluation on the placed windows: 1e-12 relative."""
+    import ctypes as C
+
+    from debvader_b200 import _ffi, _fieldops
+    from debvader_b200.deblend_cutout.optimization import FieldBand
+    from oracle import spline_numpy as sp
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    field, means, dist = g["opt_field"], g["opt_means"], g["opt_dist"]
+    F, S = field.shape[1], means.shape[1]
+    fb = FieldBand(torch.from_numpy(field).cuda())
+    assert abs(fb.sumsq - np.square(field[0, :, :, 2]).sum()) < 1e-12 * fb.sumsq
+    off = int((F - S) / 2)
+    for k in range(len(means)):
+        for d in (dist[k], dist[k] + 0.37):
+            canvas = np.zeros((F, F))
+            canvas[off : off + S, off : off + S] = means[k, :, :, 2]
+            net_output = sp.shift_cubic_constant(canvas, d)
+            stamp = torch.from_numpy(np.ascontiguousarray(means[k, :, :, 2])).cuda()
+            placed1, a1x, a1y = _fieldops.spline_place(stamp.reshape(1, S, S, 1), d[0:1], d[1:2], F)
+            E1 = placed1.shape[1]
+            E2 = _fieldops.spline_extent(E1)
+            scratch = torch.empty(E2 * E1, device="cuda", dtype=torch.float64)
+            placed2 = torch.empty(E2 * E2, device="cuda", dtype=torch.float64)
+            out_dev = torch.empty(1, device="cuda", dtype=torch.float64)
+            out_host = C.c_double(0.0)
+            for x in ((0.0, 0.0), (0.8, -1.3), (-2.9, 2.99), (1.5e-8, 0.0), (3.0, -3.0)):
+                want = sp.position_objective(x, field[0, :, :, 2], net_output)
+                _ffi.check(_ffi.lib().dbv_position_objective(_ffi.ptr(fb.field), F, fb.C, 2, _ffi.ptr(placed1), E1, int(a1x[0]), int(a1y[0]),
+                                                             x[0], x[1], _fieldops.SPLINE_MARGIN, fb.sumsq, _ffi.ptr(scratch), _ffi.ptr(placed2),
+                                                             _ffi.ptr(out_dev), C.cast(C.byref(out_host), C.c_void_p), _ffi.stream_ptr()))
+                assert abs(out_host.value - want) <= 1e-12 * want, (k, d, x, out_host.value, want)
+
+
+def test_position_fit_matches_reference(golden_dir):
+    """position_optimization of the REFERENCE (scipy least_squares on full-canvas shifts) vs the drop-in: the
+    optimiser is the same scipy call, the objective agrees to ~1e-15, so the fitted shifts agree to the optimiser's
+    own noise (2-point Jacobian with a 1.5e-8 step amplifies rounding): 1e-3 px."""
+    from debvader.deblend_cutout.optimization import position_optimization
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    field, means, dist = g["opt_field"], g["opt_means"], g["opt_dist"]
+    F, S = field.shape[1], means.shape[1]
+    off = int((F - S) / 2)
+    for k in range(len(means)):
+        canvas = np.zeros((F, F, means.shape[3]))
+        canvas[off : off + S, off : off + S] = means[k]
+        sx, sy = position_optimization(field[0], canvas, dist[k])
+        assert abs(sx - g["opt_fitted"][k, 0]) < 1e-3 and abs(sy - g["opt_fitted"][k, 1]) < 1e-3, (k, sx, sy, g["opt_fitted"][k])
+
+
+def test_deblend_field_with_optimise_positions_matches_reference(golden_dir):
+    """DeblendField.deblend_field(optimise_positions=True) driven by the fake net of tests/golden/make_golden.py."""
+    from debvader.deblend.field_deblender import DeblendField
+    from tests.golden.make_golden import fake_net
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    gf = np.load(os.path.join(golden_dir, "deblend_field_fake.npz"))
+    obj = DeblendField(fake_net, gf["field"], cutout_size=59, nb_of_bands=6)
+    rec = obj.deblend_field(gf["centres"], optimise_positions=True, mse_criterion=2.0)
+    assert list(rec["list_idx"]) == list(g["dfo_list_idx"])
+    got = np.stack(list(rec["shifts"]))
+    np.testing.assert_allclose(got, g["dfo_shifts"], rtol=0, atol=1e-3)
+    # the residual moves by |gradient| * shift error: stamps peak at ~30 here
+    np.testing.assert_allclose(obj.get_residual_field(), g["dfo_residual"], rtol=0, atol=0.1)

@@ -73,3 +73,34 @@ def test_architecture_matches_checkpoint_index(golden_dir):
         assert a["tensors"][key] == list(shape), key
     w = ow.make_random_weights(seed=1)
     assert ow.count_params(w) == a["net_summary_params"]
+
+
+# ---- sub-pixel placement (scipy.ndimage.shift restatement) ------------------------------------
+from oracle import spline_numpy as sp  # noqa: E402
+
+
+@pytest.mark.parametrize("n,shift", [(40, (0.3, -1.7)), (131, (20.25, -33.5)), (64, (3.0, 0.0)), (64, (-2.999999, 2.5)), (20, (7.6, -8.2)), (50, (0.0, 0.5))])
+def test_spline_shift_restatement_equals_scipy(n, shift):
+    ndi = pytest.importorskip("scipy.ndimage")
+    a = np.random.default_rng(n).standard_normal((n, n))
+    np.testing.assert_allclose(sp.shift_cubic_constant(a, shift), ndi.shift(a, shift), rtol=0, atol=2e-14)
+
+
+@pytest.mark.parametrize("name", ["win_odd", "win_even", "whole"])
+def test_subpixel_fields_match_reference(golden_dir, name):
+    """oracle (full-canvas shift per galaxy and band) and the kernel's windowed formulation (tests/cpu_ops.py)
+    against the reference's own get_residual_field / get_predicted_field with fractional positions."""
+    from tests import cpu_ops
+
+    g = np.load(os.path.join(golden_dir, "subpixel.npz"))
+    field, means, stds = g[f"{name}_field"], g[f"{name}_means"], g[f"{name}_stds"]
+    pos = g[f"{name}_pos"] + g[f"{name}_shifts"]
+    S = means.shape[1]
+    res = sp.residual_field_subpixel(field, means, pos[:, 0], pos[:, 1], S)
+    np.testing.assert_allclose(res, g[f"{name}_residual"], rtol=0, atol=1e-12)
+    pm = sp.predicted_field_subpixel(field.shape[1], field.shape[3], stds, pos[:, 0], pos[:, 1], S)
+    np.testing.assert_allclose(pm, g[f"{name}_pred_std"], rtol=0, atol=1e-12)
+    win = cpu_ops.windowed_axpy(field, means, pos[:, 0], pos[:, 1], -1.0)
+    np.testing.assert_allclose(win, g[f"{name}_residual"], rtol=0, atol=1e-12)
+    win = cpu_ops.windowed_axpy(None, means, pos[:, 0], pos[:, 1], 1.0, field_shape=(field.shape[1], field.shape[1], field.shape[3]))
+    np.testing.assert_allclose(win, g[f"{name}_pred_mean"], rtol=0, atol=1e-12)
