@@ -241,15 +241,41 @@ def field_extras(net, device, pk, quick=False):
     out["extract_f64_to_f32"] = {"GBps": 16384 * STAMP_ELTS * 12 / t / 1e6, "ms": t, "stamps": 16384, "bytes_per_stamp": STAMP_ELTS * 12}
     stamps32, _ = _fieldops.extract(field, plan, S, C, out_dtype=torch.float32)
     res = torch.empty_like(field)
-    t = timeit(lambda: _fieldops.window_axpy(field, stamps32, x0, y0, -1.0, out=res))
+    x0d = torch.from_numpy(x0.astype(np.int32)).to(device)  # window positions resident, like every other input of the timed region
+    y0d = torch.from_numpy(y0.astype(np.int32)).to(device)
+    t = timeit(lambda: _fieldops.window_axpy(field, stamps32, x0d, y0d, -1.0, out=res))
     alg = N * STAMP_ELTS * 20  # stamp read + f64 field window RMW
-    full = 2 * field.numel() * 8 + N * STAMP_ELTS * 4  # what the owner-computes kernel really moves: whole field in+out, stamps once
-    out["window_axpy_f64"] = {"GBps_algorithmic": alg / t / 1e6, "GBps_moved": full / t / 1e6, "ms": t, "stamps": N}
+    # get_residual_field is `field.copy()` followed by the subtractions (field_deblender.py:62): the fused kernel moves the
+    # whole field in+out plus the stamps once
+    full = 2 * field.numel() * 8 + N * STAMP_ELTS * 4
+    out["window_axpy_f64"] = {"GBps_algorithmic": alg / t / 1e6, "GBps_moved": full / t / 1e6, "ms": t, "stamps": N,
+                              "note": "residual = field.copy() - stamps in one pass (binning + owner-computes kernels)"}
     for k in out.values():
         for kk in list(k):
             if kk.startswith("GBps"):
                 k["frac" + kk[4:]] = round(k[kk] / pk["hbm_gbs"], 4)
     if not quick:
+        # sub-pixel placement (cubic-spline ndimage.shift of field_deblender.py:92-95) of the same stamps at fractional positions
+        fpos = centres + rng.uniform(-0.5, 0.5, size=centres.shape)
+        E = _fieldops.spline_extent(S)
+        t = timeit(lambda: _fieldops.spline_window_axpy(field, stamps32, fpos[:, 0], fpos[:, 1], -1.0), iters=3)
+        tp = timeit(lambda: _fieldops.spline_place(stamps32[:512], fpos[:512, 0], fpos[:512, 1], F), iters=3)
+        place_bytes = 512 * (STAMP_ELTS * 4 + 2 * E * S * C * 8 + E * E * C * 8)  # stamp in, scratch out+in, window out
+        out["subpixel_residual_f64"] = {"ms": t, "stamps": N, "window": E, "place_ms_per_512": tp, "place_GBps": place_bytes / tp / 1e6,
+                                        "place_frac": round(place_bytes / tp / 1e6 / pk["hbm_gbs"], 4),
+                                        "note": "prefilter + shift on (S+2P+2)^2 f64 windows (P=28), then the f64 window paste"}
+        from debvader_b200.deblend_cutout.optimization import FieldBand, fit_position
+        fb = FieldBand(field)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nfev = 0
+        for k in range(10):
+            r = fit_position(fb, stamps32[k, :, :, 2].double().contiguous(), centres[k], return_result=True)
+            nfev += r.nfev
+        torch.cuda.synchronize()
+        out["position_fit"] = {"ms_per_galaxy": (time.perf_counter() - t0) / 10 * 1e3, "nfev_per_galaxy": nfev / 10,
+                               "note": "scipy.optimize.least_squares on the host (as the reference), objective on the device"}
+
         def one_field():
             cut, idx = _fieldops.extract(field, plan, S, C, out_dtype=torch.float32)
             d = net(cut)

@@ -166,8 +166,13 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
     n, S = stamps.shape[0], stamps.shape[1]
     if out is None:
         out = torch.empty(shape, device=dev, dtype=dtype)
-    xs = torch.from_numpy(np.asarray(x0, dtype=np.int32)).to(dev)
-    ys = torch.from_numpy(np.asarray(y0, dtype=np.int32)).to(dev)
+    if isinstance(x0, torch.Tensor) and isinstance(y0, torch.Tensor):  # positions already on the device (int32)
+        if not (x0.is_cuda and y0.is_cuda and x0.dtype == torch.int32 and y0.dtype == torch.int32 and x0.numel() == n == y0.numel()):
+            raise TypeError("device positions must be int32 CUDA tensors of length N")
+        xs, ys = x0.contiguous(), y0.contiguous()
+    else:  # one packed upload
+        xy = torch.from_numpy(np.stack([np.asarray(x0, dtype=np.int32).reshape(-1), np.asarray(y0, dtype=np.int32).reshape(-1)])).to(dev)
+        xs, ys = xy[0], xy[1]
     with torch.cuda.device(dev):
         _ffi.check(
             _ffi.lib().dbv_window_axpy_ex(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _DT[stamps.dtype],

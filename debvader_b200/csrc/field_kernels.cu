@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace dbv {
 
@@ -484,8 +485,26 @@ extern "C" int dbv_window_axpy_ex(const void* in, void* out, int dtype, int64_t 
   bool use_bins = N > 0;
   if (const char* e = getenv("DBV_AXPY_BINS")) use_bins = use_bins && atoi(e) != 0;  // tuning knob (0 = every tile scans)
   if (use_bins) {
+    // per-device scratch kept by the library (tile counts + fixed-capacity lists); calls that share a device must be
+    // ordered on one stream, like every other use of this library's per-device state
+    static std::mutex mu;
+    static int* cache[64] = {};
+    static size_t cap[64] = {};
     const size_t bytes = (size_t)ntiles * (1 + AX_LCAP) * sizeof(int);
-    DBV_CUDA(cudaMallocAsync((void**)&bins, bytes, st));
+    int dev = 0;
+    DBV_CUDA(cudaGetDevice(&dev));
+    DBV_REQUIRE(dev >= 0 && dev < 64, "dbv_window_axpy: device index %d out of range", dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (cap[dev] < bytes) {
+        if (cache[dev]) DBV_CUDA(cudaFree(cache[dev]));
+        cache[dev] = nullptr;
+        cap[dev] = 0;
+        DBV_CUDA(cudaMalloc((void**)&cache[dev], bytes));
+        cap[dev] = bytes;
+      }
+      bins = cache[dev];
+    }
     DBV_CUDA(cudaMemsetAsync(bins, 0, (size_t)ntiles * sizeof(int), st));
     axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, F, tiles_c, bins, bins + ntiles);
     DBV_LAUNCH_CHECK();
@@ -502,7 +521,6 @@ extern "C" int dbv_window_axpy_ex(const void* in, void* out, int dtype, int64_t 
   else
     window_axpy_kernel<float, double><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);
   DBV_LAUNCH_CHECK();
-  if (bins) DBV_CUDA(cudaFreeAsync(bins, st));
   return DBV_OK;
 }
 
@@ -580,8 +598,11 @@ struct SplineLine {
   int lo, hi;
 };
 
-template <int LMAX>
-__device__ __forceinline__ void spline_prefilter_line(double* line, const SplineLine& sl, long long F) {
+// line element i of this thread lives at line[i * LS] (LS = threads per CTA: consecutive threads, consecutive words)
+#define SPL_AT(i) line[(size_t)(i) * LS]
+constexpr int SPL_THREADS = 64;
+
+__device__ __forceinline__ void spline_prefilter_line(double* line, const int LS, const SplineLine& sl, long long F) {
   const double z = -0.26794919243112270647;  // sqrt(3) - 2
   const int n = sl.hi - sl.lo;
   if (n < 2) return;  // scipy leaves lines shorter than 2 untouched (n == F == 1)
@@ -589,20 +610,28 @@ __device__ __forceinline__ void spline_prefilter_line(double* line, const Spline
     // ni_splines.c:_init_causal_mirror over the canvas line of length F (zero outside the segment)
     const double z_n_1 = pow(z, (double)(F - 1));
     const bool tail = sl.hi == F;  // canvas index F-1-i lies inside the segment only then
-    double c0 = line[0] + (tail ? z_n_1 * line[n - 1] : 0.0);
+    double c0 = SPL_AT(0) + (tail ? z_n_1 * SPL_AT(n - 1) : 0.0);
     double z_i = z;
     const int last = (long long)n - 1 < F - 2 ? n - 1 : (int)(F - 2);
     for (int i = 1; i <= last; ++i) {
       const long long j = F - 1 - i - sl.lo;
-      c0 = c0 + z_i * (line[i] + ((tail && j >= 0 && j < n) ? z_n_1 * line[j] : 0.0));
+      c0 = c0 + z_i * (SPL_AT(i) + ((tail && j >= 0 && j < n) ? z_n_1 * SPL_AT(j) : 0.0));
       z_i *= z;
     }
-    line[0] = c0 / (1.0 - z_n_1 * z_n_1);
+    SPL_AT(0) = c0 / (1.0 - z_n_1 * z_n_1);
   }
-  for (int i = 1; i < n; ++i) line[i] += z * line[i - 1];
-  if (sl.hi == F) line[n - 1] = (z * line[n - 2] + line[n - 1]) * z / (z * z - 1.0);  // _init_anticausal_mirror
-  else line[n - 1] = line[n - 1] * (z / (z * z - 1.0));                                // infinite geometric tail
-  for (int i = n - 2; i >= 0; --i) line[i] = z * (line[i + 1] - line[i]);
+  double prev = SPL_AT(0);
+  for (int i = 1; i < n; ++i) {
+    prev = SPL_AT(i) + z * prev;
+    SPL_AT(i) = prev;
+  }
+  if (sl.hi == F) prev = (z * SPL_AT(n - 2) + prev) * z / (z * z - 1.0);  // _init_anticausal_mirror
+  else prev = prev * (z / (z * z - 1.0));                                  // infinite geometric tail
+  SPL_AT(n - 1) = prev;
+  for (int i = n - 2; i >= 0; --i) {
+    prev = z * (prev - SPL_AT(i));
+    SPL_AT(i) = prev;
+  }
 }
 
 __device__ __forceinline__ long long spline_mirror_index(long long idx, long long n) {
@@ -619,7 +648,8 @@ __device__ __forceinline__ long long spline_mirror_index(long long idx, long lon
 }
 
 // value of the shifted line at canvas index i: source coordinate cc = i - pos (NI_ZoomShift)
-__device__ __forceinline__ double spline_eval(const double* line, const SplineLine& sl, long long F, long long i, double neg_pos) {
+__device__ __forceinline__ double spline_eval(const double* line, const int LS, const SplineLine& sl, long long F, long long i,
+                                              double neg_pos) {
   const double cc = (double)i + neg_pos;
   if (cc < 0.0 || cc > (double)(F - 1)) return 0.0;  // mode='constant': outside the canvas -> cval
   const double fl = floor(cc);
@@ -631,10 +661,16 @@ __device__ __forceinline__ double spline_eval(const double* line, const SplineLi
   w[3] = 1.0 - w[0] - w[1] - w[2];
   const long long start = (long long)fl - 1;
   double t = 0.0;
+  if (start >= sl.lo && start + 3 < sl.hi) {  // the common case: all four taps inside the segment (and the canvas)
+    const int u = (int)(start - sl.lo);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) t += SPL_AT(u + l) * w[l];
+    return t;
+  }
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const long long idx = spline_mirror_index(start + l, F);
-    const double c = (idx >= sl.lo && idx < sl.hi) ? line[idx - sl.lo] : 0.0;  // beyond the segment: < |z|^P
+    const double c = (idx >= sl.lo && idx < sl.hi) ? SPL_AT(idx - sl.lo) : 0.0;  // beyond the segment: < |z|^P
     t += c * w[l];
   }
   return t;
@@ -650,10 +686,14 @@ __device__ __forceinline__ SplineLine spline_segment(const SplineGeom& g, long l
 }
 
 // pass X: one thread per (stamp, column s, band): data (N,S,S,C) -> U (N, n_out, S, C)
-template <typename TS, int LMAX>
-__global__ void __launch_bounds__(128) spline_pass_x_kernel(const TS* __restrict__ data, long long N, int C, SplineGeom g,
-                                                            const int32_t* __restrict__ origin_x, const double* __restrict__ pos_x,
-                                                            const int32_t* __restrict__ ax, double* __restrict__ U) {
+template <typename TS>
+__global__ void __launch_bounds__(SPL_THREADS) spline_pass_x_kernel(const TS* __restrict__ data, long long N, int C, SplineGeom g,
+                                                                    const int32_t* __restrict__ origin_x,
+                                                                    const double* __restrict__ pos_x, const int32_t* __restrict__ ax,
+                                                                    double* __restrict__ U) {
+  extern __shared__ double spl_lines[];
+  const int LS = SPL_THREADS;
+  double* line = spl_lines + threadIdx.x;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = g.S * C;
   if (t >= N * per) return;
@@ -662,26 +702,29 @@ __global__ void __launch_bounds__(128) spline_pass_x_kernel(const TS* __restrict
   const long long origin = origin_x ? origin_x[k] : (pos_x ? g.origin : g.origin_x1);
   const SplineLine sl = spline_segment(g, origin);
   const int n = sl.hi - sl.lo;
-  double line[LMAX];
   const double gain = 6.0;  // (1 - z)(1 - 1/z)
-  for (int i = 0; i < n; ++i) line[i] = 0.0;
+  for (int i = 0; i < n; ++i) SPL_AT(i) = 0.0;
   const TS* __restrict__ src = data + k * (long long)g.S * per + sc;
   for (int r = 0; r < g.S; ++r) {
     const long long u = origin + r - sl.lo;  // data outside the canvas is dropped
-    if (u >= 0 && u < n) line[u] = gain * (double)__ldg(src + (long long)r * per);
+    if (u >= 0 && u < n) SPL_AT(u) = gain * (double)__ldg(src + (long long)r * per);
   }
-  spline_prefilter_line<LMAX>(line, sl, g.F);
+  spline_prefilter_line(line, LS, sl, g.F);
   const double neg_pos = pos_x ? -pos_x[k] : -g.pos_x1;
   const long long anchor = pos_x ? ax[k] : g.ax1;
   double* __restrict__ dst = U + k * (long long)g.n_out * per + sc;
-  for (int a = 0; a < g.n_out; ++a) dst[(long long)a * per] = spline_eval(line, sl, g.F, anchor + a, neg_pos);
+#pragma unroll 4
+  for (int a = 0; a < g.n_out; ++a) dst[(long long)a * per] = spline_eval(line, LS, sl, g.F, anchor + a, neg_pos);
 }
 
 // pass Y: one thread per (stamp, output row a, band): U (N, n_out, S, C) -> T (N, n_out, n_out, C)
-template <int LMAX>
-__global__ void __launch_bounds__(128) spline_pass_y_kernel(const double* __restrict__ U, long long N, int C, SplineGeom g,
-                                                            const int32_t* __restrict__ origin_y, const double* __restrict__ pos_y,
-                                                            const int32_t* __restrict__ ay, double* __restrict__ T) {
+__global__ void __launch_bounds__(SPL_THREADS) spline_pass_y_kernel(const double* __restrict__ U, long long N, int C, SplineGeom g,
+                                                                    const int32_t* __restrict__ origin_y,
+                                                                    const double* __restrict__ pos_y, const int32_t* __restrict__ ay,
+                                                                    double* __restrict__ T) {
+  extern __shared__ double spl_lines[];
+  const int LS = SPL_THREADS;
+  double* line = spl_lines + threadIdx.x;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = g.n_out * C;
   if (t >= N * per) return;
@@ -691,19 +734,19 @@ __global__ void __launch_bounds__(128) spline_pass_y_kernel(const double* __rest
   const long long origin = origin_y ? origin_y[k] : (pos_y ? g.origin : g.origin_y1);
   const SplineLine sl = spline_segment(g, origin);
   const int n = sl.hi - sl.lo;
-  double line[LMAX];
   const double gain = 6.0;
-  for (int i = 0; i < n; ++i) line[i] = 0.0;
+  for (int i = 0; i < n; ++i) SPL_AT(i) = 0.0;
   const double* __restrict__ src = U + (k * g.n_out + a) * (long long)g.S * C + ch;
   for (int s = 0; s < g.S; ++s) {
     const long long u = origin + s - sl.lo;
-    if (u >= 0 && u < n) line[u] = gain * src[(long long)s * C];
+    if (u >= 0 && u < n) SPL_AT(u) = gain * src[(long long)s * C];
   }
-  spline_prefilter_line<LMAX>(line, sl, g.F);
+  spline_prefilter_line(line, LS, sl, g.F);
   const double neg_pos = pos_y ? -pos_y[k] : -g.pos_y1;
   const long long anchor = pos_y ? ay[k] : g.ay1;
   double* __restrict__ dst = T + (k * g.n_out + a) * (long long)g.n_out * C + ch;
-  for (int b = 0; b < g.n_out; ++b) dst[(long long)b * C] = spline_eval(line, sl, g.F, anchor + b, neg_pos);
+#pragma unroll 4
+  for (int b = 0; b < g.n_out; ++b) dst[(long long)b * C] = spline_eval(line, LS, sl, g.F, anchor + b, neg_pos);
 }
 
 // position fit objective (deblend_cutout/optimization.py:21-33): sum over a placed window T (E,E) of
@@ -762,13 +805,26 @@ __global__ void __launch_bounds__(256) sum_final_kernel(const double* __restrict
   if (threadIdx.x == 0) out[0] = s[0];
 }
 
-constexpr int SPL_LMAX_SMALL = 128, SPL_LMAX_LARGE = 192;
+constexpr int SPL_LMAX = 192;  // samples per line: SPL_LMAX * SPL_THREADS doubles of shared memory at most (96 KB)
+
+static int spline_smem_attr() {
+  static bool done = false;
+  if (!done) {
+    const int bytes = SPL_LMAX * SPL_THREADS * (int)sizeof(double);
+    if (cudaFuncSetAttribute(spline_pass_x_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(spline_pass_x_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(spline_pass_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+      return -1;
+    done = true;
+  }
+  return 0;
+}
 
 }  // namespace dbv
 using namespace dbv;
 
 extern "C" int dbv_spline_extent(int S, int P) {
-  if (S < 1 || P < 0 || S + 2 * P > SPL_LMAX_LARGE) return fail(DBV_ERR_UNSUPPORTED, "dbv_spline_extent: S + 2P = %d exceeds the %d-sample line buffer", S + 2 * P, SPL_LMAX_LARGE);
+  if (S < 1 || P < 0 || S + 2 * P > SPL_LMAX) return fail(DBV_ERR_UNSUPPORTED, "dbv_spline_extent: S + 2P = %d exceeds the %d-sample line buffer", S + 2 * P, SPL_LMAX);
   return S + 2 * P + 2;
 }
 
@@ -785,19 +841,16 @@ extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int
   SplineGeom g = {};
   g.F = F; g.S = S; g.P = P; g.origin = origin; g.n_out = n_out;
   cudaStream_t st = (cudaStream_t)stream;
+  if (spline_smem_attr()) return fail(DBV_ERR_CUDA, "dbv_spline_place: cannot raise the dynamic shared memory limit");
   const long long tx = N * (long long)S * C, ty = N * (long long)n_out * C;
-  const unsigned gx = (unsigned)((tx + 127) / 128), gy = (unsigned)((ty + 127) / 128);
-  const bool small = S + 2 * P <= SPL_LMAX_SMALL;
-  if (data_dtype == DBV_F32) {
-    if (small) spline_pass_x_kernel<float, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
-    else spline_pass_x_kernel<float, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
-  } else {
-    if (small) spline_pass_x_kernel<double, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
-    else spline_pass_x_kernel<double, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
-  }
+  const unsigned gx = (unsigned)((tx + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((ty + SPL_THREADS - 1) / SPL_THREADS);
+  const size_t smem = (size_t)(S + 2 * P) * SPL_THREADS * sizeof(double);
+  if (data_dtype == DBV_F32)
+    spline_pass_x_kernel<float><<<gx, SPL_THREADS, smem, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
+  else
+    spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
   DBV_LAUNCH_CHECK();
-  if (small) spline_pass_y_kernel<SPL_LMAX_SMALL><<<gy, 128, 0, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
-  else spline_pass_y_kernel<SPL_LMAX_LARGE><<<gy, 128, 0, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
+  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
@@ -842,13 +895,12 @@ extern "C" int dbv_position_objective(const double* field, int64_t F, int C, int
   g.ax1 = a1x - P - 1 + (int)floor(x0);
   g.ay1 = a1y - P - 1 + (int)floor(x1);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool small = E1 + 2 * P <= SPL_LMAX_SMALL;
-  const unsigned gx = (unsigned)((E1 + 127) / 128), gy = (unsigned)((E2 + 127) / 128);
-  if (small) spline_pass_x_kernel<double, SPL_LMAX_SMALL><<<gx, 128, 0, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
-  else spline_pass_x_kernel<double, SPL_LMAX_LARGE><<<gx, 128, 0, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
+  if (spline_smem_attr()) return fail(DBV_ERR_CUDA, "dbv_position_objective: cannot raise the dynamic shared memory limit");
+  const unsigned gx = (unsigned)((E1 + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((E2 + SPL_THREADS - 1) / SPL_THREADS);
+  const size_t smem = (size_t)(E1 + 2 * P) * SPL_THREADS * sizeof(double);
+  spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
   DBV_LAUNCH_CHECK();
-  if (small) spline_pass_y_kernel<SPL_LMAX_SMALL><<<gy, 128, 0, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
-  else spline_pass_y_kernel<SPL_LMAX_LARGE><<<gy, 128, 0, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
+  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
   DBV_LAUNCH_CHECK();
   shift_objective_kernel<<<1, 256, 0, st>>>(field, F, C, band, placed2, E2, g.ax1, g.ay1, sumsq_field, out_dev);
   DBV_LAUNCH_CHECK();
