@@ -213,7 +213,7 @@ def spline_place(data, pos_x, pos_y, field_size: int, margin: int = SPLINE_MARGI
     ax, ay = _anchor(ox, px, margin), _anchor(oy, py, margin)
     pos = torch.from_numpy(np.stack([px, py])).to(dev)
     ints = torch.from_numpy(np.stack([ax, ay, ox.astype(np.int32), oy.astype(np.int32)])).to(dev)
-    scratch = torch.empty((n, E, S, Cc), device=dev, dtype=torch.float64)
+    scratch = torch.empty((int(_ffi.lib().dbv_spline_scratch_doubles(n, S, Cc, int(margin))),), device=dev, dtype=torch.float64)
     placed = torch.empty((n, E, E, Cc), device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
         _ffi.check(

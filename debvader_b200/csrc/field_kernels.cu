@@ -600,7 +600,7 @@ struct SplineLine {
 
 // line element i of this thread lives at line[i * LS] (LS = threads per CTA: consecutive threads, consecutive words)
 #define SPL_AT(i) line[(size_t)(i) * LS]
-constexpr int SPL_THREADS = 64;
+constexpr int SPL_THREADS = 64, SPL_LD = 16;
 
 __device__ __forceinline__ void spline_prefilter_line(double* line, const int LS, const SplineLine& sl, long long F) {
   const double z = -0.26794919243112270647;  // sqrt(3) - 2
@@ -647,31 +647,59 @@ __device__ __forceinline__ long long spline_mirror_index(long long idx, long lon
   return idx;
 }
 
-// value of the shifted line at canvas index i: source coordinate cc = i - pos (NI_ZoomShift)
-__device__ __forceinline__ double spline_eval(const double* line, const int LS, const SplineLine& sl, long long F, long long i,
-                                              double neg_pos) {
-  const double cc = (double)i + neg_pos;
-  if (cc < 0.0 || cc > (double)(F - 1)) return 0.0;  // mode='constant': outside the canvas -> cval
+// Interpolation weights of one output index (NI_ZoomShift + get_spline_interpolation_weights, order 3): they depend on
+// (item, axis, output index) only, so a small kernel tabulates them once instead of every line recomputing them (three
+// fp64 divisions per output).  Entry = {first tap (canvas index; < -2^40: output is cval), w0, w1, w2, w3}.
+constexpr int SPL_WSTRIDE = 5;
+constexpr double SPL_INVALID = -4.0e15;
+
+__global__ void __launch_bounds__(128) spline_weights_kernel(long long N, SplineGeom g, const double* __restrict__ pos_x,
+                                                             const double* __restrict__ pos_y, const int32_t* __restrict__ ax,
+                                                             const int32_t* __restrict__ ay, double* __restrict__ W) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * 2 * g.n_out) return;
+  const long long k = t / (2 * g.n_out);
+  const int rem = (int)(t - k * 2 * g.n_out);
+  const int axis = rem / g.n_out, a = rem - axis * g.n_out;
+  const double pos = axis == 0 ? (pos_x ? pos_x[k] : g.pos_x1) : (pos_y ? pos_y[k] : g.pos_y1);
+  const long long anchor = axis == 0 ? (pos_x ? ax[k] : g.ax1) : (pos_y ? ay[k] : g.ay1);
+  double* __restrict__ w = W + t * SPL_WSTRIDE;
+  const double cc = (double)(anchor + a) + (-pos);  // source coordinate of canvas index anchor + a
+  if (cc < 0.0 || cc > (double)(g.F - 1)) {         // mode='constant': outside the canvas -> cval
+    w[0] = SPL_INVALID;
+    w[1] = w[2] = w[3] = w[4] = 0.0;
+    return;
+  }
   const double fl = floor(cc);
   const double y = cc - fl, zc = 1.0 - y;
-  double w[4];
-  w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
-  w[2] = (zc * zc * (zc - 2.0) * 3.0 + 4.0) / 6.0;
-  w[0] = zc * zc * zc / 6.0;
-  w[3] = 1.0 - w[0] - w[1] - w[2];
-  const long long start = (long long)fl - 1;
+  const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+  const double w2 = (zc * zc * (zc - 2.0) * 3.0 + 4.0) / 6.0;
+  const double w0 = zc * zc * zc / 6.0;
+  w[0] = fl - 1.0;
+  w[1] = w0;
+  w[2] = w1;
+  w[3] = w2;
+  w[4] = 1.0 - w0 - w1 - w2;
+}
+
+// value of the shifted line for one tabulated output
+__device__ __forceinline__ double spline_eval(const double* line, const int LS, const SplineLine& sl, long long F,
+                                              const double* __restrict__ w) {
+  const double s0 = __ldg(w);
+  if (s0 < -1.0e15) return 0.0;
+  const long long start = (long long)s0;
   double t = 0.0;
   if (start >= sl.lo && start + 3 < sl.hi) {  // the common case: all four taps inside the segment (and the canvas)
     const int u = (int)(start - sl.lo);
 #pragma unroll
-    for (int l = 0; l < 4; ++l) t += SPL_AT(u + l) * w[l];
+    for (int l = 0; l < 4; ++l) t += SPL_AT(u + l) * __ldg(w + 1 + l);
     return t;
   }
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const long long idx = spline_mirror_index(start + l, F);
     const double c = (idx >= sl.lo && idx < sl.hi) ? SPL_AT(idx - sl.lo) : 0.0;  // beyond the segment: < |z|^P
-    t += c * w[l];
+    t += c * __ldg(w + 1 + l);
   }
   return t;
 }
@@ -689,7 +717,7 @@ __device__ __forceinline__ SplineLine spline_segment(const SplineGeom& g, long l
 template <typename TS>
 __global__ void __launch_bounds__(SPL_THREADS) spline_pass_x_kernel(const TS* __restrict__ data, long long N, int C, SplineGeom g,
                                                                     const int32_t* __restrict__ origin_x,
-                                                                    const double* __restrict__ pos_x, const int32_t* __restrict__ ax,
+                                                                    const double* __restrict__ pos_x, const double* __restrict__ W,
                                                                     double* __restrict__ U) {
   extern __shared__ double spl_lines[];
   const int LS = SPL_THREADS;
@@ -705,22 +733,28 @@ __global__ void __launch_bounds__(SPL_THREADS) spline_pass_x_kernel(const TS* __
   const double gain = 6.0;  // (1 - z)(1 - 1/z)
   for (int i = 0; i < n; ++i) SPL_AT(i) = 0.0;
   const TS* __restrict__ src = data + k * (long long)g.S * per + sc;
-  for (int r = 0; r < g.S; ++r) {
-    const long long u = origin + r - sl.lo;  // data outside the canvas is dropped
-    if (u >= 0 && u < n) SPL_AT(u) = gain * (double)__ldg(src + (long long)r * per);
+  for (int r0 = 0; r0 < g.S; r0 += SPL_LD) {  // SPL_LD independent loads in flight per thread
+    TS v[SPL_LD];
+#pragma unroll
+    for (int j = 0; j < SPL_LD; ++j)
+      if (r0 + j < g.S) v[j] = __ldg(src + (long long)(r0 + j) * per);
+#pragma unroll
+    for (int j = 0; j < SPL_LD; ++j) {
+      const long long u = origin + r0 + j - sl.lo;  // data outside the canvas is dropped
+      if (r0 + j < g.S && u >= 0 && u < n) SPL_AT(u) = gain * (double)v[j];
+    }
   }
   spline_prefilter_line(line, LS, sl, g.F);
-  const double neg_pos = pos_x ? -pos_x[k] : -g.pos_x1;
-  const long long anchor = pos_x ? ax[k] : g.ax1;
+  const double* __restrict__ w = W + (k * 2 + 0) * (long long)g.n_out * SPL_WSTRIDE;
   double* __restrict__ dst = U + k * (long long)g.n_out * per + sc;
 #pragma unroll 4
-  for (int a = 0; a < g.n_out; ++a) dst[(long long)a * per] = spline_eval(line, LS, sl, g.F, anchor + a, neg_pos);
+  for (int a = 0; a < g.n_out; ++a) dst[(long long)a * per] = spline_eval(line, LS, sl, g.F, w + a * SPL_WSTRIDE);
 }
 
 // pass Y: one thread per (stamp, output row a, band): U (N, n_out, S, C) -> T (N, n_out, n_out, C)
 __global__ void __launch_bounds__(SPL_THREADS) spline_pass_y_kernel(const double* __restrict__ U, long long N, int C, SplineGeom g,
                                                                     const int32_t* __restrict__ origin_y,
-                                                                    const double* __restrict__ pos_y, const int32_t* __restrict__ ay,
+                                                                    const double* __restrict__ pos_y, const double* __restrict__ W,
                                                                     double* __restrict__ T) {
   extern __shared__ double spl_lines[];
   const int LS = SPL_THREADS;
@@ -737,16 +771,22 @@ __global__ void __launch_bounds__(SPL_THREADS) spline_pass_y_kernel(const double
   const double gain = 6.0;
   for (int i = 0; i < n; ++i) SPL_AT(i) = 0.0;
   const double* __restrict__ src = U + (k * g.n_out + a) * (long long)g.S * C + ch;
-  for (int s = 0; s < g.S; ++s) {
-    const long long u = origin + s - sl.lo;
-    if (u >= 0 && u < n) SPL_AT(u) = gain * src[(long long)s * C];
+  for (int s0 = 0; s0 < g.S; s0 += SPL_LD) {
+    double v[SPL_LD];
+#pragma unroll
+    for (int j = 0; j < SPL_LD; ++j)
+      if (s0 + j < g.S) v[j] = __ldg(src + (long long)(s0 + j) * C);
+#pragma unroll
+    for (int j = 0; j < SPL_LD; ++j) {
+      const long long u = origin + s0 + j - sl.lo;
+      if (s0 + j < g.S && u >= 0 && u < n) SPL_AT(u) = gain * v[j];
+    }
   }
   spline_prefilter_line(line, LS, sl, g.F);
-  const double neg_pos = pos_y ? -pos_y[k] : -g.pos_y1;
-  const long long anchor = pos_y ? ay[k] : g.ay1;
+  const double* __restrict__ w = W + (k * 2 + 1) * (long long)g.n_out * SPL_WSTRIDE;
   double* __restrict__ dst = T + (k * g.n_out + a) * (long long)g.n_out * C + ch;
 #pragma unroll 4
-  for (int b = 0; b < g.n_out; ++b) dst[(long long)b * C] = spline_eval(line, LS, sl, g.F, anchor + b, neg_pos);
+  for (int b = 0; b < g.n_out; ++b) dst[(long long)b * C] = spline_eval(line, LS, sl, g.F, w + b * SPL_WSTRIDE);
 }
 
 // position fit objective (deblend_cutout/optimization.py:21-33): sum over a placed window T (E,E) of
@@ -823,6 +863,10 @@ static int spline_smem_attr() {
 }  // namespace dbv
 using namespace dbv;
 
+extern "C" int64_t dbv_spline_scratch_doubles(int64_t N, int S, int C, int P) {
+  return N * (int64_t)(S + 2 * P + 2) * ((int64_t)S * C + 2 * SPL_WSTRIDE);  // pass-X output + weight table
+}
+
 extern "C" int dbv_spline_extent(int S, int P) {
   if (S < 1 || P < 0 || S + 2 * P > SPL_LMAX) return fail(DBV_ERR_UNSUPPORTED, "dbv_spline_extent: S + 2P = %d exceeds the %d-sample line buffer", S + 2 * P, SPL_LMAX);
   return S + 2 * P + 2;
@@ -845,12 +889,15 @@ extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int
   const long long tx = N * (long long)S * C, ty = N * (long long)n_out * C;
   const unsigned gx = (unsigned)((tx + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((ty + SPL_THREADS - 1) / SPL_THREADS);
   const size_t smem = (size_t)(S + 2 * P) * SPL_THREADS * sizeof(double);
-  if (data_dtype == DBV_F32)
-    spline_pass_x_kernel<float><<<gx, SPL_THREADS, smem, st>>>((const float*)data, N, C, g, origin_x, pos_x, ax, scratch);
-  else
-    spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>((const double*)data, N, C, g, origin_x, pos_x, ax, scratch);
+  double* W = scratch + N * (long long)n_out * S * C;  // weight table behind the pass-X output
+  spline_weights_kernel<<<(unsigned)((N * 2 * n_out + 127) / 128), 128, 0, st>>>(N, g, pos_x, pos_y, ax, ay, W);
   DBV_LAUNCH_CHECK();
-  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, N, C, g, origin_y, pos_y, ay, placed);
+  if (data_dtype == DBV_F32)
+    spline_pass_x_kernel<float><<<gx, SPL_THREADS, smem, st>>>((const float*)data, N, C, g, origin_x, pos_x, W, scratch);
+  else
+    spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>((const double*)data, N, C, g, origin_x, pos_x, W, scratch);
+  DBV_LAUNCH_CHECK();
+  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, N, C, g, origin_y, pos_y, W, placed);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
@@ -898,9 +945,12 @@ extern "C" int dbv_position_objective(const double* field, int64_t F, int C, int
   if (spline_smem_attr()) return fail(DBV_ERR_CUDA, "dbv_position_objective: cannot raise the dynamic shared memory limit");
   const unsigned gx = (unsigned)((E1 + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((E2 + SPL_THREADS - 1) / SPL_THREADS);
   const size_t smem = (size_t)(E1 + 2 * P) * SPL_THREADS * sizeof(double);
-  spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>(placed1, 1, 1, g, nullptr, nullptr, nullptr, scratch);
+  double* W = scratch + (long long)E2 * E1;
+  spline_weights_kernel<<<(unsigned)((2 * E2 + 127) / 128), 128, 0, st>>>(1, g, nullptr, nullptr, nullptr, nullptr, W);
   DBV_LAUNCH_CHECK();
-  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, 1, 1, g, nullptr, nullptr, nullptr, placed2);
+  spline_pass_x_kernel<double><<<gx, SPL_THREADS, smem, st>>>(placed1, 1, 1, g, nullptr, nullptr, W, scratch);
+  DBV_LAUNCH_CHECK();
+  spline_pass_y_kernel<<<gy, SPL_THREADS, smem, st>>>(scratch, 1, 1, g, nullptr, nullptr, W, placed2);
   DBV_LAUNCH_CHECK();
   shift_objective_kernel<<<1, 256, 0, st>>>(field, F, C, band, placed2, E2, g.ax1, g.ay1, sumsq_field, out_dev);
   DBV_LAUNCH_CHECK();

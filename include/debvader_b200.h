@@ -144,8 +144,9 @@ int dbv_window_axpy_ex(const void* in_dev, void* out_dev, int field_dtype, int64
  *   field_deblender.py:72).  pos = the shift.  Output window k has side E = dbv_spline_extent(S,P)
  *   = S+2P+2 and starts at canvas row ax[k], col ay[k] (the caller passes origin - P - 1 + floor(pos));
  *   placed (N,E,E,C) f64 is then pasted with dbv_window_axpy_ex(..., DBV_F64, ax, ay, N, E, ...).
- *   scratch: N*E*S*C doubles.  S + 2P <= 192. */
+ *   scratch: dbv_spline_scratch_doubles(N,S,C,P) doubles (pass-X output + interpolation weights).  S + 2P <= 192. */
 int dbv_spline_extent(int S, int P);
+int64_t dbv_spline_scratch_doubles(int64_t N, int S, int C, int P);
 int dbv_spline_place(const void* data_dev, int data_dtype, int64_t N, int S, int C, int64_t F, int origin,
                      const int32_t* origin_x_dev, const int32_t* origin_y_dev, const double* pos_x_dev,
                      const double* pos_y_dev, const int32_t* ax_dev, const int32_t* ay_dev, int P, double* scratch_dev,
@@ -161,7 +162,7 @@ int dbv_shift_objective(const double* field_dev, int64_t F, int C, int band, con
                         int ay, double sumsq_field, double* out_dev, void* stream);
 /* One evaluation of `fun(x)` of optimization.py:21-33 for the already placed prediction placed1 (E1,E1) f64
  * at (a1x, a1y) (= shift(r_band_prediction, galaxy_distance_to_center), optimization.py:41-44): a second
- * placement by x = (x0, x1) into placed2 (E2 = dbv_spline_extent(E1,P) squared; scratch E2*E1 doubles), then
+ * placement by x = (x0, x1) into placed2 (E2 = dbv_spline_extent(E1,P) squared; scratch dbv_spline_scratch_doubles(1,E1,1,P) doubles), then
  * dbv_shift_objective.  Synchronous: the value is written to out_host (and out_dev). */
 int dbv_position_objective(const double* field_dev, int64_t F, int C, int band, const double* placed1_dev, int E1, int a1x,
                            int a1y, double x0, double x1, int P, double sumsq_field, double* scratch_dev,
