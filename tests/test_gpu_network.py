@@ -110,6 +110,26 @@ def test_fp32_per_layer(wts, data, ref64):
     net.close()
 
 
+def test_fp32_tiled_kernel_is_bit_identical_to_the_gather_kernel(wts, data, monkeypatch):
+    """simt_tile_kernel (shared-memory implicit GEMM) accumulates in the order of simt_conv_kernel (the naive gather
+    form kept as the cross-check, DBV_SIMT_TILED=0): every layer and both outputs must agree bit for bit, on a batch
+    that is not a multiple of any tile size."""
+    x, eps = data
+    x, eps = x[:37], eps[:37]
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DBV_SIMT_TILED", flag)
+        net = _net(wts, "fp32", chunk=64)
+        dist = net(x, eps=eps)
+        acts = {name: net.debug_activation(name, len(x), shp).clone() for name, shp in ACT_SHAPES.items()}
+        out[flag] = (net.encode(x).clone(), dist.mean().tensor.clone(), dist.stddev().tensor.clone(), acts)
+        net.close()
+    for name in ACT_SHAPES:
+        assert torch.equal(out["0"][3][name], out["1"][3][name]), name
+    for a, b in zip(out["0"][:3], out["1"][:3]):
+        assert torch.equal(a, b)
+
+
 # ---- tensor-core tiers ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision,tol_layer,tol_out", [("mixed", 2e-3, 1e-3), ("fp16x3", 2e-4, 1e-4), ("bf16x3", 2e-4, 1e-3), ("bf16", 4e-2, 5e-2)])
 def test_tensor_core_path(wts, data, ref64, precision, tol_layer, tol_out):
