@@ -163,6 +163,25 @@ def synthetic_stamps_device(n, seed, device):
     return (x + prof[..., None] * sed).contiguous()
 
 
+def executed_tensor_flops(precision, stamps_per_s, pk):
+    """What the tensor pipe really executes: the split precisions issue 3 MMAs per product (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi),
+    the fp16 tail of 'mixed' (convT6, convT7, convT8, head) 2; dec_dense1 runs on the SIMT kernel."""
+    from debvader_b200.model import spec
+
+    if precision == "fp32":
+        return {}
+    tail = ("dec_convT6", "dec_convT7", "dec_convT8", "dec_head")
+    mult = {"bf16": 1, "bf16x3": 3, "fp16x3": 3, "mixed": 3}[precision]
+    ex = 0
+    for name, macs in spec.LAYER_MACS.items():
+        if name == "dec_dense1":
+            continue
+        ex += 2 * macs * (2 if (precision == "mixed" and name in tail) else mult)
+    tf = stamps_per_s * ex / 1e12
+    return {"tflops_executed_on_tensor_pipe": round(tf, 2), "executed_frac_of_bf16_sustained": round(tf / pk["bf16_tflops_sustained"], 4),
+            "executed_flop_per_stamp": ex}
+
+
 def cpu_reference_rate(sample, threads=None):
     """stamps/s of the oracle port (torch-CPU restatement of reference model/model.py) on host cores."""
     from oracle import weights as ow
@@ -180,6 +199,36 @@ def cpu_reference_rate(sample, threads=None):
         done += x.shape[0]
     dt = time.perf_counter() - t0
     return done / dt, threads, done, dt
+
+
+def cpu_field_baseline():
+    """The reference's residual field on the host (deblend/field_deblender.py:46-97: one cubic-spline
+    scipy.ndimage.shift of a field-sized canvas per galaxy and band), timed through the oracle's restatement of that
+    loop on a bounded sample and scaled to BASELINE cfg 4 (F=4096, 2000 sources): the cost is proportional to
+    N * C * F^2, the literal run would take hours."""
+    from oracle import spline_numpy as sp
+
+    try:  # the call the reference itself makes (scipy is one of its dependencies); the numpy restatement otherwise
+        from scipy.ndimage import shift as ndi_shift
+        how = "scipy.ndimage.shift, the call the reference makes per galaxy and band (field_deblender.py:92-95)"
+    except Exception:
+        ndi_shift, how = sp.shift_cubic_constant, "numpy restatement of scipy.ndimage.shift (oracle/spline_numpy.py)"
+    F, S, C, N = 1024, 59, 6, 4
+    rng = np.random.default_rng(3)
+    field = rng.normal(0, 0.6, (1, F, F, C))
+    means = rng.random((N, S, S, C)).astype(np.float32)
+    pos = rng.integers(-400, 400, size=(N, 2)).astype(np.float64)
+    off = int((F - S) / 2)
+    t0 = time.perf_counter()
+    for k in range(N):
+        for band in range(C):
+            canvas = np.zeros((F, F))
+            canvas[off : off + S, off : off + S] = means[k, :, :, band]
+            field[0, :, :, band] -= ndi_shift(canvas, (pos[k, 0], pos[k, 1]))
+    dt = time.perf_counter() - t0
+    per_gal_4k = dt / N * (4096 / F) ** 2
+    return {"s_per_galaxy_at_1024": dt / N, "s_per_field_4096_2000_sources_extrapolated": per_gal_4k * 2000, "cores": 1, "kind": "port",
+            "sample": f"{N} galaxies x {C} bands on a {F}^2 canvas ({dt:.1f} s), scaled by (4096/{F})^2 x 2000/{N}; {how}"}
 
 
 def run_reference(args, rank):
@@ -260,10 +309,10 @@ def field_extras(net, device, pk, quick=False):
         E = _fieldops.spline_extent(S)
         t = timeit(lambda: _fieldops.spline_window_axpy(field, stamps32, fpos[:, 0], fpos[:, 1], -1.0), iters=3)
         tp = timeit(lambda: _fieldops.spline_place(stamps32[:512], fpos[:512, 0], fpos[:512, 1], F), iters=3)
-        place_bytes = 512 * (STAMP_ELTS * 4 + 2 * E * S * C * 8 + E * E * C * 8)  # stamp in, scratch out+in, window out
+        place_bytes = 512 * (STAMP_ELTS * 4 + E * E * C * 8)  # algorithmic: stamp in, f64 window out (the pass-X result stays in shared memory)
         out["subpixel_residual_f64"] = {"ms": t, "stamps": N, "window": E, "place_ms_per_512": tp, "place_GBps": place_bytes / tp / 1e6,
                                         "place_frac": round(place_bytes / tp / 1e6 / pk["hbm_gbs"], 4),
-                                        "note": "prefilter + shift on (S+2P+2)^2 f64 windows (P=28), then the f64 window paste"}
+                                        "note": "prefilter + shift on (S+2P+2)^2 f64 windows (P=28; one warp per line, latency / issue bound), then the f64 window paste"}
         from debvader_b200.deblend_cutout.optimization import FieldBand, fit_position
         fb = FieldBand(field)
         torch.cuda.synchronize()
@@ -457,7 +506,8 @@ def main():
         "clocks": clk,
         "roofline": roofline,
         "network": {"tflops_algorithmic": round(net_tf, 2), "frac_of_bf16_sustained": round(net_tf / pk["bf16_tflops_sustained"], 4),
-                    "frac_of_bf16_burst": round(net_tf / pk["bf16_tflops"], 4), "flop_per_stamp": spec.FLOP_PER_STAMP},
+                    "frac_of_bf16_burst": round(net_tf / pk["bf16_tflops"], 4), "flop_per_stamp": spec.FLOP_PER_STAMP,
+                    **executed_tensor_flops(args.precision, value / world, pk)},
         "layers": lay,
     }
     if not args.no_extras:
@@ -495,6 +545,11 @@ def main():
                                     "sample": f"{done} stamps in batches of 256 ({dt:.1f} s); torch-CPU restatement of the reference model (stand-in, not TensorFlow)"}
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+        try:
+            if isinstance(line.get("field"), dict) and "ms_per_field" in line["field"]:
+                line["field"]["cpu_baseline"] = cpu_field_baseline()
+        except Exception as e:
+            line["field"]["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

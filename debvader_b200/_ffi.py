@@ -43,7 +43,7 @@ def _declare(lib):
         "dbv_deblend_host": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "dbv_extract": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
         "dbv_window_axpy": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
-        "dbv_window_axpy_ex": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
+        "dbv_window_axpy_ex": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
         "dbv_spline_extent": (C.c_int, [C.c_int, C.c_int]),
         "dbv_spline_scratch_doubles": (c_i64, [c_i64, C.c_int, C.c_int, C.c_int]),
         "dbv_spline_place": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),

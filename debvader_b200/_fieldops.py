@@ -153,8 +153,9 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
     return out, [int(i) for i in idx]
 
 
-def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64):
-    """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy)."""
+def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64, planar=False):
+    """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy).
+    stamps (N,S,S,C), or (N,C,S,S) with planar=True (the windows of spline_place)."""
     _require_cuda(stamps, "stamps")
     dev = stamps.device
     if field_in is not None:
@@ -163,7 +164,7 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
     else:
         shape = tuple(field_shape)
     F_, Cc = shape[-3], shape[-1]
-    n, S = stamps.shape[0], stamps.shape[1]
+    n, S = stamps.shape[0], stamps.shape[2 if planar else 1]
     if out is None:
         out = torch.empty(shape, device=dev, dtype=dtype)
     if isinstance(x0, torch.Tensor) and isinstance(y0, torch.Tensor):  # positions already on the device (int32)
@@ -176,7 +177,7 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
     with torch.cuda.device(dev):
         _ffi.check(
             _ffi.lib().dbv_window_axpy_ex(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _DT[stamps.dtype],
-                                          _ffi.ptr(xs), _ffi.ptr(ys), n, S, float(alpha), _ffi.stream_ptr())
+                                          int(bool(planar)), _ffi.ptr(xs), _ffi.ptr(ys), n, S, float(alpha), _ffi.stream_ptr())
         )
     return out
 
@@ -198,7 +199,7 @@ def spline_place(data, pos_x, pos_y, field_size: int, margin: int = SPLINE_MARGI
     """scipy.ndimage.shift of a zero canvas holding `data` (field_deblender.py:66-95), on the window that matters.
 
     data (N,S,S,C) CUDA f32/f64, sample 0 at canvas (origin_x[k], origin_y[k]) — default int((F-S)/2), the padded
-    stamp of the reference; pos = the shift (float).  Returns (placed (N,E,E,C) f64, ax, ay): window k covers
+    stamp of the reference; pos = the shift (float).  Returns (placed (N,C,E,E) f64 — planar —, ax, ay): window k covers
     field rows ax[k]..ax[k]+E, cols ay[k]..ay[k]+E.
     """
     _require_cuda(data, "data")
@@ -214,10 +215,11 @@ def spline_place(data, pos_x, pos_y, field_size: int, margin: int = SPLINE_MARGI
     pos = torch.from_numpy(np.stack([px, py])).to(dev)
     ints = torch.from_numpy(np.stack([ax, ay, ox.astype(np.int32), oy.astype(np.int32)])).to(dev)
     scratch = torch.empty((int(_ffi.lib().dbv_spline_scratch_doubles(n, S, Cc, int(margin))),), device=dev, dtype=torch.float64)
-    placed = torch.empty((n, E, E, Cc), device=dev, dtype=torch.float64)
+    placed = torch.empty((n, Cc, E, E), device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
         _ffi.check(
-            _ffi.lib().dbv_spline_place(_ffi.ptr(data), _DT[data.dtype], n, S, Cc, int(field_size), int(off), _ffi.ptr(ints[2]), _ffi.ptr(ints[3]),
+            _ffi.lib().dbv_spline_place(_ffi.ptr(data), _DT[data.dtype], n, S, Cc, int(field_size), int(off),
+                                        None if origin_x is None else _ffi.ptr(ints[2]), None if origin_y is None else _ffi.ptr(ints[3]),
                                         _ffi.ptr(pos[0]), _ffi.ptr(pos[1]), _ffi.ptr(ints[0]), _ffi.ptr(ints[1]), int(margin),
                                         _ffi.ptr(scratch), _ffi.ptr(placed), _ffi.stream_ptr())
         )
@@ -240,7 +242,7 @@ def spline_window_axpy(field_in, stamps, pos_x, pos_y, alpha: float, field_shape
         sl = slice(b0, min(b0 + batch, n))
         placed, ax, ay = spline_place(stamps[sl], pos_x[sl], pos_y[sl], F_, margin)
         src = field_in if out is None else out
-        out = window_axpy(src, placed, ax, ay, alpha, out=out, field_shape=shape, dtype=dtype)
+        out = window_axpy(src, placed, ax, ay, alpha, out=out, field_shape=shape, dtype=dtype, planar=True)
     return out
 
 

@@ -45,7 +45,7 @@ def fit_position(fb: FieldBand, stamp_band_dev, galaxy_distance_to_center, margi
     S = int(stamp_band_dev.shape[0])
     d = np.asarray(galaxy_distance_to_center, dtype=np.float64)
     placed1, a1x, a1y = _fieldops.spline_place(stamp_band_dev.reshape(1, S, S, 1).contiguous(), d[0:1], d[1:2], fb.F, margin)
-    E1 = int(placed1.shape[1])
+    E1 = int(placed1.shape[-1])
     E2 = _fieldops.spline_extent(E1, margin)
     scratch = torch.empty((int(_ffi.lib().dbv_spline_scratch_doubles(1, E1, 1, int(margin))),), device=dev, dtype=torch.float64)
     placed2 = torch.empty((E2 * E2,), device=dev, dtype=torch.float64)

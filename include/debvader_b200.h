@@ -127,10 +127,11 @@ int dbv_extract(const void* field_dev, int field_dtype, int64_t F, int C, const 
 int dbv_window_axpy(const void* in_dev, void* out_dev, int field_dtype, int64_t F, int C, const float* stamps_dev,
                     const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S, double alpha, void* stream);
 
-/* The same with f32 or f64 stamps (stamp_dtype): the sub-pixel path pastes f64 stamps. */
+/* The same with f32 or f64 stamps (stamp_dtype), interleaved (N,S,S,C) or planar (N,C,S,S; stamp_planar != 0): the
+ * sub-pixel path pastes planar f64 windows. */
 int dbv_window_axpy_ex(const void* in_dev, void* out_dev, int field_dtype, int64_t F, int C, const void* stamps_dev,
-                       int stamp_dtype, const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S, double alpha,
-                       void* stream);
+                       int stamp_dtype, int stamp_planar, const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S,
+                       double alpha, void* stream);
 
 /* Sub-pixel placement: scipy.ndimage.shift(padded_canvas, shift=(x_pos, y_pos)) of
  * deblend/field_deblender.py:66-95, 121-182 and deblend_cutout/optimization.py:27-29, 41-44 (order 3,
@@ -143,7 +144,7 @@ int dbv_window_axpy_ex(const void* in_dev, void* out_dev, int field_dtype, int64
  *   canvas row origin_x[k] / col origin_y[k] (both NULL: `origin` for all, i.e. int((F-S)/2) of
  *   field_deblender.py:72).  pos = the shift.  Output window k has side E = dbv_spline_extent(S,P)
  *   = S+2P+2 and starts at canvas row ax[k], col ay[k] (the caller passes origin - P - 1 + floor(pos));
- *   placed (N,E,E,C) f64 is then pasted with dbv_window_axpy_ex(..., DBV_F64, ax, ay, N, E, ...).
+ *   placed (N,C,E,E) f64 — PLANAR — is then pasted with dbv_window_axpy_ex(..., DBV_F64, 1, ax, ay, N, E, ...).
  *   scratch: dbv_spline_scratch_doubles(N,S,C,P) doubles (pass-X output + interpolation weights).  S + 2P <= 192. */
 int dbv_spline_extent(int S, int P);
 int64_t dbv_spline_scratch_doubles(int64_t N, int S, int C, int P);

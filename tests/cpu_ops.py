@@ -24,7 +24,7 @@ def install(monkeypatch):
                 idx.append(i)
         return torch.from_numpy(out).to(out_dtype), idx
 
-    def window_axpy(field_in, stamps, x0, y0, alpha, out=None, field_shape=None, dtype=torch.float64):
+    def window_axpy(field_in, stamps, x0, y0, alpha, out=None, field_shape=None, dtype=torch.float64, planar=False):
         acc = field_in.numpy().copy() if field_in is not None else np.zeros(field_shape)
         view = acc[0] if acc.ndim == 4 else acc
         for s, a, b in zip(stamps.numpy(), x0, y0):

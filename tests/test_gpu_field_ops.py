@@ -253,7 +253,7 @@ def test_position_objective_matches_the_reference_fun(golden_dir):
             net_output = sp.shift_cubic_constant(canvas, d)
             stamp = torch.from_numpy(np.ascontiguousarray(means[k, :, :, 2])).cuda()
             placed1, a1x, a1y = _fieldops.spline_place(stamp.reshape(1, S, S, 1), d[0:1], d[1:2], F)
-            E1 = placed1.shape[1]
+            E1 = placed1.shape[-1]
             E2 = _fieldops.spline_extent(E1)
             scratch = torch.empty(int(_ffi.lib().dbv_spline_scratch_doubles(1, E1, 1, _fieldops.SPLINE_MARGIN)), device="cuda", dtype=torch.float64)
             placed2 = torch.empty(E2 * E2, device="cuda", dtype=torch.float64)

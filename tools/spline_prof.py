@@ -12,6 +12,6 @@ st = torch.randn((N, S, S, C), device=dev)
 pos = rng.integers(-(F // 2 - 70), F // 2 - 70, size=(N, 2)) + rng.uniform(-0.5, 0.5, size=(N, 2))
 for _ in range(3):
     placed, ax, ay = _fieldops.spline_place(st, pos[:, 0], pos[:, 1], F)
-    out = _fieldops.window_axpy(field, placed, ax, ay, -1.0)
+    out = _fieldops.window_axpy(field, placed, ax, ay, -1.0, planar=True)
 torch.cuda.synchronize()
 print("ok", float(out.sum()))
