@@ -181,6 +181,11 @@ struct dbv_ctx {
 
 namespace dbv {
 
+bool pdl_enabled() {
+  static const bool on = getenv("DBV_PDL") ? atoi(getenv("DBV_PDL")) != 0 : false;
+  return on;
+}
+
 static int dev_alloc(dbv_ctx* c, void** p, size_t bytes, bool zero) {
   DBV_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   c->allocs.push_back(*p);
@@ -1161,12 +1166,15 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
   if ((r = ensure_pipe(c))) return r;
   const long long before = g_launches.load();
   const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
-  // chunk schedule: a short first chunk (its H2D copy cannot overlap anything) and a short tail (neither can the last
-  // D2H copy), full chunks in between
+  // Piece schedule of the H2D / compute / D2H pipeline.  Measured on B200 (tools/e2e_breakdown.py, pcie_probe.py): a piece of n
+  // stamps costs ~0.35 ms + 1.95 us * n of compute, 1.5 us * n of H2D and 1.46 us * n of D2H; the first H2D and the last D2H
+  // cannot overlap anything.  So: start small and let the pieces GROW as fast as the copies keep up with the compute
+  // (H2D of piece k+1 <= compute of piece k: n' <= 1.25 n + 224), cap them, and finish with one short piece.  The old
+  // fixed-size schedule (DBV_HOST_PIECE=n) stalled ~0.7 ms on its second piece and paid three short tail pieces.
   std::vector<std::pair<int64_t, long long>> sched;
-  {
+  if (const char* e = getenv("DBV_HOST_PIECE")) {
     int64_t b0 = 0;
-    const long long piece = std::min<long long>(c->chunk, getenv("DBV_HOST_PIECE") ? atoll(getenv("DBV_HOST_PIECE")) : 1024);  // pipeline granularity (transfers overlap compute piece by piece)
+    const long long piece = std::max<long long>(1, std::min<long long>(c->chunk, atoll(e)));
     const long long q = std::max<long long>(piece / 4, 1);
     if (B > 2 * piece) { sched.push_back({0, q}); b0 = q; }
     while (B - b0 > piece + q) { sched.push_back({b0, piece}); b0 += piece; }
@@ -1176,6 +1184,21 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
       nb = std::min<long long>(nb, piece);
       sched.push_back({b0, nb});
       b0 += nb;
+    }
+  } else {
+    const long long cap = std::min<long long>(c->chunk, 1376), first = std::min<long long>(c->chunk, 256), last = first;
+    int64_t b0 = 0;
+    long long n = first;
+    while (B - b0 > 0) {
+      const long long rem = B - b0;
+      long long nb;
+      if (rem <= first + first / 4) nb = rem;   // the last, short piece
+      else if (rem - n >= last) nb = n;         // ramp / steady state: a tail piece still fits behind it
+      else nb = rem - last;                     // the piece before the last one
+      nb = std::min<long long>(nb, c->chunk);
+      sched.push_back({b0, nb});
+      b0 += nb;
+      n = std::min<long long>(cap, ((5 * n / 4 + 224) / 32) * 32);
     }
   }
   for (int k = 0; k < (int)sched.size(); ++k) {

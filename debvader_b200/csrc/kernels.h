@@ -17,6 +17,24 @@ struct SimtConv {
   const float* in_shift;
   OutSpec o;
 };
+// Launch with programmatic dependent launch when enabled (DBV_PDL, see tc_ptx.cuh:pdl_wait): only for kernels that call pdl_wait()
+// before their first access to anything another kernel of the stream produces or consumes.
+bool pdl_enabled();
+template <typename Kernel, typename Arg>
+static inline cudaError_t launch_pdl(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 int launch_simt_conv(const SimtConv& p, cudaStream_t st);
 int launch_latent(const float* params, const float* eps, unsigned long long seed, int sample, long long first_stamp,
                   long long B, float* z, float* loc, float* std_out, float* zp, const float* alpha0, cudaStream_t st);

@@ -48,6 +48,7 @@ struct TcCfg {
 // B_hi per pairing is worth 1.5x on the fill side.
 template <int CBK, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcLayer L) {
+  pdl_trigger();
   using Cfg = TcCfg<CBK, NT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // nothing produced or consumed by the previous kernel is touched above this line
 
   const long long total = L.total_tiles;
   const int tiles_img = L.tiles_x * L.tiles_y;
@@ -256,7 +258,7 @@ static int launch_one(const TcLayer& L, int max_ctas, cudaStream_t st) {
   if (grid <= 0) return DBV_OK;
   const int smem = L.stages * L.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   if (L.stages < 2 || L.stages > 8 || smem > TC_MAX_SMEM) return fail(DBV_ERR_STATE, "tc_conv_kernel<%d,%d>: bad stage plan (%d x %d B)", CBK, NT, L.stages, L.stage_bytes);
-  tc_conv_kernel<CBK, NT><<<(unsigned)grid, TC_THREADS, smem, st>>>(L);
+  launch_pdl(tc_conv_kernel<CBK, NT>, (unsigned)grid, TC_THREADS, smem, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -41,6 +41,7 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 // it once; the epilogue groups split the unit's (sub-unit, channel chunk) items and all release the slot.
 template <int CBK, int NT, bool NOSWZ>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
+  pdl_trigger();
   constexpr bool CG8 = !NOSWZ && CBK == 16;             // channel-group-planar input: 16-byte pixel rows, K=16 = two groups one region apart
   constexpr int ROWB = (NOSWZ || CG8) ? 16 : CBK * 2;   // activation row pitch in shared memory
   constexpr int ROWB_W = NOSWZ ? 16 : CBK * 2;          // weight rows (K-major, swizzled; conv1: host-packed core matrices)
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // nothing produced or consumed by the previous kernel is touched above this line
   const long long total = L.total_bands;
   const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
   const long long yb0 = g0 / L.B;
@@ -295,7 +297,7 @@ static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
     return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_halo_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
   const long long grid = L.total_bands < max_ctas ? L.total_bands : max_ctas;
   if (grid <= 0) return DBV_OK;
-  tc_halo_kernel<CBK, NT, NOSWZ><<<(unsigned)grid, HALO_THREADS, L.smem_bytes, st>>>(L);
+  launch_pdl(tc_halo_kernel<CBK, NT, NOSWZ>, (unsigned)grid, HALO_THREADS, L.smem_bytes, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -25,6 +25,7 @@ constexpr int TP_MAX_SMEM = 232448;
 
 template <int CBK, int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const __grid_constant__ TcLayer L) {
+  pdl_trigger();
   constexpr int ROWB = CBK * 2;
   constexpr int A_BYTES = 128 * ROWB;
   constexpr int BH_BYTES = (NT / 2) * ROWB;  // this CTA's half of one weight box
@@ -64,6 +65,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1) tc_pa
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // nothing produced or consumed by the previous kernel is touched above this line
 
   const int tiles_img = L.tiles_x * L.tiles_y;
   const long long items = L.pair_items;  // clusters' work items: n_cls x ceil(m tiles / 2) x n_tiles_n
@@ -220,7 +222,7 @@ static int launch_pair_one(const TcLayer& L, int max_ctas, cudaStream_t st) {
   const int smem = L.stages * L.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   if (L.stages < 2 || L.stages > 8 || smem > TP_MAX_SMEM)
     return fail(DBV_ERR_STATE, "tc_pair_kernel<%d,%d>: bad stage plan (%d x %d B)", CBK, NT, L.stages, L.stage_bytes);
-  tc_pair_kernel<CBK, NT><<<(unsigned)(2 * clusters), TP_THREADS, smem, st>>>(L);
+  launch_pdl(tc_pair_kernel<CBK, NT>, (unsigned)(2 * clusters), TP_THREADS, smem, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -30,6 +30,7 @@ constexpr int PH_MAX_SMEM = 232448;
 
 template <int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pairh_kernel(const __grid_constant__ PairHLayer L) {
+  pdl_trigger();
   constexpr int ROWB = 128;                  // 64 channels
   constexpr int BH_BYTES = (NT / 2) * ROWB;  // this CTA's half of one weight block
   extern __shared__ uint8_t smem_raw[];
@@ -72,6 +73,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // nothing produced or consumed by the previous kernel is touched above this line
 
   const long long items = L.pair_items * L.cls_groups;  // (tile pair, class group)
   const uint32_t cid = cluster_id_x(), ncl = nclusters_x();
@@ -224,7 +226,7 @@ static int launch_pairh_one(const PairHLayer& L, int max_ctas, cudaStream_t st) 
   if (L.pair_items <= 0) return DBV_OK;
   const long long clusters = L.pair_items < max_ctas / 2 ? L.pair_items : max_ctas / 2;
   if (L.smem_bytes > PH_MAX_SMEM) return fail(DBV_ERR_STATE, "tc_pairh_kernel<%d>: %d bytes of shared memory", NT, L.smem_bytes);
-  tc_pairh_kernel<NT><<<(unsigned)(2 * clusters), PH_THREADS, L.smem_bytes, st>>>(L);
+  launch_pdl(tc_pairh_kernel<NT>, (unsigned)(2 * clusters), PH_THREADS, L.smem_bytes, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -199,6 +199,13 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
       : "f"(b0), "f"(b1));
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream is still running (as SMs free up); it must not touch anything the predecessor reads or writes
+// before pdl_wait() returns (= the predecessor grid has completed and flushed).  Every kernel calls pdl_trigger() at its
+// start so that ITS successor becomes eligible as soon as all its CTAs are resident.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // tcgen05 instruction-descriptor A/B format bits ([7,10) and [10,13)): 0 = F16, 1 = BF16
 __device__ __forceinline__ uint32_t idesc_ab_fmt(int f16) { return f16 ? 0u : ((1u << 7) | (1u << 10)); }
 
