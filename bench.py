@@ -402,6 +402,7 @@ def main():
     t_warm0 = time.time()
     for _ in range(args.warmup):
         net.deblend_into(x, mean, std)
+    net.set_profiling(True)  # per-layer CUDA events on the launching stream, inside the timed region
     barrier()
     t_wall0 = time.time()
     l0 = _ffi.lib().dbv_global_launch_count()
@@ -416,12 +417,15 @@ def main():
     launches = int(_ffi.lib().dbv_global_launch_count() - l0)
     t_wall1 = time.time()
     clk = None
+    layers_timed = None
     if rank == 0:
         window = "timed region"
         if clocks.proc is not None and clocks.count(t_wall0, t_wall1) < 3 and clocks.count(t_warm0, t_wall1) >= 3:
             t_wall0, window = t_warm0, "warm-up steps + timed region (the same step, back to back; the timed region alone is shorter than three sampling periods)"
         elif clocks.proc is not None and clocks.count(t_wall0, t_wall1) < 3:
-            # too short for the sampler: keep the identical step running (untimed) until it has read the clocks
+            # too short for the sampler: keep the identical step running (untimed, not profiled) until it has read the clocks
+            layers_timed = net.layer_times()
+            net.set_profiling(False)
             t_end = time.time() + 0.6
             while time.time() < t_end:
                 net.deblend_into(x, mean, std)
@@ -434,15 +438,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * B * args.steps / (ms_total / 1e3)
-    # per-layer CUDA-event times: three more steps of the same work right after the timed region (no event records inside
-    # it), each layer's minimum over the three (a host hiccup while enqueueing shows up as GPU idle time in one layer)
-    net.set_profiling(True)
-    layers = None
-    for _ in range(3):
-        net.deblend_into(x, mean, std)
-        torch.cuda.synchronize()
-        cur = net.layer_times()
-        layers = cur if layers is None else [(n, min(a, b)) for (n, a), (_, b) in zip(layers, cur)]
+    layers = layers_timed if layers_timed is not None else net.layer_times()  # per-layer CUDA-event times, averaged over the K timed steps
     net.set_profiling(False)
 
     # ---- e2e through the public API with host buffers ------------------------------------------------

@@ -177,6 +177,7 @@ struct dbv_ctx {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<std::string> prof_names;
   int prof_n = 0;
+  int prof_calls = 0;  // calls recorded since dbv_set_profiling(ctx, 1); the events of all of them are kept (up to kProfMaxEvents)
 };
 
 namespace dbv {
@@ -812,8 +813,9 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
   return launch_simt_conv(p, st);
 }
 
+constexpr int kProfMaxEvents = 16384;
 static void prof_mark(dbv_ctx* c, const char* name, cudaStream_t st) {
-  if (!c->profiling) return;
+  if (!c->profiling || c->prof_n >= kProfMaxEvents) return;
   if ((int)c->prof_ev.size() <= c->prof_n) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -1096,7 +1098,7 @@ static int chunked(dbv_ctx* c, const char* fn, const float* x, int64_t B, const 
   DBV_REQUIRE(B >= 0, "%s: negative B", fn);
   cudaStream_t st = (cudaStream_t)stream;
   const long long before = g_launches.load();
-  c->prof_n = 0;
+  if (c->profiling) c->prof_calls++;
   for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
     const long long nb = std::min<long long>(c->chunk, B - b0);
     r = run_chunk(c, x ? x + b0 * STAMP_ELTS : nullptr, nb, eps ? eps + b0 * LAT : nullptr, seed, sample, first_stamp + b0,
@@ -1245,12 +1247,14 @@ extern "C" int dbv_set_profiling(dbv_ctx* c, int enabled) {
   DBV_REQUIRE(c, "dbv_set_profiling: null ctx");
   c->profiling = enabled != 0;
   c->prof_n = 0;
+  c->prof_calls = 0;
   return DBV_OK;
 }
 
 extern "C" int dbv_layer_times(dbv_ctx* c, int max_layers, float* ms_out, char* names_out) {
   DBV_REQUIRE(c && ms_out && names_out, "dbv_layer_times: null argument");
-  // sum over chunks, layers in order of first appearance; "start" marks open a new chunk
+  // average per call since profiling was switched on: sum over all recorded chunks / number of calls; layers in order of
+  // first appearance; "start" marks open a new chunk
   std::vector<std::string> names;
   std::vector<float> tot;
   for (int i = 1; i < c->prof_n; ++i) {
@@ -1265,8 +1269,9 @@ extern "C" int dbv_layer_times(dbv_ctx* c, int max_layers, float* ms_out, char* 
     tot[k] += ms;
   }
   int n = 0;
+  const float calls = (float)(c->prof_calls > 0 ? c->prof_calls : 1);
   for (; n < (int)names.size() && n < max_layers; ++n) {
-    ms_out[n] = tot[n];
+    ms_out[n] = tot[n] / calls;
     strncpy(names_out + 32 * n, names[n].c_str(), 31);
     names_out[32 * n + 31] = 0;
   }

@@ -223,7 +223,7 @@ class Deblender:
         _ffi.check(_ffi.lib().dbv_set_profiling(self._ctx, int(bool(on))))
 
     def layer_times(self):
-        """[(layer name, ms)] of the last chunk run with profiling on (CUDA events)."""
+        """[(layer name, ms)] per call, averaged over the calls made since profiling was switched on (CUDA events)."""
         n = 64
         ms = (C.c_float * n)()
         names = C.create_string_buffer(32 * n)

@@ -184,8 +184,8 @@ int64_t dbv_mse_scratch_bytes(void);
 /* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */
 int64_t dbv_launch_count(const dbv_ctx* ctx);
 int64_t dbv_global_launch_count(void);
-/* name / elapsed ms of the per-layer CUDA-event timers of the last dbv_deblend call made with
- * profiling enabled; returns the number of layers. */
+/* name / elapsed ms per call of the per-layer CUDA-event timers, averaged over the dbv_deblend calls made since
+ * profiling was enabled (the caller synchronises first); returns the number of layers. */
 int dbv_set_profiling(dbv_ctx* ctx, int enabled);
 int dbv_layer_times(dbv_ctx* ctx, int max_layers, float* ms_out, char* names_out /* max_layers*32 bytes */);
 /* copy an internal activation buffer (debug / per-layer parity): writes fp32 NHWC */

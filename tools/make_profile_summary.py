@@ -69,7 +69,7 @@ with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
     f.write("## ncu launch list of the timed region (`--metrics gpu__time_duration.sum --clock-control none`, 2 steps)\n\nPer-launch times are cold-cache / serialised: compare SHARES.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
     for k, (t, n) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
         f.write(f"| `{k}` | {n} | {t:.3f} | {100 * t / all_ms:.1f}% |\n")
-    f.write("\n## CUDA-event per-layer times of the last timed step (ms per step) and algorithmic TFLOP/s\n\n| layer | ms | share | TFLOP/s | frac of sustained bf16 peak |\n|---|---|---|---|---|\n")
+    f.write("\n## CUDA-event per-layer times averaged over the timed steps (ms per step) and algorithmic TFLOP/s\n\n| layer | ms | share | TFLOP/s | frac of sustained bf16 peak |\n|---|---|---|---|---|\n")
     for l in L:
         f.write(f"| {l['layer']} | {l['ms']:.3f} | {100 * l['ms'] / ev_ms:.1f}% | {l['tflops']} | {l['frac']} |\n")
     f.write(f"\nroofline object: {json.dumps(bench['roofline'])}\n\n")
