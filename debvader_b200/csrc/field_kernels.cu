@@ -307,26 +307,43 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
             else if (in) acc[j] = *reinterpret_cast<const V2*>(in + idx[j]);
           }
         }
-        if (cnt > 0) {
+        // stamps in groups of KU: all the (independent) stamp loads of a group are issued before its additions, which
+        // run in ascending k for every accumulator (the order of the sequential host loop)
+        constexpr int KU = 2;  // 4 costs 124 registers (2 CTAs per SM): measured slower, also for the plain copy tiles
+        for (int k0 = 0; k0 < cnt; k0 += KU) {
+          VS v[KU][AX_U];
+          bool hit[KU][AX_U];
 #pragma unroll
-          for (int j = 0; j < AX_U; ++j) {
-            if (!ok[j]) continue;
-            for (int k = 0; k < cnt; ++k) {
-              const int dx = X[j] - s_x[k], dy = Y[j] - s_y[k];
-              if ((unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S) {
-                VS v;
+          for (int kk = 0; kk < KU; ++kk) {
+            const int k = k0 + kk;
+            const bool live = k < cnt;
+            const int sx = live ? s_x[k] : 0, sy = live ? s_y[k] : 0;
+            const long long sbase = live ? s_id[k] * stamp_sz : 0;
+#pragma unroll
+            for (int j = 0; j < AX_U; ++j) {
+              const int dx = X[j] - sx, dy = Y[j] - sy;
+              hit[kk][j] = live && ok[j] && (unsigned)dx < (unsigned)S && (unsigned)dy < (unsigned)S;
+              v[kk][j].x = (TS)0;
+              v[kk][j].y = (TS)0;
+              if (hit[kk][j]) {
                 if (planar) {  // (N, C, S, S): the two bands of the pair live in different planes
-                  const TS* sp = stamps + s_id[k] * stamp_sz + ((long long)ch[j] * S + dx) * S + dy;
-                  v.x = __ldg(sp);
-                  v.y = __ldg(sp + (long long)S * S);
+                  const TS* sp = stamps + sbase + ((long long)ch[j] * S + dx) * S + dy;
+                  v[kk][j].x = __ldg(sp);
+                  v[kk][j].y = __ldg(sp + (long long)S * S);
                 } else {
-                  v = __ldg(reinterpret_cast<const VS*>(stamps + s_id[k] * stamp_sz + ((long long)dx * S + dy) * C + ch[j]));
+                  v[kk][j] = __ldg(reinterpret_cast<const VS*>(stamps + sbase + ((long long)dx * S + dy) * C + ch[j]));
                 }
-                acc[j].x = add_rn<T>(acc[j].x, mul_rn<T>(alpha, (T)v.x));
-                acc[j].y = add_rn<T>(acc[j].y, mul_rn<T>(alpha, (T)v.y));
               }
             }
           }
+#pragma unroll
+          for (int kk = 0; kk < KU; ++kk)
+#pragma unroll
+            for (int j = 0; j < AX_U; ++j)
+              if (hit[kk][j]) {
+                acc[j].x = add_rn<T>(acc[j].x, mul_rn<T>(alpha, (T)v[kk][j].x));
+                acc[j].y = add_rn<T>(acc[j].y, mul_rn<T>(alpha, (T)v[kk][j].y));
+              }
         }
 #pragma unroll
         for (int j = 0; j < AX_U; ++j)

@@ -298,3 +298,20 @@ def test_deblend_field_with_optimise_positions_matches_reference(golden_dir):
     np.testing.assert_allclose(got, g["dfo_shifts"], rtol=0, atol=1e-3)
     # the residual moves by |gradient| * shift error: stamps peak at ~30 here
     np.testing.assert_allclose(obj.get_residual_field(), g["dfo_residual"], rtol=0, atol=0.1)
+
+
+def test_extract_broadcast_window_through_the_bulk_copy_kernel(ops):
+    """a window clipped to ONE row / column is broadcast over the stamp (numpy assignment): the f64, C=6 case
+    goes through extract_bulk_kernel, whose per-stamp broadcast branch is exercised here next to regular windows."""
+    F, S, C = 259, 59, 6
+    rng = np.random.default_rng(9)
+    field = rng.normal(size=(1, F, F, C))
+    centres = np.array([[158.0, 0.0], [0.0, 158.0], [158.0, 158.0], [10.0, -20.0], [158.0, 99.0]])  # xs = F-1 -> one row left
+    want, widx = fo.extract_cutouts(field, F, centres, S, C)
+    assert widx == [0, 1, 2, 3, 4]
+    plan = ops.plan_windows(centres, S, F)
+    got, idx = ops.extract(torch.from_numpy(field).cuda(), plan, S, C, out_dtype=torch.float64)
+    assert idx == widx
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    got32, _ = ops.extract(torch.from_numpy(field).cuda(), plan, S, C, out_dtype=torch.float32)
+    np.testing.assert_array_equal(got32.cpu().numpy(), want.astype(np.float32))
