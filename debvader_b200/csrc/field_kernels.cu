@@ -997,16 +997,26 @@ __global__ void __launch_bounds__(256) sum_final_kernel(const double* __restrict
 
 constexpr int SPL_LMAX = 192;  // samples per line: SPL_LMAX * SPL_THREADS doubles of shared memory at most (96 KB)
 
-static int spline_smem_attr() {
-  static bool done = false;
-  if (!done) {
-    const int bytes = SPL_LMAX * SPL_THREADS * (int)sizeof(double);
-    if (cudaFuncSetAttribute(spline_pass_x_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(spline_pass_x_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(spline_pass_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
-      return -1;
-    done = true;
-  }
+// per-device one-time set-up of the spline kernels (function attributes and the z^m table are per device)
+static int spline_device_setup() {
+  static bool done[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return 0;
+  const int bytes = SPL_LMAX * SPL_THREADS * (int)sizeof(double);
+  double zp[SPW_ZPOW];
+  zp[0] = 1.0;
+  for (int i = 1; i < SPW_ZPOW; ++i) zp[i] = zp[i - 1] * -0.26794919243112270647;
+  if (cudaFuncSetAttribute(spline_pass_x_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(spline_pass_x_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(spline_pass_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(spline_place_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(spline_place_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaMemcpyToSymbol(c_zpow, zp, sizeof zp) != cudaSuccess)
+    return -1;
+  done[dev] = true;
   return 0;
 }
 
@@ -1035,7 +1045,7 @@ extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int
   SplineGeom g = {};
   g.F = F; g.S = S; g.P = P; g.origin = origin; g.n_out = n_out;
   cudaStream_t st = (cudaStream_t)stream;
-  if (spline_smem_attr()) return fail(DBV_ERR_CUDA, "dbv_spline_place: cannot raise the dynamic shared memory limit");
+  if (spline_device_setup()) return fail(DBV_ERR_CUDA, "dbv_spline_place: per-device set-up of the spline kernels failed");
   const long long tx = N * (long long)S * C, ty = N * (long long)n_out * C;
   const unsigned gx = (unsigned)((tx + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((ty + SPL_THREADS - 1) / SPL_THREADS);
   const size_t smem = (size_t)(S + 2 * P) * SPL_THREADS * sizeof(double);
@@ -1046,17 +1056,7 @@ extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int
   bool fast = !origin_x && S <= 64 && P + 1 < SPW_ZPOW && (long long)origin - P > 0 && (long long)origin + S + P < F && N * (long long)C < (1ll << 31);
   if (const char* e = getenv("DBV_SPLINE_WARP")) fast = fast && atoi(e) != 0;  // 0: thread-per-line kernels (cross-check)
   if (fast) {
-    static bool init = false;
     const size_t smem_w = ((size_t)n_out * (S | 1) + SPW_ZPOW + (size_t)SPW_WARPS * (S + 2 * P + 6)) * sizeof(double);
-    if (!init) {
-      double zp[SPW_ZPOW];
-      zp[0] = 1.0;
-      for (int i = 1; i < SPW_ZPOW; ++i) zp[i] = zp[i - 1] * -0.26794919243112270647;
-      DBV_CUDA(cudaMemcpyToSymbol(c_zpow, zp, sizeof zp));
-      DBV_CUDA(cudaFuncSetAttribute(spline_place_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      DBV_CUDA(cudaFuncSetAttribute(spline_place_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      init = true;
-    }
     if (smem_w <= 200 * 1024) {
       if (data_dtype == DBV_F32)
         spline_place_warp_kernel<float><<<(unsigned)(N * C), 32 * SPW_WARPS, smem_w, st>>>((const float*)data, C, g, W, placed);
@@ -1116,7 +1116,7 @@ extern "C" int dbv_position_objective(const double* field, int64_t F, int C, int
   g.ax1 = a1x - P - 1 + (int)floor(x0);
   g.ay1 = a1y - P - 1 + (int)floor(x1);
   cudaStream_t st = (cudaStream_t)stream;
-  if (spline_smem_attr()) return fail(DBV_ERR_CUDA, "dbv_position_objective: cannot raise the dynamic shared memory limit");
+  if (spline_device_setup()) return fail(DBV_ERR_CUDA, "dbv_position_objective: per-device set-up of the spline kernels failed");
   const unsigned gx = (unsigned)((E1 + SPL_THREADS - 1) / SPL_THREADS), gy = (unsigned)((E2 + SPL_THREADS - 1) / SPL_THREADS);
   const size_t smem = (size_t)(E1 + 2 * P) * SPL_THREADS * sizeof(double);
   double* W = scratch + (long long)E2 * E1;
