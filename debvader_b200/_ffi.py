@@ -41,6 +41,7 @@ def _declare(lib):
         "dbv_decode": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
         "dbv_deblend": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
         "dbv_deblend_host": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, C.c_uint64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "dbv_host_schedule": (c_i64, [c_i64, c_i64, c_vp, c_i64]),
         "dbv_extract": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
         "dbv_window_axpy": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
         "dbv_window_axpy_ex": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),

@@ -1157,26 +1157,17 @@ static int ensure_pipe(dbv_ctx* c) {
   return DBV_OK;
 }
 
-extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int64_t B, const float* eps_host, uint64_t seed,
-                                int sample, float* mean_host, float* stddev_host, float* z_host, float* mean_dev,
-                                float* stddev_dev) {
-  int r = check_ready(c, "dbv_deblend_host");
-  if (r) return r;
-  DBV_REQUIRE(B == 0 || (x_host && mean_host), "dbv_deblend_host: null buffer");
-  DBV_REQUIRE(x_dtype == DBV_F32 || x_dtype == DBV_F64, "dbv_deblend_host: bad dtype %d", x_dtype);
-  DBV_REQUIRE(B >= 0, "dbv_deblend_host: negative B");
-  if ((r = ensure_pipe(c))) return r;
-  const long long before = g_launches.load();
-  const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
-  // Piece schedule of the H2D / compute / D2H pipeline.  Measured on B200 (tools/e2e_breakdown.py, pcie_probe.py): a piece of n
-  // stamps costs ~0.35 ms + 1.95 us * n of compute, 1.5 us * n of H2D and 1.46 us * n of D2H; the first H2D and the last D2H
-  // cannot overlap anything.  So: start small and let the pieces GROW as fast as the copies keep up with the compute
-  // (H2D of piece k+1 <= compute of piece k: n' <= 1.25 n + 224), cap them, and finish with one short piece.  The old
-  // fixed-size schedule (DBV_HOST_PIECE=n) stalled ~0.7 ms on its second piece and paid three short tail pieces.
+// Piece schedule of the H2D / compute / D2H pipeline of dbv_deblend_host: (first stamp, count) of every piece.
+// Measured on B200 (tools/e2e_breakdown.py, pcie_probe.py): a piece of n stamps costs ~0.35 ms + 1.95 us * n of compute,
+// 1.5 us * n of H2D and 1.46 us * n of D2H; the first H2D and the last D2H cannot overlap anything.  So: start small and let
+// the pieces GROW as fast as the copies keep up with the compute (H2D of piece k+1 <= compute of piece k: n' <= 1.25 n + 224),
+// cap them, and finish with one short piece.  The old fixed-size schedule (DBV_HOST_PIECE=n) stalled ~0.7 ms on its second
+// piece and paid three short tail pieces.
+static std::vector<std::pair<int64_t, long long>> host_schedule(int64_t B, long long chunk) {
   std::vector<std::pair<int64_t, long long>> sched;
   if (const char* e = getenv("DBV_HOST_PIECE")) {
     int64_t b0 = 0;
-    const long long piece = std::max<long long>(1, std::min<long long>(c->chunk, atoll(e)));
+    const long long piece = std::max<long long>(1, std::min<long long>(chunk, atoll(e)));
     const long long q = std::max<long long>(piece / 4, 1);
     if (B > 2 * piece) { sched.push_back({0, q}); b0 = q; }
     while (B - b0 > piece + q) { sched.push_back({b0, piece}); b0 += piece; }
@@ -1188,7 +1179,7 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
       b0 += nb;
     }
   } else {
-    const long long cap = std::min<long long>(c->chunk, 1376), first = std::min<long long>(c->chunk, 256), last = first;
+    const long long cap = std::min<long long>(chunk, 1376), first = std::min<long long>(chunk, 256), last = first;
     int64_t b0 = 0;
     long long n = first;
     while (B - b0 > 0) {
@@ -1197,12 +1188,34 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
       if (rem <= first + first / 4) nb = rem;   // the last, short piece
       else if (rem - n >= last) nb = n;         // ramp / steady state: a tail piece still fits behind it
       else nb = rem - last;                     // the piece before the last one
-      nb = std::min<long long>(nb, c->chunk);
+      nb = std::min<long long>(nb, chunk);
       sched.push_back({b0, nb});
       b0 += nb;
       n = std::min<long long>(cap, ((5 * n / 4 + 224) / 32) * 32);
     }
   }
+  return sched;
+}
+
+extern "C" int64_t dbv_host_schedule(int64_t B, int64_t chunk, int64_t* counts, int64_t max_pieces) {
+  if (B < 0 || chunk <= 0 || (max_pieces > 0 && !counts)) return DBV_ERR_INVALID;
+  const auto sched = host_schedule(B, chunk);
+  for (size_t i = 0; i < sched.size() && (int64_t)i < max_pieces; ++i) counts[i] = sched[i].second;
+  return (int64_t)sched.size();
+}
+
+extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int64_t B, const float* eps_host, uint64_t seed,
+                                int sample, float* mean_host, float* stddev_host, float* z_host, float* mean_dev,
+                                float* stddev_dev) {
+  int r = check_ready(c, "dbv_deblend_host");
+  if (r) return r;
+  DBV_REQUIRE(B == 0 || (x_host && mean_host), "dbv_deblend_host: null buffer");
+  DBV_REQUIRE(x_dtype == DBV_F32 || x_dtype == DBV_F64, "dbv_deblend_host: bad dtype %d", x_dtype);
+  DBV_REQUIRE(B >= 0, "dbv_deblend_host: negative B");
+  if ((r = ensure_pipe(c))) return r;
+  const long long before = g_launches.load();
+  const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
+  const std::vector<std::pair<int64_t, long long>> sched = host_schedule(B, c->chunk);
   for (int k = 0; k < (int)sched.size(); ++k) {
     const int s = k & 1;
     const int64_t b0 = sched[k].first;

@@ -108,6 +108,11 @@ int dbv_deblend_host(dbv_ctx* ctx, const void* x_host, int x_dtype, int64_t B, c
                      uint64_t seed, int sample, float* mean_host, float* stddev_host, float* z_host,
                      float* mean_dev, float* stddev_dev);
 
+/* The piece sizes dbv_deblend_host uses for a batch of B stamps on a context of `chunk` stamps (pure host function, no
+ * device needed): fills counts[0..min(n, max_pieces)) and returns n.  Small first piece, pieces growing as fast as the
+ * copies keep up with the compute, one short last piece; DBV_HOST_PIECE=n selects fixed-size pieces instead. */
+int64_t dbv_host_schedule(int64_t B, int64_t chunk, int64_t* counts_host, int64_t max_pieces);
+
 /* ---- field operators: device buffers -------------------------------------------------------- */
 /* extract_cutouts: extract/extraction.py:21-36.  For k in [0,N): copies the window of `field`
  * (1,F,F,C) whose first row/col is (sx[k], sy[k]) into out[slot[k]] (S,S,C).  flags[k] bit0 / bit1

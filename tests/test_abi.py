@@ -53,3 +53,31 @@ def test_non_dc2_architecture_is_refused():
 
     with pytest.raises(NotImplementedError):
         load_deblender("dc2", (64, 64, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights="random")
+
+
+def test_host_pipeline_schedule(lib, monkeypatch):
+    """piece sizes of dbv_deblend_host (pure host function): they cover the batch exactly, never exceed the context's
+    chunk, start small, grow no faster than the copies keep up with the compute and end with one short piece."""
+    monkeypatch.delenv("DBV_HOST_PIECE", raising=False)
+
+    def sched(B, chunk=4096):
+        buf = (ctypes.c_int64 * 4096)()
+        n = lib.dbv_host_schedule(B, chunk, ctypes.cast(buf, ctypes.c_void_p), 4096)
+        assert 0 <= n <= 4096
+        return list(buf[:n])
+
+    assert sched(0) == []
+    assert sched(1) == [1] and sched(300) == [300]
+    assert sched(512) == [256, 256]
+    assert sched(4096) == [256, 544, 896, 1344, 800, 256]
+    for chunk in (64, 256, 1024, 4096):
+        for B in list(range(1, 3000, 7)) + [4096, 8192, 100000]:
+            s = sched(B, chunk)
+            assert sum(s) == B and min(s) > 0 and max(s) <= chunk, (B, chunk, s)
+            for a, b in zip(s, s[1:-1]):  # growth bound of the ramp (the last piece is the short one)
+                assert b <= 5 * a // 4 + 224 or b <= a, (B, chunk, s)
+    big = sched(100000)
+    assert big[0] == 256 and big[-1] <= 320 and max(big) == 1376
+    monkeypatch.setenv("DBV_HOST_PIECE", "1024")
+    assert sched(4096) == [256, 1024, 1024, 1024, 384, 256, 128]
+    assert lib.dbv_host_schedule(-1, 4096, None, 0) < 0
