@@ -226,10 +226,11 @@ def spline_place(data, pos_x, pos_y, field_size: int, margin: int = SPLINE_MARGI
     return placed, ax, ay
 
 
-def spline_window_axpy(field_in, stamps, pos_x, pos_y, alpha: float, field_shape=None, dtype=torch.float64, batch: int = 512,
+def spline_window_axpy(field_in, stamps, pos_x, pos_y, alpha: float, field_shape=None, dtype=torch.float64, batch: int = 2048,
                        margin: int = SPLINE_MARGIN):
     """out = field_in + alpha * sum_k ndimage.shift(padded stamps[k], (pos_x[k], pos_y[k])), stamps applied in ascending k
-    (batches of `batch` stamps keep the placed windows, 0.66 MB each for DC2, bounded)."""
+    (batches of `batch` stamps bound the memory of the placed windows — 0.66 MB each for DC2 plus 0.34 MB of scratch —; every
+    batch is one more pass over the field, so the default covers a whole 2000-source field in one)."""
     _require_cuda(stamps, "stamps")
     if field_in is not None:
         shape, dtype = tuple(field_in.shape), field_in.dtype

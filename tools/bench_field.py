@@ -49,6 +49,8 @@ E = _fieldops.spline_extent(S)
 t = timeit(lambda: _fieldops.spline_place(st[:512], fpos[:512, 0], fpos[:512, 1], F), iters=5)
 print(f"spline_place 512 stamps -> ({E},{E}) f64 windows: {t:.3f} ms  ({512*(S*S*C*4 + E*E*C*8)/t/1e6:.0f} GB/s of stamp read + window write)")
 t = timeit(lambda: _fieldops.spline_window_axpy(field, st, fpos[:, 0], fpos[:, 1], -1.0), iters=3)
+print(f"sub-pixel residual of {N} stamps (place + paste, one batch): {t:.3f} ms")
+t = timeit(lambda: _fieldops.spline_window_axpy(field, st, fpos[:, 0], fpos[:, 1], -1.0, batch=512), iters=3)
 print(f"sub-pixel residual of {N} stamps (place + paste, batches of 512): {t:.3f} ms")
 # ---- position fit ---------------------------------------------------------------------------------
 import time
