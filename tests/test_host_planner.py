@@ -56,3 +56,17 @@ def test_integer_positions_rejects_subpixel():
     assert list(_fieldops.integer_positions([1.0, -3.0], [0, 0])) == [1, -3]
     with pytest.raises(NotImplementedError):
         _fieldops.integer_positions([1.5], [0])
+
+
+def test_positions_and_spline_anchors():
+    import pytest
+
+    p, integer = _fieldops.positions([1.0, -3.0, 2.0], [0.0, 0.0, 1.0])
+    assert integer and list(p) == [1.0, -3.0, 3.0]
+    p, integer = _fieldops.positions([1.0, -3.0], [0.25, 0.0])
+    assert not integer and list(p) == [1.25, -3.0]
+    with pytest.raises(ValueError):
+        _fieldops.positions([float("nan")], [0.0])
+    # window anchor of the sub-pixel placement: origin - P - 1 + floor(pos), floor toward -inf
+    a = _fieldops._anchor(np.array([100, 100, 100]), np.array([0.0, -0.25, 7.75]), 28)
+    assert a.dtype == np.int32 and list(a) == [71, 70, 78]
