@@ -506,7 +506,9 @@ def main():
                     **executed_tensor_flops(args.precision, value / world, pk)},
         "layers": lay,
     }
-    if not args.no_extras:
+    # extras (other precisions, field kernels, CPU baselines) belong to the N=1 line only: at N>1 the other ranks would sit in
+    # the final barrier (spinning on their host threads) while rank 0 runs them
+    if not args.no_extras and world == 1:
         try:
             alt = {}
             for prec in [p for p in ("bf16", "bf16x3", "fp16x3", "mixed", "fp32") if p != args.precision]:
