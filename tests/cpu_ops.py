@@ -156,3 +156,47 @@ def windowed_objective(r_field, stamp_r, dist, x, P=28):
     t = T2[x0 - ax : x1 - ax, y0 - ay : y1 - ay, 0]
     v = r_field[x0:x1, y0:y1]
     return (np.square(r_field).sum() + (t * t - 2.0 * v * t).sum()) / (F * F)
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy emulation of spw_prefilter (csrc/field_kernels.cu): the cubic prefilter of one line as two warp scans —
+# two samples per lane, Kogge-Stone over the 32 lanes with multiplier z^2 — plus the closed-form head and tail.
+# ---------------------------------------------------------------------------------------------
+def warp_scan_prefilter(x):
+    """x: the S <= 64 data samples of a line (gain already applied).  Returns (c[0..S), c[0], c+[S-1]) as the kernel
+    computes them (zero state before the data, infinite geometric tail after it)."""
+    from oracle.spline_numpy import POLE as z
+
+    S = len(x)
+    assert S <= 64
+    xs = np.zeros(64)
+    xs[:S] = x
+    x0, x1 = xs[0::2].copy(), xs[1::2].copy()  # lane l holds samples 2l, 2l+1
+    lanes = np.arange(32)
+    q = [z**2, z**4, z**8, z**16, z**32]
+    kappa = z / (z * z - 1.0)
+    # causal
+    t0, t1 = x0, x1 + z * x0
+    v = t1.copy()
+    for d, qd in zip((1, 2, 4, 8, 16), q):
+        u = np.concatenate([np.zeros(d), v[:-d]])  # shfl_up
+        v = np.where(lanes >= d, v + qd * u, v)
+    carry = np.concatenate([[0.0], v[:-1]])
+    cp0, cp1 = t0 + z * carry, t1 + z * z * carry
+    cplast = (cp1 if (S - 1) & 1 else cp0)[(S - 1) >> 1]
+    # anti-causal, c[64] = kappa z c+[63]
+    u0, u1 = -z * cp0, -z * cp1
+    u1 = u1.copy()
+    u1[31] += z * (kappa * z * cp1[31])
+    r1 = u1
+    r0 = u0 + z * r1
+    v = r0.copy()
+    for d, qd in zip((1, 2, 4, 8, 16), q):
+        u = np.concatenate([v[d:], np.zeros(d)])  # shfl_down
+        v = np.where(lanes + d < 32, v + qd * u, v)
+    carry = np.concatenate([v[1:], [0.0]])
+    c1 = r1 + z * carry
+    c0 = r0 + z * z * carry
+    c = np.empty(64)
+    c[0::2], c[1::2] = c0, c1
+    return c[:S], c0[0], cplast

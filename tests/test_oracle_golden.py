@@ -104,3 +104,25 @@ def test_subpixel_fields_match_reference(golden_dir, name):
     np.testing.assert_allclose(win, g[f"{name}_residual"], rtol=0, atol=1e-12)
     win = cpu_ops.windowed_axpy(None, means, pos[:, 0], pos[:, 1], 1.0, field_shape=(field.shape[1], field.shape[1], field.shape[3]))
     np.testing.assert_allclose(win, g[f"{name}_pred_mean"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("S", [59, 64, 7, 2])
+def test_warp_scan_prefilter_equals_the_sequential_recursion(S):
+    """the scan formulation of spline_place_warp_kernel (tests/cpu_ops.py:warp_scan_prefilter) against scipy's own prefilter
+    of a long zero canvas holding the line: coefficients inside the data, and the closed-form head / tail outside."""
+    from tests import cpu_ops
+
+    ndi = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(S)
+    x = rng.standard_normal(S) * 10
+    pad = 60
+    canvas = np.zeros(S + 2 * pad)
+    canvas[pad : pad + S] = x
+    want = ndi.spline_filter1d(canvas, order=3, mode="mirror")
+    c, cfirst, cplast = cpu_ops.warp_scan_prefilter(6.0 * x)
+    np.testing.assert_allclose(c, want[pad : pad + S], rtol=0, atol=1e-13 * np.abs(want).max())
+    z = sp.POLE
+    kappa = z / (z * z - 1.0)
+    for m in (1, 2, 5, 28):
+        assert abs(z**m * cfirst - want[pad - m]) < 1e-13 * np.abs(want).max()
+        assert abs(kappa * z**m * cplast - want[pad + S - 1 + m]) < 1e-13 * np.abs(want).max()
