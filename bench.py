@@ -234,7 +234,7 @@ def cpu_field_baseline():
 def run_reference(args, rank):
     if rank != 0:
         return
-    sample = 1024
+    sample = int(os.environ.get("DBV_REF_SAMPLE", "1024"))  # stamps per step (the contract test uses a small one)
     vals = []
     for i in range(args.warmup + args.steps):
         v, threads, done, dt = cpu_reference_rate(sample)
