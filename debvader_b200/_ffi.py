@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEBVADER_B200_LIB") or os.path.join(_HERE, "libdebvader_b200.so")  # env override: A/B builds of the same source
 
-ABI_VERSION = 3  # must equal DBV_ABI_VERSION in include/debvader_b200.h
+ABI_VERSION = 4  # must equal DBV_ABI_VERSION in include/debvader_b200.h
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4}
 F32, F64 = 0, 1
 
@@ -45,6 +45,10 @@ def _declare(lib):
         "dbv_extract": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
         "dbv_window_axpy": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
         "dbv_window_axpy_ex": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_double, c_vp]),
+        "dbv_window_axpy_scratch_bytes": (c_i64, [c_i64, c_i64]),
+        "dbv_window_axpy_rect": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_double,
+                                           c_vp, c_i64, c_vp]),
+        "dbv_sqdiff_sum_rect": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
         "dbv_spline_extent": (C.c_int, [C.c_int, C.c_int]),
         "dbv_spline_scratch_doubles": (c_i64, [c_i64, C.c_int, C.c_int, C.c_int]),
         "dbv_spline_place": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),

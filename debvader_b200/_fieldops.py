@@ -117,7 +117,7 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
     _require_cuda(field_dev, "field")
     S = int(cutout_size)
     n = len(plan["ok"])
-    F_ = field_dev.shape[1]
+    F_ = field_dev.shape[2]  # row pitch in pixels (the field may be a rectangular local region: the planner owns bounds)
     Cf = field_dev.shape[3]
     ok = plan["ok"]
     dev = field_dev.device
@@ -125,7 +125,7 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
     if Cf != nb_of_bands:
         if Cf != 1:  # numpy cannot broadcast (.., Cf) into (.., nb): every stamp raises ValueError in the reference
             return torch.zeros(shape, device=dev, dtype=out_dtype), []
-        field_dev = field_dev.expand(1, F_, F_, nb_of_bands).contiguous()
+        field_dev = field_dev.expand(1, field_dev.shape[1], F_, nb_of_bands).contiguous()
     idx = np.nonzero(ok)[0]
     # rejected stamps stay zero like the reference's np.zeros; when all are accepted skip the memset
     out = torch.empty(shape, device=dev, dtype=out_dtype) if idx.size == n else torch.zeros(shape, device=dev, dtype=out_dtype)
@@ -154,8 +154,10 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
 
 
 def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64, planar=False):
-    """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy).
-    stamps (N,S,S,C), or (N,C,S,S) with planar=True (the windows of spline_place)."""
+    """out = field_in + alpha * sum_k paste(stamps[k] at (x0[k], y0[k])), deterministic (see dbv_window_axpy_rect).
+    stamps (N,S,S,C), or (N,C,S,S) with planar=True (the windows of spline_place).  The field may be rectangular
+    ((1,FH,FW,C): a rank's local region of a tiled field; positions are relative to it and windows are clipped).
+    ``out is field_in`` is the in-place form: only the covered elements are read and written."""
     _require_cuda(stamps, "stamps")
     dev = stamps.device
     if field_in is not None:
@@ -163,10 +165,20 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
         shape, dtype = tuple(field_in.shape), field_in.dtype
     else:
         shape = tuple(field_shape)
-    F_, Cc = shape[-3], shape[-1]
+    FH, FW, Cc = shape[-3], shape[-2], shape[-1]
     n, S = stamps.shape[0], stamps.shape[2 if planar else 1]
     if out is None:
         out = torch.empty(shape, device=dev, dtype=dtype)
+    else:
+        _require_cuda(out, "out")
+        if tuple(out.shape) != shape or out.dtype != dtype:
+            raise ValueError("out must have the field's shape and dtype")
+    if n == 0:
+        if field_in is None:
+            out.zero_()
+        elif out is not field_in:
+            out.copy_(field_in)
+        return out
     if isinstance(x0, torch.Tensor) and isinstance(y0, torch.Tensor):  # positions already on the device (int32)
         if not (x0.is_cuda and y0.is_cuda and x0.dtype == torch.int32 and y0.dtype == torch.int32 and x0.numel() == n == y0.numel()):
             raise TypeError("device positions must be int32 CUDA tensors of length N")
@@ -174,10 +186,15 @@ def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=No
     else:  # one packed upload
         xy = torch.from_numpy(np.stack([np.asarray(x0, dtype=np.int32).reshape(-1), np.asarray(y0, dtype=np.int32).reshape(-1)])).to(dev)
         xs, ys = xy[0], xy[1]
+    lib = _ffi.lib()
     with torch.cuda.device(dev):
+        # binning scratch from torch's stream-ordered caching allocator: private to this call's stream
+        sb = int(lib.dbv_window_axpy_scratch_bytes(FH, FW))
+        scratch = torch.empty((sb // 4,), device=dev, dtype=torch.int32)
         _ffi.check(
-            _ffi.lib().dbv_window_axpy_ex(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], F_, Cc, _ffi.ptr(stamps), _DT[stamps.dtype],
-                                          int(bool(planar)), _ffi.ptr(xs), _ffi.ptr(ys), n, S, float(alpha), _ffi.stream_ptr())
+            lib.dbv_window_axpy_rect(_ffi.ptr(field_in), _ffi.ptr(out), _DT[dtype], FH, FW, Cc, _ffi.ptr(stamps), _DT[stamps.dtype],
+                                     int(bool(planar)), _ffi.ptr(xs), _ffi.ptr(ys), n, S, float(alpha), _ffi.ptr(scratch), sb,
+                                     _ffi.stream_ptr())
         )
     return out
 
@@ -278,3 +295,25 @@ def mse(a, b) -> float:
     with torch.cuda.device(ta.device):
         _ffi.check(lib.dbv_mse(_ffi.ptr(ta), _ffi.ptr(tb), _DT[ta.dtype], n, _ffi.ptr(out), _ffi.ptr(scratch), sb, _ffi.stream_ptr()))
     return float(out.item())
+
+
+def sqdiff_sum_rect(a, b, r0: int, r1: int, c0: int, c1: int) -> torch.Tensor:
+    """sum((a-b)^2) over rows [r0,r1) x cols [c0,c1) (all bands) of two (1,H,W,C) CUDA tensors of the same shape:
+    the owner-tile partial sum of a tiled field MSE.  Returns a (1,) float64 CUDA tensor (no host sync)."""
+    _require_cuda(a, "a")
+    _require_cuda(b, "b")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("a and b must have the same shape and dtype")
+    H, W, Cc = a.shape[-3], a.shape[-2], a.shape[-1]
+    if not (0 <= r0 < r1 <= H and 0 <= c0 < c1 <= W):
+        raise ValueError("bad sub-rectangle")
+    lib = _ffi.lib()
+    sb = int(lib.dbv_mse_scratch_bytes())
+    scratch = torch.empty((sb // 8,), device=a.device, dtype=torch.float64)
+    out = torch.empty((1,), device=a.device, dtype=torch.float64)
+    esz = a.element_size()
+    off = (r0 * W + c0) * Cc * esz
+    with torch.cuda.device(a.device):
+        _ffi.check(lib.dbv_sqdiff_sum_rect(C.c_void_p(a.data_ptr() + off), C.c_void_p(b.data_ptr() + off), _DT[a.dtype], r1 - r0,
+                                           (c1 - c0) * Cc, W * Cc, W * Cc, _ffi.ptr(out), _ffi.ptr(scratch), sb, _ffi.stream_ptr()))
+    return out

@@ -183,13 +183,13 @@ template <> __device__ __forceinline__ double add_rn<double>(double a, double b)
 template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
 
 __global__ void __launch_bounds__(256) axpy_bin_kernel(const int32_t* __restrict__ x0, const int32_t* __restrict__ y0, int N, int S,
-                                                       long long F, int tiles_c, int* __restrict__ cnt, int* __restrict__ list) {
+                                                       long long FH, long long FW, int tiles_c, int* __restrict__ cnt, int* __restrict__ list) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const long long xi = x0[i], yi = y0[i];
-  if (xi + S <= 0 || xi >= F || yi + S <= 0 || yi >= F) return;
-  const int r_lo = (int)((xi > 0 ? xi : 0) / AX_TR), r_hi = (int)((xi + S - 1 < F - 1 ? xi + S - 1 : F - 1) / AX_TR);
-  const int c_lo = (int)((yi > 0 ? yi : 0) / AX_TC), c_hi = (int)((yi + S - 1 < F - 1 ? yi + S - 1 : F - 1) / AX_TC);
+  if (xi + S <= 0 || xi >= FH || yi + S <= 0 || yi >= FW) return;
+  const int r_lo = (int)((xi > 0 ? xi : 0) / AX_TR), r_hi = (int)((xi + S - 1 < FH - 1 ? xi + S - 1 : FH - 1) / AX_TR);
+  const int c_lo = (int)((yi > 0 ? yi : 0) / AX_TC), c_hi = (int)((yi + S - 1 < FW - 1 ? yi + S - 1 : FW - 1) / AX_TC);
   for (int r = r_lo; r <= r_hi; ++r)
     for (int c = c_lo; c <= c_hi; ++c) {
       const int t = r * tiles_c + c;
@@ -199,12 +199,15 @@ __global__ void __launch_bounds__(256) axpy_bin_kernel(const int32_t* __restrict
 }
 
 template <typename T, typename TS>
-__global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T* out, long long F, int C,
+__global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T* out, long long FH, long long F, int C,
                                                                   const TS* __restrict__ stamps,
                                                                   const int32_t* __restrict__ x0, const int32_t* __restrict__ y0,
                                                                   int N, int S, double alpha_d, int tiles_c,
                                                                   const int* __restrict__ bin_cnt, const int* __restrict__ bin_list,
-                                                                  int planar) {
+                                                                  int planar, int inplace) {
+  // F = columns of the (FH, F, C) field = its row pitch in pixels.  inplace (in == out): only the elements a stamp
+  // actually covers are read and written back, so the traffic is the algorithmic one (window read-modify-write +
+  // stamp), not a pass over the whole field; a tile no stamp touches returns at once.
   __shared__ int s_id[AX_CAP], s_x[AX_CAP], s_y[AX_CAP];
   __shared__ int s_wcnt[AX_THREADS / 32];
   __shared__ int s_count, s_next;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
   const int nelt = AX_TR * AX_TC * C;
   const long long stamp_sz = (long long)S * S * C;
   const int binned = bin_cnt ? bin_cnt[blockIdx.x] : -1;
+  if (inplace && binned == 0) return;
   int start = 0;
   bool first = true;
   do {
@@ -278,7 +282,8 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
       }
     }
     const int cnt = s_count;
-    if ((cnt > 0 || first) && (C & 1) == 0) {
+    const bool work = cnt > 0 || (first && !inplace);
+    if (work && (C & 1) == 0) {
       // vector path: 2 bands per thread (16-byte field accesses for f64); a pixel's C values start at an even
       // element index, so the pairs never straddle pixels
       using V2 = typename Vec2<T>::type;
@@ -298,7 +303,12 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
           X[j] = tr0 + pr;
           Y[j] = tc0 + (2 * rem) / C;
           ch[j] = 2 * rem - ((2 * rem) / C) * C;
-          ok[j] = e < nvec && X[j] < F && Y[j] < F;
+          ok[j] = e < nvec && X[j] < FH && Y[j] < F;
+          if (inplace && ok[j]) {  // untouched elements are neither read nor written
+            bool any = false;
+            for (int k = 0; k < cnt; ++k) any = any || ((unsigned)(X[j] - s_x[k]) < (unsigned)S && (unsigned)(Y[j] - s_y[k]) < (unsigned)S);
+            ok[j] = any;
+          }
           idx[j] = ((long long)X[j] * F + Y[j]) * C + ch[j];
           acc[j].x = (T)0;
           acc[j].y = (T)0;
@@ -349,13 +359,13 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
         for (int j = 0; j < AX_U; ++j)
           if (ok[j]) *reinterpret_cast<V2*>(out + idx[j]) = acc[j];
       }
-    } else if (cnt > 0 || first) {
+    } else if (work) {
       for (int e = threadIdx.x; e < nelt; e += AX_THREADS) {
         const int ch = e % C;
         const int pc = (e / C) % AX_TC;
         const int pr = e / (C * AX_TC);
         const int X = tr0 + pr, Y = tc0 + pc;
-        if (X >= F || Y >= F) continue;
+        if (X >= FH || Y >= F) continue;
         const long long idx = ((long long)X * F + Y) * C + ch;
         T acc = first ? (in ? in[idx] : (T)0) : out[idx];
         for (int k = 0; k < cnt; ++k) {
@@ -412,6 +422,30 @@ __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const T* __restrict
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double d = (double)__ldg(a + i) - (double)__ldg(b + i);
     acc += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) sqdiff_rect_kernel(const T* __restrict__ a, const T* __restrict__ b, long long rows, long long cols,
+                                                          long long pitch_a, long long pitch_b, double* __restrict__ partial) {
+  // one row per CTA iteration (rows in grid stride, columns in thread stride): sub-rectangles of two pitched arrays
+  __shared__ double s[8];
+  double acc = 0.0;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const T* pa = a + r * pitch_a;
+    const T* pb = b + r * pitch_b;
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) {
+      const double d = (double)__ldg(pa + c) - (double)__ldg(pb + c);
+      acc += d * d;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -496,6 +530,58 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   return DBV_OK;
 }
 
+// out = in + alpha * sum_k paste(stamps[k]) on a (FH, FW, C) field; `bins` = caller scratch of
+// dbv_window_axpy_scratch_bytes(FH, FW) bytes (tile counts + fixed-capacity lists), or NULL (every tile scans all stamps)
+static int window_axpy_impl(const void* in, void* out, int dtype, int64_t FH, int64_t FW, int C, const void* stamps, int stamp_dtype,
+                            int stamp_planar, const int32_t* x0, const int32_t* y0, int64_t N, int S, double alpha, int* bins,
+                            cudaStream_t st) {
+  const int tiles_r = (int)((FH + AX_TR - 1) / AX_TR), tiles_c = (int)((FW + AX_TC - 1) / AX_TC);
+  const int ntiles = tiles_r * tiles_c;
+  const int inplace = (in == out) ? 1 : 0;
+  if (N == 0 && inplace) return DBV_OK;
+  if (N == 0) bins = nullptr;
+  if (bins) {
+    DBV_CUDA(cudaMemsetAsync(bins, 0, (size_t)ntiles * sizeof(int), st));
+    axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, FH, FW, tiles_c, bins, bins + ntiles);
+    DBV_LAUNCH_CHECK();
+  }
+  const int* bc = bins;
+  const int* bl = bins ? bins + ntiles : nullptr;
+  dim3 grid((unsigned)ntiles), block(AX_THREADS);
+  if (dtype == DBV_F64 && stamp_dtype == DBV_F32)
+    window_axpy_kernel<double, float><<<grid, block, 0, st>>>((const double*)in, (double*)out, FH, FW, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0, inplace);
+  else if (dtype == DBV_F32 && stamp_dtype == DBV_F32)
+    window_axpy_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, FH, FW, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0, inplace);
+  else if (dtype == DBV_F64 && stamp_dtype == DBV_F64)
+    window_axpy_kernel<double, double><<<grid, block, 0, st>>>((const double*)in, (double*)out, FH, FW, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0, inplace);
+  else
+    window_axpy_kernel<float, double><<<grid, block, 0, st>>>((const float*)in, (float*)out, FH, FW, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0, inplace);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+extern "C" int64_t dbv_window_axpy_scratch_bytes(int64_t FH, int64_t FW) {
+  if (FH <= 0 || FW <= 0) return DBV_ERR_INVALID;
+  const int64_t ntiles = ((FH + AX_TR - 1) / AX_TR) * ((FW + AX_TC - 1) / AX_TC);
+  return ntiles * (1 + AX_LCAP) * (int64_t)sizeof(int);
+}
+
+extern "C" int dbv_window_axpy_rect(const void* in, void* out, int dtype, int64_t FH, int64_t FW, int C, const void* stamps,
+                                    int stamp_dtype, int stamp_planar, const int32_t* x0, const int32_t* y0, int64_t N, int S,
+                                    double alpha, void* scratch, int64_t scratch_bytes, void* stream) {
+  DBV_REQUIRE(out, "dbv_window_axpy_rect: null out");
+  DBV_REQUIRE(N == 0 || (stamps && x0 && y0), "dbv_window_axpy_rect: null stamp arrays");
+  DBV_REQUIRE(FH > 0 && FW > 0 && C > 0 && S > 0 && N >= 0 && N < (1ll << 31), "dbv_window_axpy_rect: bad sizes");
+  DBV_REQUIRE(FH * FW * C < (1ll << 40), "dbv_window_axpy_rect: field too large");
+  DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_window_axpy_rect: bad dtype %d", dtype);
+  DBV_REQUIRE(stamp_dtype == DBV_F64 || stamp_dtype == DBV_F32, "dbv_window_axpy_rect: bad stamp dtype %d", stamp_dtype);
+  DBV_REQUIRE(scratch == nullptr || scratch_bytes >= dbv_window_axpy_scratch_bytes(FH, FW), "dbv_window_axpy_rect: scratch too small");
+  return window_axpy_impl(in, out, dtype, FH, FW, C, stamps, stamp_dtype, stamp_planar, x0, y0, N, S, alpha, (int*)scratch,
+                          (cudaStream_t)stream);
+}
+
+// square field, library-allocated scratch: taken from the device's stream-ordered pool on the caller's stream and
+// returned to it right after the launch, so concurrent calls on different streams never share it
 extern "C" int dbv_window_axpy_ex(const void* in, void* out, int dtype, int64_t F, int C, const void* stamps, int stamp_dtype,
                                   int stamp_planar, const int32_t* x0, const int32_t* y0, int64_t N, int S, double alpha, void* stream) {
   DBV_REQUIRE(out, "dbv_window_axpy: null out");
@@ -504,50 +590,11 @@ extern "C" int dbv_window_axpy_ex(const void* in, void* out, int dtype, int64_t 
   DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_window_axpy: bad dtype %d", dtype);
   DBV_REQUIRE(stamp_dtype == DBV_F64 || stamp_dtype == DBV_F32, "dbv_window_axpy: bad stamp dtype %d", stamp_dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_r = (int)((F + AX_TR - 1) / AX_TR), tiles_c = (int)((F + AX_TC - 1) / AX_TC);
-  const int ntiles = tiles_r * tiles_c;
-  // binning pass (stream-ordered scratch: tile counts + fixed-capacity lists)
-  int* bins = nullptr;
-  bool use_bins = N > 0;
-  if (const char* e = getenv("DBV_AXPY_BINS")) use_bins = use_bins && atoi(e) != 0;  // tuning knob (0 = every tile scans)
-  if (use_bins) {
-    // per-device scratch kept by the library (tile counts + fixed-capacity lists); calls that share a device must be
-    // ordered on one stream, like every other use of this library's per-device state
-    static std::mutex mu;
-    static int* cache[64] = {};
-    static size_t cap[64] = {};
-    const size_t bytes = (size_t)ntiles * (1 + AX_LCAP) * sizeof(int);
-    int dev = 0;
-    DBV_CUDA(cudaGetDevice(&dev));
-    DBV_REQUIRE(dev >= 0 && dev < 64, "dbv_window_axpy: device index %d out of range", dev);
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      if (cap[dev] < bytes) {
-        if (cache[dev]) DBV_CUDA(cudaFree(cache[dev]));
-        cache[dev] = nullptr;
-        cap[dev] = 0;
-        DBV_CUDA(cudaMalloc((void**)&cache[dev], bytes));
-        cap[dev] = bytes;
-      }
-      bins = cache[dev];
-    }
-    DBV_CUDA(cudaMemsetAsync(bins, 0, (size_t)ntiles * sizeof(int), st));
-    axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, F, tiles_c, bins, bins + ntiles);
-    DBV_LAUNCH_CHECK();
-  }
-  const int* bc = bins;
-  const int* bl = bins ? bins + ntiles : nullptr;
-  dim3 grid((unsigned)ntiles), block(AX_THREADS);
-  if (dtype == DBV_F64 && stamp_dtype == DBV_F32)
-    window_axpy_kernel<double, float><<<grid, block, 0, st>>>((const double*)in, (double*)out, F, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0);
-  else if (dtype == DBV_F32 && stamp_dtype == DBV_F32)
-    window_axpy_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0);
-  else if (dtype == DBV_F64 && stamp_dtype == DBV_F64)
-    window_axpy_kernel<double, double><<<grid, block, 0, st>>>((const double*)in, (double*)out, F, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0);
-  else
-    window_axpy_kernel<float, double><<<grid, block, 0, st>>>((const float*)in, (float*)out, F, C, (const double*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0);
-  DBV_LAUNCH_CHECK();
-  return DBV_OK;
+  void* bins = nullptr;
+  if (N > 0) DBV_CUDA(cudaMallocAsync(&bins, (size_t)dbv_window_axpy_scratch_bytes(F, F), st));
+  const int r = window_axpy_impl(in, out, dtype, F, F, C, stamps, stamp_dtype, stamp_planar, x0, y0, N, S, alpha, (int*)bins, st);
+  if (bins) cudaFreeAsync(bins, st);
+  return r;
 }
 
 extern "C" int dbv_window_axpy(const void* in, void* out, int dtype, int64_t F, int C, const float* stamps,
@@ -590,6 +637,27 @@ extern "C" int dbv_mse(const void* a, const void* b, int dtype, int64_t n, doubl
     return fail(DBV_ERR_INVALID, "dbv_mse: bad dtype %d", dtype);
   DBV_LAUNCH_CHECK();
   sqdiff_final_kernel<<<1, 256, 0, st>>>((const double*)scratch, nb, n, out);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+// sum of squared differences over a rows x cols sub-rectangle of two pitched arrays (the owner tile of a rank's local
+// region): the partial sum a tiled field MSE all-reduces.  out[0] = sum, fixed reduction order.
+extern "C" int dbv_sqdiff_sum_rect(const void* a, const void* b, int dtype, int64_t rows, int64_t cols, int64_t pitch_a,
+                                   int64_t pitch_b, double* out, void* scratch, int64_t scratch_bytes, void* stream) {
+  DBV_REQUIRE(a && b && out && scratch, "dbv_sqdiff_sum_rect: null pointer");
+  DBV_REQUIRE(rows > 0 && cols > 0 && pitch_a >= cols && pitch_b >= cols, "dbv_sqdiff_sum_rect: bad sizes");
+  DBV_REQUIRE(scratch_bytes >= dbv_mse_scratch_bytes(), "dbv_sqdiff_sum_rect: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)(rows < MSE_BLOCKS ? rows : MSE_BLOCKS);
+  if (dtype == DBV_F64)
+    sqdiff_rect_kernel<double><<<nb, 256, 0, st>>>((const double*)a, (const double*)b, rows, cols, pitch_a, pitch_b, (double*)scratch);
+  else if (dtype == DBV_F32)
+    sqdiff_rect_kernel<float><<<nb, 256, 0, st>>>((const float*)a, (const float*)b, rows, cols, pitch_a, pitch_b, (double*)scratch);
+  else
+    return fail(DBV_ERR_INVALID, "dbv_sqdiff_sum_rect: bad dtype %d", dtype);
+  DBV_LAUNCH_CHECK();
+  sqdiff_final_kernel<<<1, 256, 0, st>>>((const double*)scratch, nb, 1, out);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

@@ -1,31 +1,35 @@
 """B200-native drop-in for reference deblend/field_deblender.py (class DeblendField).
 
 Same constructor, methods, attributes and record layout as the reference; the field lives on the
-device, extraction / network / centre-MSE / subtract-back are CUDA kernels, and only the record
-materialisation (a numpy recarray of per-stamp arrays, as the reference returns) touches the host.
-Fractional positions in get_residual_field / get_predicted_field go through the cubic-spline placement kernels
-(the reference's ndimage.shift, evaluated only where it matters); ``optimise_positions=True`` runs the
-reference's own scipy least-squares call with the objective evaluated on the device
+device, extraction / network / centre-MSE / subtract-back are CUDA kernels, and the per-stamp record
+columns are lazy device-backed proxies (``_records.DeviceStamp``: an ndarray to every caller, fetched
+from the device only when somebody looks at the values).  Fractional positions in get_residual_field /
+get_predicted_field go through the cubic-spline placement kernels (the reference's ndimage.shift,
+evaluated only where it matters); ``optimise_positions=True`` fits all galaxies at once on the device
 (deblend_cutout/optimization.py).
+
+Multi-GPU (extension): ``DeblendField(..., tiled=True)`` inside a torch.distributed job
+(one process per GPU) keeps only this rank's owner tile + 30-px halo of the field on the device
+(``parallel.LocalField``); ``deblend_field`` then deblends the sources this rank owns, and
+``get_residual_field`` exchanges the overlapping stamps once (NCCL all_to_all) and assembles the
+rank's region, bit-identical to the single-GPU result.
 """
 import numpy as np
-import pandas as pd
 import torch
 
-from .. import _fieldops
+from .. import _fieldops, _records
 from ..deblend_cutout.deblender import deblend
 from ..model.model import Deblender
 
+_EMPTY = {"cutout_images": None, "output_images_mean": None, "output_images_stddev": None, "shifts": None, "list_idx": None}
+
 
 class DeblendField:
-    def __init__(self, net, field_image, cutout_size=59, nb_of_bands=6, epistemic_uncertainty_estimation=False, normalise=False):
-        """field_deblender.py:13-44."""
+    def __init__(self, net, field_image, cutout_size=59, nb_of_bands=6, epistemic_uncertainty_estimation=False, normalise=False,
+                 *, tiled=False, group=None):
+        """field_deblender.py:13-44.  ``field_image``: (1,F,F,C) ndarray (copied, as the reference does) or CUDA tensor
+        (kept on the device; ``.field_image`` downloads it on first access).  tiled=True: see the module docstring."""
         self.net = net
-        if isinstance(field_image, torch.Tensor):
-            self.field_image = field_image.detach().cpu().numpy().copy()
-        else:
-            self.field_image = np.asarray(field_image).copy()
-        self.field_size = self.field_image.shape[1]
         self.cutout_size = cutout_size
         self.nb_of_bands = nb_of_bands
         self.epistemic_uncertainty_estimation = epistemic_uncertainty_estimation
@@ -35,15 +39,51 @@ class DeblendField:
         self.res_deblend = None
         self.mse = []
         device = net.device if isinstance(net, Deblender) else None
-        self._field_dev = _fieldops.to_device_field(field_image if isinstance(field_image, torch.Tensor) else self.field_image, device)
-        self._dev_cache = None  # (id(records), means_dev, stddev_dev) of the last deblend_field call
+        self._group = group
+        self._local = None
+        self._tile_state = None  # (records, TilePlan, mine) of the last tiled deblend_field call
+        self._host_field = None
+        if tiled:
+            from .. import parallel
+
+            rank, world = parallel._world(group)
+            if isinstance(field_image, parallel.LocalField):
+                self._local = field_image
+            else:
+                self._local = parallel.LocalField.from_full(field_image, rank, world, device)
+                if not isinstance(field_image, torch.Tensor):
+                    self._host_field = field_image  # the caller's full host array (not copied: every rank would hold 8 copies)
+            self._field_dev = self._local.data
+            self.field_size = self._local.field_size
+        else:
+            if not isinstance(field_image, torch.Tensor):
+                self._host_field = np.asarray(field_image).copy()
+            self._field_dev = _fieldops.to_device_field(field_image if isinstance(field_image, torch.Tensor) else self._host_field, device)
+            self.field_size = self._field_dev.shape[1]
+
+    @property
+    def field_image(self):
+        """the reference's ``self.field_image`` (host ndarray); tiled fields gather their owner tiles."""
+        if self._host_field is None:
+            if self._local is not None:
+                from .. import parallel
+
+                self._host_field = parallel.gather_field(self._local, group=self._group)
+            else:
+                self._host_field = self._field_dev.detach().cpu().numpy()
+        return self._host_field
+
+    @property
+    def field_tensor(self):
+        """the device-resident field (tiled: this rank's local region)."""
+        return self._field_dev
 
     # ------------------------------------------------------------------------------------------
     def _positions(self, res_deblend):
         """x_pos / y_pos of field_deblender.py:83-90 (float64) and whether every one is integer-valued."""
-        dx = np.array([r["galaxy_distances_to_center_x"] for r in res_deblend], dtype=np.float64)
-        dy = np.array([r["galaxy_distances_to_center_y"] for r in res_deblend], dtype=np.float64)
-        sh = np.array([np.asarray(r["shifts"], dtype=np.float64) for r in res_deblend]).reshape(-1, 2)
+        dx = np.asarray(res_deblend["galaxy_distances_to_center_x"], dtype=np.float64)
+        dy = np.asarray(res_deblend["galaxy_distances_to_center_y"], dtype=np.float64)
+        sh = np.array([np.asarray(s, dtype=np.float64) for s in res_deblend["shifts"]]).reshape(-1, 2)
         px, ix = _fieldops.positions(dx, sh[:, 0])
         py, iy = _fieldops.positions(dy, sh[:, 1])
         return px, py, ix and iy
@@ -59,17 +99,41 @@ class DeblendField:
         return _fieldops.spline_window_axpy(base, stamps, px, py, alpha, field_shape=shape, dtype=torch.float64)
 
     def _stamps_dev(self, res_deblend, column):
-        c = self._dev_cache
-        if c is not None and c[0] is res_deblend and column in c[1]:
-            return c[1][column]
-        a = np.stack([np.asarray(r[column], dtype=np.float32) for r in res_deblend])
-        return torch.from_numpy(a).to(self._field_dev.device)
+        return _records.column_tensor(res_deblend, column, self._field_dev.device)
+
+    def _tiled_paste(self, res_deblend, column, alpha, base):
+        """tiled get_residual_field / get_predicted_field: exchange the overlapping stamps of `column` once and apply
+        them to this rank's region in ascending global index."""
+        from .. import parallel
+
+        st = self._tile_state
+        if st is None or st[0] is not res_deblend:
+            raise NotImplementedError("a tiled DeblendField assembles the records of its own last deblend_field call")
+        _, tp, mine = st
+        px, py, integer = self._positions(res_deblend) if len(res_deblend) else (None, None, True)
+        if not integer:
+            raise NotImplementedError("tiled fields place stamps on whole pixels only")
+        S, C = self.cutout_size, self.nb_of_bands
+        dev = self._field_dev.device
+        own = self._stamps_dev(res_deblend, column) if len(res_deblend) else torch.empty((0, S, S, C), device=dev, dtype=torch.float32)
+        stamps, ids = parallel.exchange_halo_stamps(own.contiguous(), mine, tp.owner, tp.touches, self._group)
+        if len(ids) == 0:
+            return self._field_dev.clone() if base == "field" else torch.zeros_like(self._field_dev)
+        return parallel.subtract_local(self._local, tp, stamps, ids, alpha, base=base)
 
     def get_residual_field(self, res_deblend=None, as_tensor=False):
-        """field_deblender.py:46-97: field minus every predicted galaxy (all rows, whatever passed_cuts)."""
+        """field_deblender.py:46-97: field minus every predicted galaxy (all rows, whatever passed_cuts).
+        as_tensor=True keeps the result on the device (tiled: this rank's local region, halo included)."""
         if res_deblend is None:
             res_deblend = self.res_deblend
         base = self._field_dev
+        if self._local is not None:
+            from .. import parallel
+
+            if res_deblend is None:
+                res_deblend = self._tile_state[0] if self._tile_state is not None else None
+            out = base.clone() if res_deblend is None else self._tiled_paste(res_deblend, "output_images_mean", -1.0, "field")
+            return out if as_tensor else parallel.gather_field(self._local, out, self._group)
         if res_deblend is None or len(res_deblend) == 0:
             out = base.clone()
         else:
@@ -87,7 +151,16 @@ class DeblendField:
         cols = ("output_images_mean", "output_images_stddev", "epistemic_uncertainty")
         out = {}
         for name, col in zip(names, cols):
-            if res_deblend is None or len(res_deblend) == 0 or (col == "epistemic_uncertainty" and not self.epistemic_uncertainty_estimation):
+            skip = col == "epistemic_uncertainty" and not self.epistemic_uncertainty_estimation
+            if self._local is not None:
+                from .. import parallel
+
+                if res_deblend is None and self._tile_state is not None:
+                    res_deblend = self._tile_state[0]
+                f = torch.zeros_like(self._field_dev) if (res_deblend is None or skip) else self._tiled_paste(res_deblend, col, 1.0, "zeros")
+                out[name] = f if as_tensor else parallel.gather_field(self._local, f.to(torch.float64), self._group)[0]
+                continue
+            if res_deblend is None or len(res_deblend) == 0 or skip:
                 f = torch.zeros((F_, F_, C), device=dev, dtype=torch.float64)
             else:
                 px, py, integer = self._positions(res_deblend)
@@ -101,35 +174,69 @@ class DeblendField:
         meta.update(self.get_predicted_field(res_deblend))
         return meta
 
+    def field_mse(self, a, b):
+        """training/metrics.py:4-12 of two fields on the device (tiled: owner-tile partial sums + one all-reduce)."""
+        if self._local is not None:
+            from .. import parallel
+
+            return parallel.field_mse_tiled(self._local, a, b, self._group)
+        return _fieldops.mse(a, b)
+
     # ------------------------------------------------------------------------------------------
     def deblend_field(self, galaxy_distances_to_center, cutout_images=None, optimise_positions=False, epistemic_criterion=100.0,
                       mse_criterion=100.0, field_image=None):
-        """field_deblender.py:219-382."""
-        res_deblend = {"cutout_images": None, "output_images_mean": None, "output_images_stddev": None, "shifts": None, "list_idx": None}
-        if field_image is None:
-            field_dev = self._field_dev
-        else:
-            field_dev = _fieldops.to_device_field(field_image, self._field_dev.device)
-        field_size = field_dev.shape[1]
-        dev = field_dev.device
+        """field_deblender.py:219-382.  Tiled: the records are those of the sources THIS rank owns, ``list_idx`` stays
+        global (the order contract holds across ranks: concatenating the ranks' records and sorting by list_idx gives
+        the single-GPU records)."""
+        res_deblend = dict(_EMPTY)
         S, C = self.cutout_size, self.nb_of_bands
+        tp = mine = None
+        if self._local is not None:
+            from .. import parallel
 
-        if isinstance(cutout_images, np.ndarray):
-            cut_dev = torch.from_numpy(np.ascontiguousarray(cutout_images)).to(dev)
-            list_idx = list(range(len(cutout_images)))
-            sel = cut_dev
-        else:
-            plan = _fieldops.plan_windows(galaxy_distances_to_center, S, field_size)
-            cut_dev, list_idx = _fieldops.extract(field_dev, plan, S, C, out_dtype=torch.float64)
-            if len(list_idx) != len(plan["ok"]):
+            if cutout_images is not None or optimise_positions:
+                raise NotImplementedError("tiled fields: precomputed cutouts / position fits are single-GPU options")
+            local = self._local
+            if field_image is not None:
+                local = field_image if isinstance(field_image, parallel.LocalField) else self._local.like(field_image)
+            field_dev = local.data
+            dev = field_dev.device
+            tp = parallel.TilePlan(galaxy_distances_to_center, local.field_size, local.world, S)
+            mine = tp.mine(local.rank)
+            if len(tp.idx) != tp.n_sources:
                 print("Some galaxies are too close from the border of the field to be considered here.")
-            sel = cut_dev[torch.as_tensor(list_idx, device=dev, dtype=torch.long)] if len(list_idx) != cut_dev.shape[0] else cut_dev
-        if list_idx == []:
-            print("No galaxy deblended. End of the iterative procedure.")
-            return res_deblend
+            if len(tp.idx) == 0:
+                print("No galaxy deblended. End of the iterative procedure.")
+                self._tile_state = None
+                return res_deblend
+            sel = parallel.extract_local(local, tp, mine, C, out_dtype=torch.float64)
+            list_idx = [int(i) for i in tp.idx[mine]]
+            n_detected, n_deblended = tp.n_sources, len(tp.idx)
+        else:
+            field_dev = self._field_dev if field_image is None else _fieldops.to_device_field(field_image, self._field_dev.device)
+            field_size = field_dev.shape[1]
+            dev = field_dev.device
+            if isinstance(cutout_images, (np.ndarray, torch.Tensor)):
+                sel = cutout_images if isinstance(cutout_images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cutout_images))
+                sel = sel.to(dev)
+                list_idx = list(range(len(cutout_images)))
+            else:
+                plan = _fieldops.plan_windows(galaxy_distances_to_center, S, field_size)
+                cut_dev, list_idx = _fieldops.extract(field_dev, plan, S, C, out_dtype=torch.float64)
+                if len(list_idx) != len(plan["ok"]):
+                    print("Some galaxies are too close from the border of the field to be considered here.")
+                sel = cut_dev[torch.as_tensor(list_idx, device=dev, dtype=torch.long)] if len(list_idx) != cut_dev.shape[0] else cut_dev
+            if list_idx == []:
+                print("No galaxy deblended. End of the iterative procedure.")
+                return res_deblend
+            n_detected, n_deblended = len(list(galaxy_distances_to_center)), len(list_idx)
 
+        n = len(list_idx)
         # network on the device-resident stamps (deblend(): cast to fp32, net, mean / stddev)
-        if isinstance(self.net, Deblender) and not self.normalise:
+        if n == 0:
+            mean_dev = torch.empty((0, S, S, C), device=dev, dtype=torch.float32)
+            std_dev = torch.empty_like(mean_dev)
+        elif isinstance(self.net, Deblender) and not self.normalise:
             dist = self.net(sel)
             mean_dev, std_dev = dist.mean().tensor, dist.stddev().tensor
         else:
@@ -137,57 +244,54 @@ class DeblendField:
             mean_dev = torch.from_numpy(np.ascontiguousarray(mean_np, dtype=np.float32)).to(dev)
             std_dev = torch.as_tensor(np.asarray(dist.stddev().numpy(), dtype=np.float32)).to(dev)
 
-        n = len(list_idx)
-        if self.epistemic_uncertainty_estimation:
+        if self.epistemic_uncertainty_estimation and n:
             # field_deblender.py:303-316: std over 100 stochastic passes of each stamp, normalised by the r-band flux
             if isinstance(self.net, Deblender) and not self.normalise:
                 e_dev = self.net.epistemic_std(sel, 100)  # batched: encoder once, 100 latent draws + decoder passes per stamp
-                norm_dev = e_dev[:, :, :, 2].sum(dim=(1, 2)) / mean_dev[:, :, :, 2].double().sum(dim=(1, 2))
-                epistemic = list(e_dev.cpu().numpy())
-                epistemic_norm = norm_dev.cpu().numpy()
             else:
-                epistemic, norm = [], []
+                e_dev = torch.empty((n, S, S, C), device=dev, dtype=torch.float64)
                 for i in range(n):
                     rep = sel[i : i + 1].expand(100, S, S, C).contiguous()
                     m100 = torch.as_tensor(deblend(self.net, rep.cpu().numpy(), normalise=self.normalise)[0]).to(dev)
-                    e = m100.double().std(dim=0, unbiased=False)
-                    epistemic.append(e.cpu().numpy())
-                    norm.append(float(e[:, :, 2].sum() / mean_dev[i, :, :, 2].double().sum()))
-                epistemic_norm = np.array(norm)
+                    e_dev[i] = m100.double().std(dim=0, unbiased=False)
+            epistemic_norm = (e_dev[:, :, :, 2].sum(dim=(1, 2)) / mean_dev[:, :, :, 2].double().sum(dim=(1, 2))).cpu().numpy()
+            epistemic = _records.stamp_column(e_dev)
         else:
-            epistemic = list(np.zeros((n, S, S, C)))
+            epistemic = _records.stamp_column(np.zeros((n, S, S, C)))
             epistemic_norm = np.zeros(n)
 
         lo, hi = int(S / 2) - 5, int(S / 2) + 5
-        mse_center = _fieldops.center_mse(sel.contiguous(), mean_dev.contiguous(), lo, hi).cpu().numpy()
-        passed_cuts = [not ((epistemic_norm[i] > epistemic_criterion) or (mse_center[i] > mse_criterion)) for i in range(n)]
+        mse_center = _fieldops.center_mse(sel.contiguous(), mean_dev.contiguous(), lo, hi).cpu().numpy() if n else np.zeros(0)
+        passed_cuts = [bool(v) for v in ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))]
 
         gx = [galaxy_distances_to_center[k][0] for k in list_idx]
         gy = [galaxy_distances_to_center[k][1] for k in list_idx]
         if optimise_positions:
             # field_deblender.py:337-352: bounded least-squares fit of a sub-pixel shift per galaxy on the r band
             # (the reference pads with self.field_size; it only works when field_image has that size too)
-            from ..deblend_cutout.optimization import FieldBand, fit_position
+            from ..deblend_cutout.optimization import fit_positions
 
-            fb = FieldBand(field_dev)
             r_band = mean_dev[:, :, :, 2].contiguous()
-            shifts = [np.array(fit_position(fb, r_band[i], galaxy_distances_to_center[k])) for i, k in enumerate(list_idx)]
+            fitted = fit_positions(field_dev, r_band, np.array([[galaxy_distances_to_center[k][0], galaxy_distances_to_center[k][1]] for k in list_idx], dtype=np.float64))
+            shifts = [np.array(s) for s in fitted]
         else:
             shifts = [np.array([0, 0]) for _ in range(n)]
 
-        self.nb_of_detected_objects += [len(list(galaxy_distances_to_center))]
-        self.nb_of_deblended_galaxies += [len(list_idx)]
+        self.nb_of_detected_objects += [n_detected]
+        self.nb_of_deblended_galaxies += [n_deblended]
 
-        res_deblend["cutout_images"] = list(sel.cpu().numpy())
-        res_deblend["output_images_mean"] = list(mean_dev.cpu().numpy())
-        res_deblend["output_images_stddev"] = list(std_dev.cpu().numpy())
-        res_deblend["shifts"] = shifts
-        res_deblend["list_idx"] = list_idx
-        res_deblend["galaxy_distances_to_center_x"] = gx
-        res_deblend["galaxy_distances_to_center_y"] = gy
-        res_deblend["epistemic_uncertainty"] = epistemic
-        res_deblend["passed_cuts"] = passed_cuts
-
-        self.res_deblend = pd.DataFrame(res_deblend).to_records(index=False)
-        self._dev_cache = (self.res_deblend, {"output_images_mean": mean_dev, "output_images_stddev": std_dev})
+        cols = {
+            "cutout_images": _records.stamp_column(sel),
+            "output_images_mean": _records.stamp_column(mean_dev),
+            "output_images_stddev": _records.stamp_column(std_dev),
+            "shifts": shifts,
+            "list_idx": np.asarray(list_idx, dtype=np.int64),
+            "galaxy_distances_to_center_x": gx,
+            "galaxy_distances_to_center_y": gy,
+            "epistemic_uncertainty": epistemic,
+            "passed_cuts": np.asarray(passed_cuts, dtype=bool),
+        }
+        self.res_deblend = _records.make_records(cols)
+        if tp is not None:
+            self._tile_state = (self.res_deblend, tp, mine)
         return self.res_deblend

@@ -66,6 +66,12 @@ def fit_position(fb: FieldBand, stamp_band_dev, galaxy_distance_to_center, margi
     return opt.x[0], opt.x[1]
 
 
+def fit_positions(field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN):
+    """position_optimization for all galaxies of a field: r_band_batch (N,S,S) CUDA, centres (N,2) -> (N,2) shifts."""
+    fb = FieldBand(field_dev)
+    return np.array([fit_position(fb, r_band_batch[i].contiguous(), centres[i], margin) for i in range(len(centres))], dtype=np.float64).reshape(-1, 2)
+
+
 def position_optimization(field_image, output_image_mean_padded, galaxy_distance_to_center, cutout_size=59):
     """optimization.py:6-52, same arguments (field_image (F,F,C), the padded prediction (F,F,C), the detected
     offset); `cutout_size` (extension) tells where the stamp sits inside the padded canvas."""

@@ -29,8 +29,10 @@
 extern "C" {
 #endif
 
-#define DBV_ABI_VERSION 3  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
-                              3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective */
+#define DBV_ABI_VERSION 4  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
+                              3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective
+                              4: dbv_window_axpy_rect (rectangular local regions, caller scratch, in-place),
+                                 dbv_sqdiff_sum_rect, dbv_position_fit_batch */
 
 typedef enum {
   DBV_OK = 0,
@@ -138,6 +140,19 @@ int dbv_window_axpy_ex(const void* in_dev, void* out_dev, int field_dtype, int64
                        int stamp_dtype, int stamp_planar, const int32_t* x0_dev, const int32_t* y0_dev, int64_t N, int S,
                        double alpha, void* stream);
 
+/* The same operator on a RECTANGULAR field (1,FH,FW,C) — a rank's local region (owner tile + 30-px halo) of a field
+ * tiled across GPUs, positions relative to the region's origin (windows are clipped to the region) — with the binning
+ * scratch supplied by the caller (dbv_window_axpy_scratch_bytes(FH, FW) bytes of device memory, used only on `stream`:
+ * calls on different streams never share state; NULL = no binning, every tile scans all stamps).
+ * in_dev == out_dev is the IN-PLACE form for a device-resident iterative loop: only the elements a stamp covers are
+ * read and written back (the algorithmic traffic of SURVEY section 8d: window read-modify-write + stamp), tiles no stamp
+ * touches return at once.  Same ordering guarantee: bit-identical to the sequential loop restricted to the region. */
+int64_t dbv_window_axpy_scratch_bytes(int64_t FH, int64_t FW);
+int dbv_window_axpy_rect(const void* in_dev, void* out_dev, int field_dtype, int64_t FH, int64_t FW, int C,
+                         const void* stamps_dev, int stamp_dtype, int stamp_planar, const int32_t* x0_dev,
+                         const int32_t* y0_dev, int64_t N, int S, double alpha, void* scratch_dev, int64_t scratch_bytes,
+                         void* stream);
+
 /* Sub-pixel placement: scipy.ndimage.shift(padded_canvas, shift=(x_pos, y_pos)) of
  * deblend/field_deblender.py:66-95, 121-182 and deblend_cutout/optimization.py:27-29, 41-44 (order 3,
  * mode 'constant', prefilter=True; scipy==1.11.2, requirements.txt:7), evaluated on the window of the
@@ -184,6 +199,11 @@ int dbv_center_mse(const void* cutouts_dev, int cutouts_dtype, const float* mean
 int dbv_mse(const void* a_dev, const void* b_dev, int dtype, int64_t n, double* out_dev, void* scratch_dev,
             int64_t scratch_bytes, void* stream);
 int64_t dbv_mse_scratch_bytes(void);
+/* out[0] = sum((a-b)^2) over a rows x cols sub-rectangle of two row-pitched arrays (pitches in elements): the partial
+ * sum of a rank's OWNER TILE inside its local region; a tiled field's mse (iterative_deblender.py:52,75) is the
+ * all-reduced sum of these divided by the element count.  scratch as for dbv_mse. */
+int dbv_sqdiff_sum_rect(const void* a_dev, const void* b_dev, int dtype, int64_t rows, int64_t cols, int64_t pitch_a,
+                        int64_t pitch_b, double* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 /* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */

@@ -73,10 +73,10 @@ def subtract_offset(field_size: int, cutout_size: int) -> int:
 def _paste(acc, stamp, x0, y0, sign):
     """acc[x0:x0+S, y0:y0+S] += sign*stamp, clipped to the field: scipy.ndimage.shift
     with mode='constant' drops whatever leaves the canvas (field_deblender.py:92-95)."""
-    F_ = acc.shape[0]
+    FH, FW = acc.shape[0], acc.shape[1]  # square for a whole field; a rank's local region of a tiled field is rectangular
     S = stamp.shape[0]
-    ax0, ax1 = max(x0, 0), min(x0 + S, F_)
-    ay0, ay1 = max(y0, 0), min(y0 + S, F_)
+    ax0, ax1 = max(x0, 0), min(x0 + S, FH)
+    ay0, ay1 = max(y0, 0), min(y0 + S, FW)
     if ax0 >= ax1 or ay0 >= ay1:
         return
     part = stamp[ax0 - x0 : ax1 - x0, ay0 - y0 : ay1 - y0].astype(np.float64)

@@ -29,7 +29,14 @@ def install(monkeypatch):
         view = acc[0] if acc.ndim == 4 else acc
         for s, a, b in zip(stamps.numpy(), x0, y0):
             fo._paste(view, s, int(a), int(b), -1 if alpha < 0 else +1)
+        if out is not None:
+            out.copy_(torch.from_numpy(acc))
+            return out
         return torch.from_numpy(acc)
+
+    def sqdiff_sum_rect(a, b, r0, r1, c0, c1):
+        d = a.numpy()[0, r0:r1, c0:c1].astype(np.float64) - b.numpy()[0, r0:r1, c0:c1].astype(np.float64)
+        return torch.tensor([float(np.sum(d * d))], dtype=torch.float64)
 
     def center_mse(cutouts, means, lo, hi):
         c, m = cutouts.numpy(), means.numpy()
@@ -50,7 +57,7 @@ def install(monkeypatch):
         return torch.from_numpy(sp.predicted_field_subpixel(field_shape[0], field_shape[2], stamps.numpy(), pos_x, pos_y, stamps.shape[1]))
 
     for name, fn in dict(to_device_field=to_device_field, extract=extract, window_axpy=window_axpy, center_mse=center_mse, mse=mse,
-                         spline_window_axpy=spline_window_axpy).items():
+                         spline_window_axpy=spline_window_axpy, sqdiff_sum_rect=sqdiff_sum_rect).items():
         monkeypatch.setattr(_fieldops, name, fn)
 
 

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.dbv_abi_version() == 3
+    assert lib.dbv_abi_version() == _ffi.ABI_VERSION == 4
     assert lib.dbv_mse_scratch_bytes() > 0
 
 
