@@ -172,6 +172,9 @@ struct dbv_ctx {
   float* stage_eps[2] = {nullptr, nullptr};
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool pipe_ready = false;
+  // A ctx owns ONE set of activation buffers: whatever the device-pointer entry points last enqueued on a caller's stream
+  // is marked by this event, and the host pipeline (which computes on its own stream) waits for it before its first piece
+  cudaEvent_t ev_user = nullptr;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -698,20 +701,28 @@ static int build_halo_layer(dbv_ctx* c, int li) {
       }
   }
   const long long Bt = std::min<long long>(c->chunk, 592);  // 4 stamps per SM: enough bands per CTA for a stable ranking
-  cudaEvent_t e0, e1;
-  DBV_CUDA(cudaEventCreate(&e0));
-  DBV_CUDA(cudaEventCreate(&e1));
+  struct TunerRes {  // released on every return path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float *hm = nullptr, *hs = nullptr;
+    ~TunerRes() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (hm) cudaFree(hm);
+      if (hs) cudaFree(hs);
+    }
+  } tr;
+  DBV_CUDA(cudaEventCreate(&tr.e0));
+  DBV_CUDA(cudaEventCreate(&tr.e1));
+  cudaEvent_t e0 = tr.e0, e1 = tr.e1;
   float best_ms = 1e30f;
   HaloLayer best{};
   bool found = false;
   OutSpec o = R.ospec;
-  std::vector<float> scratch_out;
-  float *hm = nullptr, *hs = nullptr;
   if (li == I_HEAD) {  // the head writes the caller's buffers: give the tuner scratch ones
-    DBV_CUDA(cudaMalloc(&hm, (size_t)Bt * STAMP_ELTS * 4));
-    DBV_CUDA(cudaMalloc(&hs, (size_t)Bt * STAMP_ELTS * 4));
-    o.out = hm;
-    o.out2 = hs;
+    DBV_CUDA(cudaMalloc(&tr.hm, (size_t)Bt * STAMP_ELTS * 4));
+    DBV_CUDA(cudaMalloc(&tr.hs, (size_t)Bt * STAMP_ELTS * 4));
+    o.out = tr.hm;
+    o.out2 = tr.hs;
   }
   for (const Cand& cd : cand) {
     const int r = cd.r, nbuf = cd.nbuf;
@@ -736,10 +747,6 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate R=%d nbuf=%d U=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, r, nbuf, cd.U, T.ntiles, T.smem_bytes, ms, Bt);
     if (ms < best_ms) { best_ms = ms; best = T; found = true; }
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  if (hm) cudaFree(hm);
-  if (hs) cudaFree(hs);
   if (!found && must) return fail(DBV_ERR_STATE, "%s: no valid halo plan (there is no other tensor-core kernel for this layer in this precision)", L.name);
   if (!found) return DBV_OK;
   R.halo = best;
@@ -922,6 +929,7 @@ extern "C" int dbv_destroy(dbv_ctx* c) {
     if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
   }
   for (auto e : c->prof_ev) cudaEventDestroy(e);
+  if (c->ev_user) cudaEventDestroy(c->ev_user);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1107,6 +1115,10 @@ static int chunked(dbv_ctx* c, const char* fn, const float* x, int64_t B, const 
                   stddev ? stddev + b0 * STAMP_ELTS : nullptr, enc, lat, dec, st);
     if (r) return r;
   }
+  if (B > 0) {
+    if (!c->ev_user) DBV_CUDA(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+    DBV_CUDA(cudaEventRecord(c->ev_user, st));
+  }
   c->launches += g_launches.load() - before;
   return DBV_OK;
 }
@@ -1216,6 +1228,21 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
   const long long before = g_launches.load();
   const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
   const std::vector<std::pair<int64_t, long long>> sched = host_schedule(B, c->chunk);
+  // the activation buffers may still be in use by a dbv_deblend / dbv_encode / dbv_decode call enqueued on a caller's stream
+  if (c->ev_user) DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_user, 0));
+  // on an error in the middle of the pipeline the copies already enqueued may still be writing the caller's host buffers:
+  // drain the three streams before returning
+  auto drain = [&](int rc) {
+    cudaStreamSynchronize(c->s_d2h);
+    cudaStreamSynchronize(c->s_comp);
+    cudaStreamSynchronize(c->s_h2d);
+    return rc;
+  };
+#define DBV_PIPE(expr)                                                                                            \
+  do {                                                                                                            \
+    cudaError_t e_ = (expr);                                                                                      \
+    if (e_ != cudaSuccess) return drain(fail(DBV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)));             \
+  } while (0)
   for (int k = 0; k < (int)sched.size(); ++k) {
     const int s = k & 1;
     const int64_t b0 = sched[k].first;
@@ -1224,33 +1251,34 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
     // slot s is free for new input once the compute that used it (chunk k-2) is done, and its
     // outputs are free once the D2H of chunk k-2 is done
     if (k >= 2) {
-      DBV_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[s], 0));
-      DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[s], 0));
+      DBV_PIPE(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[s], 0));
+      DBV_PIPE(cudaStreamWaitEvent(c->s_comp, c->ev_out[s], 0));
     }
     void* dst = x_dtype == DBV_F64 ? c->stage_in[s] : (void*)c->stage_x[s];
-    DBV_CUDA(cudaMemcpyAsync(dst, (const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, n * esz, cudaMemcpyHostToDevice, c->s_h2d));
+    DBV_PIPE(cudaMemcpyAsync(dst, (const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, n * esz, cudaMemcpyHostToDevice, c->s_h2d));
     if (eps_host)
-      DBV_CUDA(cudaMemcpyAsync(c->stage_eps[s], eps_host + b0 * LAT, (size_t)nb * LAT * 4, cudaMemcpyHostToDevice, c->s_h2d));
-    DBV_CUDA(cudaEventRecord(c->ev_in[s], c->s_h2d));
-    DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[s], 0));
-    if (x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return r;
+      DBV_PIPE(cudaMemcpyAsync(c->stage_eps[s], eps_host + b0 * LAT, (size_t)nb * LAT * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    DBV_PIPE(cudaEventRecord(c->ev_in[s], c->s_h2d));
+    DBV_PIPE(cudaStreamWaitEvent(c->s_comp, c->ev_in[s], 0));
+    if (x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return drain(r);
     // outputs: the caller's resident device buffers when given, else the double-buffered staging slots
     float* d_mean = mean_dev ? mean_dev + (size_t)b0 * STAMP_ELTS : c->stage_mean[s];
     float* d_std = stddev_dev ? stddev_dev + (size_t)b0 * STAMP_ELTS : (stddev_host ? c->stage_std[s] : nullptr);
     r = run_chunk(c, c->stage_x[s], nb, eps_host ? c->stage_eps[s] : nullptr, seed, sample, b0, nullptr, c->stage_z[s], nullptr,
                   nullptr, d_mean, d_std, true, true, true, c->s_comp);
-    if (r) return r;
-    DBV_CUDA(cudaEventRecord(c->ev_comp[s], c->s_comp));
-    DBV_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
-    DBV_CUDA(cudaMemcpyAsync(mean_host + (size_t)b0 * STAMP_ELTS, d_mean, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (r) return drain(r);
+    DBV_PIPE(cudaEventRecord(c->ev_comp[s], c->s_comp));
+    DBV_PIPE(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
+    DBV_PIPE(cudaMemcpyAsync(mean_host + (size_t)b0 * STAMP_ELTS, d_mean, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     if (stddev_host)
-      DBV_CUDA(cudaMemcpyAsync(stddev_host + (size_t)b0 * STAMP_ELTS, d_std, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-    if (z_host) DBV_CUDA(cudaMemcpyAsync(z_host + b0 * LAT, c->stage_z[s], (size_t)nb * LAT * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-    DBV_CUDA(cudaEventRecord(c->ev_out[s], c->s_d2h));
+      DBV_PIPE(cudaMemcpyAsync(stddev_host + (size_t)b0 * STAMP_ELTS, d_std, n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (z_host) DBV_PIPE(cudaMemcpyAsync(z_host + b0 * LAT, c->stage_z[s], (size_t)nb * LAT * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    DBV_PIPE(cudaEventRecord(c->ev_out[s], c->s_d2h));
   }
   DBV_CUDA(cudaStreamSynchronize(c->s_d2h));
   DBV_CUDA(cudaStreamSynchronize(c->s_comp));
   DBV_CUDA(cudaStreamSynchronize(c->s_h2d));
+#undef DBV_PIPE
   c->launches += g_launches.load() - before;
   return DBV_OK;
 }

@@ -54,6 +54,7 @@ class Deblender:
         self.precision = precision
         self._seed = int(seed)
         self._calls = 0
+        self.sample = True  # default of net(x): z is SAMPLED like the reference; set False for z = loc (deterministic passes)
         self._ctx = C.c_void_p()
         _ffi.check(lib.dbv_create(C.byref(self._ctx), self.device_index, _ffi.PREC[precision], int(chunk)))
         table = dict(spec.tensor_table())
@@ -131,11 +132,13 @@ class Deblender:
             _ffi.check(_ffi.lib().dbv_decode(self._ctx, _ffi.ptr(z), B, _ffi.ptr(mean), _ffi.ptr(std), _ffi.stream_ptr()))
         return NormalOutput(mean, std)
 
-    def __call__(self, x, eps=None, sample=True, seed=None, return_z=False):
+    def __call__(self, x, eps=None, sample=None, seed=None, return_z=False):
         """net(x) (deblend_cutout/deblender.py:18) on device-resident data.
 
         By default z is *sampled* like the reference (the TFP layer's convert_to_tensor_fn is
-        Distribution.sample); pass ``eps=`` for a given draw or ``sample=False`` for z = loc."""
+        Distribution.sample); pass ``eps=`` for a given draw or ``sample=False`` for z = loc
+        (``net.sample = False`` changes the default of the instance)."""
+        sample = self.sample if sample is None else sample
         x = self._check_x(_as_device_f32(x, self.device))
         B = x.shape[0]
         if eps is not None:
@@ -172,19 +175,26 @@ class Deblender:
 
     def deblend_into(self, x, mean, stddev=None, z=None, eps=None, sample=True, seed=None):
         """net(x) into caller-provided CUDA tensors (no allocation; what bench.py times)."""
+        B = self._check_x(x).shape[0]
+        for name, t, shape in (("x", x, (B, S, S, NB)), ("mean", mean, (B, S, S, NB)), ("stddev", stddev, (B, S, S, NB)), ("z", z, (B, LAT)), ("eps", eps, (B, LAT))):
+            if t is None:
+                continue
+            if not (isinstance(t, torch.Tensor) and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape):
+                raise ValueError(f"{name} must be a contiguous float32 tensor of shape {shape} on {self.device}")
         _ffi.check(
             _ffi.lib().dbv_deblend(self._ctx, _ffi.ptr(x), x.shape[0], _ffi.ptr(eps), self._next_seed(seed), int(bool(sample)),
                                    _ffi.ptr(mean), _ffi.ptr(stddev), _ffi.ptr(z), _ffi.stream_ptr())
         )
 
     # ---- host buffers: the end-to-end call ---------------------------------------------------------
-    def deblend_host(self, images, eps=None, sample=True, seed=None, want_stddev=True, out_mean=None, out_stddev=None, resident=False):
+    def deblend_host(self, images, eps=None, sample=None, seed=None, want_stddev=True, out_mean=None, out_stddev=None, resident=False):
         """Host ndarray in, host ndarrays out, H2D / compute / D2H pipelined inside the C-ABI
         (dbv_deblend_host).  float64 input is cast on the device.  Returns (mean, stddev|None).
 
         resident=True keeps both outputs on the device as well and copies only the MEAN back
         (``deblend()`` returns the mean ndarray plus a distribution whose stddev is fetched on demand);
         it returns (mean ndarray, mean CUDA tensor, stddev CUDA tensor)."""
+        sample = self.sample if sample is None else sample
         a = images if isinstance(images, np.ndarray) else np.asarray(images)
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float32)
@@ -194,6 +204,10 @@ class Deblender:
         # outputs live in pinned host memory (torch's caching host allocator recycles the blocks), so the
         # D2H copies of the pipeline are asynchronous DMA transfers
         new = lambda: torch.empty((B, S, S, NB), dtype=torch.float32, pin_memory=True).numpy()
+        for name, arr in (("out_mean", out_mean), ("out_stddev", out_stddev)):
+            if arr is not None and not (isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags.c_contiguous and arr.shape == (B, S, S, NB)
+                                        and arr.flags.writeable):
+                raise ValueError(f"{name} must be a writeable C-contiguous float32 ndarray of shape {(B, S, S, NB)}")
         mean = out_mean if out_mean is not None else new()
         std = (out_stddev if out_stddev is not None else new()) if (want_stddev and not resident) else None
         mean_dev = std_dev = None
@@ -201,7 +215,8 @@ class Deblender:
             with torch.cuda.device(self.device):
                 mean_dev = torch.empty((B, S, S, NB), device=self.device, dtype=torch.float32)
                 std_dev = torch.empty_like(mean_dev)
-                # the library runs on its own streams: make sure nothing queued on torch's stream still uses these blocks
+                # the library computes on its own streams (ordered after this ctx's earlier device-pointer calls by an
+                # event inside the library): make sure nothing queued on torch's stream still uses these fresh blocks
                 torch.cuda.current_stream().synchronize()
         e = None
         if eps is not None:

@@ -99,6 +99,58 @@ def test_field_tiled_over_two_gpus_is_bit_identical():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["tiles_bit_identical_to_single_gpu"] is True and line["n_gpus"] == 2
+    assert line["field_share_per_rank"] < 0.6  # half the field + halo, never the whole field
+    assert abs(line["mse_tiled"] - line["mse_single"]) <= 1e-12 * line["mse_single"]
+    assert line["iterative"]["steps"] == [150, 300, 75]
+
+
+def test_tiled_api_on_one_gpu_equals_the_plain_path(wts):
+    """DeblendField(tiled=True) outside a distributed job is a 1x1 tiling: the LocalField code path (region-relative
+    extraction, rectangular window_axpy, owner-tile MSE) must reproduce the plain path bit for bit."""
+    from debvader import DeblendField
+    from debvader.model.model import load_deblender
+
+    rng = np.random.default_rng(9)
+    F = 300
+    field = rng.normal(0, 0.3, (1, F, F, 6))
+    centres = rng.integers(-(F // 2) - 3, F // 2 + 3, size=(80, 2)).astype(np.float64)
+    net = load_deblender(*CFG, weights=wts, precision="bf16x3", seed=3)
+    net.sample = False
+    a = DeblendField(net, field)
+    ra = a.deblend_field(centres)
+    b = DeblendField(net, field, tiled=True)
+    rb = b.deblend_field(centres)
+    assert list(ra["list_idx"]) == list(rb["list_idx"]) and list(ra["passed_cuts"]) == list(rb["passed_cuts"])
+    np.testing.assert_array_equal(np.stack(list(ra["output_images_mean"])), np.stack(list(rb["output_images_mean"])))
+    np.testing.assert_array_equal(a.get_residual_field(), b.get_residual_field())
+    ta, tb = a.get_residual_field(as_tensor=True), b.get_residual_field(as_tensor=True)
+    assert abs(a.field_mse(a.field_tensor, ta) - b.field_mse(b.field_tensor, tb)) <= 1e-13
+    np.testing.assert_array_equal(a.get_predicted_field()["predicted_stddev_field"], b.get_predicted_field()["predicted_stddev_field"])
+    net.close()
+
+
+def test_records_are_lazy_and_behave_like_arrays(wts):
+    """record columns hold device-backed proxies: nothing crosses PCIe until a caller looks at the values"""
+    from debvader import DeblendField
+    from debvader.model.model import load_deblender
+    from debvader_b200._records import DeviceStamp
+
+    rng = np.random.default_rng(1)
+    field = torch.from_numpy(rng.normal(0, 0.3, (1, 259, 259, 6))).cuda()
+    net = load_deblender(*CFG, weights=wts, precision="bf16x3", seed=3)
+    obj = DeblendField(net, field)  # CUDA tensor in: no host copy is made
+    assert obj._host_field is None
+    rec = obj.deblend_field(np.array([[0.0, 0.0], [30.0, -40.0], [-70.0, 10.0]]))
+    m0 = rec["output_images_mean"][0]
+    assert isinstance(m0, DeviceStamp) and m0.batch._host is None and m0.shape == (59, 59, 6) and m0.dtype == np.float32
+    res = obj.get_residual_field(as_tensor=True)  # device path: still nothing downloaded
+    assert m0.batch._host is None and res.is_cuda
+    a = np.asarray(m0)
+    assert a.shape == (59, 59, 6) and m0.batch._host is not None
+    np.testing.assert_array_equal((m0 + 1.0)[3, 4], a[3, 4] + 1.0)
+    assert float(m0.sum()) == float(a.sum()) and np.array_equal(m0[:, :, 2], a[:, :, 2])
+    np.testing.assert_array_equal(obj.field_image, field.cpu().numpy())
+    net.close()
 
 
 def test_epistemic_uncertainty_batched_matches_the_reference_loop(wts):

@@ -315,3 +315,66 @@ def test_extract_broadcast_window_through_the_bulk_copy_kernel(ops):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
     got32, _ = ops.extract(torch.from_numpy(field).cuda(), plan, S, C, out_dtype=torch.float32)
     np.testing.assert_array_equal(got32.cpu().numpy(), want.astype(np.float32))
+
+
+@pytest.mark.parametrize("shape", [(130, 77), (64, 200), (33, 33)])
+def test_window_axpy_rectangular_region_and_in_place(ops, shape):
+    """dbv_window_axpy_rect: a rank's local region of a tiled field is rectangular, positions are relative to it and
+    windows are clipped; the in-place form (out is field) touches only covered elements and gives the same bits."""
+    FH, FW = shape
+    S, C, N = 59, 6, 120
+    rng = np.random.default_rng(FH * 1000 + FW)
+    field = rng.normal(size=(1, FH, FW, C))
+    x0 = rng.integers(-S, FH + 5, size=N)
+    y0 = rng.integers(-S, FW + 5, size=N)
+    stamps = rng.random((N, S, S, C)).astype(np.float32)
+    want = field.copy()
+    for k in range(N):
+        fo._paste(want[0], stamps[k], int(x0[k]), int(y0[k]), -1)
+    fdev = torch.from_numpy(field).cuda()
+    sdev = torch.from_numpy(stamps).cuda()
+    got = ops.window_axpy(fdev, sdev, x0, y0, -1.0)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    inpl = fdev.clone()
+    ret = ops.window_axpy(inpl, sdev, x0, y0, -1.0, out=inpl)
+    assert ret is inpl
+    np.testing.assert_array_equal(inpl.cpu().numpy(), want)
+    # f32 field, + sign, from zeros
+    wz = np.zeros((FH, FW, C), dtype=np.float64)
+    for k in range(N):
+        fo._paste(wz, stamps[k], int(x0[k]), int(y0[k]), +1)
+    gz = ops.window_axpy(None, sdev, x0, y0, 1.0, field_shape=(FH, FW, C))
+    np.testing.assert_array_equal(gz.cpu().numpy(), wz)
+    # no stamps: copy / untouched
+    e = sdev[:0]
+    assert torch.equal(ops.window_axpy(fdev, e, x0[:0], y0[:0], -1.0), fdev)
+
+
+def test_in_place_window_axpy_on_two_streams_does_not_share_scratch(ops):
+    """the binning scratch used to be one static buffer per device; it now comes from the caller's stream."""
+    F, S, C, N = 300, 59, 6, 400
+    rng = np.random.default_rng(8)
+    fields = [torch.from_numpy(rng.normal(size=(1, F, F, C))).cuda() for _ in range(2)]
+    pos = [rng.integers(-20, F - 30, size=(N, 2)) for _ in range(2)]
+    stamps = [torch.from_numpy(rng.random((N, S, S, C)).astype(np.float32)).cuda() for _ in range(2)]
+    want = [ops.window_axpy(f, s, p[:, 0], p[:, 1], -1.0).cpu().numpy() for f, s, p in zip(fields, stamps, pos)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [None, None]
+    for rep in range(20):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = ops.window_axpy(fields[i], stamps[i], pos[i][:, 0], pos[i][:, 1], -1.0)
+        torch.cuda.synchronize()
+        for i in range(2):
+            np.testing.assert_array_equal(outs[i].cpu().numpy(), want[i])
+
+
+def test_sqdiff_sum_rect(ops):
+    rng = np.random.default_rng(4)
+    a, b = rng.normal(size=(1, 90, 141, 6)), rng.normal(size=(1, 90, 141, 6))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    for r0, r1, c0, c1 in [(0, 90, 0, 141), (30, 60, 30, 111), (89, 90, 140, 141)]:
+        want = float(np.sum((a[0, r0:r1, c0:c1] - b[0, r0:r1, c0:c1]) ** 2))
+        got = float(ops.sqdiff_sum_rect(ta, tb, r0, r1, c0, c1).item())
+        assert abs(got - want) <= 1e-13 * want
