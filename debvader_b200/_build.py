@@ -1,6 +1,13 @@
 """Build libdebvader_b200.so in-tree with nvcc for sm_100a (no torch, no cmake).
 
-    python -m debvader_b200._build [--force] [--verbose]
+    python -m debvader_b200._build [--force] [--verbose] [--ablate]
+
+Two variants of the same sources:
+  libdebvader_b200.so         the product: no environment switches, no debug hooks in the kernels
+  libdebvader_b200_ablate.so  -DDBV_ABLATE: DBV_* environment switches (kernel A/B selection, timing ablations, tuning
+                              knobs), the tcgen05 descriptor probes (tc_probe.cu, include/debvader_b200_debug.h) and
+                              the clock64 instrumentation of the halo kernel; used by tools/ and by the cross-check
+                              tests (DEBVADER_B200_LIB=... selects it)
 
 The library links cudart statically and resolves cuTensorMapEncodeTiled through
 cudaGetDriverEntryPoint, so it loads (and exports its symbols) on a machine
@@ -16,8 +23,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdebvader_b200.so")
-SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "tc_probe.cu"]
-HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", "tc_pair_ptx.cuh", os.path.join("..", "..", "include", "debvader_b200.h")]
+LIB_ABLATE = os.path.join(HERE, "libdebvader_b200_ablate.so")
+SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "posfit.cu"]
+SOURCES_ABLATE = SOURCES + ["tc_probe.cu"]
+HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", "tc_pair_ptx.cuh", os.path.join("..", "..", "include", "debvader_b200.h"),
+           os.path.join("..", "..", "include", "debvader_b200_debug.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -34,26 +44,30 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def needs_build(ablate: bool = False) -> bool:
+    lib = LIB_ABLATE if ablate else LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = os.path.getmtime(lib)
+    deps = [os.path.join(CSRC, s) for s in (SOURCES_ABLATE if ablate else SOURCES) + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
+def build(force: bool = False, verbose: bool = False, ablate: bool = False) -> str:
+    """Compile one variant (parallel nvcc per source, then link).  Returns the library path."""
+    lib = LIB_ABLATE if ablate else LIB
+    if not force and not needs_build(ablate):
+        return lib
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "ablate" if ablate else "product")
     os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + (["-DDBV_ABLATE"] if ablate else [])
     procs = []
     objs = []
-    for s in SOURCES:
+    for s in SOURCES_ABLATE if ablate else SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -68,14 +82,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    tmp = LIB + ".tmp"
+    tmp = lib + ".tmp"
     cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl", "-lpthread", "-lrt"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build(force, verbose, ablate=False), build(force, verbose, ablate=True)
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--ablate" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ablate=True))
+    else:
+        for l in build_all(force="--force" in sys.argv, verbose="--verbose" in sys.argv):
+            print(l)

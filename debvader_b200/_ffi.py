@@ -64,7 +64,6 @@ def _declare(lib):
         "dbv_set_profiling": (C.c_int, [c_vp, C.c_int]),
         "dbv_layer_times": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
         "dbv_debug_activation": (C.c_int, [c_vp, C.c_char_p, c_i64, c_vp, c_vp]),
-        "dbv_probe": (C.c_int, [C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -95,9 +94,32 @@ def lib():
     return _lib
 
 
-def check(rc: int) -> int:
+_dbg = None
+ABLATE_LIB_PATH = os.path.join(_HERE, "libdebvader_b200_ablate.so")
+
+
+def debug_lib():
+    """The ablation build (-DDBV_ABLATE): DBV_* environment switches, dbv_probe, dbv_halo_counters
+    (include/debvader_b200_debug.h).  A separate shared object with its own state; never used by the product path."""
+    global _dbg
+    if _dbg is None:
+        with _lock:
+            if _dbg is None:
+                if not os.path.exists(ABLATE_LIB_PATH):
+                    raise ImportError(f"{ABLATE_LIB_PATH} is missing. Build it with `python -m debvader_b200._build --ablate`.")
+                l = C.CDLL(ABLATE_LIB_PATH)
+                _declare(l)
+                l.dbv_probe.restype = C.c_int
+                l.dbv_probe.argtypes = [C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]
+                l.dbv_halo_counters.restype = C.c_int
+                l.dbv_halo_counters.argtypes = [c_vp, C.c_int]
+                _dbg = l
+    return _dbg
+
+
+def check(rc: int, l=None) -> int:
     if rc < 0:
-        raise DbvError(rc, lib().dbv_last_error().decode("utf-8", "replace"))
+        raise DbvError(rc, (l or lib()).dbv_last_error().decode("utf-8", "replace"))
     return rc
 
 

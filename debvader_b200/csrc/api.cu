@@ -56,7 +56,7 @@ static const LayerDesc kLayers[] = {
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 // first layer of the decoder tail that reads a channel-group-planar input (19 = head only ... 17 = convT7, convT8, head; 20 = none)
 static int cg8_first() {
-  static const int v = getenv("DBV_CG8_FIRST") ? atoi(getenv("DBV_CG8_FIRST")) : 20;
+  static const int v = dbv_env("DBV_CG8_FIRST") ? atoi(dbv_env("DBV_CG8_FIRST")) : 20;
   return v;
 }
 constexpr int PH_SMEM_BUDGET = 232448 - 1024 - 512 - 2048;
@@ -186,7 +186,7 @@ struct dbv_ctx {
 namespace dbv {
 
 bool pdl_enabled() {
-  static const bool on = getenv("DBV_PDL") ? atoi(getenv("DBV_PDL")) != 0 : false;
+  static const bool on = dbv_env("DBV_PDL") ? atoi(dbv_env("DBV_PDL")) != 0 : false;
   return on;
 }
 
@@ -458,7 +458,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   }
   if (!tc_layer_supported(G.CBK, G.NT)) return fail(DBV_ERR_UNSUPPORTED, "%s: no kernel for CBK=%d NT=%d", L.name, G.CBK, G.NT);
   R.has_tc = true;
-  if (tc_pair_supported(G.CBK, G.NT) && Ntot % G.NT == 0 && !getenv("DBV_NO_PAIR")) {
+  if (tc_pair_supported(G.CBK, G.NT) && Ntot % G.NT == 0 && !dbv_env("DBV_NO_PAIR")) {
     R.tcp = T;
     uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};
     uint64_t bs[1] = {(uint64_t)G.CBK * 2};
@@ -478,7 +478,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   const bool x3 = prec_x3(c->precision);
-  if (!x3 || !R.has_tc || getenv("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
+  if (!x3 || !R.has_tc || dbv_env("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
   if (L.kind == L_CONV && L.stride != 1) return DBV_OK;
   const OutSpec& in = c->rt[li - 1].ospec;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
@@ -641,7 +641,8 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   T.w_bytes = w_bytes;
   T.nbuf = nbuf;
   T.U = U;
-  T.dbg_skip = getenv("DBV_HALO_SKIP") ? atoi(getenv("DBV_HALO_SKIP")) : 0;
+  T.dbg_skip = dbv_env("DBV_HALO_SKIP") ? atoi(dbv_env("DBV_HALO_SKIP")) : 0;
+  T.dbg_id = li;
   T.wide = x3 ? 1 : 0;
   T.tail_pad = tail_pad;
   T.smem_bytes = (int)smem;
@@ -675,7 +676,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
-  if (getenv("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
+  if (dbv_env("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
   const bool must = li == I_CONV1 || mixed_tail(c->precision, li) || consumes_cg8(li);  // these layers have no other tensor-core kernel
   if ((!R.has_tc && !must) || L.kind == L_DENSE) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
@@ -1177,7 +1178,7 @@ static int ensure_pipe(dbv_ctx* c) {
 // piece and paid three short tail pieces.
 static std::vector<std::pair<int64_t, long long>> host_schedule(int64_t B, long long chunk) {
   std::vector<std::pair<int64_t, long long>> sched;
-  if (const char* e = getenv("DBV_HOST_PIECE")) {
+  if (const char* e = dbv_env("DBV_HOST_PIECE")) {
     int64_t b0 = 0;
     const long long piece = std::max<long long>(1, std::min<long long>(chunk, atoll(e)));
     const long long q = std::max<long long>(piece / 4, 1);

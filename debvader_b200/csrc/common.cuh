@@ -1,5 +1,6 @@
 // Shared helpers for the debvader_b200 C-ABI library (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -48,6 +49,17 @@ extern std::atomic<long long> g_launches;  // every kernel this library launches
   do {                                                          \
     if (!(cond)) return dbv::fail(DBV_ERR_INVALID, __VA_ARGS__); \
   } while (0)
+
+// Environment switches (kernel A/B selection, ablations, tuning knobs) exist only in the ablation build
+// (-DDBV_ABLATE: libdebvader_b200_ablate.so, used by tools/ and a few cross-check tests).  The product library reads
+// no environment variable that changes what it computes or which kernel runs (DBV_VERBOSE only prints the plans).
+#ifdef DBV_ABLATE
+static inline const char* dbv_env(const char* name) { return getenv(name); }
+#define DBV_DBG(x) (x)
+#else
+static inline const char* dbv_env(const char*) { return nullptr; }
+#define DBV_DBG(x) 0
+#endif
 
 constexpr int kNumSMs = 148;
 

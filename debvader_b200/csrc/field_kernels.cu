@@ -489,12 +489,12 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   bool bulk = ((size_t)C * isz) % 16 == 0 && ((uintptr_t)field % 16) == 0 && row_bytes <= 48 * 1024 && ((S * C) & 1) == 0;
   if (isz == osz) bulk = bulk && ((uintptr_t)out % 16) == 0;  // S*S*C*size and r0*row_bytes are multiples of 16 given the row is
   else bulk = bulk && ((uintptr_t)out % 8) == 0;
-  if (const char* e = getenv("DBV_EXTRACT_BULK")) bulk = bulk && atoi(e) != 0;  // tuning knob (0 = vector kernel)
+  if (const char* e = dbv_env("DBV_EXTRACT_BULK")) bulk = bulk && atoi(e) != 0;  // tuning knob (0 = vector kernel)
   if (bulk) {
     int rows = (int)((44 * 1024) / row_bytes);  // <= 44 KB of shared memory per CTA: 5 CTAs per SM
     if (rows > S) rows = S;
     if (rows < 1) rows = 1;
-    if (const char* e = getenv("DBV_EXTRACT_ROWS")) rows = atoi(e) > 0 && (size_t)atoi(e) * row_bytes <= 48 * 1024 ? atoi(e) : rows;
+    if (const char* e = dbv_env("DBV_EXTRACT_ROWS")) rows = atoi(e) > 0 && (size_t)atoi(e) * row_bytes <= 48 * 1024 ? atoi(e) : rows;
     dim3 grid((unsigned)N, (unsigned)((S + rows - 1) / rows)), block(128);
     const size_t smem = (size_t)rows * row_bytes;
     if (field_dtype == DBV_F64 && out_dtype == DBV_F64)
@@ -514,7 +514,7 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   int per = 2;
   if (N < 2048) per = 4;
   if (N < 256) per = 8;
-  if (const char* e = getenv("DBV_EXTRACT_PER")) per = atoi(e) > 0 ? atoi(e) : per;  // tuning knob
+  if (const char* e = dbv_env("DBV_EXTRACT_PER")) per = atoi(e) > 0 ? atoi(e) : per;  // tuning knob
   dim3 grid((unsigned)N, per), block(256);
   if (field_dtype == DBV_F64 && out_dtype == DBV_F64)
     extract_kernel<double, double><<<grid, block, 0, st>>>((const double*)field, F, C, sx, sy, flags, slot, S, (double*)out);
@@ -1122,7 +1122,7 @@ extern "C" int dbv_spline_place(const void* data, int data_dtype, int64_t N, int
   DBV_LAUNCH_CHECK();
   // fast path: every item's data sits at `origin` with its +-P margin strictly inside the canvas
   bool fast = !origin_x && S <= 64 && P + 1 < SPW_ZPOW && (long long)origin - P > 0 && (long long)origin + S + P < F && N * (long long)C < (1ll << 31);
-  if (const char* e = getenv("DBV_SPLINE_WARP")) fast = fast && atoi(e) != 0;  // 0: thread-per-line kernels (cross-check)
+  if (const char* e = dbv_env("DBV_SPLINE_WARP")) fast = fast && atoi(e) != 0;  // 0: thread-per-line kernels (cross-check)
   if (fast) {
     const size_t smem_w = ((size_t)n_out * (S | 1) + SPW_ZPOW + (size_t)SPW_WARPS * (S + 2 * P + 6)) * sizeof(double);
     if (smem_w <= 200 * 1024) {

@@ -162,6 +162,7 @@ struct HaloLayer {
   int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)
   int smem_bytes;
   int dbg_skip;      // timing ablations only (env DBV_HALO_SKIP): bit0 skip the MMAs, bit1 skip the epilogue body
+  int dbg_id;        // layer index for the clock64 counters of the ablation build
   int bands_per_img;
   long long B, total_bands;
   OutSpec o;

@@ -418,13 +418,13 @@ int launch_simt_conv(const SimtConv& p, cudaStream_t st) {
   const long long threads = (long long)p.B * p.Hout * p.Wout * (p.CoutP >> 2);
   if (threads == 0) return DBV_OK;
   bool tiled = (p.CoutP & 3) == 0 && (p.mode == 0 || ((p.Hout & 1) == 0 && (p.Wout & 1) == 0 && p.ksz == 3));
-  if (const char* e = getenv("DBV_SIMT_TILED")) tiled = tiled && atoi(e) != 0;  // 0: the naive gather kernel (cross-check)
+  if (const char* e = dbv_env("DBV_SIMT_TILED")) tiled = tiled && atoi(e) != 0;  // 0: the naive gather kernel (cross-check)
   if (tiled) {
     if (p.CoutP >= 64) {
-      static const int kc = getenv("DBV_SIMT_KC") ? atoi(getenv("DBV_SIMT_KC")) : 32;  // tuning knob (measured: 32 is 6-8 % faster than 16)
+      static const int kc = dbv_env("DBV_SIMT_KC") ? atoi(dbv_env("DBV_SIMT_KC")) : 32;  // tuning knob (measured: 32 is 6-8 % faster than 16)
       return (kc == 32 && p.Cin >= 32) ? launch_simt_tile<64, 32>(p, st) : launch_simt_tile<64, 16>(p, st);
     }
-    static const int kcs = getenv("DBV_SIMT_KC_SMALL") ? atoi(getenv("DBV_SIMT_KC_SMALL")) : 16;  // tuning knob (8 measured 3-4 % slower)
+    static const int kcs = dbv_env("DBV_SIMT_KC_SMALL") ? atoi(dbv_env("DBV_SIMT_KC_SMALL")) : 16;  // tuning knob (8 measured 3-4 % slower)
     if (p.CoutP >= 32) return (p.Cin <= 8 || kcs == 8) ? launch_simt_tile<32, 8>(p, st) : launch_simt_tile<32, 16>(p, st);  // conv1: Cin = 6
     return kcs == 8 ? launch_simt_tile<16, 8>(p, st) : launch_simt_tile<16, 16>(p, st);
   }

@@ -110,10 +110,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const uint32_t sS = base + (uint32_t)stage * stage_bytes, bar = bar_full + 8 * stage;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           mbar_expect_tx(bar, tx);
-          tma_load_5d(sS, &L.tmA, bar, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
+          tma_load_5d(sS, &L.tmA, bar, K.c_off, x0 + K.dx, y0 + K.dy, K.plane, b0 - DBV_DBG(L.dbg_shift_rows));
           tma_load_2d(sS + offB, &L.tmB, bar, 0, K.b_row + nt * NT);
           if (L.x3) {
-            tma_load_5d(sS + Cfg::A_BYTES, &L.tmA, bar, K.c_off + L.lo_coff, x0 + K.dx, y0 + K.dy, K.plane, b0 - L.dbg_shift_rows);
+            tma_load_5d(sS + Cfg::A_BYTES, &L.tmA, bar, K.c_off + L.lo_coff, x0 + K.dx, y0 + K.dy, K.plane, b0 - DBV_DBG(L.dbg_shift_rows));
             tma_load_2d(sS + offB + Cfg::B_BYTES, &L.tmB, bar, 0, K.b_row + L.lo_brow + nt * NT);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sS = base + (uint32_t)stage * stage_bytes;
-          uint32_t a_addr = sS + L.dbg_shift_rows * Cfg::ROWB;
+          uint32_t a_addr = sS + DBV_DBG(L.dbg_shift_rows) * Cfg::ROWB;
           uint32_t ahi = kSmemDescLoConst | ((a_addr & 0x3FFFFu) >> 4);
           uint32_t HIA = HI;
-          if (L.dbg_base_mode == 1) HIA |= ((a_addr >> 7) & 7u) << 17;  // base_offset field (bits 49-51 of the descriptor)
+          if (DBV_DBG(L.dbg_base_mode) == 1) HIA |= ((a_addr >> 7) & 7u) << 17;  // base_offset field (bits 49-51 of the descriptor)
           const uint32_t alo = ahi + (Cfg::A_BYTES >> 4);
           const uint32_t bhi = kSmemDescLoConst | (((sS + offB) & 0x3FFFFu) >> 4);
           const uint32_t blo = bhi + (Cfg::B_BYTES >> 4);

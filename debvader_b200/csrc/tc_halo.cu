@@ -18,6 +18,22 @@
 #include <mutex>
 #include <type_traits>
 
+#ifdef DBV_ABLATE
+#include "../../include/debvader_b200_debug.h"
+// clock64 instrumentation (ablation build only): cycles per role, summed over CTAs / warps with atomics at kernel end
+//  0 mma: total            1 mma: waiting for a halo band (afull)     2 mma: waiting for a free accumulator slot (tempty)
+//  3 mma: issuing (list walk + tcgen05.mma + commits)                 4 mma: MMAs issued        5 mma: units
+//  6 tma: total            7 tma: waiting for a free halo buffer (aempty)
+//  8 epi: total (sum over the epilogue warps)   9 epi: waiting for the accumulators (tfull)   10 epi: tcgen05.ld issue -> wait::ld return
+// 11 epi: alpha load issue (address math + ld)  12 epi: math + stores   13 epi: items   14 CTAs   15 epi: slot release (fence + arrive)
+__device__ unsigned long long g_halo_ctr[DBV_HALO_NLAYERS][DBV_HALO_NCOUNTERS];  // [layer index (kLayers)][counter]
+#define HCLK() clock64()
+#define HADD(i, v) atomicAdd(&g_halo_ctr[L.dbg_id][i], (unsigned long long)(v))
+#else
+#define HCLK() 0ll
+#define HADD(i, v) ((void)0)
+#endif
+
 namespace dbv {
 
 #ifndef DBV_HALO_EPI_GROUPS
@@ -114,8 +130,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int b = b_first, y0 = (int)yb0 * L.R;
+      [[maybe_unused]] const long long tk0 = HCLK();
+      [[maybe_unused]] long long tk_wait = 0;
       for (long long g = g0; g < g1; ++g) {
+        [[maybe_unused]] const long long tka = HCLK();
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
+        tk_wait += HCLK() - tka;
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(L.n_regions * L.a_box_bytes));
         if constexpr (CG8) {  // one box: all channel-group planes, whole rows of 16-byte pixels (x in u64 units)
           tma_load_5d(sA + stage * L.buf_bytes, &L.tmA, bar_afull + 8 * stage, -2 * L.pad, y0 - L.pad_top, 0, b, 0);
@@ -126,6 +146,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
         if (++b == (int)L.B) { b = 0; y0 += L.R; }
       }
+      HADD(6, HCLK() - tk0);
+      HADD(7, tk_wait);
+      HADD(14, 1);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -143,15 +166,21 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       const uint32_t LOA = CG8 ? ((uint32_t)(L.region_bytes >> 4) << 16) : kSmemDescLoConst;
       constexpr uint32_t MSTEP = (128 * ROWB) >> 4;
       const uint32_t w16 = LOB | (sW >> 4);
-      const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;
+      const int ncls = (DBV_DBG(L.dbg_skip) & 1) ? 0 : L.n_cls;
+      [[maybe_unused]] const long long mk0 = HCLK();
+      [[maybe_unused]] long long mk_afull = 0, mk_tempty = 0, mk_n = 0;
       for (long long g = g0; g < g1; ++g) {
+        [[maybe_unused]] const long long mka = HCLK();
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
+        mk_afull += HCLK() - mka;
         const uint32_t a16 = LOA | ((sA + stage * L.buf_bytes) >> 4);
         for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
           const uint32_t slot = u & (nslot - 1);
+          [[maybe_unused]] const long long mkb = HCLK();
           mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
           tc_fence_after();
+          mk_tempty += HCLK() - mkb;
           const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
           uint32_t d = tmem_base + slot * SW;
           for (int sidx = s0; sidx < s1; ++sidx, d += DW) {
@@ -164,11 +193,23 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
               const HaloMma e = L.mma[kb0 + i];
               umma_f16(d, desc64(HI, am + e.a), desc64(HIB, w16 + (e.b & 0x7fffffffu)), (e.b >> 31) ? IDESC2 : IDESC, i != 0 ? 1u : 0u);
             }
+#ifdef DBV_ABLATE
+            mk_n += nkb;
+#endif
           }
           umma_commit(bar_tfull + 8 * slot);
         }
         umma_commit(bar_aempty + 8 * stage);
         if (++stage == L.nbuf) { stage = 0; phase ^= 1u; }
+      }
+      {
+        [[maybe_unused]] const long long tot = HCLK() - mk0;
+        HADD(0, tot);
+        HADD(1, mk_afull);
+        HADD(2, mk_tempty);
+        HADD(3, tot - mk_afull - mk_tempty);
+        HADD(4, mk_n);
+        HADD(5, u);
       }
     }
   } else {
@@ -179,8 +220,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     constexpr int NV = (HALO_EPI_GROUPS > 3 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int ncls = (L.dbg_skip & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
-    const bool has_alpha = L.o.alpha != nullptr && !(L.dbg_skip & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
+    const int ncls = (DBV_DBG(L.dbg_skip) & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
+    const bool has_alpha = L.o.alpha != nullptr && !(DBV_DBG(L.dbg_skip) & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
     const float4* alpha4 = reinterpret_cast<const float4*>(L.o.alpha);
     const uint32_t npix = (uint32_t)(L.o.OH * L.o.OW);
     // The output layout (mode / planes / 16-bit format) is constant for a launch: the loops are instantiated once per
@@ -195,6 +236,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       }
       uint32_t u = 0;
       int b = b_first, y0 = (int)yb0 * L.R;
+      [[maybe_unused]] const long long ek0 = HCLK();
+      [[maybe_unused]] long long ek_tfull = 0, ek_ld = 0, ek_alpha = 0, ek_math = 0, ek_items = 0, ek_rel = 0;
       for (long long g = g0; g < g1; ++g) {
         for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
           const uint32_t slot = u & (nslot - 1);
@@ -208,23 +251,26 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
             const int c = L.ntiles == 1 ? sidx : (int)__umulhi((uint32_t)sidx, L.magic_nt), m = sidx - c * L.ntiles;  // (2^32 / 1 does not fit)
             const int p = 128 * m + row;
             const int ly = (int)__umulhi((uint32_t)p, L.magic_wp), sx = p - ly * L.WP, sy = y0 + ly;
-            const bool ok = ly < L.R && sx < L.W && sy < L.H && !(L.dbg_skip & 2);
+            const bool ok = ly < L.R && sx < L.W && sy < L.H && !(DBV_DBG(L.dbg_skip) & 2);
             const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
             const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
             const int c0 = q * NV;
             // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
             // requested before the accumulator wait
             float4 al[NV / 4];
+            [[maybe_unused]] const long long eka = HCLK();
             if (has_alpha && ok) {
               const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
   #pragma unroll
               for (int j = 0; j < NV / 4; ++j) al[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
             }
+            [[maybe_unused]] const long long ekb = HCLK();
             if (!waited) {
               mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
               tc_fence_after();
               waited = true;
             }
+            [[maybe_unused]] const long long ekc = HCLK();
             float v[NV];
             if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the sub-unit's columns
               float w[NV];
@@ -238,8 +284,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
               tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
               tmem_ld_wait<NV>(v);
             }
+            [[maybe_unused]] const long long ekd = HCLK();
             if (ok) {
-              if (!(L.dbg_skip & 4)) {
+              if (!(DBV_DBG(L.dbg_skip) & 4)) {
   #pragma unroll
                 for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];  // bias from the constant bank
                 if (has_alpha) {
@@ -255,19 +302,40 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
                   for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
               }
-              if (!(L.dbg_skip & 8)) store_act<NV>(o, b, oy, ox, c0, v);
+              if (!(DBV_DBG(L.dbg_skip) & 8)) store_act<NV>(o, b, oy, ox, c0, v);
               else if (v[0] == 123.456f) store_act<NV>(o, b, oy, ox, c0, v);  // keep the loads / math alive
             }
+#ifdef DBV_ABLATE
+            {
+              const long long eke = HCLK();
+              ek_alpha += ekb - eka;
+              ek_tfull += ekc - ekb;
+              ek_ld += ekd - ekc;
+              ek_math += eke - ekd;
+              ek_items += 1;
+            }
+#endif
           }
           if (!waited) {  // a group without a sub-unit in this unit still takes part in the hand-over, in phase order
             mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
             tc_fence_after();
           }
+          [[maybe_unused]] const long long ekr = HCLK();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+          ek_rel += HCLK() - ekr;
         }
         if (++b == (int)L.B) { b = 0; y0 += L.R; }
+      }
+      if (lane == 0) {
+        HADD(8, HCLK() - ek0);
+        HADD(9, ek_tfull);
+        HADD(10, ek_ld);
+        HADD(11, ek_alpha);
+        HADD(12, ek_math);
+        HADD(13, ek_items);
+        HADD(15, ek_rel);
       }
     };
     using std::integral_constant;
@@ -301,6 +369,23 @@ static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
+
+}  // namespace dbv
+#ifdef DBV_ABLATE
+extern "C" int dbv_halo_counters(unsigned long long* out_host, int reset) {
+  if (out_host) {
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, g_halo_ctr, sizeof(g_halo_ctr));
+    if (e != cudaSuccess) return dbv::fail(DBV_ERR_CUDA, "dbv_halo_counters: %s", cudaGetErrorString(e));
+  }
+  if (reset) {
+    static unsigned long long z[DBV_HALO_NLAYERS][DBV_HALO_NCOUNTERS] = {};
+    cudaError_t e = cudaMemcpyToSymbol(g_halo_ctr, z, sizeof(z));
+    if (e != cudaSuccess) return dbv::fail(DBV_ERR_CUDA, "dbv_halo_counters: %s", cudaGetErrorString(e));
+  }
+  return DBV_OK;
+}
+#endif
+namespace dbv {
 
 bool halo_layer_supported(int CBK, int NT) {
   if (CBK == 16) return NT == 16 || NT == 32 || NT == 64;  // conv1 (no-swizzle pair trick, NT = 32) / channel-group-planar inputs

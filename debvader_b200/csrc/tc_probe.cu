@@ -5,6 +5,7 @@
 //   which = 0 : CBK = 64 (128-byte rows, SWIZZLE_128B)
 //   which = 1 : CBK = 32 ( 64-byte rows, SWIZZLE_64B)
 #include "kernels.h"
+#include "../../include/debvader_b200_debug.h"
 #include <vector>
 
 using namespace dbv;

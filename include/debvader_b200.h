@@ -216,10 +216,6 @@ int dbv_layer_times(dbv_ctx* ctx, int max_layers, float* ms_out, char* names_out
 /* copy an internal activation buffer (debug / per-layer parity): writes fp32 NHWC */
 int dbv_debug_activation(dbv_ctx* ctx, const char* name, int64_t B, float* out_dev, void* stream);
 
-/* tcgen05 / TMA self-test kernels (descriptor conventions this library relies on).  `which`
- * selects the probe; out_dev receives the kernel result, see csrc/tc_probe.cu. */
-int dbv_probe(int which, const void* a_dev, const void* b_dev, float* out_dev, int M, int N, int K, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,19 @@ def test_header_symbols_exported(lib):
     assert set(names) == set(_ffi.EXPORTS), "ctypes signatures out of sync with the header"
 
 
+def test_product_library_has_no_environment_switches_or_debug_exports(lib):
+    """kernel A/B switches, timing ablations and the descriptor probes live in the ablation build
+    (libdebvader_b200_ablate.so, -DDBV_ABLATE) only."""
+    data = open(_ffi.LIB_PATH, "rb").read()
+    names = set(re.findall(rb"DBV_[A-Z0-9_]{3,}", data))
+    assert names <= {b"DBV_VERBOSE"}, names  # DBV_VERBOSE only prints the plans the autotuner picked
+    assert not hasattr(lib, "dbv_probe") and not hasattr(lib, "dbv_halo_counters")
+    _build.build(ablate=True)
+    dbg = ctypes.CDLL(_ffi.ABLATE_LIB_PATH)
+    assert hasattr(dbg, "dbv_probe") and hasattr(dbg, "dbv_halo_counters") and dbg.dbv_abi_version() == _ffi.ABI_VERSION
+    assert b"DBV_HALO_SKIP" in open(_ffi.ABLATE_LIB_PATH, "rb").read()
+
+
 def test_abi_version(lib):
     assert lib.dbv_abi_version() == _ffi.ABI_VERSION == 4
     assert lib.dbv_mse_scratch_bytes() > 0
@@ -78,6 +91,6 @@ def test_host_pipeline_schedule(lib, monkeypatch):
                 assert b <= 5 * a // 4 + 224 or b <= a, (B, chunk, s)
     big = sched(100000)
     assert big[0] == 256 and big[-1] <= 320 and max(big) == 1376
-    monkeypatch.setenv("DBV_HOST_PIECE", "1024")
-    assert sched(4096) == [256, 1024, 1024, 1024, 384, 256, 128]
+    monkeypatch.setenv("DBV_HOST_PIECE", "1024")  # a tuning knob of the ablation build only: the product library ignores it
+    assert sched(4096) == [256, 544, 896, 1344, 800, 256]
     assert lib.dbv_host_schedule(-1, 4096, None, 0) < 0

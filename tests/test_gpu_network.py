@@ -73,7 +73,7 @@ def test_tcgen05_gemm_probe(which, N, K):
     b = torch.randn((N, K), device="cuda", generator=g).bfloat16()
     bp = b.reshape(N, K // CBK, CBK).permute(1, 0, 2).contiguous()  # [K/CBK][N][CBK]
     out = torch.full((M, N), float("nan"), device="cuda")
-    _ffi.check(_ffi.lib().dbv_probe(which, _ffi.ptr(a), _ffi.ptr(bp), _ffi.ptr(out), M, N, K, _ffi.stream_ptr()))
+    _ffi.check(_ffi.debug_lib().dbv_probe(which, _ffi.ptr(a), _ffi.ptr(bp), _ffi.ptr(out), M, N, K, _ffi.stream_ptr()), _ffi.debug_lib())
     torch.cuda.synchronize()
     want = a.float() @ b.float().T
     err = float((out - want).abs().max() / want.abs().max())
@@ -110,24 +110,50 @@ def test_fp32_per_layer(wts, data, ref64):
     net.close()
 
 
-def test_fp32_tiled_kernel_is_bit_identical_to_the_gather_kernel(wts, data, monkeypatch):
+def _run_variant(code, env):
+    """run `code` (which saves its result to sys.argv[1] with np.savez) in a subprocess on the ABLATION build of the
+    library with the given DBV_* switches; returns the loaded arrays"""
+    import subprocess
+    import sys
+    import tempfile
+
+    from debvader_b200 import _build, _ffi
+
+    _build.build(ablate=True)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as f:
+        path = f.name
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n" % root + code, path],
+                       env={**os.environ, "DEBVADER_B200_LIB": _ffi.ABLATE_LIB_PATH, **env}, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with np.load(path) as z:
+        out = {k: z[k] for k in z.files}
+    os.unlink(path)
+    return out
+
+
+def test_fp32_tiled_kernel_is_bit_identical_to_the_gather_kernel():
     """simt_tile_kernel (shared-memory implicit GEMM) accumulates in the order of simt_conv_kernel (the naive gather
-    form kept as the cross-check, DBV_SIMT_TILED=0): every layer and both outputs must agree bit for bit, on a batch
-    that is not a multiple of any tile size."""
-    x, eps = data
-    x, eps = x[:37], eps[:37]
-    out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("DBV_SIMT_TILED", flag)
-        net = _net(wts, "fp32", chunk=64)
-        dist = net(x, eps=eps)
-        acts = {name: net.debug_activation(name, len(x), shp).clone() for name, shp in ACT_SHAPES.items()}
-        out[flag] = (net.encode(x).clone(), dist.mean().tensor.clone(), dist.stddev().tensor.clone(), acts)
-        net.close()
-    for name in ACT_SHAPES:
-        assert torch.equal(out["0"][3][name], out["1"][3][name]), name
-    for a, b in zip(out["0"][:3], out["1"][:3]):
-        assert torch.equal(a, b)
+    form kept as the cross-check in the ablation build, DBV_SIMT_TILED=0): every layer and both outputs must agree bit for
+    bit, on a batch that is not a multiple of any tile size."""
+    code = (
+        "import numpy as np, torch\n"
+        "from oracle import weights as ow\n"
+        "from debvader_b200.model.model import load_deblender\n"
+        "from tests.test_gpu_network import ACT_SHAPES\n"
+        "w = ow.make_random_weights(seed=1234); x = ow.synthetic_stamps(37, seed=11)\n"
+        "eps = np.random.default_rng(0).normal(size=(37, 32)).astype(np.float32)\n"
+        "net = load_deblender('dc2', (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights=w, precision='fp32', chunk=64)\n"
+        "d = net(x, eps=eps)\n"
+        "out = {n: net.debug_activation(n, 37, s).cpu().numpy() for n, s in ACT_SHAPES.items()}\n"
+        "out.update(params=net.encode(x).cpu().numpy(), mean=d.mean().numpy(), std=d.stddev().numpy())\n"
+        "np.savez(sys.argv[1], **out)\n"
+    )
+    a = _run_variant(code, {"DBV_SIMT_TILED": "0"})
+    b = _run_variant(code, {"DBV_SIMT_TILED": "1"})
+    assert set(a) == set(b) and len(a) > 10
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
 # ---- tensor-core tiers ---------------------------------------------------------------------------------
@@ -293,7 +319,7 @@ def test_probe_descriptor_row_shift(which):
     for shift in (0, 1, 2, 3, 4, 7, 8, 9, 17):
         for mode in (0, 1):
             out = torch.zeros((M, N), device="cuda")
-            _ffi.check(_ffi.lib().dbv_probe(which | (shift << 8) | (mode << 16), _ffi.ptr(a), _ffi.ptr(bp), _ffi.ptr(out), M, N, K, _ffi.stream_ptr()))
+            _ffi.check(_ffi.debug_lib().dbv_probe(which | (shift << 8) | (mode << 16), _ffi.ptr(a), _ffi.ptr(bp), _ffi.ptr(out), M, N, K, _ffi.stream_ptr()), _ffi.debug_lib())
             torch.cuda.synchronize()
             ok_rows = 128 - shift  # rows of each tile whose shifted source row is still inside the stage
             e = max(float((out[t * 128 : t * 128 + ok_rows] - want[t * 128 : t * 128 + ok_rows]).abs().max()) for t in range(2))
@@ -302,29 +328,17 @@ def test_probe_descriptor_row_shift(which):
     assert res[(0, 0)] < 1e-4 and res[(8, 0)] < 1e-4
 
 
-def test_channel_group_planar_tail_matches(wts, data):
-    """The optional channel-group-planar (CG8) layout of the decoder tail (env DBV_CG8_FIRST; measured neutral, off by
-    default) must give the same numbers as the default pixel-major layout: run it in a subprocess (the switch is read once)."""
-    import subprocess
-    import sys
-
+def test_channel_group_planar_tail_matches():
+    """The optional channel-group-planar (CG8) layout of the decoder tail (ablation build, env DBV_CG8_FIRST; measured
+    neutral, not in the product) must give the same numbers as the default pixel-major layout."""
     code = (
-        "import numpy as np, torch, sys\n"
-        "sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
         "from oracle import weights as ow\n"
         "from debvader_b200.model.model import load_deblender\n"
         "w = ow.make_random_weights(seed=1234); x = ow.synthetic_stamps(40, seed=11)\n"
         "net = load_deblender('dc2', (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3], weights=w, precision='mixed')\n"
-        "d = net(x, sample=False); np.save(sys.argv[1], d.mean().numpy())\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    import tempfile
-
-    outs = []
-    for first in ("20", "18"):
-        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
-            path = f.name
-        r = subprocess.run([sys.executable, "-c", code, path], env={**os.environ, "DBV_CG8_FIRST": first}, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(np.load(path))
-        os.unlink(path)
-    np.testing.assert_array_equal(outs[0], outs[1])
+        "d = net(x, sample=False); np.savez(sys.argv[1], mean=d.mean().numpy())\n"
+    )
+    a = _run_variant(code, {"DBV_CG8_FIRST": "20"})
+    b = _run_variant(code, {"DBV_CG8_FIRST": "18"})
+    np.testing.assert_array_equal(a["mean"], b["mean"])
