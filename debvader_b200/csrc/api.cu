@@ -580,8 +580,19 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   const int n_regions = in.planes * nchunk * npar * (cg8 ? 2 : 1);  // CG8: two 8-channel group planes per K = 16 chunk
   if ((!cg8 && n_regions > 8) || bandR < 1 || bandR > H) return 0;
   const int ntiles = (bandR * WP + 127) / 128;
-  if (U * G.NT * (x3 ? 2 : 1) > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
-  if (hrows > 256 || WP > 256) return 0;
+  const int CW = G.NT * (x3 ? 2 : 1);           // accumulator columns of one (class, tile): [hi-weight part | lo-weight part]
+  // Stride-2 transposed conv: the four output-parity classes that share an INPUT SHIFT are concatenated along N — shift
+  // (0,0) feeds all four classes (one MMA of N = 4*CW instead of four), (0,-1) and (-1,0) two each, (-1,-1) one: 4 MMAs per
+  // k-step instead of 9, and the activation operand (whose shared-memory fetch bounds these few-channel layers) is read
+  // 4 times instead of 9.  Column order of the classes inside a tile's accumulator: [2, 0, 1, 3], so that every shift's
+  // class set is contiguous.
+  const bool concat = ncls == 4 && 4 * CW <= 256 && !dbv_env("DBV_NO_CONCAT");
+  const int DW = concat ? 4 * CW : CW;          // accumulator columns of a sub-unit
+  const int nsub = concat ? ntiles : ncls * ntiles;  // sub-units per band (class-major when not concatenated)
+  if (U * DW > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
+  if (hrows > 256 || WP > 256 || ntiles > 32) return 0;
+  int slot_cols = 32;
+  while (slot_cols < U * DW) slot_cols *= 2;
   // >= one zeroed slack slot after the box; CG8: the regions of a buffer are ONE contiguous TMA box, the slack follows the buffer
   const long long region = cg8 ? (long long)hrows * WP * ROWB : (((long long)hrows * WP * ROWB + ROWB + 1023) / 1024) * 1024;
   const long long buf = cg8 ? ((n_regions * region + 16 + 1023) / 1024) * 1024 : n_regions * region;
@@ -591,40 +602,127 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   const int tail_pad = w_bytes >= overread ? 0 : ((overread - w_bytes + 1023) / 1024) * 1024;
   const long long smem = 1024 + w_bytes + (long long)nbuf * buf + tail_pad + 2048;  // + barriers
   if (smem > HALO_MAX_SMEM) return 0;
+  if (n_wblk > HALO_MAX_WBLK) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
-  int nkb = 0;
   for (int cl = 0; cl < ncls; ++cl) {
-    T.cls[cl].kb_begin = nkb;
-    for (size_t ti = 0; ti < taps.size(); ++ti) {
-      if (taps[ti].cls != cl) continue;
-      // one entry per MMA: (tap, channel chunk, pairing, k-step).  bf16x3: (A_hi x [B_hi | B_lo]) as ONE MMA of
-      // N = 2*NT (the hi and lo weight blocks are adjacent in shared memory) + (A_lo x B_hi): A_hi is fetched once
-      for (int ch = 0; ch < nchunk; ++ch)
-        for (int pr = 0; pr < in.planes; ++pr)  // pr = 1: the lo activation plane (absent for single-plane inputs)
-          for (int k = 0; k < (c1 ? 1 : G.CBK / 16); ++k) {
-            if (nkb >= TC_MAX_KB) return 0;
-            const int a_lo = (pr == 1);
-            const long long areg = cg8 ? (a_lo * nchunk + ch) * 2 : (a_lo * nchunk + ch) * npar + taps[ti].plane;
-            const long long a_off = areg * region + (long long)((taps[ti].dy + pad_top) * WP + taps[ti].dx + pad) * ROWB + 32 * k;
-            const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * G.NT * ROWB_W + 32 * k;
-            if ((a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return 0;
-            T.mma[nkb].a = (uint32_t)(a_off >> 4);  // 16-byte units, added to the low descriptor word by the MMA issuer
-            T.mma[nkb].b = (uint32_t)(b_off >> 4) | ((x3 && pr == 0) ? 0x80000000u : 0u);
-            ++nkb;
-          }
-    }
-    T.cls[cl].nkb = nkb - T.cls[cl].kb_begin;
     T.cls[cl].oy0 = ncls == 4 ? (cl >> 1) : 0;
     T.cls[cl].ox0 = ncls == 4 ? (cl & 1) : 0;
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
+  const int f16 = layer_f16(c->precision, li);
+  auto idesc_of = [&](int n) { return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); };
+  const long long MSTEP = 128ll * ROWB;  // bytes between consecutive 128-position tiles of a band
+  const int ksteps = c1 ? 1 : G.CBK / 16;
+  const long long wblk_bytes = (long long)G.NT * ROWB_W;
+  // ---- resident weight layout -------------------------------------------------------------------------------------
+  // plain: block j = packed block j = ((tap * nchunk + chunk) * parts + part).  concat: for every (shift, chunk) the
+  // blocks of the classes using that shift, in column order, each as [hi, lo] — contiguous rows = one N-concatenated B operand.
+  static const int col_order[4] = {2, 0, 1, 3};
+  int ccol[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) ccol[col_order[i]] = i * CW;
+  struct ShiftUse { int dy, dx; std::vector<std::pair<int, int>> cls_tap; };  // (class, tap index) in column order
+  std::vector<ShiftUse> shifts;
+  std::vector<long long> wblk_of;  // concat: smem block index of (shift s, chunk ch, k-th class of the shift, part) = wblk_of[s] + (ch * n_s + k) * parts
+  if (concat) {
+    for (int dy = 0; dy >= -1; --dy)
+      for (int dx = 0; dx >= -1; --dx) {
+        ShiftUse su{dy, dx, {}};
+        for (int i = 0; i < 4; ++i)
+          for (size_t ti = 0; ti < taps.size(); ++ti)
+            if (taps[ti].cls == col_order[i] && taps[ti].dy == dy && taps[ti].dx == dx) su.cls_tap.push_back({col_order[i], (int)ti});
+        shifts.push_back(su);
+      }
+    int j = 0;
+    for (const ShiftUse& su : shifts) {
+      wblk_of.push_back(j);
+      for (int ch = 0; ch < nchunk; ++ch)
+        for (const auto& ct : su.cls_tap)
+          for (int part = 0; part < parts_w; ++part) T.w_src[j++] = (uint8_t)((ct.second * nchunk + ch) * parts_w + part);
+    }
+    if (j != n_wblk) return fail(DBV_ERR_STATE, "%s: concatenated weight layout has %d blocks, expected %d", L.name, j, n_wblk);
+  } else {
+    for (int j = 0; j < n_wblk; ++j) T.w_src[j] = (uint8_t)j;
+  }
+  // ---- ops + items of one band --------------------------------------------------------------------------------------
+  int nops = 0, nitems = 0, nunits = 0;
+  const int NV = (G.NT % 32 != 0) ? 16 : 32;  // channels per epilogue item (must match tc_halo_kernel)
+  const int NCHK = G.NT / NV;
+  auto push_op = [&](long long a_off, long long b_off, int n, int dcol, bool acc) -> bool {
+    if (nops >= HALO_MAX_OPS || (a_off >> 4) > 0x3fff || (b_off >> 4) > 0x3fff) return false;
+    T.ops[nops].a = (uint32_t)(a_off >> 4);
+    T.ops[nops].b = (uint32_t)(b_off >> 4);
+    T.ops[nops].idesc = idesc_of(n);
+    T.ops[nops].d = (uint32_t)dcol | (acc ? 0x10000u : 0u);
+    ++nops;
+    return true;
+  };
+  auto a_region = [&](int ch, int a_lo, int plane) -> long long { return cg8 ? (long long)(a_lo * nchunk + ch) * 2 : (long long)(a_lo * nchunk + ch) * npar + plane; };
+  for (int s0 = 0; s0 < nsub; s0 += U) {
+    if (nunits >= HALO_MAX_UNITS) return 0;
+    const int s1 = std::min(s0 + U, nsub);
+    for (int sidx = s0; sidx < s1; ++sidx) {
+      const int dbase = (sidx - s0) * DW;
+      if (!concat) {
+        const int cl = sidx / ntiles, m = sidx % ntiles;
+        bool first = true;
+        for (size_t ti = 0; ti < taps.size(); ++ti) {
+          if (taps[ti].cls != cl) continue;
+          // (A_hi x [B_hi | B_lo]) as ONE MMA of N = 2*NT (the hi and lo weight blocks are adjacent in shared memory)
+          // + (A_lo x B_hi): A_hi is fetched once
+          for (int ch = 0; ch < nchunk; ++ch)
+            for (int pr = 0; pr < in.planes; ++pr)  // pr = 1: the lo activation plane (absent for single-plane inputs)
+              for (int k = 0; k < ksteps; ++k) {
+                const long long a_off = a_region(ch, pr, taps[ti].plane) * region + (long long)((taps[ti].dy + pad_top) * WP + taps[ti].dx + pad) * ROWB + 32 * k + m * MSTEP;
+                const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * wblk_bytes + 32 * k;
+                if (!push_op(a_off, b_off, (x3 && pr == 0) ? 2 * G.NT : G.NT, dbase, !first)) return 0;
+                first = false;
+              }
+        }
+        for (int q = 0; q < NCHK; ++q) {
+          if (nitems >= HALO_MAX_ITEMS) return 0;
+          T.items[nitems++] = (uint32_t)(dbase + q * NV) | ((uint32_t)cl << 9) | ((uint32_t)m << 11) | ((uint32_t)q << 16);
+        }
+      } else {
+        const int m = sidx;
+        bool first = true;
+        for (size_t si = 0; si < shifts.size(); ++si) {
+          const ShiftUse& su = shifts[si];
+          const int ns = (int)su.cls_tap.size();
+          const int dcol0 = dbase + ccol[su.cls_tap[0].first];
+          for (int ch = 0; ch < nchunk; ++ch)
+            for (int pr = 0; pr < in.planes; ++pr)
+              for (int k = 0; k < ksteps; ++k) {
+                const long long a_off = a_region(ch, pr, 0) * region + (long long)((su.dy + pad_top) * WP + su.dx + pad) * ROWB + 32 * k + m * MSTEP;
+                const long long blk0 = wblk_of[si] + (long long)ch * ns * parts_w;
+                if (pr == 0) {  // A (hi) x [class blocks, each hi|lo]: one MMA of N = ns * CW
+                  if (!push_op(a_off, blk0 * wblk_bytes + 32 * k, ns * CW, dcol0, !first)) return 0;
+                  first = false;
+                } else {        // A_lo x B_hi: the hi blocks are not adjacent, one MMA of N = NT per class
+                  for (int kc = 0; kc < ns; ++kc)
+                    if (!push_op(a_off, (blk0 + (long long)kc * parts_w) * wblk_bytes + 32 * k, G.NT, dbase + ccol[su.cls_tap[kc].first], true)) return 0;
+                }
+              }
+        }
+        for (int i = 0; i < 4; ++i)
+          for (int q = 0; q < NCHK; ++q) {
+            if (nitems >= HALO_MAX_ITEMS) return 0;
+            const int cl = col_order[i];
+            T.items[nitems++] = (uint32_t)(dbase + ccol[cl] + q * NV) | ((uint32_t)cl << 9) | ((uint32_t)m << 11) | ((uint32_t)q << 16);
+          }
+      }
+    }
+    T.unit_op_end[nunits] = (uint16_t)nops;
+    T.unit_item_end[nunits] = (uint16_t)nitems;
+    ++nunits;
+  }
+  T.n_units = nunits;
+  T.slot_cols = slot_cols;
   T.ab_f16 = layer_f16(c->precision, li);
   for (int i = 0; i < 64; ++i) T.bias_c[i] = i < L.Cout ? R.bias_host[i] : 0.f;
   T.W = W; T.H = H; T.R = bandR; T.WP = WP; T.pad = pad; T.pad_top = pad_top;
   T.ntiles = ntiles;
   T.magic_wp = (uint32_t)(((1ull << 32) + WP - 1) / WP);
-  T.magic_nt = (uint32_t)(((1ull << 32) + ntiles - 1) / ntiles);
   T.n_regions = n_regions;
   for (int r = 0; r < n_regions; ++r) {  // r = ((plane_hi_lo * nchunk + chunk) * npar + parity plane)
     const int pc = r / npar;

@@ -126,18 +126,35 @@ bool tc_pairh_supported(int NT);
 
 // ---- tcgen05 convolution with a resident halo tile (tc_halo.cu) ----------------------------------------
 constexpr int HALO_MAX_SMEM = 232448;  // 227 KB
-struct HaloMma {  // one tcgen05.mma (K = 16) of a unit: descriptor start offsets (bytes >> 4) and the N selector
-  uint32_t a;     // A window inside one halo buffer: region of the (plane, channel chunk) + tap shift + k-step
-  uint32_t b;     // resident weight block + k-step; bit 31: wide (N = 2*NT over the adjacent hi|lo blocks)
+// One tcgen05.mma (K = 16) of a halo band.  The whole band is a FLAT, host-made list of these, cut into units by
+// unit_op_end[]: the issuing thread reads an entry with one uniform 128-bit constant load, adds the two smem bases
+// and issues — no per-tile / per-class index arithmetic (measured in round 2 with clock64: the old per-sub-unit loop
+// set-up cost ~300 cycles and the per-MMA descriptor selection ~20, all of it tensor-pipe idle time because the MMA
+// queue is shallow).
+struct HaloOp {
+  uint32_t a;      // A descriptor start (bytes >> 4) inside one halo buffer: region + tap shift + k-step + tile
+  uint32_t b;      // B descriptor start (bytes >> 4) inside the resident weights
+  uint32_t idesc;  // instruction descriptor (M = 128, this op's N, operand formats)
+  uint32_t d;      // bits 0-15: first accumulator column inside the unit's slot; bit 16: accumulate (0 = overwrite)
 };
+constexpr int HALO_MAX_OPS = 288;    // MMAs per band
+constexpr int HALO_MAX_UNITS = 64;   // units (one accumulator slot, one commit) per band
+constexpr int HALO_MAX_ITEMS = 256;  // epilogue items (128 positions x NV channels of one class) per band
+constexpr int HALO_MAX_WBLK = 96;    // resident weight blocks
 struct HaloLayer {
   CUtensorMap tmA;  // 5D (C, W, H, 1, B) bf16, box (CBK, W+2, R+2, 1, 1)
   CUtensorMap tmB;  // packed weights, box (CBK, NT)
   float bias_c[64];        // the layer's bias (zero padded to NT) in the kernel's constant bank: added without a load
-  HaloMma mma[TC_MAX_KB];  // flat MMA list per class (cls[c].kb_begin / nkb index it): taps x chunks x pairings x k-steps,
-                           // precomputed on the host so that the single issuing thread does nothing but issue
+  HaloOp ops[HALO_MAX_OPS];
+  uint16_t unit_op_end[HALO_MAX_UNITS];    // ops of unit k of a band: [unit_op_end[k-1], unit_op_end[k])
+  uint16_t unit_item_end[HALO_MAX_UNITS];  // epilogue items of unit k: [unit_item_end[k-1], unit_item_end[k])
+  uint32_t items[HALO_MAX_ITEMS];  // bits 0-8: first accumulator column of the item inside the slot; 9-10: output class;
+                                   // 11-15: tile of the band; 16-18: channel chunk (c0 = chunk * NV)
+  uint8_t w_src[HALO_MAX_WBLK];    // resident weight block j is block w_src[j] of the packed weight tensor
   TcClass cls[TC_MAX_CLS];
   int n_cls;
+  int n_units;       // units per band
+  int slot_cols;     // accumulator columns of a slot (power of two <= 256); the ring has 512 / slot_cols slots (<= 8)
   int ab_f16;        // operand format of this layer's activations and weights: 0 = bf16, 1 = fp16
   int W, H;          // tile-space extents (valid outputs sx < W, sy < H)
   int R, WP;         // output rows per band, W + 2*pad
@@ -152,13 +169,13 @@ struct HaloLayer {
   int a_box_bytes;   // (R+2) * WP * ROWB
   int n_wblk, w_rows_per_blk, w_bytes;
   const void* w_img;  // no-swizzle mode (conv1): the resident weights as one ready-made shared-memory image (bulk copy)
-  uint32_t magic_wp, magic_nt;  // ceil(2^32 / WP), ceil(2^32 / ntiles): n / d == __umulhi(n, magic) for n, d < 2^16 (epilogue coordinates)
+  uint32_t magic_wp;  // ceil(2^32 / WP): n / WP == __umulhi(n, magic) for n, WP < 2^16 (epilogue coordinates)
   int cg8;           // the input is OUT_BF16_CG8: ONE un-swizzled TMA box (u64 tensor map (2W, H, planes*Cin/8, B, 1)) fills all
                      // group-plane regions; the A operand is un-swizzled with LBO = region_bytes (K=16 = two groups)
   int nbuf;          // halo buffers in the ring (1 or 2)
-  int U;             // sub-units (tile x class) per accumulator slot / commit: 1, 2 or 4 with U * accumulator width <= 256 columns
-  int wide;          // bf16x3: accumulator tile = [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo] (2*NT columns, summed by the epilogue);
-                     // kb[].dy == 1 marks the k-blocks issued with N = 2*NT over the adjacent (hi, lo) weight blocks
+  int U;             // sub-units per unit (plan parameter, kept for the logs)
+  int wide;          // hi/lo weights: a class tile's accumulator = [A*B_hi (+ A_lo*B_hi) | A*B_lo] (2*NT columns, summed by the
+                     // epilogue)
   int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)
   int smem_bytes;
   int dbg_skip;      // timing ablations only (env DBV_HALO_SKIP): bit0 skip the MMAs, bit1 skip the epilogue body

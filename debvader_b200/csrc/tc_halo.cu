@@ -61,8 +61,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   constexpr bool CG8 = !NOSWZ && CBK == 16;             // channel-group-planar input: 16-byte pixel rows, K=16 = two groups one region apart
   constexpr int ROWB = (NOSWZ || CG8) ? 16 : CBK * 2;   // activation row pitch in shared memory
   constexpr int ROWB_W = NOSWZ ? 16 : CBK * 2;          // weight rows (K-major, swizzled; conv1: host-packed core matrices)
-  const uint32_t IDESC = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t IDESC2 = (1u << 4) | idesc_ab_fmt(L.ab_f16) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                              // nbuf x n_regions x region_bytes
@@ -74,16 +72,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t DW = (uint32_t)(L.wide ? 2 * NT : NT);  // accumulator columns per sub-unit (one tile of one class)
-  // A "unit" = up to U consecutive sub-units of a band sharing ONE accumulator slot, one tempty wait and one commit: the
-  // issuing thread pays its per-unit overhead (barrier wait ~100 cycles, commit, loop set-up: ~300 cycles measured, which
-  // showed up 1:1 as tensor-pipe idle time) once per 256 accumulator columns instead of once per 128-row tile.
-  const uint32_t U = (uint32_t)L.U;                    // sub-units per unit (U * DW <= 256; autotuned with the band plan)
-  const uint32_t SW = U * DW;                          // slot width
+  // A "unit" = the sub-units (one 128-position tile of one output class — or of all four classes of a stride-2 transposed
+  // conv, concatenated along N) that share ONE accumulator slot, one tempty wait and one commit.  The host lays the whole
+  // band out as flat tables: ops[] (one entry per tcgen05.mma, cut into units by unit_op_end[]) and items[] (one entry per
+  // epilogue item, cut by unit_item_end[]).
+  const uint32_t SW = (uint32_t)L.slot_cols;           // slot width (power of two)
   const uint32_t nslot = (512u / SW) < (uint32_t)HALO_NSLOT_MAX ? (512u / SW) : (uint32_t)HALO_NSLOT_MAX;  // power of two
   const uint32_t slot_shift = 31u - (uint32_t)__clz((int)nslot);
-  const int nsub = L.n_cls * L.ntiles;                 // sub-units per band, class-major
-  const int units_per_band = (nsub + (int)U - 1) / (int)U;
+  const int units_per_band = L.n_units;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.tmA);
     if (!NOSWZ) tma_prefetch_desc(&L.tmB);
@@ -125,7 +121,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         bulk_load(sW, L.w_img, (uint32_t)L.w_bytes, bar_w);
       } else {
         mbar_expect_tx(bar_w, (uint32_t)(L.n_wblk * NT * ROWB_W));
-        for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB_W), &L.tmB, bar_w, 0, blk * L.w_rows_per_blk);
+        for (int blk = 0; blk < L.n_wblk; ++blk) tma_load_2d(sW + blk * (NT * ROWB_W), &L.tmB, bar_w, 0, (int)L.w_src[blk] * L.w_rows_per_blk);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -164,9 +160,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       // A low word: LBO = distance (>>4) between the two K-halves of a K=16 operand: 16 B = the next pixel (conv1), one region =
       // the next channel group (CG8); unused (1) for swizzled rows
       const uint32_t LOA = CG8 ? ((uint32_t)(L.region_bytes >> 4) << 16) : kSmemDescLoConst;
-      constexpr uint32_t MSTEP = (128 * ROWB) >> 4;
       const uint32_t w16 = LOB | (sW >> 4);
-      const int ncls = (DBV_DBG(L.dbg_skip) & 1) ? 0 : L.n_cls;
+      const int nunits = (DBV_DBG(L.dbg_skip) & 1) ? 0 : units_per_band;
       [[maybe_unused]] const long long mk0 = HCLK();
       [[maybe_unused]] long long mk_afull = 0, mk_tempty = 0, mk_n = 0;
       for (long long g = g0; g < g1; ++g) {
@@ -175,27 +170,23 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
         tc_fence_after();
         mk_afull += HCLK() - mka;
         const uint32_t a16 = LOA | ((sA + stage * L.buf_bytes) >> 4);
-        for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
+        int i = 0;
+        for (int k = 0; k < nunits; ++k, ++u) {
           const uint32_t slot = u & (nslot - 1);
           [[maybe_unused]] const long long mkb = HCLK();
           mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
           tc_fence_after();
           mk_tempty += HCLK() - mkb;
-          const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
-          uint32_t d = tmem_base + slot * SW;
-          for (int sidx = s0; sidx < s1; ++sidx, d += DW) {
-            const int c = sidx / L.ntiles, m = sidx - c * L.ntiles;
-            const int kb0 = L.cls[c].kb_begin, nkb = L.cls[c].nkb;
-            const uint32_t am = a16 + (uint32_t)m * MSTEP;
-            // flat list, one entry per MMA (read with uniform constant loads): the loop is pure issue
-#pragma unroll 4
-            for (int i = 0; i < nkb; ++i) {
-              const HaloMma e = L.mma[kb0 + i];
-              umma_f16(d, desc64(HI, am + e.a), desc64(HIB, w16 + (e.b & 0x7fffffffu)), (e.b >> 31) ? IDESC2 : IDESC, i != 0 ? 1u : 0u);
-            }
+          const uint32_t d0 = tmem_base + slot * SW;
+          const int iend = L.unit_op_end[k];
 #ifdef DBV_ABLATE
-            mk_n += nkb;
+          mk_n += iend - i;
 #endif
+          // flat list, one 16-byte entry per MMA read with a uniform constant load: the loop is pure issue
+#pragma unroll 4
+          for (; i < iend; ++i) {
+            const HaloOp e = L.ops[i];
+            umma_f16(d0 + (e.d & 0xffffu), desc64(HI, a16 + e.a), desc64(HIB, w16 + e.b), e.idesc, e.d >> 16);
           }
           umma_commit(bar_tfull + 8 * slot);
         }
@@ -218,7 +209,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     constexpr int NV = (HALO_EPI_GROUPS > 3 || NT % 32 != 0) ? 16 : 32;  // channels per item: 16 keeps 16 epilogue warps spill-free
-    constexpr int NCHK = NT / NV;
+    static_assert(NT % NV == 0, "items cover whole channel chunks");
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int ncls = (DBV_DBG(L.dbg_skip) & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
     const bool has_alpha = L.o.alpha != nullptr && !(DBV_DBG(L.dbg_skip) & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
@@ -241,19 +232,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       for (long long g = g0; g < g1; ++g) {
         for (int k = 0; k < (ncls ? units_per_band : 0); ++k, ++u) {
           const uint32_t slot = u & (nslot - 1);
-          const int s0 = k * (int)U, s1 = (s0 + (int)U < nsub) ? s0 + (int)U : nsub;
           bool waited = false;
-          const int nitems = (s1 - s0) * NCHK;  // items of this unit: (sub-unit, NV-channel chunk); group g takes items g, g + G, ...
+          // items of this unit (host-made table: accumulator column, class, tile, channel chunk); group g takes items g, g + G, ...
+          const int it0 = k ? (int)L.unit_item_end[k - 1] : 0, it1 = (int)L.unit_item_end[k];
   #pragma unroll 1
-          for (int item = grp; item < nitems; item += HALO_EPI_GROUPS) {
-            const int sidx = s0 + item / NCHK, q = item % NCHK;
-            // (class, tile) of the sub-unit and this thread's output pixel: divisions by multiply-high with host-made magics
-            const int c = L.ntiles == 1 ? sidx : (int)__umulhi((uint32_t)sidx, L.magic_nt), m = sidx - c * L.ntiles;  // (2^32 / 1 does not fit)
+          for (int item = it0 + grp; item < it1; item += HALO_EPI_GROUPS) {
+            const uint32_t it = L.items[item];
+            const int c = (int)((it >> 9) & 3u), m = (int)((it >> 11) & 31u), q = (int)((it >> 16) & 7u);
             const int p = 128 * m + row;
             const int ly = (int)__umulhi((uint32_t)p, L.magic_wp), sx = p - ly * L.WP, sy = y0 + ly;
             const bool ok = ly < L.R && sx < L.W && sy < L.H && !(DBV_DBG(L.dbg_skip) & 2);
             const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
-            const uint32_t tcol = lane_base + slot * SW + (uint32_t)(sidx - s0) * DW;
+            const uint32_t tcol = lane_base + slot * SW + (it & 511u);  // first column of this item's NV channels
             const int c0 = q * NV;
             // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
             // requested before the accumulator wait
@@ -274,14 +264,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
             float v[NV];
             if (L.wide) {  // + the A_hi x B_lo partial product held in the second half of the sub-unit's columns
               float w[NV];
-              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
-              tmem_ld_issue<NV>(tcol + (uint32_t)(NT + c0), w);
+              tmem_ld_issue<NV>(tcol, v);
+              tmem_ld_issue<NV>(tcol + (uint32_t)NT, w);
               tmem_ld_wait<NV>(v);
               tmem_ld_wait<NV>(w);
   #pragma unroll
               for (int j = 0; j < NV; ++j) v[j] += w[j];
             } else {
-              tmem_ld_issue<NV>(tcol + (uint32_t)c0, v);
+              tmem_ld_issue<NV>(tcol, v);
               tmem_ld_wait<NV>(v);
             }
             [[maybe_unused]] const long long ekd = HCLK();

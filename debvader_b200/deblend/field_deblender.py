@@ -257,7 +257,12 @@ class DeblendField:
             epistemic_norm = (e_dev[:, :, :, 2].sum(dim=(1, 2)) / mean_dev[:, :, :, 2].double().sum(dim=(1, 2))).cpu().numpy()
             epistemic = _records.stamp_column(e_dev)
         else:
-            epistemic = _records.stamp_column(np.zeros((n, S, S, C)))
+            # the reference stores n separate zero maps (field_deblender.py:317-321): one shared read-only map here
+            zero = np.zeros((S, S, C))
+            zero.setflags(write=False)
+            epistemic = np.empty(n, dtype=object)
+            for i in range(n):
+                epistemic[i] = zero
             epistemic_norm = np.zeros(n)
 
         lo, hi = int(S / 2) - 5, int(S / 2) + 5
