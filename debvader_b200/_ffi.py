@@ -59,6 +59,7 @@ def _declare(lib):
         "dbv_center_mse": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
         "dbv_mse": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_i64, c_vp]),
         "dbv_mse_scratch_bytes": (c_i64, []),
+        "dbv_fp16_overflow": (C.c_int, [c_vp, C.c_int]),
         "dbv_launch_count": (c_i64, [c_vp]),
         "dbv_global_launch_count": (c_i64, []),
         "dbv_set_profiling": (C.c_int, [c_vp, C.c_int]),

@@ -12,7 +12,6 @@ caller looks at the values.  The record layout (names, order, scalar dtypes) is 
 from __future__ import annotations
 
 import numpy as np
-import pandas as pd
 import torch
 
 _NP = {torch.float32: np.float32, torch.float64: np.float64}
@@ -163,12 +162,33 @@ def column_tensor(records, column, device):
 
 
 def make_records(columns: dict):
-    """``pd.DataFrame(res).to_records(index=False)`` (field_deblender.py:380) with the stamp columns passed through as
-    ready-made object arrays, so that pandas never inspects (and never downloads) their elements."""
-    data = {}
+    """``pd.DataFrame(res).to_records(index=False)`` (field_deblender.py:380) built directly with numpy: a recarray
+    with the same field names, order and dtypes pandas infers (object for the per-stamp arrays and the shifts, int64 /
+    float64 / bool for the scalar columns) — without pandas inspecting, and thereby downloading, the stamp proxies."""
+    arrays, names = [], []
+    n = None
     for name, v in columns.items():
         if isinstance(v, np.ndarray) and v.dtype == object:
-            data[name] = pd.Series(v, dtype=object)
+            a = v
+        elif isinstance(v, np.ndarray):
+            a = v
+        elif len(v) and isinstance(v[0], (np.ndarray, list, tuple)):  # e.g. shifts: one small array per galaxy -> object column
+            a = np.empty(len(v), dtype=object)
+            for i, x in enumerate(v):
+                a[i] = x
         else:
-            data[name] = v
-    return pd.DataFrame(data).to_records(index=False)
+            a = np.asarray(v)
+            if a.dtype.kind in "US" or a.ndim != 1:
+                b = np.empty(len(v), dtype=object)
+                for i, x in enumerate(v):
+                    b[i] = x
+                a = b
+        n = len(a) if n is None else n
+        if len(a) != n:
+            raise ValueError("All arrays must be of the same length")  # pandas' message for ragged columns
+        arrays.append(a)
+        names.append(name)
+    if n == 0:
+        dt = [(nm, a.dtype if a.dtype != np.float64 or nm.startswith("galaxy") else object) for nm, a in zip(names, arrays)]
+        return np.recarray((0,), dtype=dt)
+    return np.rec.fromarrays(arrays, names=names)

@@ -175,6 +175,8 @@ struct dbv_ctx {
   // A ctx owns ONE set of activation buffers: whatever the device-pointer entry points last enqueued on a caller's stream
   // is marked by this event, and the host pipeline (which computes on its own stream) waits for it before its first piece
   cudaEvent_t ev_user = nullptr;
+  int* ovf_host = nullptr;  // host-mapped flag the fp16-tail epilogues set when an activation saturates (DBV_PREC_MIXED)
+  int* ovf_dev = nullptr;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -601,7 +603,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   const int overread = 131 * ROWB;
   const int tail_pad = w_bytes >= overread ? 0 : ((overread - w_bytes + 1023) / 1024) * 1024;
   const long long smem = 1024 + w_bytes + (long long)nbuf * buf + tail_pad + 2048;  // + barriers
-  if (smem > HALO_MAX_SMEM) return 0;
+  if (smem > HALO_MAX_SMEM || nbuf < 1 || nbuf > 4) return 0;
   if (n_wblk > HALO_MAX_WBLK) return 0;
   memset(&T, 0, sizeof T);
   T.n_cls = ncls;
@@ -791,7 +793,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   for (int nt = 1; nt <= 16; ++nt) {
     int r = std::min(H, nt * 128 / WP);
     if (r < 1) continue;
-    for (int nbuf = 2; nbuf >= 1; --nbuf)
+    for (int nbuf = 3; nbuf >= 1; --nbuf)
       for (int U = 1; U <= 4; U *= 2) {
         if (U > ncls * nt && U > 1) continue;  // no band has that many sub-units
         bool dup = false;
@@ -1029,6 +1031,7 @@ extern "C" int dbv_destroy(dbv_ctx* c) {
   }
   for (auto e : c->prof_ev) cudaEventDestroy(e);
   if (c->ev_user) cudaEventDestroy(c->ev_user);
+  if (c->ovf_host) cudaFreeHost(c->ovf_host);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1080,6 +1083,11 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     const HostTensor* a0;
     if ((r = check_shape(c, wkey(0, 0, "alpha"), {32}, &a0))) return r;
     if ((r = upload(c, &c->dec_alpha0, a0->data))) return r;
+  }
+  if (c->precision == DBV_PREC_MIXED) {
+    DBV_CUDA(cudaHostAlloc((void**)&c->ovf_host, sizeof(int), cudaHostAllocMapped));
+    *c->ovf_host = 0;
+    DBV_CUDA(cudaHostGetDevicePointer((void**)&c->ovf_dev, c->ovf_host, 0));
   }
   // ---- per-layer weights ------------------------------------------------------------------------
   for (int li = 0; li < kNumLayers; ++li) {
@@ -1142,6 +1150,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     o.alpha = R.alpha;
     o.alpha2 = R.alpha2;
     o.relu = L.relu_head;
+    o.ovf = (!fp32 && o.mode == OUT_BF16_NHWC && o.planes == 1 && o.f16 == 1 && c->precision == DBV_PREC_MIXED) ? c->ovf_dev : nullptr;
     const size_t el = out_elems_per_stamp(o);
     const size_t esz = (o.mode == OUT_F32_NHWC) ? 4 : 2;
     R.out_bytes_per_stamp = el * esz;
@@ -1380,6 +1389,14 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
 #undef DBV_PIPE
   c->launches += g_launches.load() - before;
   return DBV_OK;
+}
+
+extern "C" int dbv_fp16_overflow(dbv_ctx* c, int reset) {
+  DBV_REQUIRE(c, "dbv_fp16_overflow: null ctx");
+  if (!c->ovf_host) return 0;
+  const int v = *reinterpret_cast<volatile int*>(c->ovf_host);
+  if (reset) *reinterpret_cast<volatile int*>(c->ovf_host) = 0;
+  return v != 0 ? 1 : 0;
 }
 
 // ---- introspection -----------------------------------------------------------------------------------

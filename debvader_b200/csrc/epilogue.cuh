@@ -39,6 +39,8 @@ struct OutSpec {
   const float* alpha;  // PReLU slopes of the (OH,OW,Cout) map in the library's layout [Cout/4][OH*OW][4] (see alpha_index), or null
   const float* alpha2; // second PReLU (encoder Flatten PReLU, model/model.py:95), same layout, or null
   int relu;
+  int* ovf;            // single-plane fp16 outputs (the tail of DBV_PREC_MIXED): host-mapped flag set to 1 when a value saturates
+                       // at +-65504, so that leaving the fp16 range fails loudly instead of silently (dbv_fp16_overflow); or null
 };
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
@@ -195,6 +197,16 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = pack_f16x2(a - hf.x, b - hf.y);
 }
+// running max |h| of packed fp16 pairs (saturation watch of the single-plane fp16 outputs): one HMNMX2 per pair
+__device__ __forceinline__ uint32_t habs2_max(uint32_t m, uint32_t q) {
+  uint32_t a;
+  asm("abs.f16x2 %0, %1;" : "=r"(a) : "r"(q));
+  asm("max.f16x2 %0, %1, %2;" : "=r"(m) : "r"(m), "r"(a));
+  return m;
+}
+__device__ __forceinline__ void ovf_report(int* flag, uint32_t m) {
+  if ((m & 0xffffu) >= 0x7bffu || (m >> 16) >= 0x7bffu) *reinterpret_cast<volatile int*>(flag) = 1;  // 0x7bff = 65504, the saturation value
+}
 // format-dispatching versions (f16 is warp-uniform)
 __device__ __forceinline__ uint32_t pack16x2(int f16, float a, float b) { return f16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
 __device__ __forceinline__ float round16(int f16, float a) {
@@ -312,6 +324,11 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
           q1.z = pack16x2(o.f16, v[j + 12], v[j + 13]);
           q1.w = pack16x2(o.f16, v[j + 14], v[j + 15]);
           l0 = l1 = make_uint4(0u, 0u, 0u, 0u);
+          if (o.ovf) {
+            uint32_t m = habs2_max(habs2_max(habs2_max(habs2_max(0u, q0.x), q0.y), q0.z), q0.w);
+            m = habs2_max(habs2_max(habs2_max(habs2_max(m, q1.x), q1.y), q1.z), q1.w);
+            ovf_report(o.ovf, m);
+          }
         }
         if (a32) {
           stg256(p + j, q0, q1);
@@ -331,6 +348,7 @@ __device__ __forceinline__ void store_act(const OutSpec& o, long long b, int y, 
         uint2 q;
         q.x = pack16x2(o.f16, v[j], v[j + 1]);
         q.y = pack16x2(o.f16, v[j + 2], v[j + 3]);
+        if (o.ovf && o.planes == 1) ovf_report(o.ovf, habs2_max(habs2_max(0u, q.x), q.y));
         *reinterpret_cast<uint2*>(p + j) = q;
         if (o.planes == 2) {
           uint2 r;

@@ -304,14 +304,25 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
           Y[j] = tc0 + (2 * rem) / C;
           ch[j] = 2 * rem - ((2 * rem) / C) * C;
           ok[j] = e < nvec && X[j] < FH && Y[j] < F;
-          if (inplace && ok[j]) {  // untouched elements are neither read nor written
-            bool any = false;
-            for (int k = 0; k < cnt; ++k) any = any || ((unsigned)(X[j] - s_x[k]) < (unsigned)S && (unsigned)(Y[j] - s_y[k]) < (unsigned)S);
-            ok[j] = any;
-          }
           idx[j] = ((long long)X[j] * F + Y[j]) * C + ch[j];
           acc[j].x = (T)0;
           acc[j].y = (T)0;
+        }
+        if (inplace) {  // untouched elements are neither read nor written (kept out of the load loop below, so that its AX_U
+                        // independent loads are still issued back to back)
+          bool any[AX_U];
+#pragma unroll
+          for (int j = 0; j < AX_U; ++j) any[j] = false;
+          for (int k = 0; k < cnt; ++k) {
+            const int sx = s_x[k], sy = s_y[k];
+#pragma unroll
+            for (int j = 0; j < AX_U; ++j) any[j] = any[j] || ((unsigned)(X[j] - sx) < (unsigned)S && (unsigned)(Y[j] - sy) < (unsigned)S);
+          }
+#pragma unroll
+          for (int j = 0; j < AX_U; ++j) ok[j] = ok[j] && any[j];
+        }
+#pragma unroll
+        for (int j = 0; j < AX_U; ++j) {
           if (ok[j]) {
             if (!first) acc[j] = *reinterpret_cast<const V2*>(out + idx[j]);
             else if (in) acc[j] = *reinterpret_cast<const V2*>(in + idx[j]);

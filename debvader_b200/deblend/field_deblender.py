@@ -81,6 +81,11 @@ class DeblendField:
     # ------------------------------------------------------------------------------------------
     def _positions(self, res_deblend):
         """x_pos / y_pos of field_deblender.py:83-90 (float64) and whether every one is integer-valued."""
+        pc = getattr(self, "_pos_cache", None)
+        if pc is not None and pc[0] is res_deblend:
+            px, ix = _fieldops.positions(pc[1], 0.0)
+            py, iy = _fieldops.positions(pc[2], 0.0)
+            return px, py, ix and iy
         dx = np.asarray(res_deblend["galaxy_distances_to_center_x"], dtype=np.float64)
         dy = np.asarray(res_deblend["galaxy_distances_to_center_y"], dtype=np.float64)
         sh = np.array([np.asarray(s, dtype=np.float64) for s in res_deblend["shifts"]]).reshape(-1, 2)
@@ -265,30 +270,45 @@ class DeblendField:
                 epistemic[i] = zero
             epistemic_norm = np.zeros(n)
 
+        # everything above only ENQUEUED device work; the record columns are built on the host while the GPU runs, and the
+        # one value the host needs from the device (the centre-window MSE behind passed_cuts) is fetched last
         lo, hi = int(S / 2) - 5, int(S / 2) + 5
-        mse_center = _fieldops.center_mse(sel.contiguous(), mean_dev.contiguous(), lo, hi).cpu().numpy() if n else np.zeros(0)
-        passed_cuts = [bool(v) for v in ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))]
-
-        gx = [galaxy_distances_to_center[k][0] for k in list_idx]
-        gy = [galaxy_distances_to_center[k][1] for k in list_idx]
+        mse_dev = _fieldops.center_mse(sel.contiguous(), mean_dev.contiguous(), lo, hi) if n else None
+        gdc = galaxy_distances_to_center
+        if isinstance(gdc, np.ndarray) and gdc.ndim == 2:
+            li = np.asarray(list_idx, dtype=np.int64)
+            gx, gy = gdc[li, 0], gdc[li, 1]
+        else:
+            gx = [gdc[k][0] for k in list_idx]
+            gy = [gdc[k][1] for k in list_idx]
+        col_cut = _records.stamp_column(sel)
+        col_mean = _records.stamp_column(mean_dev)
+        col_std = _records.stamp_column(std_dev)
         if optimise_positions:
             # field_deblender.py:337-352: bounded least-squares fit of a sub-pixel shift per galaxy on the r band
             # (the reference pads with self.field_size; it only works when field_image has that size too)
             from ..deblend_cutout.optimization import fit_positions
 
             r_band = mean_dev[:, :, :, 2].contiguous()
-            fitted = fit_positions(field_dev, r_band, np.array([[galaxy_distances_to_center[k][0], galaxy_distances_to_center[k][1]] for k in list_idx], dtype=np.float64))
-            shifts = [np.array(s) for s in fitted]
+            fitted = fit_positions(field_dev, r_band, np.array([[gdc[k][0], gdc[k][1]] for k in list_idx], dtype=np.float64))
+            shifts = np.empty(n, dtype=object)
+            for i in range(n):
+                shifts[i] = np.array(fitted[i])
         else:
-            shifts = [np.array([0, 0]) for _ in range(n)]
+            shifts = np.empty(n, dtype=object)
+            zero_shift = np.array([0, 0])
+            for i in range(n):
+                shifts[i] = zero_shift.copy() if n <= 64 else zero_shift  # large fields share one (0, 0)
+        mse_center = mse_dev.cpu().numpy() if n else np.zeros(0)
+        passed_cuts = ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))
 
         self.nb_of_detected_objects += [n_detected]
         self.nb_of_deblended_galaxies += [n_deblended]
 
         cols = {
-            "cutout_images": _records.stamp_column(sel),
-            "output_images_mean": _records.stamp_column(mean_dev),
-            "output_images_stddev": _records.stamp_column(std_dev),
+            "cutout_images": col_cut,
+            "output_images_mean": col_mean,
+            "output_images_stddev": col_std,
             "shifts": shifts,
             "list_idx": np.asarray(list_idx, dtype=np.int64),
             "galaxy_distances_to_center_x": gx,
@@ -297,6 +317,8 @@ class DeblendField:
             "passed_cuts": np.asarray(passed_cuts, dtype=bool),
         }
         self.res_deblend = _records.make_records(cols)
+        if not optimise_positions:  # integer shifts (0, 0): positions known without walking the records again
+            self._pos_cache = (self.res_deblend, np.asarray(gx, dtype=np.float64), np.asarray(gy, dtype=np.float64))
         if tp is not None:
             self._tile_state = (self.res_deblend, tp, mine)
         return self.res_deblend

@@ -89,6 +89,18 @@ class Deblender:
         self._calls += 1
         return (self._seed * 0x9E3779B97F4A7C15 + self._calls) & (2**64 - 1)
 
+    def fp16_overflow(self, reset: bool = False) -> bool:
+        """True if an activation of the fp16 tail of precision="mixed" has saturated at +-65504 in a call that has
+        completed (sticky).  Such a result is outside the 1e-3 tolerance: use precision="bf16x3" (fp32 range)."""
+        return bool(_ffi.lib().dbv_fp16_overflow(self._ctx, int(bool(reset))))
+
+    def _raise_on_overflow(self):
+        if self.precision == "mixed" and self.fp16_overflow(reset=True):
+            raise FloatingPointError(
+                'precision="mixed" keeps the inputs of the four large-image decoder layers in fp16 and one of them left the fp16 range '
+                "(+-65504) in an earlier call: those results are not within the 1e-3 tolerance. Use precision=\"bf16x3\" (fp32 range, ~16 % slower)."
+            )
+
     @property
     def launches(self) -> int:
         return int(_ffi.lib().dbv_launch_count(self._ctx))
@@ -139,6 +151,7 @@ class Deblender:
         Distribution.sample); pass ``eps=`` for a given draw or ``sample=False`` for z = loc
         (``net.sample = False`` changes the default of the instance)."""
         sample = self.sample if sample is None else sample
+        self._raise_on_overflow()  # of an EARLIER call (this one is asynchronous); synchronous callers use fp16_overflow()
         x = self._check_x(_as_device_f32(x, self.device))
         B = x.shape[0]
         if eps is not None:
@@ -229,6 +242,7 @@ class Deblender:
                                         self._next_seed(seed), int(bool(sample)), vp(mean), vp(std), None,
                                         _ffi.ptr(mean_dev), _ffi.ptr(std_dev))
         )
+        self._raise_on_overflow()  # dbv_deblend_host is synchronous: this call's own flag
         if resident:
             return mean, mean_dev, std_dev
         return mean, std

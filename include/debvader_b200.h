@@ -205,6 +205,13 @@ int64_t dbv_mse_scratch_bytes(void);
 int dbv_sqdiff_sum_rect(const void* a_dev, const void* b_dev, int dtype, int64_t rows, int64_t cols, int64_t pitch_a,
                         int64_t pitch_b, double* out_dev, void* scratch_dev, int64_t scratch_bytes, void* stream);
 
+/* DBV_PREC_MIXED stores the activations entering convT6, convT7, convT8 and the head in fp16 (range +-65504).  The
+ * epilogues that write them watch for saturation and set a sticky host-mapped flag: returns 1 if any activation of a
+ * call completed so far left the fp16 range (its result is then NOT within the 1e-3 tolerance: use DBV_PREC_BF16X3,
+ * which has the fp32 range), 0 otherwise; reset != 0 clears the flag.  Valid after the caller has synchronised the
+ * stream the call was enqueued on.  Always 0 for the other precisions. */
+int dbv_fp16_overflow(dbv_ctx* ctx, int reset);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */
 int64_t dbv_launch_count(const dbv_ctx* ctx);
