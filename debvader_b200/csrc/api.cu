@@ -801,7 +801,10 @@ static int build_halo_layer(dbv_ctx* c, int li) {
         if (!dup) cand.push_back({r, nbuf, U});
       }
   }
-  const long long Bt = std::min<long long>(c->chunk, 592);  // 4 stamps per SM: enough bands per CTA for a stable ranking
+  // 16 stamps per SM: enough bands per CTA for a stable ranking AND a working set (input + output of the layer) well beyond
+  // the 126 MB L2, as in a full 4096-stamp pass — with 592 stamps the large-image layers ran out of L2 and the ranking
+  // did not carry over (round 2: convT7 flipped between two plans 10 % apart at full size)
+  const long long Bt = std::min<long long>(c->chunk, 2368);
   struct TunerRes {  // released on every return path
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float *hm = nullptr, *hs = nullptr;

@@ -228,10 +228,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
       }
       uint32_t u = 0;
       int b = b_first, y0 = (int)yb0 * L.R;
-      float4 pf[NV / 4];      // PReLU slopes prefetched for this warp's next item
-      bool pf_valid = false;  // ... valid only if that item's pixel was in bounds (per thread)
-  #pragma unroll
-      for (int j = 0; j < NV / 4; ++j) pf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       [[maybe_unused]] const long long ek0 = HCLK();
       [[maybe_unused]] long long ek_tfull = 0, ek_ld = 0, ek_alpha = 0, ek_math = 0, ek_items = 0, ek_rel = 0;
       for (long long g = g0; g < g1; ++g) {
@@ -240,9 +236,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
           bool waited = false;
           // items of this unit (host-made table: accumulator column, class, tile, channel chunk); group g takes items g, g + G, ...
           const int it0 = k ? (int)L.unit_item_end[k - 1] : 0, it1 = (int)L.unit_item_end[k];
-          // PReLU slopes are fetched ONE ITEM AHEAD (they come from L2: the shared-memory carve-out leaves little L1, and
-          // their ~700-cycle latency used to be exposed in every item's math): al holds the current item's slopes, the
-          // next item's are requested right after the current ones have been consumed into registers
   #pragma unroll 1
           for (int item = it0 + grp; item < it1; item += HALO_EPI_GROUPS) {
             const uint32_t it = L.items[item];
@@ -253,46 +246,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
             const int oy = L.cls[c].oy0 + L.cls[c].osy * sy, ox = L.cls[c].ox0 + L.cls[c].osx * sx;
             const uint32_t tcol = lane_base + slot * SW + (it & 511u);  // first column of this item's NV channels
             const int c0 = q * NV;
-            [[maybe_unused]] const long long eka = HCLK();
+            // PReLU slopes of this thread's pixel ([C/4][pixels][4] layout: 32-bit element offsets, one 16-byte load per 4 channels),
+            // requested before the accumulator wait
             float4 al[NV / 4];
-            if (has_alpha) {
-              if (!pf_valid && ok) {  // first item of this warp (or after an item without a prefetch): load now
-                const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
+            [[maybe_unused]] const long long eka = HCLK();
+            if (has_alpha && ok) {
+              const uint32_t off = (uint32_t)(c0 >> 2) * npix + (uint32_t)(oy * L.o.OW + ox);
   #pragma unroll
-                for (int j = 0; j < NV / 4; ++j) pf[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
-              }
-  #pragma unroll
-              for (int j = 0; j < NV / 4; ++j) al[j] = pf[j];
-              // the next item this warp will take: the next one of this unit, else the first one of the next unit (same
-              // band or, at the band's end, the same table position of the next band: b / y0 advance as in the loop below)
-              int nitem = item + HALO_EPI_GROUPS;
-              int ny0 = y0;
-              bool more = true;
-              if (nitem >= it1) {
-                int nk = k + 1;
-                if (nk >= units_per_band) {
-                  nk = 0;
-                  more = g + 1 < g1;
-                  ny0 = (b + 1 == (int)L.B) ? y0 + L.R : y0;
-                }
-                // (a group may have no item in a unit: look no further than the next unit, pf_valid says whether it matched)
-                nitem = (nk ? (int)L.unit_item_end[nk - 1] : 0) + grp;
-                more = more && nitem < (int)L.unit_item_end[nk];
-              }
-              pf_valid = false;
-              if (more) {
-                const uint32_t nit = L.items[nitem];
-                const int nc = (int)((nit >> 9) & 3u), nm = (int)((nit >> 11) & 31u), nq = (int)((nit >> 16) & 7u);
-                const int np_ = 128 * nm + row;
-                const int nly = (int)__umulhi((uint32_t)np_, L.magic_wp), nsx = np_ - nly * L.WP, nsy = ny0 + nly;
-                if (nly < L.R && nsx < L.W && nsy < L.H) {
-                  const int noy = L.cls[nc].oy0 + L.cls[nc].osy * nsy, nox = L.cls[nc].ox0 + L.cls[nc].osx * nsx;
-                  const uint32_t off = (uint32_t)((nq * NV) >> 2) * npix + (uint32_t)(noy * L.o.OW + nox);
-  #pragma unroll
-                  for (int j = 0; j < NV / 4; ++j) pf[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
-                  pf_valid = true;
-                }
-              }
+              for (int j = 0; j < NV / 4; ++j) al[j] = __ldg(alpha4 + off + (uint32_t)j * npix);
             }
             [[maybe_unused]] const long long ekb = HCLK();
             if (!waited) {
@@ -393,16 +354,6 @@ static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
   });
   if (attr_err != cudaSuccess)
     return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_halo_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
-  // Shared memory and L1 share one 256 KB array per SM: ask for no more carve-out than this plan's halo ring + weights need
-  // (one CTA per SM), so that the rest serves as L1 for the PReLU slopes of the band row the CTA works on (the same for every
-  // stamp) and for the output stores.  Several layers share a kernel instance with different plans: set per launch.
-  {
-    int pct = (int)((L.smem_bytes + 1024ll) * 100 / (228 * 1024)) + 1;  // + 1 KB the runtime reserves per CTA
-    if (pct > 100) pct = 100;
-    if (dbv_env("DBV_HALO_CARVEOUT")) pct = atoi(dbv_env("DBV_HALO_CARVEOUT"));
-    cudaError_t e = cudaFuncSetAttribute(tc_halo_kernel<CBK, NT, NOSWZ>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    if (e != cudaSuccess) return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(carveout %d%%): %s", pct, cudaGetErrorString(e));
-  }
   const long long grid = L.total_bands < max_ctas ? L.total_bands : max_ctas;
   if (grid <= 0) return DBV_OK;
   launch_pdl(tc_halo_kernel<CBK, NT, NOSWZ>, (unsigned)grid, HALO_THREADS, L.smem_bytes, st, L);

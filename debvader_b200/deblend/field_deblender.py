@@ -296,9 +296,8 @@ class DeblendField:
                 shifts[i] = np.array(fitted[i])
         else:
             shifts = np.empty(n, dtype=object)
-            zero_shift = np.array([0, 0])
-            for i in range(n):
-                shifts[i] = zero_shift.copy() if n <= 64 else zero_shift  # large fields share one (0, 0)
+            for i, row in enumerate(np.zeros((n, 2), dtype=np.int64)):  # np.array([0, 0]) per galaxy (field_deblender.py:354)
+                shifts[i] = row
         mse_center = mse_dev.cpu().numpy() if n else np.zeros(0)
         passed_cuts = ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))
 

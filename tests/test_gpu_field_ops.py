@@ -378,3 +378,14 @@ def test_sqdiff_sum_rect(ops):
         want = float(np.sum((a[0, r0:r1, c0:c1] - b[0, r0:r1, c0:c1]) ** 2))
         got = float(ops.sqdiff_sum_rect(ta, tb, r0, r1, c0, c1).item())
         assert abs(got - want) <= 1e-13 * want
+
+
+def test_reference_test_file_verbatim_on_the_gpu():
+    """tests/test_extraction.py of the reference, executed verbatim (read from the reference tree, never copied) against the
+    drop-in package on the GPU.  The GPU box has no reference tree: there the restated cases above cover it."""
+    path = "/root/reference/tests/test_extraction.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this machine")
+    ns = {"__name__": "reference_test_extraction"}
+    exec(compile(open(path).read(), path, "exec"), ns)
+    ns["test_cutouts_border"]()

@@ -157,8 +157,20 @@ def test_fp32_tiled_kernel_is_bit_identical_to_the_gather_kernel():
 
 
 # ---- tensor-core tiers ---------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol_layer,tol_out", [("mixed", 2e-3, 1e-3), ("fp16x3", 2e-4, 1e-4), ("bf16x3", 2e-4, 1e-3), ("bf16", 4e-2, 5e-2)])
-def test_tensor_core_path(wts, data, ref64, precision, tol_layer, tol_out):
+# per-layer tolerances (max abs error / max abs value of the layer's activation, fp64 oracle): measured on B200 x ~2.5.
+# bf16x3 / fp16x3: 6e-6 (conv1) growing to 6e-5 (convT8); bf16: 3e-3 .. 1.1e-2; mixed = bf16x3 up to convT5, then the
+# single-plane fp16 inputs of convT6 / convT7 / convT8 add ~2e-4 each.
+TAIL = ("dec_convT6", "dec_convT7", "dec_convT8")
+LAYER_TOL = {
+    "bf16x3": lambda n: 1.5e-4,
+    "fp16x3": lambda n: 1.5e-4,
+    "mixed": lambda n: 1.0e-3 if n in TAIL else 1.5e-4,
+    "bf16": lambda n: 2.5e-2,
+}
+
+
+@pytest.mark.parametrize("precision,tol_out", [("mixed", 1e-3), ("fp16x3", 1e-4), ("bf16x3", 1e-3), ("bf16", 5e-2)])
+def test_tensor_core_path(wts, data, ref64, precision, tol_out):
     x, eps = data
     net = _net(wts, precision, chunk=64)
     dist, z = net(x, eps=eps, return_z=True)
@@ -173,8 +185,94 @@ def test_tensor_core_path(wts, data, ref64, precision, tol_layer, tol_out):
     e_std = float((dist.stddev().tensor.double().cpu() - ref64["stddev"]).abs().max()) / peak
     print(f"{precision}: mean err/peak={e_mean:.3e} std err/peak={e_std:.3e} z rel err={_relerr(z, ref64['z']):.3e}")
     for name, v in worst.items():
-        assert v < tol_layer * 25, f"{precision} {name}: {v}"  # gross-error guard (layout / tap bugs give O(1))
+        assert v < LAYER_TOL[precision](name), f"{precision} {name}: {v}"
     assert e_mean <= tol_out and e_std <= tol_out
+    assert not net.fp16_overflow()
+    net.close()
+
+
+def _scaled(w, gamma=1.0, kernels=1.0):
+    out = dict(w)
+    k = "layer_with_weights-0/layer_with_weights-0/gamma"
+    out[k] = w[k] * np.float32(gamma)
+    if kernels != 1.0:
+        out = {kk: (v * np.float32(kernels) if kk.endswith("kernel") else v) for kk, v in out.items()}
+    return out
+
+
+@pytest.mark.parametrize("case", ["gamma_x0.1", "gamma_x10", "gamma_x100", "stamp_peak_1e4", "kernels_x0.5"])
+def test_mixed_holds_1e3_under_adversarial_scales(wts, data, case):
+    """the default tier stores the inputs of convT6..head in fp16.  Its 1e-3 bound is relative, so it
+    must survive other dynamic ranges than the random-init one: BatchNorm gains x0.1 / x10 / x100 (activations up to ~150),
+    a stamp with peak flux 1e4 (activations up to ~2700), kernels x0.5 (activations ~0.1)."""
+    x, eps = data
+    x, eps = x[:12].copy(), eps[:12]
+    w = wts
+    if case.startswith("gamma_x"):
+        w = _scaled(wts, gamma=float(case.split("x")[1]))
+    elif case == "stamp_peak_1e4":
+        x[0] *= np.float32(1e4 / np.abs(x[0]).max())
+    elif case == "kernels_x0.5":
+        w = _scaled(wts, kernels=0.5)
+    o = TorchOracle(w, dtype=torch.float64).forward(x.astype(np.float64), eps.astype(np.float64))
+    net = _net(w, "mixed", chunk=64)
+    d = net(x, eps=eps)
+    torch.cuda.synchronize()
+    # per stamp: error relative to that stamp's own peak flux (the peak-1e4 stamp must not hide the others)
+    err = (d.mean().tensor.double().cpu() - o["mean"]).abs().amax(dim=(1, 2, 3)) / o["mean"].abs().amax(dim=(1, 2, 3))
+    print(case, "max err/peak per stamp:", float(err.max()))
+    assert float(err.max()) <= 1e-3
+    assert not net.fp16_overflow()
+    net.close()
+
+
+def test_mixed_fails_loudly_when_the_fp16_tail_saturates(wts, data):
+    """kernels x2 blows the decoder activations up to ~6e5 (> 65504): the fp16 tail of `mixed` saturates.  The library
+    must say so (sticky flag -> FloatingPointError) instead of returning a wrong image; bf16x3 (fp32 range) still holds 1e-3."""
+    x, eps = data
+    x, eps = x[:6], eps[:6]
+    w = _scaled(wts, kernels=2.0)
+    o = TorchOracle(w, dtype=torch.float64).forward(x.astype(np.float64), eps.astype(np.float64))
+    net = _net(w, "mixed", chunk=64)
+    net(x, eps=eps)
+    torch.cuda.synchronize()
+    assert net.fp16_overflow()
+    with pytest.raises(FloatingPointError, match="bf16x3"):
+        net(x, eps=eps)  # the next call reports the earlier overflow
+    assert not net.fp16_overflow()  # raising cleared it
+    from debvader_b200.deblend_cutout.deblender import deblend
+
+    with pytest.raises(FloatingPointError):
+        deblend(net, x, eps=eps)  # the synchronous host path reports its own call
+    net.close()
+    safe = _net(w, "bf16x3", chunk=64)
+    d = safe(x, eps=eps)
+    peak = float(o["mean"].abs().max())
+    assert float((d.mean().tensor.double().cpu() - o["mean"]).abs().max()) / peak <= 1e-3
+    assert not safe.fp16_overflow()
+    safe.close()
+
+
+def test_deblend_normalise_branch(wts, data):
+    """deblend(net, images, normalise=True) (deblender.py:20-24, intended semantics: tanh(arcsinh(x)) in, sinh(arctanh(mean)) out)."""
+    from debvader_b200.deblend_cutout.deblender import deblend
+    from debvader_b200.normalize.normalize import denormalize_non_linear, normalize_non_linear
+
+    x, eps = data
+    x, eps = x[:5], eps[:5]
+    net = _net(wts, "bf16x3", chunk=64)
+    mean, dist = deblend(net, x.astype(np.float64), normalise=True, eps=eps)
+    xn = normalize_non_linear(x.astype(np.float64))
+    assert float(np.abs(xn).max()) < 1.0
+    want, _ = deblend(net, xn, eps=eps)
+    np.testing.assert_array_equal(mean, denormalize_non_linear(want))
+    np.testing.assert_array_equal(dist.mean().numpy(), want)  # the distribution stays in the normalised space
+    o = TorchOracle(wts, dtype=torch.float64).forward(xn, eps.astype(np.float64))
+    peak = float(o["mean"].abs().max())
+    assert float(np.abs(want - o["mean"].numpy()).max()) <= 1e-3 * peak
+    # a CUDA tensor input takes the same branch
+    m2, _ = deblend(net, torch.from_numpy(x).cuda(), normalise=True, eps=eps)
+    np.testing.assert_allclose(m2, mean, rtol=0, atol=1e-6)
     net.close()
 
 

@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
@@ -70,3 +71,24 @@ def test_positions_and_spline_anchors():
     # window anchor of the sub-pixel placement: origin - P - 1 + floor(pos), floor toward -inf
     a = _fieldops._anchor(np.array([100, 100, 100]), np.array([0.0, -0.25, 7.75]), 28)
     assert a.dtype == np.int32 and list(a) == [71, 70, 78]
+
+
+def test_reference_test_extraction_runs_verbatim(monkeypatch):
+    """The reference's ONLY test (tests/test_extraction.py:6-62), executed verbatim — the file is read from the reference tree,
+    never copied — against the drop-in ``debvader.extract.extraction`` with the oracle-backed CPU stand-ins of the device
+    operators (the same four cases run through the CUDA kernels in tests/test_gpu_field_ops.py::
+    test_reference_unit_test_cases_through_the_drop_in_path and, when the reference tree is present next to a GPU, in
+    test_gpu_field_ops.py::test_reference_test_file_verbatim_on_the_gpu)."""
+    import os
+    import sys
+
+    path = "/root/reference/tests/test_extraction.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present (it never is on the GPU box)")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops
+
+    cpu_ops.install(monkeypatch)
+    ns = {"__name__": "reference_test_extraction"}
+    exec(compile(open(path).read(), path, "exec"), ns)
+    ns["test_cutouts_border"]()
