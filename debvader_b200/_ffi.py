@@ -54,6 +54,7 @@ def _declare(lib):
         "dbv_spline_place": (C.c_int, [c_vp, C.c_int, c_i64, C.c_int, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
         "dbv_band_sumsq": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp]),
         "dbv_shift_objective": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, c_vp, c_vp]),
+        "dbv_shift_objective_batch": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp]),
         "dbv_position_objective": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                              C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "dbv_center_mse": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),

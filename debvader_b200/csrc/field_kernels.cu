@@ -1042,6 +1042,32 @@ __global__ void __launch_bounds__(256) shift_objective_kernel(const double* __re
   if (threadIdx.x == 0) out[0] = (sumsq_field + s[0]) / ((double)F * (double)F);
 }
 
+// The same for a batch: item i = placed window T[i] (E x E) at (ax[i], ay[i]); one CTA per item, fixed order.
+__global__ void __launch_bounds__(256) shift_objective_batch_kernel(const double* __restrict__ field, long long F, int C, int band,
+                                                                    const double* __restrict__ T, int E, const int32_t* __restrict__ ax,
+                                                                    const int32_t* __restrict__ ay, double sumsq_field,
+                                                                    double* __restrict__ out) {
+  __shared__ double s[256];
+  const long long i = blockIdx.x;
+  const double* Ti = T + i * (long long)E * E;
+  const long long x0 = ax[i], y0 = ay[i];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < E * E; e += 256) {
+    const int a = e / E, b = e - a * E;
+    const long long X = x0 + a, Y = y0 + b;
+    if (X < 0 || X >= F || Y < 0 || Y >= F) continue;
+    const double t = Ti[e], v = field[(X * F + Y) * C + band];
+    acc += t * t - 2.0 * v * t;
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = (sumsq_field + s[0]) / ((double)F * (double)F);
+}
+
 // sum of squares of one band of the field (two deterministic passes through `partial`)
 __global__ void __launch_bounds__(256) band_sumsq_kernel(const double* __restrict__ field, long long npix, int C, int band,
                                                          double* __restrict__ partial) {
@@ -1176,6 +1202,17 @@ extern "C" int dbv_shift_objective(const double* field, int64_t F, int C, int ba
   DBV_REQUIRE(field && placed && out, "dbv_shift_objective: null pointer");
   DBV_REQUIRE(F > 0 && C > 0 && band >= 0 && band < C && E > 0, "dbv_shift_objective: bad sizes");
   shift_objective_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(field, F, C, band, placed, E, ax, ay, sumsq_field, out);
+  DBV_LAUNCH_CHECK();
+  return DBV_OK;
+}
+
+extern "C" int dbv_shift_objective_batch(const double* field, int64_t F, int C, int band, const double* placed, int E,
+                                         const int32_t* ax, const int32_t* ay, int64_t M, double sumsq_field, double* out, void* stream) {
+  DBV_REQUIRE(M >= 0 && M < (1ll << 31), "dbv_shift_objective_batch: bad batch size");
+  if (M == 0) return DBV_OK;
+  DBV_REQUIRE(field && placed && ax && ay && out, "dbv_shift_objective_batch: null pointer");
+  DBV_REQUIRE(F > 0 && C > 0 && band >= 0 && band < C && E > 0, "dbv_shift_objective_batch: bad sizes");
+  shift_objective_batch_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(field, F, C, band, placed, E, ax, ay, sumsq_field, out);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }

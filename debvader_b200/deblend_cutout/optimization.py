@@ -3,12 +3,12 @@
 The reference minimises, with scipy.optimize.least_squares (bounds +-3 px, 2-point Jacobian), the scalar
 ``fun(x) = mean((r_band_field - ndimage.shift(net_output, x))**2)`` where ``net_output`` is the padded
 r-band prediction already shifted to the detected position — every evaluation is a cubic-spline shift of
-the WHOLE field-sized canvas (optimization.py:21-46).  Here the optimiser is the same scipy call (host
-control flow, a dependency the reference already has), and every evaluation of ``fun`` runs on the
-device on the only pixels where the shifted prediction is not negligible
-(``dbv_position_objective``: two placed windows + one fixed-order reduction; the field's own sum of
-squares is computed once).  fp64, same arithmetic as scipy's spline code to ~1e-15 relative, so the
-optimiser follows the same path up to the noise of its own finite differences.
+the WHOLE field-sized canvas (optimization.py:21-46), one galaxy after the other.  Here every evaluation of ``fun``
+runs on the device on the only pixels where the shifted prediction is not negligible (two placed windows + one
+fixed-order reduction; the field's own sum of squares is computed once; fp64, same arithmetic as scipy's spline
+code to ~1e-15 relative), and ALL galaxies of a field are fitted at once (``fit_positions``: a batched bounded
+Levenberg-Marquardt iteration, ~10 batched objective evaluations in total instead of ~40 per galaxy).
+``fit_position`` keeps the reference's own scipy call around the device objective for one galaxy (cross-check).
 """
 import ctypes as C
 
@@ -66,10 +66,116 @@ def fit_position(fb: FieldBand, stamp_band_dev, galaxy_distance_to_center, margi
     return opt.x[0], opt.x[1]
 
 
-def fit_positions(field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN):
-    """position_optimization for all galaxies of a field: r_band_batch (N,S,S) CUDA, centres (N,2) -> (N,2) shifts."""
-    fb = FieldBand(field_dev)
-    return np.array([fit_position(fb, r_band_batch[i].contiguous(), centres[i], margin) for i in range(len(centres))], dtype=np.float64).reshape(-1, 2)
+class BatchObjective:
+    """fun(x) of optimization.py:21-33 for ALL galaxies of a field at once: the r-band predictions are placed at their
+    detected positions once (the reference's first ndimage.shift, optimization.py:41-44); ``__call__(X)`` then evaluates the
+    objective of every galaxy at its own trial shift X[k] with one batched second placement + one batched reduction."""
+
+    def __init__(self, field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN):
+        self.fb = FieldBand(field_dev)
+        self.margin = int(margin)
+        r = r_band_batch.contiguous()
+        self.n, S = int(r.shape[0]), int(r.shape[1])
+        c = np.asarray(centres, dtype=np.float64).reshape(-1, 2)
+        placed1, self.a1x, self.a1y = _fieldops.spline_place(r.reshape(self.n, S, S, 1), c[:, 0], c[:, 1], self.fb.F, self.margin)
+        self.E1 = int(placed1.shape[-1])
+        self.data = placed1.reshape(self.n, self.E1, self.E1, 1)
+        self.nfev = 0
+
+    def __call__(self, X, rows=None):
+        """X (m,2) trial shifts for galaxies `rows` (default: all, m = n) -> (m,) float64 ndarray."""
+        X = np.asarray(X, dtype=np.float64).reshape(-1, 2)
+        data = self.data if rows is None else self.data[torch.as_tensor(rows, device=self.data.device, dtype=torch.long)]
+        ox = self.a1x if rows is None else self.a1x[rows]
+        oy = self.a1y if rows is None else self.a1y[rows]
+        placed2, ax, ay = _fieldops.spline_place(data, X[:, 0], X[:, 1], self.fb.F, self.margin, origin_x=ox, origin_y=oy)
+        m, E2 = int(placed2.shape[0]), int(placed2.shape[-1])
+        dev = placed2.device
+        a = torch.from_numpy(np.stack([np.asarray(ax, dtype=np.int32), np.asarray(ay, dtype=np.int32)])).to(dev)
+        out = torch.empty((m,), device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _ffi.check(_ffi.lib().dbv_shift_objective_batch(_ffi.ptr(self.fb.field), self.fb.F, self.fb.C, self.fb.band, _ffi.ptr(placed2), E2,
+                                                            _ffi.ptr(a[0]), _ffi.ptr(a[1]), m, self.fb.sumsq, _ffi.ptr(out), _ffi.stream_ptr()))
+        self.nfev += m
+        return out.cpu().numpy()
+
+
+def fit_positions(field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN, bound=3.0, h=1e-3, max_iter=40, xtol=1e-7,
+                  return_info=False):
+    """position_optimization (optimization.py:6-52) for all galaxies of a field, batched on the device.
+
+    r_band_batch (N,S,S) CUDA (the r band of the predictions), centres (N,2) detected offsets -> (N,2) fitted shifts.
+    The reference minimises fun(x) per galaxy with scipy's bounded trust-region least squares from x = (0, 0) inside
+    [-3, 3]^2 (a local minimum reached by descent).  Here every galaxy runs the same kind of descent simultaneously: a
+    bounded Levenberg-Marquardt / Newton iteration on fun itself, with gradient and Hessian from central differences of the
+    device objective (6 evaluations per iteration, all galaxies and all 6 points in ONE batched placement), an active set
+    for the bounds, step acceptance on decrease (damping up on rejection), stopping per galaxy when the step is below
+    `xtol` px.  fun is a smooth piecewise polynomial of the shift, so this converges to the minimiser the reference's
+    optimiser approaches (tests: within 1e-3 px of the reference's own results)."""
+    obj = BatchObjective(field_dev, r_band_batch, centres, margin)
+    n = obj.n
+    x = np.zeros((n, 2))
+    if n == 0:
+        return (x, {"nfev": 0, "iterations": 0}) if return_info else x
+    lam = np.full(n, 1e-3)
+    active = np.ones(n, dtype=bool)
+    offs = np.array([[0, 0], [h, 0], [-h, 0], [0, h], [0, -h], [h, h]])
+    f_cur = None
+    it = 0
+    for it in range(1, max_iter + 1):
+        rows = np.nonzero(active)[0]
+        if rows.size == 0:
+            break
+        m = rows.size
+        X = (x[rows, None, :] + offs[None, :, :]).reshape(-1, 2)
+        f = obj(X, np.repeat(rows, 6)).reshape(m, 6)
+        f0, fpx, fmx, fpy, fmy, fpp = (f[:, k] for k in range(6))
+        g = np.stack([(fpx - fmx) / (2 * h), (fpy - fmy) / (2 * h)], axis=1)
+        hxx = (fpx - 2 * f0 + fmx) / h**2
+        hyy = (fpy - 2 * f0 + fmy) / h**2
+        hxy = (fpp - fpx - fpy + f0) / h**2
+        xr = x[rows]
+        # active set: a coordinate sitting on a bound whose gradient pushes outward stays there
+        at_lo = (xr <= -bound) & (g > 0)
+        at_hi = (xr >= bound) & (g < 0)
+        fixed = at_lo | at_hi
+        scale = np.maximum(np.abs(hxx) + np.abs(hyy), 1e-300)
+        step = np.zeros((m, 2))
+        accepted = np.zeros(m, dtype=bool)
+        lam_r = lam[rows].copy()
+        for _try in range(8):
+            todo = ~accepted
+            if not todo.any():
+                break
+            d = lam_r * scale
+            a11, a22, a12 = hxx + d, hyy + d, hxy.copy()
+            # fixed coordinates: decouple (unit diagonal, zero gradient)
+            gg = np.where(fixed, 0.0, g)
+            a11 = np.where(fixed[:, 0], 1.0, a11)
+            a22 = np.where(fixed[:, 1], 1.0, a22)
+            a12 = np.where(fixed.any(axis=1), 0.0, a12)
+            det = a11 * a22 - a12 * a12
+            pd = (a11 > 0) & (det > 0)
+            px = np.where(pd, -(a22 * gg[:, 0] - a12 * gg[:, 1]) / np.where(pd, det, 1.0), -gg[:, 0] / (np.abs(hxx) + d + 1e-300))
+            py = np.where(pd, -(-a12 * gg[:, 0] + a11 * gg[:, 1]) / np.where(pd, det, 1.0), -gg[:, 1] / (np.abs(hyy) + d + 1e-300))
+            p = np.stack([px, py], axis=1)
+            p = np.clip(p, -1.0, 1.0)  # at most one pixel per iteration
+            xn = np.clip(xr + p, -bound, bound)
+            tr = np.nonzero(todo)[0]
+            fn = obj(xn[tr], rows[tr])
+            ok = fn <= f0[tr] + 1e-15 * np.abs(f0[tr])
+            good = tr[ok]
+            step[good] = xn[good] - xr[good]
+            accepted[good] = True
+            lam_r[good] = np.maximum(lam_r[good] / 10, 1e-9)
+            lam_r[tr[~ok]] *= 10
+        x[rows] = xr + step
+        lam[rows] = lam_r
+        done = (np.abs(step).max(axis=1) < xtol) | ~accepted  # no acceptable step left: at the minimum to rounding
+        active[rows[done]] = False
+    if return_info:
+        return x, {"nfev": obj.nfev, "iterations": it, "nfev_per_galaxy": obj.nfev / max(n, 1)}
+    return x
 
 
 def position_optimization(field_image, output_image_mean_padded, galaxy_distance_to_center, cutout_size=59):
@@ -78,7 +184,7 @@ def position_optimization(field_image, output_image_mean_padded, galaxy_distance
     field = np.asarray(field_image, dtype=np.float64)
     F = field.shape[0]
     dev_field = _fieldops.to_device_field(field[None])
-    fb = FieldBand(dev_field)
     off = _fieldops.subtract_offset(F, cutout_size)
     block = np.ascontiguousarray(np.asarray(output_image_mean_padded)[off : off + cutout_size, off : off + cutout_size, R_BAND], dtype=np.float64)
-    return fit_position(fb, torch.from_numpy(block).to(dev_field.device), galaxy_distance_to_center)
+    x = fit_positions(dev_field, torch.from_numpy(block[None]).to(dev_field.device), np.asarray(galaxy_distance_to_center, dtype=np.float64)[None, :2])
+    return float(x[0, 0]), float(x[0, 1])

@@ -32,7 +32,7 @@ extern "C" {
 #define DBV_ABI_VERSION 4  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
                               3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective
                               4: dbv_window_axpy_rect (rectangular local regions, caller scratch, in-place),
-                                 dbv_sqdiff_sum_rect, dbv_position_fit_batch */
+                                 dbv_sqdiff_sum_rect, dbv_shift_objective_batch, dbv_fp16_overflow */
 
 typedef enum {
   DBV_OK = 0,
@@ -181,6 +181,12 @@ int dbv_band_sumsq(const double* field_dev, int64_t F, int C, int band, double* 
                    int64_t scratch_bytes, void* stream);
 int dbv_shift_objective(const double* field_dev, int64_t F, int C, int band, const double* placed_dev, int E, int ax,
                         int ay, double sumsq_field, double* out_dev, void* stream);
+/* The objective for a BATCH of placed windows (the batched position fit evaluates every galaxy of a field, at all the trial
+ * shifts of one optimiser iteration, with one dbv_spline_place + one call of this): placed (M,E,E) f64, window i at
+ * (ax[i], ay[i]) (device int32 arrays); out[i] = (sumsq_field + sum_window_i(T^2 - 2 field T)) / F^2. */
+int dbv_shift_objective_batch(const double* field_dev, int64_t F, int C, int band, const double* placed_dev, int E,
+                              const int32_t* ax_dev, const int32_t* ay_dev, int64_t M, double sumsq_field, double* out_dev,
+                              void* stream);
 /* One evaluation of `fun(x)` of optimization.py:21-33 for the already placed prediction placed1 (E1,E1) f64
  * at (a1x, a1y) (= shift(r_band_prediction, galaxy_distance_to_center), optimization.py:41-44): a second
  * placement by x = (x0, x1) into placed2 (E2 = dbv_spline_extent(E1,P) squared; scratch dbv_spline_scratch_doubles(1,E1,1,P) doubles), then

@@ -268,9 +268,10 @@ def test_position_objective_matches_the_reference_fun(golden_dir):
 
 
 def test_position_fit_matches_reference(golden_dir):
-    """position_optimization of the REFERENCE (scipy least_squares on full-canvas shifts) vs the drop-in: the
-    optimiser is the same scipy call, the objective agrees to ~1e-15, so the fitted shifts agree to the optimiser's
-    own noise (2-point Jacobian with a 1.5e-8 step amplifies rounding): 1e-3 px."""
+    """position_optimization of the REFERENCE (scipy least_squares on full-canvas shifts) vs the drop-in (batched bounded
+    Levenberg-Marquardt on the device objective, which agrees with the reference's fun(x) to ~1e-15): both descend from
+    (0, 0) to the same minimiser of fun inside [-3, 3]^2; the reference's optimiser stops within its own tolerances
+    (2-point Jacobian with a 1.5e-8 step): 1e-3 px."""
     from debvader.deblend_cutout.optimization import position_optimization
 
     g = np.load(os.path.join(golden_dir, "subpixel.npz"))
@@ -282,6 +283,43 @@ def test_position_fit_matches_reference(golden_dir):
         canvas[off : off + S, off : off + S] = means[k]
         sx, sy = position_optimization(field[0], canvas, dist[k])
         assert abs(sx - g["opt_fitted"][k, 0]) < 1e-3 and abs(sy - g["opt_fitted"][k, 1]) < 1e-3, (k, sx, sy, g["opt_fitted"][k])
+
+
+def test_batched_position_fit_agrees_with_the_scipy_path():
+    """fit_positions (all galaxies at once: batched bounded LM on the device objective) vs fit_position (the reference's own
+    scipy.optimize.least_squares call around the same device objective, one galaxy at a time) on blobs displaced by known
+    sub-pixel offsets: same minimiser within 1e-3 px, and the recovered shift is the displacement."""
+    from debvader_b200.deblend_cutout.optimization import FieldBand, fit_position, fit_positions
+
+    rng = np.random.default_rng(12)
+    F, S, N = 400, 59, 24
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float64)
+    centres = rng.integers(-150, 150, size=(N, 2)).astype(np.float64)
+    true = rng.uniform(-1.5, 1.5, size=(N, 2))
+    true[0] = (2.95, -2.95)   # near the bound
+    true[1] = (4.0, 0.3)      # beyond the +-3 bound on one axis: the fit must stop on the bound
+    field = rng.normal(0, 0.02, (1, F, F, 6))
+    off = int((F - S) / 2)
+    stamps = np.zeros((N, S, S))
+    for k in range(N):
+        sx, sy = rng.uniform(2.0, 4.0, size=2)
+        amp = rng.uniform(5, 30)
+        stamps[k] = amp * np.exp(-0.5 * (((yy - 29) / sx) ** 2 + ((xx - 29) / sy) ** 2))
+        # the galaxy in the field sits at centre + true shift (sub-pixel): sample the analytic profile there
+        r0, c0 = off + int(centres[k, 0]), off + int(centres[k, 1])
+        g = amp * np.exp(-0.5 * (((yy - 29 - true[k, 0]) / sx) ** 2 + ((xx - 29 - true[k, 1]) / sy) ** 2))
+        field[0, r0 : r0 + S, c0 : c0 + S, 2] += g
+    fdev = torch.from_numpy(field).cuda()
+    sdev = torch.from_numpy(stamps).cuda()
+    got, info = fit_positions(fdev, sdev, centres, return_info=True)
+    assert got.shape == (N, 2) and np.abs(got).max() <= 3.0 + 1e-12
+    fb = FieldBand(fdev)
+    for k in range(N):
+        want = np.array(fit_position(fb, sdev[k].contiguous(), centres[k]))
+        assert np.abs(got[k] - want).max() < 1e-3, (k, got[k], want)
+    np.testing.assert_allclose(got[2:], true[2:], atol=0.05)  # and the shifts are the displacements (noise-limited)
+    assert abs(got[1, 0] - 3.0) < 1e-6  # clipped to the bound
+    assert info["nfev_per_galaxy"] < 120
 
 
 def test_deblend_field_with_optimise_positions_matches_reference(golden_dir):
