@@ -317,7 +317,7 @@ def field_extras(net, device, pk, quick=False):
                                         "note": "prefilter + shift on (S+2P+2)^2 f64 windows (P=28; one warp per line, latency / issue bound), then the f64 window paste"}
         from debvader_b200.deblend_cutout.optimization import fit_positions
 
-        # position_optimization (optimization.py:6-52) for ALL sources of the field at once: batched bounded LM on the device objective
+        # position_optimization (optimization.py:6-52) for ALL sources of the field at once: scipy's TRF path per galaxy, batched evaluations
         rb = stamps32[:, :, :, 2].double().contiguous()
         fit_positions(field, rb[:64], centres[:64])  # warm-up
         torch.cuda.synchronize()
@@ -325,8 +325,8 @@ def field_extras(net, device, pk, quick=False):
         xfit, info = fit_positions(field, rb, centres, return_info=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        out["position_fit"] = {"ms_per_galaxy": dt / N * 1e3, "galaxies": N, "ms_total": dt * 1e3, "nfev_per_galaxy": info["nfev_per_galaxy"], "iterations": info["iterations"],
-                               "note": "batched bounded Levenberg-Marquardt on the device objective, all galaxies of the field at once (the reference runs scipy least_squares per galaxy; round 1: 9.6 ms per galaxy with scipy on the host around the device objective)"}
+        out["position_fit"] = {"ms_per_galaxy": dt / N * 1e3, "galaxies": N, "ms_total": dt * 1e3, "nfev_per_galaxy": info["nfev_per_galaxy"], "rounds": info["rounds"],
+                               "note": "scipy's Trust Region Reflective path restated for all galaxies of the field at once (deblend_cutout/trf_batch.py), every round of objective evaluations one batched device call (the reference runs scipy least_squares per galaxy; round 1: 9.6 ms per galaxy with scipy on the host around the device objective)"}
 
         def one_field():
             cut, idx = _fieldops.extract(field, plan, S, C, out_dtype=torch.float32)

@@ -6,8 +6,8 @@ r-band prediction already shifted to the detected position — every evaluation 
 the WHOLE field-sized canvas (optimization.py:21-46), one galaxy after the other.  Here every evaluation of ``fun``
 runs on the device on the only pixels where the shifted prediction is not negligible (two placed windows + one
 fixed-order reduction; the field's own sum of squares is computed once; fp64, same arithmetic as scipy's spline
-code to ~1e-15 relative), and ALL galaxies of a field are fitted at once (``fit_positions``: a batched bounded
-Levenberg-Marquardt iteration, ~10 batched objective evaluations in total instead of ~40 per galaxy).
+code to ~1e-15 relative), and ALL galaxies of a field are fitted at once (``fit_positions``: scipy's Trust Region
+Reflective iteration restated for many problems, every round of evaluations one batched device call).
 ``fit_position`` keeps the reference's own scipy call around the device objective for one galaxy (cross-check).
 """
 import ctypes as C
@@ -100,81 +100,22 @@ class BatchObjective:
         return out.cpu().numpy()
 
 
-def fit_positions(field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN, bound=3.0, h=1e-3, max_iter=40, xtol=1e-7,
-                  return_info=False):
+def fit_positions(field_dev, r_band_batch, centres, margin=_fieldops.SPLINE_MARGIN, bound=3.0, return_info=False):
     """position_optimization (optimization.py:6-52) for all galaxies of a field, batched on the device.
 
     r_band_batch (N,S,S) CUDA (the r band of the predictions), centres (N,2) detected offsets -> (N,2) fitted shifts.
-    The reference minimises fun(x) per galaxy with scipy's bounded trust-region least squares from x = (0, 0) inside
-    [-3, 3]^2 (a local minimum reached by descent).  Here every galaxy runs the same kind of descent simultaneously: a
-    bounded Levenberg-Marquardt / Newton iteration on fun itself, with gradient and Hessian from central differences of the
-    device objective (6 evaluations per iteration, all galaxies and all 6 points in ONE batched placement), an active set
-    for the bounds, step acceptance on decrease (damping up on rejection), stopping per galaxy when the step is below
-    `xtol` px.  fun is a smooth piecewise polynomial of the shift, so this converges to the minimiser the reference's
-    optimiser approaches (tests: within 1e-3 px of the reference's own results)."""
+    The reference calls ``scipy.optimize.least_squares(fun, (0, 0), bounds=(-3, 3))`` per galaxy.  fun is multi-modal at the
+    noise level, so the answer depends on the optimiser's path: every galaxy here walks scipy's own Trust Region Reflective
+    path (``trf_batch.least_squares_trf_batch``, a batched restatement checked against scipy itself), while each round of
+    evaluations — trial points and forward-difference Jacobian points of ALL galaxies still running — is one batched
+    placement + one batched reduction on the device (~30-60 rounds per field instead of ~40 evaluations per galaxy)."""
+    from .trf_batch import least_squares_trf_batch
+
     obj = BatchObjective(field_dev, r_band_batch, centres, margin)
-    n = obj.n
-    x = np.zeros((n, 2))
-    if n == 0:
-        return (x, {"nfev": 0, "iterations": 0}) if return_info else x
-    lam = np.full(n, 1e-3)
-    active = np.ones(n, dtype=bool)
-    offs = np.array([[0, 0], [h, 0], [-h, 0], [0, h], [0, -h], [h, h]])
-    f_cur = None
-    it = 0
-    for it in range(1, max_iter + 1):
-        rows = np.nonzero(active)[0]
-        if rows.size == 0:
-            break
-        m = rows.size
-        X = (x[rows, None, :] + offs[None, :, :]).reshape(-1, 2)
-        f = obj(X, np.repeat(rows, 6)).reshape(m, 6)
-        f0, fpx, fmx, fpy, fmy, fpp = (f[:, k] for k in range(6))
-        g = np.stack([(fpx - fmx) / (2 * h), (fpy - fmy) / (2 * h)], axis=1)
-        hxx = (fpx - 2 * f0 + fmx) / h**2
-        hyy = (fpy - 2 * f0 + fmy) / h**2
-        hxy = (fpp - fpx - fpy + f0) / h**2
-        xr = x[rows]
-        # active set: a coordinate sitting on a bound whose gradient pushes outward stays there
-        at_lo = (xr <= -bound) & (g > 0)
-        at_hi = (xr >= bound) & (g < 0)
-        fixed = at_lo | at_hi
-        scale = np.maximum(np.abs(hxx) + np.abs(hyy), 1e-300)
-        step = np.zeros((m, 2))
-        accepted = np.zeros(m, dtype=bool)
-        lam_r = lam[rows].copy()
-        for _try in range(8):
-            todo = ~accepted
-            if not todo.any():
-                break
-            d = lam_r * scale
-            a11, a22, a12 = hxx + d, hyy + d, hxy.copy()
-            # fixed coordinates: decouple (unit diagonal, zero gradient)
-            gg = np.where(fixed, 0.0, g)
-            a11 = np.where(fixed[:, 0], 1.0, a11)
-            a22 = np.where(fixed[:, 1], 1.0, a22)
-            a12 = np.where(fixed.any(axis=1), 0.0, a12)
-            det = a11 * a22 - a12 * a12
-            pd = (a11 > 0) & (det > 0)
-            px = np.where(pd, -(a22 * gg[:, 0] - a12 * gg[:, 1]) / np.where(pd, det, 1.0), -gg[:, 0] / (np.abs(hxx) + d + 1e-300))
-            py = np.where(pd, -(-a12 * gg[:, 0] + a11 * gg[:, 1]) / np.where(pd, det, 1.0), -gg[:, 1] / (np.abs(hyy) + d + 1e-300))
-            p = np.stack([px, py], axis=1)
-            p = np.clip(p, -1.0, 1.0)  # at most one pixel per iteration
-            xn = np.clip(xr + p, -bound, bound)
-            tr = np.nonzero(todo)[0]
-            fn = obj(xn[tr], rows[tr])
-            ok = fn <= f0[tr] + 1e-15 * np.abs(f0[tr])
-            good = tr[ok]
-            step[good] = xn[good] - xr[good]
-            accepted[good] = True
-            lam_r[good] = np.maximum(lam_r[good] / 10, 1e-9)
-            lam_r[tr[~ok]] *= 10
-        x[rows] = xr + step
-        lam[rows] = lam_r
-        done = (np.abs(step).max(axis=1) < xtol) | ~accepted  # no acceptable step left: at the minimum to rounding
-        active[rows[done]] = False
+    x, info = least_squares_trf_batch(obj, obj.n, x0=(0.0, 0.0), bounds=(-bound, bound), return_info=True)
     if return_info:
-        return x, {"nfev": obj.nfev, "iterations": it, "nfev_per_galaxy": obj.nfev / max(n, 1)}
+        info["nfev_per_galaxy"] = obj.nfev / max(obj.n, 1)
+        return x, info
     return x
 
 

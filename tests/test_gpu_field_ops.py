@@ -268,10 +268,10 @@ def test_position_objective_matches_the_reference_fun(golden_dir):
 
 
 def test_position_fit_matches_reference(golden_dir):
-    """position_optimization of the REFERENCE (scipy least_squares on full-canvas shifts) vs the drop-in (batched bounded
-    Levenberg-Marquardt on the device objective, which agrees with the reference's fun(x) to ~1e-15): both descend from
-    (0, 0) to the same minimiser of fun inside [-3, 3]^2; the reference's optimiser stops within its own tolerances
-    (2-point Jacobian with a 1.5e-8 step): 1e-3 px."""
+    """position_optimization of the REFERENCE (scipy least_squares on full-canvas shifts) vs the drop-in (scipy's TRF path
+    restated for a batch, on the device objective, which agrees with the reference's fun(x) to ~1e-15).  fun is multi-modal
+    at the noise level (golden case 1 has a LOWER minimum at (0.55, -0.23) that the reference steps over), so the path is
+    what is pinned; the 2-point Jacobian with its 1.5e-8 step amplifies rounding differences of fun: 1e-3 px."""
     from debvader.deblend_cutout.optimization import position_optimization
 
     g = np.load(os.path.join(golden_dir, "subpixel.npz"))
@@ -286,7 +286,7 @@ def test_position_fit_matches_reference(golden_dir):
 
 
 def test_batched_position_fit_agrees_with_the_scipy_path():
-    """fit_positions (all galaxies at once: batched bounded LM on the device objective) vs fit_position (the reference's own
+    """fit_positions (all galaxies at once: the batched TRF restatement on the device objective) vs fit_position (the reference's own
     scipy.optimize.least_squares call around the same device objective, one galaxy at a time) on blobs displaced by known
     sub-pixel offsets: same minimiser within 1e-3 px, and the recovered shift is the displacement."""
     from debvader_b200.deblend_cutout.optimization import FieldBand, fit_position, fit_positions
