@@ -126,7 +126,12 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
         if Cf != 1:  # numpy cannot broadcast (.., Cf) into (.., nb): every stamp raises ValueError in the reference
             return torch.zeros(shape, device=dev, dtype=out_dtype), []
         field_dev = field_dev.expand(1, field_dev.shape[1], F_, nb_of_bands).contiguous()
-    idx = np.nonzero(ok)[0]
+    # accepted indices (and their Python-list form, the reference's list_idx) are cached on the plan: a repeated extraction
+    # is then one kernel launch, not an O(n) walk on the host
+    if "_idx" not in plan:
+        plan["_idx"] = np.nonzero(ok)[0]
+        plan["_idx_list"] = [int(i) for i in plan["_idx"]]
+    idx = plan["_idx"]
     # rejected stamps stay zero like the reference's np.zeros; when all are accepted skip the memset
     out = torch.empty(shape, device=dev, dtype=out_dtype) if idx.size == n else torch.zeros(shape, device=dev, dtype=out_dtype)
     if idx.size == 0:
@@ -150,7 +155,7 @@ def extract(field_dev, plan, cutout_size: int, nb_of_bands: int, out_dtype=torch
             _ffi.lib().dbv_extract(_ffi.ptr(field_dev), _DT[field_dev.dtype], F_, nb_of_bands, _ffi.ptr(sx), _ffi.ptr(sy), _ffi.ptr(fl),
                                    _ffi.ptr(slot), int(idx.size), S, _ffi.ptr(out), _DT[out_dtype], _ffi.stream_ptr())
         )
-    return out, [int(i) for i in idx]
+    return out, list(plan["_idx_list"])
 
 
 def window_axpy(field_in, stamps, x0, y0, alpha: float, out=None, field_shape=None, dtype=torch.float64, planar=False):

@@ -183,7 +183,7 @@ template <> __device__ __forceinline__ double add_rn<double>(double a, double b)
 template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
 
 __global__ void __launch_bounds__(256) axpy_bin_kernel(const int32_t* __restrict__ x0, const int32_t* __restrict__ y0, int N, int S,
-                                                       long long FH, long long FW, int tiles_c, int* __restrict__ cnt, int* __restrict__ list) {
+                                                       long long FH, long long FW, int tiles_c, int* __restrict__ cnt, int4* __restrict__ list) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const long long xi = x0[i], yi = y0[i];
@@ -194,8 +194,31 @@ __global__ void __launch_bounds__(256) axpy_bin_kernel(const int32_t* __restrict
     for (int c = c_lo; c <= c_hi; ++c) {
       const int t = r * tiles_c + c;
       const int p = atomicAdd(cnt + t, 1);
-      if (p < AX_LCAP) list[(long long)t * AX_LCAP + p] = i;
+      if (p < AX_LCAP) list[(long long)t * AX_LCAP + p] = make_int4(i, (int)xi, (int)yi, 0);  // the tile needs no second look-up
     }
+}
+
+// Sorted copy of a tile's binned list (<= AX_LCAP = 32 records (stamp, x, y), appended in arbitrary order) into the shared
+// lists: warp 0 alone, one record per lane, rank by shuffles (the indices are distinct) — no barrier, no second global
+// look-up (the records carry the positions).  The caller's next __syncthreads() publishes it.
+static_assert(AX_LCAP == 32, "one binned record per lane of warp 0");
+__device__ __forceinline__ int4 ax_load_bin_record(const int4* __restrict__ bin_list) {
+  // issued BEFORE the tile's count is known (one global round trip instead of two); slots past the count hold stale bytes
+  // of the caller's scratch and are masked out by ax_sorted_bin
+  return (bin_list && threadIdx.x < 32) ? __ldg(bin_list + (long long)blockIdx.x * AX_LCAP + threadIdx.x) : make_int4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void ax_sorted_bin(int binned, int4 e, int* s_id, int* s_x, int* s_y) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  if (lane >= binned) e.x = 0x7fffffff;
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, e.x, j) < e.x;
+  if (lane < binned) {
+    s_id[rank] = e.x;
+    s_x[rank] = e.y;
+    s_y[rank] = e.z;
+  }
 }
 
 template <typename T, typename TS>
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
                                                                   const TS* __restrict__ stamps,
                                                                   const int32_t* __restrict__ x0, const int32_t* __restrict__ y0,
                                                                   int N, int S, double alpha_d, int tiles_c,
-                                                                  const int* __restrict__ bin_cnt, const int* __restrict__ bin_list,
+                                                                  const int* __restrict__ bin_cnt, const int4* __restrict__ bin_list,
                                                                   int planar, int inplace) {
   // F = columns of the (FH, F, C) field = its row pitch in pixels.  inplace (in == out): only the elements a stamp
   // actually covers are read and written back, so the traffic is the algorithmic one (window read-modify-write +
@@ -217,6 +240,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
   const T alpha = (T)alpha_d;
   const int nelt = AX_TR * AX_TC * C;
   const long long stamp_sz = (long long)S * S * C;
+  const int4 rec = ax_load_bin_record(bin_list);
   const int binned = bin_cnt ? bin_cnt[blockIdx.x] : -1;
   if (inplace && binned == 0) return;
   int start = 0;
@@ -224,22 +248,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
   do {
     if (binned >= 0 && binned <= AX_LCAP) {
       // sorted copy of the binned list (rank sort: the indices are distinct)
-      int mine = 0;
-      if ((int)threadIdx.x < binned) {
-        mine = bin_list[(long long)blockIdx.x * AX_LCAP + threadIdx.x];
-        s_id[AX_CAP - 1 - threadIdx.x] = mine;  // staging area at the far end of the list
-      }
-      __syncthreads();
-      int rank = 0;
-      if ((int)threadIdx.x < binned) {
-        for (int j = 0; j < binned; ++j) rank += s_id[AX_CAP - 1 - j] < mine;
-      }
-      __syncthreads();
-      if ((int)threadIdx.x < binned) {
-        s_id[rank] = mine;
-        s_x[rank] = x0[mine];
-        s_y[rank] = y0[mine];
-      }
+      ax_sorted_bin(binned, rec, s_id, s_x, s_y);
       if (threadIdx.x == 0) { s_count = binned; s_next = N; }
       __syncthreads();
     } else {
@@ -396,6 +405,146 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
   } while (start < N);
 }
 
+// The same operator for pixel-interleaved stamps and a compile-time band count (C even), laid out so that nothing is
+// computed per element: a WARP owns a tile row (X is warp-uniform, so "does stamp k reach this row" is a uniform branch
+// and a stamp that misses the row costs one comparison per warp), and lane v of it owns the 16-byte vectors v, v + 32, ...
+// of the row's AX_TC * C contiguous values — the field offset (row base + 2v) and the stamp offset
+// ((X - sx) * S + tc0 - sy) * C + 2v are both affine in v, every access is a fully coalesced 512-byte warp transaction,
+// and all NI field loads of a row are in flight together.  ~64 registers: 4 CTAs per SM (the generic kernel: 104 -> 2).
+// INPLACE: elements no stamp covers are neither read nor written (per-lane mask from a first walk over the list).
+// Stamps are applied in ascending index with one rounding per addition: bit-identical to the sequential host loop.
+template <typename T, typename TS, int C, bool INPLACE>
+__global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T* in, T* out, long long FH, long long F,
+                                                                         const TS* __restrict__ stamps, const int32_t* __restrict__ x0,
+                                                                         const int32_t* __restrict__ y0, int N, int S, double alpha_d, int tiles_c,
+                                                                         const int* __restrict__ bin_cnt, const int4* __restrict__ bin_list) {
+  static_assert((C & 1) == 0 && (AX_TC * C / 2) % 32 == 0, "a tile row is a whole number of 32-vector groups");
+  constexpr int RV = AX_TC * C / 2;  // 16-byte (f64) / 8-byte (f32) vectors per tile row
+  constexpr int NI = RV / 32;        // vectors per lane and row
+  using V2 = typename Vec2<T>::type;
+  using VS = typename Vec2<TS>::type;
+  __shared__ int s_id[AX_CAP], s_x[AX_CAP], s_y[AX_CAP];
+  __shared__ int s_wcnt[AX_THREADS / 32];
+  __shared__ int s_count, s_next;
+  const int tr0 = (blockIdx.x / tiles_c) * AX_TR;
+  const int tc0 = (blockIdx.x % tiles_c) * AX_TC;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const T alpha = (T)alpha_d;
+  const long long stamp_sz = (long long)S * S * C;
+  const int4 rec = ax_load_bin_record(bin_list);
+  const int binned = bin_cnt ? bin_cnt[blockIdx.x] : -1;
+  if (INPLACE && binned == 0) return;
+  // this lane's columns: vector v = lane + 32 i covers values 2v, 2v + 1 of the row = band pair (2v % C) of pixel tc0 + 2v / C
+  int Ycol[NI];
+  bool okc[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    Ycol[i] = tc0 + (2 * (lane + 32 * i)) / C;
+    okc[i] = Ycol[i] < F;
+  }
+  int start = 0;
+  bool first = true;
+  do {
+    if (binned >= 0 && binned <= AX_LCAP) {
+      ax_sorted_bin(binned, rec, s_id, s_x, s_y);
+      if (threadIdx.x == 0) { s_count = binned; s_next = N; }
+      __syncthreads();
+    } else {
+      if (threadIdx.x == 0) { s_count = 0; s_next = N; }
+      __syncthreads();
+      for (int i0 = start; i0 < N; i0 += AX_THREADS) {
+        const int i = i0 + threadIdx.x;
+        int ov = 0, xi = 0, yi = 0;
+        if (i < N) {
+          xi = x0[i];
+          yi = y0[i];
+          ov = (xi < tr0 + AX_TR) && (xi + S > tr0) && (yi < tc0 + AX_TC) && (yi + S > tc0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (lane == 0) s_wcnt[wid] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < AX_THREADS / 32; ++w) {
+          const int c = s_wcnt[w];
+          if (w < wid) before += c;
+          tot += c;
+        }
+        const int base = s_count;
+        const bool fits = base + tot <= AX_CAP;
+        if (fits && ov) {
+          const int p = base + before + __popc(m & ((1u << lane) - 1u));
+          s_id[p] = i;
+          s_x[p] = xi;
+          s_y[p] = yi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          if (fits) s_count = base + tot;
+          else s_next = i0;
+        }
+        __syncthreads();
+        if (!fits) break;
+      }
+    }
+    const int cnt = s_count;
+    if (cnt > 0 || (first && !INPLACE)) {
+      for (int pr = wid; pr < AX_TR; pr += AX_THREADS / 32) {
+        const int X = tr0 + pr;
+        if (X >= FH) break;
+        const long long rowbase = ((long long)X * F + tc0) * C + 2 * lane;
+        unsigned touched = INPLACE ? 0u : ~0u;
+        if (INPLACE) {
+          for (int k = 0; k < cnt; ++k) {
+            if ((unsigned)(X - s_x[k]) >= (unsigned)S) continue;  // warp-uniform
+            const int sy = s_y[k];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) touched |= ((unsigned)(Ycol[i] - sy) < (unsigned)S ? 1u : 0u) << i;
+          }
+          if (!__any_sync(0xffffffffu, touched != 0u)) continue;
+        }
+        V2 acc[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          acc[i].x = (T)0;
+          acc[i].y = (T)0;
+          if (okc[i] && ((touched >> i) & 1u)) {
+            if (!first || INPLACE) acc[i] = *reinterpret_cast<const V2*>(out + rowbase + 64 * i);
+            else if (in) acc[i] = *reinterpret_cast<const V2*>(in + rowbase + 64 * i);
+          }
+        }
+        for (int k = 0; k < cnt; ++k) {
+          const int dx = X - s_x[k];
+          if ((unsigned)dx >= (unsigned)S) continue;  // warp-uniform
+          const int sy = s_y[k];
+          const TS* sp = stamps + s_id[k] * stamp_sz + ((long long)dx * S + (tc0 - sy)) * C + 2 * lane;
+          VS v[NI];
+          bool hit[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            hit[i] = okc[i] && (unsigned)(Ycol[i] - sy) < (unsigned)S;
+            v[i].x = (TS)0;
+            v[i].y = (TS)0;
+            if (hit[i]) v[i] = __ldg(reinterpret_cast<const VS*>(sp + 64 * i));
+          }
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
+            if (hit[i]) {
+              acc[i].x = add_rn<T>(acc[i].x, mul_rn<T>(alpha, (T)v[i].x));
+              acc[i].y = add_rn<T>(acc[i].y, mul_rn<T>(alpha, (T)v[i].y));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          if (okc[i] && ((touched >> i) & 1u)) *reinterpret_cast<V2*>(out + rowbase + 64 * i) = acc[i];
+      }
+    }
+    first = false;
+    start = s_next;
+    __syncthreads();
+  } while (start < N);
+}
+
 // ---------------------------------------------------------------------------------------------
 // centre-window MSE: one warp per stamp, fp64, fixed shuffle tree.
 // ---------------------------------------------------------------------------------------------
@@ -541,6 +690,8 @@ extern "C" int dbv_extract(const void* field, int field_dtype, int64_t F, int C,
   return DBV_OK;
 }
 
+static inline int64_t ax_list_offset(int64_t ntiles) { return (ntiles + 3) / 4 * 4; }  // ints before the 16-byte-aligned record lists
+
 // out = in + alpha * sum_k paste(stamps[k]) on a (FH, FW, C) field; `bins` = caller scratch of
 // dbv_window_axpy_scratch_bytes(FH, FW) bytes (tile counts + fixed-capacity lists), or NULL (every tile scans all stamps)
 static int window_axpy_impl(const void* in, void* out, int dtype, int64_t FH, int64_t FW, int C, const void* stamps, int stamp_dtype,
@@ -551,14 +702,29 @@ static int window_axpy_impl(const void* in, void* out, int dtype, int64_t FH, in
   const int inplace = (in == out) ? 1 : 0;
   if (N == 0 && inplace) return DBV_OK;
   if (N == 0) bins = nullptr;
+  if (bins && (reinterpret_cast<uintptr_t>(bins) & 15)) return fail(DBV_ERR_INVALID, "window_axpy: the binning scratch must be 16-byte aligned");
   if (bins) {
     DBV_CUDA(cudaMemsetAsync(bins, 0, (size_t)ntiles * sizeof(int), st));
-    axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, FH, FW, tiles_c, bins, bins + ntiles);
+    axpy_bin_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x0, y0, (int)N, S, FH, FW, tiles_c, bins, reinterpret_cast<int4*>(bins + ax_list_offset(ntiles)));
     DBV_LAUNCH_CHECK();
   }
   const int* bc = bins;
-  const int* bl = bins ? bins + ntiles : nullptr;
+  const int4* bl = bins ? reinterpret_cast<const int4*>(bins + ax_list_offset(ntiles)) : nullptr;
   dim3 grid((unsigned)ntiles), block(AX_THREADS);
+  if (C == 6 && !stamp_planar && !dbv_env("DBV_AXPY_GENERIC")) {  // the DC2 band count, pixel-interleaved stamps: warp-per-row kernel
+#define DBV_AXPY_ROWS(T, TS)                                                                                                              \
+  do {                                                                                                                                     \
+    if (inplace) window_axpy_rows_kernel<T, TS, 6, true><<<grid, block, 0, st>>>((const T*)in, (T*)out, FH, FW, (const TS*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl); \
+    else window_axpy_rows_kernel<T, TS, 6, false><<<grid, block, 0, st>>>((const T*)in, (T*)out, FH, FW, (const TS*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl);       \
+  } while (0)
+    if (dtype == DBV_F64 && stamp_dtype == DBV_F32) DBV_AXPY_ROWS(double, float);
+    else if (dtype == DBV_F32 && stamp_dtype == DBV_F32) DBV_AXPY_ROWS(float, float);
+    else if (dtype == DBV_F64 && stamp_dtype == DBV_F64) DBV_AXPY_ROWS(double, double);
+    else DBV_AXPY_ROWS(float, double);
+#undef DBV_AXPY_ROWS
+    DBV_LAUNCH_CHECK();
+    return DBV_OK;
+  }
   if (dtype == DBV_F64 && stamp_dtype == DBV_F32)
     window_axpy_kernel<double, float><<<grid, block, 0, st>>>((const double*)in, (double*)out, FH, FW, C, (const float*)stamps, x0, y0, (int)N, S, alpha, tiles_c, bc, bl, stamp_planar != 0, inplace);
   else if (dtype == DBV_F32 && stamp_dtype == DBV_F32)
@@ -574,7 +740,7 @@ static int window_axpy_impl(const void* in, void* out, int dtype, int64_t FH, in
 extern "C" int64_t dbv_window_axpy_scratch_bytes(int64_t FH, int64_t FW) {
   if (FH <= 0 || FW <= 0) return DBV_ERR_INVALID;
   const int64_t ntiles = ((FH + AX_TR - 1) / AX_TR) * ((FW + AX_TC - 1) / AX_TC);
-  return ntiles * (1 + AX_LCAP) * (int64_t)sizeof(int);
+  return (ax_list_offset(ntiles) + ntiles * AX_LCAP * 4) * (int64_t)sizeof(int);  // counts (padded to 16 bytes) + 16-byte records
 }
 
 extern "C" int dbv_window_axpy_rect(const void* in, void* out, int dtype, int64_t FH, int64_t FW, int C, const void* stamps,

@@ -318,7 +318,7 @@ def test_batched_position_fit_agrees_with_the_scipy_path():
         want = np.array(fit_position(fb, sdev[k].contiguous(), centres[k]))
         assert np.abs(got[k] - want).max() < 1e-3, (k, got[k], want)
     np.testing.assert_allclose(got[2:], true[2:], atol=0.05)  # and the shifts are the displacements (noise-limited)
-    assert abs(got[1, 0] - 3.0) < 1e-6  # clipped to the bound
+    assert 3.0 - 1e-4 < got[1, 0] < 3.0  # runs into the bound (TRF keeps its iterates strictly inside, as the reference's does)
     assert info["nfev_per_galaxy"] < 120
 
 
@@ -353,6 +353,28 @@ def test_extract_broadcast_window_through_the_bulk_copy_kernel(ops):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
     got32, _ = ops.extract(torch.from_numpy(field).cuda(), plan, S, C, out_dtype=torch.float32)
     np.testing.assert_array_equal(got32.cpu().numpy(), want.astype(np.float32))
+
+
+@pytest.mark.parametrize("fdt,sdt", [(np.float64, np.float32), (np.float32, np.float32), (np.float64, np.float64), (np.float32, np.float64)])
+def test_window_axpy_six_band_kernel_multi_pass_and_dtypes(ops, fdt, sdt):
+    """The warp-per-row kernel (C = 6, pixel-interleaved stamps) with more overlapping stamps than its shared-memory list
+    holds (768): several passes over the tile, copy and in-place form, every field / stamp dtype pairing — bit-identical to
+    the sequential loop in the field's dtype."""
+    F, S, C, N = 100, 59, 6, 900
+    rng = np.random.default_rng(3)
+    field = rng.normal(size=(1, F, F, C)).astype(fdt)
+    pos = rng.integers(-5, 6, size=(N, 2))
+    stamps = rng.random((N, S, S, C)).astype(sdt)
+    off = ops.subtract_offset(F, S)
+    want = field.copy()
+    for k in range(N):  # the reference's loop (field_deblender.py:76-97) in the field's dtype: one rounding per addition
+        fo._paste(want[0], stamps[k].astype(fdt), int(off + pos[k, 0]), int(off + pos[k, 1]), -1)
+    fdev, sdev = torch.from_numpy(field).cuda(), torch.from_numpy(stamps).cuda()
+    got = ops.window_axpy(fdev, sdev, off + pos[:, 0], off + pos[:, 1], -1.0)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    inpl = fdev.clone()
+    ops.window_axpy(inpl, sdev, off + pos[:, 0], off + pos[:, 1], -1.0, out=inpl)
+    np.testing.assert_array_equal(inpl.cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("shape", [(130, 77), (64, 200), (33, 33)])

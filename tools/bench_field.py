@@ -38,6 +38,9 @@ print(f"window_axpy N={N}: {t:.3f} ms  moved {moved/t/1e6:.0f} GB/s, algorithmic
 xd = torch.from_numpy((off + c[:, 0]).astype(np.int32)).to(dev); yd = torch.from_numpy((off + c[:, 1]).astype(np.int32)).to(dev)
 t = timeit(lambda: _fieldops.window_axpy(field, st, xd, yd, -1.0, out=res))
 print(f"window_axpy N={N} (positions resident): {t:.3f} ms  moved {moved/t/1e6:.0f} GB/s, algorithmic {N*S*S*C*20/t/1e6:.0f} GB/s")
+work = field.clone()
+t = timeit(lambda: _fieldops.window_axpy(work, st, xd, yd, -1.0, out=work))
+print(f"window_axpy N={N} in place (positions resident): {t:.3f} ms  algorithmic {N*S*S*C*20/t/1e6:.0f} GB/s")
 t = timeit(lambda: _fieldops.window_axpy(field, st[:0], xd[:0], yd[:0], -1.0, out=res))
 print(f"window_axpy N=0 (plain tiled copy): {t:.3f} ms  {2*field.numel()*8/t/1e6:.0f} GB/s")
 t = timeit(lambda: res.copy_(field)); print(f"torch copy of the field alone: {t:.3f} ms {2*field.numel()*8/t/1e6:.0f} GB/s")
