@@ -227,7 +227,11 @@ class TilePlan:
         if ((lx != S) | (ly != S)).any():
             raise NotImplementedError("tiled fields take plain in-bounds windows only (a broadcast length-1 window was accepted by the planner)")
         half = int(S / 2)
-        centres = np.asarray([np.asarray(c, dtype=np.float64)[:2] for c in galaxy_distances_to_center], dtype=np.float64).reshape(-1, 2)
+        gdc = galaxy_distances_to_center
+        if isinstance(gdc, np.ndarray) and gdc.ndim == 2 and gdc.dtype != object:  # the usual case: no per-source Python work
+            centres = np.asarray(gdc[:, :2], dtype=np.float64)
+        else:
+            centres = np.asarray([np.asarray(c, dtype=np.float64)[:2] for c in gdc], dtype=np.float64).reshape(-1, 2)
         want_x = -half + np.trunc(centres[self.idx, 0]).astype(np.int64) + int(F_ / 2)
         want_y = -half + np.trunc(centres[self.idx, 1]).astype(np.int64) + int(F_ / 2)
         if not (np.array_equal(want_x, sx) and np.array_equal(want_y, sy)):
