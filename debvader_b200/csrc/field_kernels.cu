@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
 // of the row's AX_TC * C contiguous values — the field offset (row base + 2v) and the stamp offset
 // ((X - sx) * S + tc0 - sy) * C + 2v are both affine in v, every access is a fully coalesced 512-byte warp transaction,
 // and all NI field loads of a row are in flight together.  ~64 registers: 4 CTAs per SM (the generic kernel: 104 -> 2).
-// INPLACE: elements no stamp covers are neither read nor written (per-lane mask from a first walk over the list).
+// INPLACE: only the column span of the stamps reaching a row is read and written (a first, warp-uniform walk over the list).
 // Stamps are applied in ascending index with one rounding per addition: bit-identical to the sequential host loop.
 template <typename T, typename TS, int C, bool INPLACE>
 __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T* in, T* out, long long FH, long long F,
@@ -489,19 +489,48 @@ __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T
     }
     const int cnt = s_count;
     if (cnt > 0 || (first && !INPLACE)) {
+      if (INPLACE) {
+        // The in-place form is latency bound (each row of a warp waits for its field and stamp segments in turn, and the
+        // registers that hold loaded values limit how many rows can be in flight): pull every segment this warp is going
+        // to touch into L2 first — prefetches hold no registers, one 128-byte line per lane.
+        for (int pr = wid; pr < AX_TR; pr += AX_THREADS / 32) {
+          const int X = tr0 + pr;
+          if (X >= FH) break;
+          for (int k = 0; k < cnt; ++k) {
+            const int dx = X - s_x[k];
+            if ((unsigned)dx >= (unsigned)S) continue;  // warp-uniform
+            const int sy = s_y[k];
+            const int y_lo = max(tc0, sy), y_hi = min(min(tc0 + AX_TC, sy + S), (int)F);
+            if (y_hi <= y_lo) continue;
+            const char* fp = reinterpret_cast<const char*>(out + ((long long)X * F + y_lo) * C);
+            const char* sp = reinterpret_cast<const char*>(stamps + s_id[k] * stamp_sz + ((long long)dx * S + (y_lo - sy)) * C);
+            const int fb = (y_hi - y_lo) * C * (int)sizeof(T), sb = (y_hi - y_lo) * C * (int)sizeof(TS);
+            const int fo = (int)(reinterpret_cast<uintptr_t>(fp) & 127), so = (int)(reinterpret_cast<uintptr_t>(sp) & 127);
+            for (int o = lane * 128; o < fb + fo; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp - fo + o));
+            for (int o = lane * 128; o < sb + so; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp - so + o));
+          }
+        }
+      }
       for (int pr = wid; pr < AX_TR; pr += AX_THREADS / 32) {
         const int X = tr0 + pr;
         if (X >= FH) break;
         const long long rowbase = ((long long)X * F + tc0) * C + 2 * lane;
-        unsigned touched = INPLACE ? 0u : ~0u;
+        unsigned touched = ~0u;
         if (INPLACE) {
+          // column span [lo, hi) of the stamps reaching this row (warp-uniform, two operations per stamp): elements inside it
+          // are read and written back — a gap between two stamps of the same row is rewritten with the value just read,
+          // harmless because every element has exactly one owner thread
+          int lo = 0x7fffffff, hi = -0x7fffffff;
           for (int k = 0; k < cnt; ++k) {
-            if ((unsigned)(X - s_x[k]) >= (unsigned)S) continue;  // warp-uniform
+            if ((unsigned)(X - s_x[k]) >= (unsigned)S) continue;
             const int sy = s_y[k];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) touched |= ((unsigned)(Ycol[i] - sy) < (unsigned)S ? 1u : 0u) << i;
+            lo = min(lo, sy);
+            hi = max(hi, sy + S);
           }
-          if (!__any_sync(0xffffffffu, touched != 0u)) continue;
+          if (hi <= lo) continue;  // no stamp reaches this row
+          touched = 0u;
+#pragma unroll
+          for (int i = 0; i < NI; ++i) touched |= ((Ycol[i] >= lo && Ycol[i] < hi) ? 1u : 0u) << i;
         }
         V2 acc[NI];
 #pragma unroll

@@ -274,10 +274,10 @@ def test_deblend_normalise_branch(wts, data):
     # (normalised in float32 on the device instead of float64 on the host: inputs differ by ~1e-7, outputs by ~1e-6; a
     # random-init net also predicts values >= 1, where arctanh is nan / inf in either path)
     m2, d2 = deblend(net, torch.from_numpy(x).cuda(), normalise=True, eps=eps)
-    np.testing.assert_allclose(d2.mean().numpy(), want, rtol=0, atol=2e-5)  # in the normalised space
+    np.testing.assert_allclose(d2.mean().numpy(), want, rtol=0, atol=2e-4)  # in the normalised space (bf16x3: ~5e-5 of peak per path)
     fin = np.isfinite(m2) & np.isfinite(mean) & (np.abs(want) < 0.9)  # sinh(arctanh(v)) amplifies by (1 - v^2)^-1.5 near |v| = 1
     assert fin.mean() > 0.5
-    np.testing.assert_allclose(m2[fin], mean[fin], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(m2[fin], mean[fin], rtol=5e-3, atol=1e-3)
     net.close()
 
 
