@@ -114,6 +114,13 @@ struct TcTable {
   const TcGeom& operator[](int i) const { return g[i]; }
 };
 static const TcTable kTc;
+// DBV_PREC_FP32TC: the many-channel layers run on tc_conv_kernel with promoted partial sums; an epilogue thread then holds
+// NT / 2 accumulators in registers, so the 256-channel layers are N-tiled by 128
+static TcGeom tc_geom(int precision, int li) {
+  TcGeom g = kTc[li];
+  if (precision == DBV_PREC_FP32TC && g.NT == 256) g.NT = 128;
+  return g;
+}
 
 struct LayerRt {
   // device weights
@@ -305,12 +312,14 @@ static bool consumes_cg8(int li) { return li >= cg8_first() && li <= I_HEAD; }
 // Storage of the activations ENTERING layer li (and the format of its weights) in the tensor-core modes.
 // DBV_PREC_MIXED: the four large-image decoder layers read single-plane fp16 activations with fp16 hi/lo weights.
 static bool mixed_tail(int precision, int li) { return precision == DBV_PREC_MIXED && li >= I_T6 && li <= I_HEAD; }
-static int layer_f16(int precision, int li) { return (precision == DBV_PREC_FP16X3 || mixed_tail(precision, li)) ? 1 : 0; }
+static int layer_f16(int precision, int li) { return (precision == DBV_PREC_FP16X3 || precision == DBV_PREC_FP32TC || mixed_tail(precision, li)) ? 1 : 0; }
 static int layer_in_planes(int precision, int li) {
   if (precision == DBV_PREC_BF16) return 1;
   return mixed_tail(precision, li) ? 1 : 2;
 }
-static bool prec_x3(int precision) { return precision == DBV_PREC_BF16X3 || precision == DBV_PREC_FP16X3 || precision == DBV_PREC_MIXED; }
+static bool prec_x3(int precision) {
+  return precision == DBV_PREC_BF16X3 || precision == DBV_PREC_FP16X3 || precision == DBV_PREC_MIXED || precision == DBV_PREC_FP32TC;
+}
 
 // describe how layer li's OUTPUT is stored in the tensor-core modes
 static void tc_out_layout(int li, int precision, OutSpec* o) {
@@ -343,7 +352,7 @@ static size_t out_elems_per_stamp(const OutSpec& o) {
 
 static int build_tc_layer(dbv_ctx* c, int li) {
   const LayerDesc& L = kLayers[li];
-  const TcGeom& G = kTc[li];
+  const TcGeom G = tc_geom(c->precision, li);
   LayerRt& R = c->rt[li];
   const bool x3 = prec_x3(c->precision);
   const HostTensor* W = find_w(c, wkey(L.enc, L.wn, "kernel"));
@@ -431,7 +440,7 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   T.tiles_x = (T.SW + T.TW - 1) / T.TW;
   T.tiles_y = (T.SH + T.TH - 1) / T.TH;
   T.n_tiles_n = Ntot / G.NT;
-  T.nt_pixel_mode = (li == I_DENSE2);
+  T.nt_pixel_mode = (li == I_DENSE2) ? 256 / G.NT : 0;
   T.a_bytes = G.CBK * 2 * G.TW * G.TH * G.TB;
   T.b_bytes = G.NT * G.CBK * 2;
   T.x3 = x3 ? 1 : 0;
@@ -460,6 +469,12 @@ static int build_tc_layer(dbv_ctx* c, int li) {
   }
   if (!tc_layer_supported(G.CBK, G.NT)) return fail(DBV_ERR_UNSUPPORTED, "%s: no kernel for CBK=%d NT=%d", L.name, G.CBK, G.NT);
   R.has_tc = true;
+  if (c->precision == DBV_PREC_FP32TC) {
+    // accumulate at most 128 values of K (x 3 products) per TMEM accumulator, then promote (tc_conv.cu); the layers whose
+    // whole K is short (conv2/3, convT6-8, head: K <= 576) run on the resident-halo kernel with one chain
+    if (tc_seg_supported(G.CBK, G.NT)) T.seg_kb = std::max(1, 128 / G.CBK);
+    return DBV_OK;  // no CTA-pair plans in this precision
+  }
   if (tc_pair_supported(G.CBK, G.NT) && Ntot % G.NT == 0 && !dbv_env("DBV_NO_PAIR")) {
     R.tcp = T;
     uint64_t bd[2] = {(uint64_t)G.CBK, (uint64_t)(nblk * Ntot)};
@@ -480,7 +495,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   const bool x3 = prec_x3(c->precision);
-  if (!x3 || !R.has_tc || dbv_env("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
+  if (!x3 || c->precision == DBV_PREC_FP32TC || !R.has_tc || dbv_env("DBV_NO_PAIRH") || G.CBK != 64 || !tc_pairh_supported(G.NT) || L.kind == L_DENSE) return DBV_OK;
   if (L.kind == L_CONV && L.stride != 1) return DBV_OK;
   const OutSpec& in = c->rt[li - 1].ospec;
   const int ncls = (L.kind == L_CONVT && L.stride == 2) ? 4 : 1;
@@ -589,7 +604,13 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   // 4 times instead of 9.  Column order of the classes inside a tile's accumulator: [2, 0, 1, 3], so that every shift's
   // class set is contiguous.
   const bool concat = ncls == 4 && 4 * CW <= 256 && !dbv_env("DBV_NO_CONCAT");
-  const int DW = concat ? 4 * CW : CW;          // accumulator columns of a sub-unit
+  // DBV_PREC_FP32TC: tcgen05 does not round its fp32 accumulation to nearest, so a chain of K = 288 .. 576 values x 3 products
+  // costs 1.4e-6 .. 1.8e-6 of the output scale (tools/tc_accum_probe.cu).  The 3x3 taps of a stride-1 layer are therefore
+  // spread over nseg accumulators side by side (chains of <= 96 .. 320 values of K) that the epilogue adds up in fp32
+  // registers.  The stride-2 transposed convs have at most 4 taps per output class: one chain.
+  int nseg = 1;
+  if (c->precision == DBV_PREC_FP32TC && ncls == 1 && !c1) nseg = std::max(1, std::min(3, 256 / CW));
+  const int DW = concat ? 4 * CW : nseg * CW;   // accumulator columns of a sub-unit
   const int nsub = concat ? ntiles : ncls * ntiles;  // sub-units per band (class-major when not concatenated)
   if (U * DW > 256 || (U != 1 && U != 2 && U != 4)) return 0;  // a unit (U sub-units) must fit 256 TMEM columns
   if (hrows > 256 || WP > 256 || ntiles > 32) return 0;
@@ -668,8 +689,13 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
       if (!concat) {
         const int cl = sidx / ntiles, m = sidx % ntiles;
         bool first = true;
+        int ntap_cl = 0, tap_no = 0, cur_seg = 0;
+        for (size_t ti = 0; ti < taps.size(); ++ti) ntap_cl += taps[ti].cls == cl;
         for (size_t ti = 0; ti < taps.size(); ++ti) {
           if (taps[ti].cls != cl) continue;
+          const int seg = tap_no++ * nseg / ntap_cl;  // accumulator of this tap
+          if (seg != cur_seg) { cur_seg = seg; first = true; }
+          const int dseg = dbase + seg * CW;
           // (A_hi x [B_hi | B_lo]) as ONE MMA of N = 2*NT (the hi and lo weight blocks are adjacent in shared memory)
           // + (A_lo x B_hi): A_hi is fetched once
           for (int ch = 0; ch < nchunk; ++ch)
@@ -677,7 +703,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
               for (int k = 0; k < ksteps; ++k) {
                 const long long a_off = a_region(ch, pr, taps[ti].plane) * region + (long long)((taps[ti].dy + pad_top) * WP + taps[ti].dx + pad) * ROWB + 32 * k + m * MSTEP;
                 const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * wblk_bytes + 32 * k;
-                if (!push_op(a_off, b_off, (x3 && pr == 0) ? 2 * G.NT : G.NT, dbase, !first)) return 0;
+                if (!push_op(a_off, b_off, (x3 && pr == 0) ? 2 * G.NT : G.NT, dseg, !first)) return 0;
                 first = false;
               }
         }
@@ -744,6 +770,8 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   T.dbg_skip = dbv_env("DBV_HALO_SKIP") ? atoi(dbv_env("DBV_HALO_SKIP")) : 0;
   T.dbg_id = li;
   T.wide = x3 ? 1 : 0;
+  T.nseg = nseg;
+  T.seg_cols = CW;
   T.tail_pad = tail_pad;
   T.smem_bytes = (int)smem;
   T.bands_per_img = (H + bandR - 1) / bandR;
@@ -905,7 +933,8 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
     const long long btiles = (B + T.TB - 1) / T.TB;
     T.tiles_per_cls = btiles * T.tiles_x * T.tiles_y * T.n_tiles_n;
     T.total_tiles = T.tiles_per_cls * T.n_cls;
-    return launch_tc_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
+    const TcGeom G = tc_geom(c->precision, li);
+    return launch_tc_layer(T, G.CBK, G.NT, kNumSMs, st);
   }
   SimtConv p{};
   p.in = (const float*)input_f32;
@@ -1000,7 +1029,7 @@ extern "C" int64_t dbv_launch_count(const dbv_ctx* c) { return c ? c->launches :
 
 extern "C" int dbv_create(dbv_ctx** out, int device, int precision, int64_t chunk) {
   DBV_REQUIRE(out, "dbv_create: null out");
-  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_MIXED, "dbv_create: bad precision %d", precision);
+  DBV_REQUIRE(precision >= DBV_PREC_FP32 && precision <= DBV_PREC_FP32TC, "dbv_create: bad precision %d", precision);
   DBV_REQUIRE(chunk >= 0 && chunk <= (1 << 20), "dbv_create: bad chunk %lld", (long long)chunk);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1067,7 +1096,7 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
   DBV_CUDA(cudaSetDevice(c->device));
   const bool fp32 = c->precision == DBV_PREC_FP32;
   const int planes = prec_x3(c->precision) ? 2 : 1;  // conv1's operand (and every layer outside the mixed tail)
-  const int f16 = c->precision == DBV_PREC_FP16X3 ? 1 : 0;
+  const int f16 = (c->precision == DBV_PREC_FP16X3 || c->precision == DBV_PREC_FP32TC) ? 1 : 0;
   int r;
   // ---- BatchNorm (model/model.py:79; Keras eps 1e-3) folded to scale/shift -----------------------
   {

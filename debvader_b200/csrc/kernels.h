@@ -72,7 +72,9 @@ struct TcLayer {
   int SH, SW;         // tile-space image extents (valid outputs)
   int tiles_x, tiles_y;
   int n_tiles_n;      // N tiling (dense layers); channel offset = nt * NT
-  int nt_pixel_mode;  // Dense -> Reshape(4,4,256): N tile nt IS output pixel nt (channel offset 0, bias offset nt*NT)
+  int nt_pixel_mode;  // Dense -> Reshape(4,4,256): 0 = off, else N tiles per output pixel (256 / NT): tile nt covers channels
+                      // (nt % m) * NT.. of pixel nt / m, bias index = flat (pixel, channel)
+  int seg_kb;         // > 0 (DBV_PREC_FP32TC): k-blocks chained per TMEM accumulator before the epilogue promotes the partial sum
   long long B;        // stamps in this launch
   long long tiles_per_cls;
   long long total_tiles;
@@ -100,6 +102,7 @@ int launch_tc_pair(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t
 bool tc_pair_supported(int CBK, int NT);
 void tc_pair_stage_plan(TcLayer& L, int CBK, int NT);
 bool tc_layer_supported(int CBK, int NT);
+bool tc_seg_supported(int CBK, int NT);
 
 // ---- CTA-pair GEMM with a per-chunk halo box (tc_pairh.cu): 8x8 .. 16x16 maps, N = 128 / 256 -----------------------------
 struct PairHLayer {
@@ -174,6 +177,8 @@ struct HaloLayer {
                      // group-plane regions; the A operand is un-swizzled with LBO = region_bytes (K=16 = two groups)
   int nbuf;          // halo buffers in the ring (1 or 2)
   int U;             // sub-units per unit (plan parameter, kept for the logs)
+  int nseg;          // DBV_PREC_FP32TC: a (class, tile)'s taps are spread over nseg accumulators seg_cols columns apart (shorter
+  int seg_cols;      // tcgen05 accumulation chains); the epilogue sums them with round-to-nearest adds.  1 otherwise
   int wide;          // hi/lo weights: a class tile's accumulator = [A*B_hi (+ A_lo*B_hi) | A*B_lo] (2*NT columns, summed by the
                      // epilogue)
   int tail_pad;      // readable slack after the last halo buffer (garbage positions over-read < 129 rows)

@@ -46,7 +46,13 @@ struct TcCfg {
 //   else              :  D += A_hi x B_hi;  D += A_hi x B_lo;  D += A_lo x B_hi
 // Shared-memory bandwidth (TMA fill + MMA operand fetch) is what bounds these layers, so not re-loading A_hi and
 // B_hi per pairing is worth 1.5x on the fill side.
-template <int CBK, int NT>
+// SEG (DBV_PREC_FP32TC): tcgen05 accumulates in fp32 WITHOUT rounding to nearest, so a long accumulation chain loses ~1 ulp per
+// MMA with a bias (measured, tools/tc_accum_probe.cu: 5.5e-6 of the output scale at K = 2304 against 1.3e-6 for an fp32 FMA
+// chain).  In this mode a tile's k-blocks are cut into segments of L.seg_kb k-blocks (<= 128 values of K); each segment
+// accumulates into its own slot of the TMEM ring and the epilogue warps PROMOTE it: tcgen05.ld + add.rn.f32 into register
+// accumulators (7.4e-7 at K = 2304).  Both epilogue groups work on every tile, each on alternate NV-column chunks, so a
+// thread holds at most NT / 2 accumulators.
+template <int CBK, int NT, bool SEG>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcLayer L) {
   pdl_trigger();
   using Cfg = TcCfg<CBK, NT>;
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
     for (int s = 0; s < TC_NSLOT_MAX; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, SEG ? 8 : 4);  // SEG: both epilogue groups drain every segment
     }
     fence_barrier_init();
   }
@@ -127,46 +133,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       uint32_t u = 0;
       constexpr uint32_t HI = smem_desc_hi<Cfg::ROWB>();
       const uint32_t IDESC = Cfg::IDESC | idesc_ab_fmt(L.ab_f16), IDESC2 = Cfg::IDESC2 | idesc_ab_fmt(L.ab_f16);
-      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
+      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         const int c = (int)(t / L.tiles_per_cls);
         const int nkb = L.cls[c].nkb;
-        const uint32_t slot = u & (nslot - 1);
-        mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + slot * slot_pitch;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
+        const int seg = SEG ? L.seg_kb : nkb;  // k-blocks chained into one accumulator
+        for (int kb0 = 0; kb0 < nkb; kb0 += seg, ++u) {
+          const uint32_t slot = u & (nslot - 1);
+          mbar_wait(bar_tempty + 8 * slot, ((u >> slot_shift) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t sS = base + (uint32_t)stage * stage_bytes;
-          uint32_t a_addr = sS + DBV_DBG(L.dbg_shift_rows) * Cfg::ROWB;
-          uint32_t ahi = kSmemDescLoConst | ((a_addr & 0x3FFFFu) >> 4);
-          uint32_t HIA = HI;
-          if (DBV_DBG(L.dbg_base_mode) == 1) HIA |= ((a_addr >> 7) & 7u) << 17;  // base_offset field (bits 49-51 of the descriptor)
-          const uint32_t alo = ahi + (Cfg::A_BYTES >> 4);
-          const uint32_t bhi = kSmemDescLoConst | (((sS + offB) & 0x3FFFFu) >> 4);
-          const uint32_t blo = bhi + (Cfg::B_BYTES >> 4);
-          if (L.wide) {
+          const uint32_t d_tmem = tmem_base + slot * slot_pitch;
+          const int kb1 = kb0 + seg < nkb ? kb0 + seg : nkb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sS = base + (uint32_t)stage * stage_bytes;
+            uint32_t a_addr = sS + DBV_DBG(L.dbg_shift_rows) * Cfg::ROWB;
+            uint32_t ahi = kSmemDescLoConst | ((a_addr & 0x3FFFFu) >> 4);
+            uint32_t HIA = HI;
+            if (DBV_DBG(L.dbg_base_mode) == 1) HIA |= ((a_addr >> 7) & 7u) << 17;  // base_offset field (bits 49-51 of the descriptor)
+            const uint32_t alo = ahi + (Cfg::A_BYTES >> 4);
+            const uint32_t bhi = kSmemDescLoConst | (((sS + offB) & 0x3FFFFu) >> 4);
+            const uint32_t blo = bhi + (Cfg::B_BYTES >> 4);
+            const int kbs = kb - kb0;  // 0: first k-block of this accumulator
+            if (L.wide) {
 #pragma unroll
-            for (int k = 0; k < CBK / 16; ++k) {
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC2, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
+              for (int k = 0; k < CBK / 16; ++k) {
+                umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC2, (kbs | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
+              }
+            } else if (L.x3) {
+#pragma unroll
+              for (int k = 0; k < CBK / 16; ++k) {
+                umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kbs | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, blo + 2 * k), IDESC, 1u);
+                umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < CBK / 16; ++k)
+                umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kbs | k) != 0 ? 1u : 0u);
             }
-          } else if (L.x3) {
-#pragma unroll
-            for (int k = 0; k < CBK / 16; ++k) {
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, blo + 2 * k), IDESC, 1u);
-              umma_f16(d_tmem, desc64(HIA, alo + 2 * k), desc64(HI, bhi + 2 * k), IDESC, 1u);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < CBK / 16; ++k)
-              umma_f16(d_tmem, desc64(HIA, ahi + 2 * k), desc64(HI, bhi + 2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit(bar_tfull + 8 * slot);
         }
-        umma_commit(bar_tfull + 8 * slot);
       }
     }
   } else {
@@ -182,8 +193,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     constexpr int NCHK = NT / NV;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t u = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
-      if ((int)(u & 1u) != grp) continue;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      if constexpr (!SEG) {
+        if ((int)(u & 1u) != grp) { ++u; continue; }
+      }
       const int c = (int)(t / L.tiles_per_cls);
       long long r = t - (long long)c * L.tiles_per_cls;
       const int nt = (int)(r % L.n_tiles_n);
@@ -196,12 +209,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const bool ok = row_ok && b < L.B && sx < L.SW && sy < L.SH;
       int oy = cl.oy0 + cl.osy * sy, ox = cl.ox0 + cl.osx * sx;
       int cbase = nt * NT, boff = 0;
-      if (L.nt_pixel_mode) {
-        oy = nt / L.o.OW;
-        ox = nt - oy * L.o.OW;
-        cbase = 0;
-        boff = nt * NT;
+      if (L.nt_pixel_mode) {  // Dense -> Reshape(4,4,C): nt_pixel_mode N tiles per output pixel, bias indexed by the flat (pixel, channel)
+        const int pix = nt / L.nt_pixel_mode;
+        oy = pix / L.o.OW;
+        ox = pix - oy * L.o.OW;
+        cbase = (nt - pix * L.nt_pixel_mode) * NT;
+        boff = pix * L.nt_pixel_mode * NT;
       }
+      if constexpr (SEG) {
+        // this group's chunks: q = grp, grp + 2, ...; partial sums promoted segment by segment
+        constexpr int NMINE = (NCHK + 1) / 2;
+        float acc[NMINE][NV];
+#pragma unroll
+        for (int i = 0; i < NMINE; ++i)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) acc[i][j] = 0.f;
+        const int nkb = cl.nkb;
+        for (int kb0 = 0; kb0 < nkb; kb0 += L.seg_kb, ++u) {
+          const uint32_t slot = u & (nslot - 1);
+          const uint32_t tcol = lane_base + slot * slot_pitch;
+          mbar_wait(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < NMINE; ++i) {
+            const int q = grp + 2 * i;
+            if (q < NCHK) {
+              float v[NV];
+              if (L.wide) {
+                float w[NV];
+                tmem_ld_issue<NV>(tcol + (uint32_t)(q * NV), v);
+                tmem_ld_issue<NV>(tcol + (uint32_t)(NT + q * NV), w);
+                tmem_ld_wait<NV>(v);
+                tmem_ld_wait<NV>(w);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) acc[i][j] = __fadd_rn(acc[i][j], __fadd_rn(v[j], w[j]));
+              } else {
+                tmem_ld_issue<NV>(tcol + (uint32_t)(q * NV), v);
+                tmem_ld_wait<NV>(v);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) acc[i][j] = __fadd_rn(acc[i][j], v[j]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+        }
+#pragma unroll
+        for (int i = 0; i < NMINE; ++i) {
+          const int q = grp + 2 * i;
+          if (q < NCHK && ok) {
+            ActRegs<NV> ra;
+            act_prefetch<NV>(L.o, ok, oy, ox, cbase + q * NV, boff, ra);
+            act_apply<NV>(L.o, oy, ox, cbase + q * NV, boff, ra, acc[i]);
+            store_act<NV>(L.o, b, oy, ox, cbase + q * NV, acc[i]);
+          }
+        }
+      } else {
       const uint32_t slot = u & (nslot - 1);
       const uint32_t tcol = lane_base + slot * slot_pitch;
       ActRegs<NV> ra;
@@ -232,6 +296,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+      ++u;
+      }
     }
   }
 
@@ -245,12 +311,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 
 constexpr int TC_MAX_SMEM = 232448;  // 227 KB
 
-template <int CBK, int NT>
+template <int CBK, int NT, bool SEG = false>
 static int launch_one(const TcLayer& L, int max_ctas, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_conv_kernel<CBK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM);
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel<CBK, NT, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM);
   });
   if (attr_err != cudaSuccess)
     return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_conv_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
@@ -258,7 +324,7 @@ static int launch_one(const TcLayer& L, int max_ctas, cudaStream_t st) {
   if (grid <= 0) return DBV_OK;
   const int smem = L.stages * L.stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   if (L.stages < 2 || L.stages > 8 || smem > TC_MAX_SMEM) return fail(DBV_ERR_STATE, "tc_conv_kernel<%d,%d>: bad stage plan (%d x %d B)", CBK, NT, L.stages, L.stage_bytes);
-  launch_pdl(tc_conv_kernel<CBK, NT>, (unsigned)grid, TC_THREADS, smem, st, L);
+  launch_pdl(tc_conv_kernel<CBK, NT, SEG>, (unsigned)grid, TC_THREADS, smem, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
@@ -278,7 +344,16 @@ bool tc_layer_supported(int CBK, int NT) {
   return false;
 }
 
+bool tc_seg_supported(int CBK, int NT) { return CBK == 64 && (NT == 64 || NT == 112 || NT == 128); }
+
 int launch_tc_layer(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
+  if (L.seg_kb > 0) {  // promoted partial sums (DBV_PREC_FP32TC)
+    if (!L.wide) return fail(DBV_ERR_STATE, "segmented accumulation runs the hi/lo split layout with 2*NT <= 256 columns");
+    if (CBK == 64 && NT == 64) return launch_one<64, 64, true>(L, max_ctas, st);
+    if (CBK == 64 && NT == 112) return launch_one<64, 112, true>(L, max_ctas, st);
+    if (CBK == 64 && NT == 128) return launch_one<64, 128, true>(L, max_ctas, st);
+    return fail(DBV_ERR_UNSUPPORTED, "no segmented tcgen05 kernel instance for CBK=%d NT=%d", CBK, NT);
+  }
 #define DBV_TC_CASE(cb, nt) \
   if (CBK == cb && NT == nt) return launch_one<cb, nt>(L, max_ctas, st);
   DBV_TC_CASE(32, 16)

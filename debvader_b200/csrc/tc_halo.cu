@@ -56,7 +56,7 @@ constexpr int HALO_NSLOT_MAX = 8;          // accumulator slots in the TMEM ring
 // Accumulators: TMEM is a ring of 512 / (U*DW) slots; a "unit" = up to U consecutive sub-units (one 128-position tile of
 // one output-parity class each) of a band.  The MMA warp issues all MMAs of a unit into the next free slot and commits
 // it once; the epilogue groups split the unit's (sub-unit, channel chunk) items and all release the slot.
-template <int CBK, int NT, bool NOSWZ>
+template <int CBK, int NT, bool NOSWZ, bool SEGS>
 __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_constant__ HaloLayer L) {
   pdl_trigger();
   constexpr bool CG8 = !NOSWZ && CBK == 16;             // channel-group-planar input: 16-byte pixel rows, K=16 = two groups one region apart
@@ -271,6 +271,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
               tmem_ld_wait<NV>(w);
   #pragma unroll
               for (int j = 0; j < NV; ++j) v[j] += w[j];
+              if constexpr (SEGS) {  // DBV_PREC_FP32TC: the other partial accumulators of this tile, promoted in fp32 registers
+                for (int sg = 1; sg < L.nseg; ++sg) {
+                  float w2[NV];
+                  tmem_ld_issue<NV>(tcol + (uint32_t)(sg * L.seg_cols), w);
+                  tmem_ld_issue<NV>(tcol + (uint32_t)(sg * L.seg_cols + NT), w2);
+                  tmem_ld_wait<NV>(w);
+                  tmem_ld_wait<NV>(w2);
+  #pragma unroll
+                  for (int j = 0; j < NV; ++j) v[j] = __fadd_rn(v[j], __fadd_rn(w[j], w2[j]));
+                }
+              }
             } else {
               tmem_ld_issue<NV>(tcol, v);
               tmem_ld_wait<NV>(v);
@@ -345,18 +356,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
   }
 }
 
-template <int CBK, int NT, bool NOSWZ = false>
+template <int CBK, int NT, bool NOSWZ = false, bool SEGS = false>
 static int launch_halo_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_halo_kernel<CBK, NT, NOSWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_MAX_SMEM);
+    attr_err = cudaFuncSetAttribute(tc_halo_kernel<CBK, NT, NOSWZ, SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_MAX_SMEM);
   });
   if (attr_err != cudaSuccess)
     return fail(DBV_ERR_CUDA, "cudaFuncSetAttribute(tc_halo_kernel<%d,%d>): %s", CBK, NT, cudaGetErrorString(attr_err));
   const long long grid = L.total_bands < max_ctas ? L.total_bands : max_ctas;
   if (grid <= 0) return DBV_OK;
-  launch_pdl(tc_halo_kernel<CBK, NT, NOSWZ>, (unsigned)grid, HALO_THREADS, L.smem_bytes, st, L);
+  launch_pdl(tc_halo_kernel<CBK, NT, NOSWZ, SEGS>, (unsigned)grid, HALO_THREADS, L.smem_bytes, st, L);
   DBV_LAUNCH_CHECK();
   return DBV_OK;
 }
@@ -386,6 +397,14 @@ bool halo_layer_supported(int CBK, int NT) {
 }
 
 int launch_halo_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
+  if (L.nseg > 1) {  // several partial accumulators per tile (DBV_PREC_FP32TC): the instances whose epilogue adds them up
+    if (L.cg8 || !L.wide) return fail(DBV_ERR_STATE, "segmented halo accumulators: hi/lo split layers with NHWC inputs only");
+    if (CBK == 32 && NT == 16) return launch_halo_one<32, 16, false, true>(L, max_ctas, st);
+    if (CBK == 32 && NT == 32) return launch_halo_one<32, 32, false, true>(L, max_ctas, st);
+    if (CBK == 32 && NT == 64) return launch_halo_one<32, 64, false, true>(L, max_ctas, st);
+    if (CBK == 64 && NT == 64) return launch_halo_one<64, 64, false, true>(L, max_ctas, st);
+    return fail(DBV_ERR_UNSUPPORTED, "no segmented halo kernel instance for CBK=%d NT=%d", CBK, NT);
+  }
 #define DBV_HALO_CASE(cb, nt) \
   if (CBK == cb && NT == nt) return launch_halo_one<cb, nt>(L, max_ctas, st);
   if (CBK == 16 && L.cg8) {

@@ -50,11 +50,15 @@ typedef enum {
                           product, ~16-bit mantissa): <=1e-3 of peak flux                   */
   DBV_PREC_FP16X3 = 3, /* tcgen05, hi/lo fp16 split, same cost as BF16X3; activations saturate
                           at +-65504 (fp16 range)                                           */
-  DBV_PREC_MIXED = 4   /* BF16X3, except that the activations entering the four large-image
+  DBV_PREC_MIXED = 4,  /* BF16X3, except that the activations entering the four large-image
                           decoder layers (convT6, convT7, convT8, head: 55 % of the step) are
                           stored ONCE in fp16 (11-bit mantissa, saturating at +-65504) and
                           multiplied by fp16 hi/lo weights: 2 MMAs per product instead of 3
                           and half the activation traffic there; ~5e-4 of peak flux         */
+  DBV_PREC_FP32TC = 5  /* the <=1e-5 tier on the tensor cores: FP16X3 operands (~22-bit mantissa)
+                          with the tcgen05 accumulation chain cut every <=128 values of K and the
+                          partial sums promoted into fp32 registers with round-to-nearest adds
+                          (tcgen05 accumulates without rounding to nearest: ~1 ulp lost per MMA) */
 } dbv_precision;
 
 typedef enum { DBV_F32 = 0, DBV_F64 = 1 } dbv_dtype;
