@@ -114,17 +114,17 @@ class DeblendField:
         st = self._tile_state
         if st is None or st[0] is not res_deblend:
             raise NotImplementedError("a tiled DeblendField assembles the records of its own last deblend_field call")
-        _, tp, mine = st
+        _, tp, mine, xp = st
         px, py, integer = self._positions(res_deblend) if len(res_deblend) else (None, None, True)
         if not integer:
             raise NotImplementedError("tiled fields place stamps on whole pixels only")
         S, C = self.cutout_size, self.nb_of_bands
         dev = self._field_dev.device
         own = self._stamps_dev(res_deblend, column) if len(res_deblend) else torch.empty((0, S, S, C), device=dev, dtype=torch.float32)
-        stamps, ids = parallel.exchange_halo_stamps(own.contiguous(), mine, tp.owner, tp.touches, self._group)
+        stamps, ids = parallel.exchange_halo_stamps(own.contiguous(), mine, tp.owner, tp.touches, self._group, plan=xp)
         if len(ids) == 0:
             return self._field_dev.clone() if base == "field" else torch.zeros_like(self._field_dev)
-        return parallel.subtract_local(self._local, tp, stamps, ids, alpha, base=base)
+        return parallel.subtract_local(self._local, tp, stamps, ids, alpha, base=base, plan=xp)
 
     def get_residual_field(self, res_deblend=None, as_tensor=False):
         """field_deblender.py:46-97: field minus every predicted galaxy (all rows, whatever passed_cuts).
@@ -195,7 +195,7 @@ class DeblendField:
         the single-GPU records)."""
         res_deblend = dict(_EMPTY)
         S, C = self.cutout_size, self.nb_of_bands
-        tp = mine = None
+        tp = mine = xp = None
         if self._local is not None:
             from .. import parallel
 
@@ -207,7 +207,9 @@ class DeblendField:
             field_dev = local.data
             dev = field_dev.device
             tp = parallel.TilePlan(galaxy_distances_to_center, local.field_size, local.world, S)
-            mine = tp.mine(local.rank)
+            # exchange / subtraction indices go to the device now, while it is idle (see parallel.ExchangePlan)
+            xp = parallel.ExchangePlan(tp, local.rank, local.world, dev, local.region)
+            mine = xp.mine
             if len(tp.idx) != tp.n_sources:
                 print("Some galaxies are too close from the border of the field to be considered here.")
             if len(tp.idx) == 0:
@@ -319,5 +321,5 @@ class DeblendField:
         if not optimise_positions:  # integer shifts (0, 0): positions known without walking the records again
             self._pos_cache = (self.res_deblend, np.asarray(gx, dtype=np.float64), np.asarray(gy, dtype=np.float64))
         if tp is not None:
-            self._tile_state = (self.res_deblend, tp, mine)
+            self._tile_state = (self.res_deblend, tp, mine, xp)
         return self.res_deblend

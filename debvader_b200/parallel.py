@@ -125,14 +125,60 @@ def overlap_matrix(x0, y0, S: int, field_size: int, world: int, halo: int = 0):
     return m
 
 
-def exchange_halo_stamps(local_stamps, local_ids, owner, touches, group=None):
+class ExchangePlan:
+    """Everything the halo exchange and the subtraction of one rank need besides the stamps themselves, derived from the
+    TilePlan alone and uploaded in two small copies BEFORE the pass enqueues its device work: a pageable host-to-device copy
+    is ordered after everything already on the stream, so an upload made between the network and the exchange would stall the
+    host until the network has finished."""
+
+    def __init__(self, tp, rank: int, world: int, device, region):
+        mine = tp.mine(rank)
+        self.mine = mine
+        pos = np.full(len(tp.owner), -1, dtype=np.int64)
+        pos[mine] = np.arange(len(mine))
+        if world == 1:
+            send_ids = [mine[tp.touches[mine, 0]]]
+            recv_ids = list(send_ids)
+        else:
+            send_ids = [mine[tp.touches[mine, dst]] for dst in range(world)]
+            recv_ids = [np.nonzero((tp.owner == src) & tp.touches[:, rank])[0].astype(np.int64) for src in range(world)]
+        self.send_counts = [len(i) for i in send_ids]
+        self.recv_counts = [len(i) for i in recv_ids]
+        ids = np.concatenate(recv_ids) if recv_ids else np.zeros(0, dtype=np.int64)
+        order = np.argsort(ids, kind="stable")
+        self.ids = ids[order]  # global (accepted-source) indices of the stamps this rank applies, ascending
+        self.reorder = not np.array_equal(order, np.arange(len(order)))
+        sel = np.concatenate([pos[i] for i in send_ids]) if send_ids else np.zeros(0, dtype=np.int64)
+        self.send_all_in_order = world == 1 and len(sel) == len(mine)
+        R0, _, C0, _ = region
+        idx64 = torch.from_numpy(np.concatenate([sel, order]).astype(np.int64)).to(device)
+        xy = torch.from_numpy(np.stack([tp.x0[self.ids] - R0, tp.y0[self.ids] - C0]).astype(np.int32)).to(device)
+        self.sel = idx64[: len(sel)]
+        self.order = idx64[len(sel) :]
+        self.x0, self.y0 = xy[0], xy[1]
+
+
+def exchange_halo_stamps(local_stamps, local_ids, owner, touches, group=None, plan=None):
     """Halo exchange of overlapping stamps.
 
     local_stamps (n_local,S,S,C) tensor of the stamps this rank owns, local_ids their global
     indices (ascending).  `owner` (N,) and `touches` (N,world) are known to every rank (they only
     depend on the centres).  Returns (stamps, ids): every stamp whose window touches this rank's
-    tile / region, sorted by global index.  One all_to_all_single; no other communication."""
+    tile / region, sorted by global index.  One all_to_all_single; no other communication.
+    `plan` (ExchangePlan): the index tensors prepared — and uploaded — ahead of the device work."""
     rank, world = _world(group)
+    if plan is not None:
+        if world == 1:
+            return (local_stamps if plan.send_all_in_order else local_stamps.index_select(0, plan.sel)), plan.ids
+        per = int(np.prod(local_stamps.shape[1:]))
+        send = local_stamps.index_select(0, plan.sel).reshape(-1) if len(plan.sel) else local_stamps.new_zeros((0,))
+        recv = local_stamps.new_empty((sum(plan.recv_counts) * per,))
+        dist.all_to_all_single(recv, send, output_split_sizes=[n * per for n in plan.recv_counts],
+                               input_split_sizes=[n * per for n in plan.send_counts], group=group)
+        stamps = recv.reshape((-1,) + tuple(local_stamps.shape[1:]))
+        if plan.reorder:
+            stamps = stamps.index_select(0, plan.order)
+        return stamps, plan.ids
     local_ids = np.asarray(local_ids, dtype=np.int64)
     dev = local_stamps.device
     if world == 1:
@@ -263,14 +309,16 @@ def extract_local(local: LocalField, tp: TilePlan, mine, nb_of_bands: int, out_d
     return cut
 
 
-def subtract_local(local: LocalField, tp: TilePlan, stamps, ids, alpha: float = -1.0, out=None, base="field"):
+def subtract_local(local: LocalField, tp: TilePlan, stamps, ids, alpha: float = -1.0, out=None, base="field", plan=None):
     """region + alpha * (every exchanged stamp, ascending global index), clipped to the region
-    (deblend/field_deblender.py:46-97 restricted to the local region).  base="zeros" starts from zeros (predicted fields)."""
+    (deblend/field_deblender.py:46-97 restricted to the local region).  base="zeros" starts from zeros (predicted fields).
+    `plan` (ExchangePlan): region-relative window positions already on the device."""
     from . import _fieldops
 
     R0, _, C0, _ = local.region
     src = local.data if base == "field" else None
-    return _fieldops.window_axpy(src, stamps.contiguous(), tp.x0[ids] - R0, tp.y0[ids] - C0, alpha, out=out,
+    x0, y0 = (plan.x0, plan.y0) if plan is not None else (tp.x0[ids] - R0, tp.y0[ids] - C0)
+    return _fieldops.window_axpy(src, stamps.contiguous(), x0, y0, alpha, out=out,
                                  field_shape=tuple(local.data.shape), dtype=local.data.dtype)
 
 
@@ -320,12 +368,13 @@ def deblend_field_tiled(net, field_image, galaxy_distances_to_center, group=None
     rank, world = _world(group)
     local = field_image if isinstance(field_image, LocalField) else LocalField.from_full(field_image, rank, world, device)
     tp = TilePlan(galaxy_distances_to_center, local.field_size, world, cutout_size)
-    mine = tp.mine(rank)
+    xp = ExchangePlan(tp, rank, world, local.data.device, local.region)
+    mine = xp.mine
     cut = extract_local(local, tp, mine, nb_of_bands, out_dtype=torch.float32)
     if len(mine):
         mean = net(cut, sample=sample, seed=seed).mean().tensor
     else:
         mean = torch.empty((0, tp.S, tp.S, nb_of_bands), device=local.data.device, dtype=torch.float32)
-    stamps, ids = exchange_halo_stamps(mean.contiguous(), mine, tp.owner, tp.touches, group)
-    res = subtract_local(local, tp, stamps, ids, -1.0) if len(ids) else local.data.clone()
+    stamps, ids = exchange_halo_stamps(mean.contiguous(), mine, tp.owner, tp.touches, group, plan=xp)
+    res = subtract_local(local, tp, stamps, ids, -1.0, plan=xp) if len(ids) else local.data.clone()
     return local.like(res), [int(i) for i in tp.idx], tp

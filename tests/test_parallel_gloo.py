@@ -55,6 +55,15 @@ def _worker(rank, world, port, q):
             fo._paste(canvas, st, int(x0[k]), int(y0[k]), +1)
             tile -= canvas[r0:r1, c0:c1]
         assert np.array_equal(tile, full_res[0, r0:r1, c0:c1]), "tile assembly must be bit-identical to the sequential result"
+        # the same exchange through a prepared ExchangePlan (index tensors made — on a GPU: uploaded — ahead of the device work)
+        import types
+
+        tp = types.SimpleNamespace(owner=owner, touches=touches, x0=x0, y0=y0, mine=lambda r: np.nonzero(owner == r)[0])
+        region = par.region_bounds(F, world, 0)[rank]
+        xp = par.ExchangePlan(tp, rank, world, torch.device("cpu"), region)
+        got2, ids2 = par.exchange_halo_stamps(torch.from_numpy(stamps[mine]), mine, owner, touches, plan=xp)
+        assert list(ids2) == list(want) and np.array_equal(got2.numpy(), stamps[want])
+        assert np.array_equal(xp.x0.numpy(), (x0[want] - region[0]).astype(np.int32)) and np.array_equal(xp.y0.numpy(), (y0[want] - region[2]).astype(np.int32))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
