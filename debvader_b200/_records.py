@@ -34,9 +34,11 @@ class StampBatch:
 
     def column(self):
         """1-D object array of proxies, one per stamp (what goes into the record column)."""
-        col = np.empty(len(self), dtype=object)
-        for i in range(len(self)):
-            col[i] = DeviceStamp(self, i)
+        n = len(self)
+        col = np.empty(n, dtype=object)
+        new = DeviceStamp
+        for i in range(n):  # element-wise on purpose: numpy must not probe the proxies as sequences (that would download them)
+            col[i] = new(self, i)
         return col
 
 
@@ -47,7 +49,8 @@ class DeviceStamp:
     __array_priority__ = 100.0
 
     def __init__(self, batch: StampBatch, index: int):
-        self.batch, self.index = batch, int(index)
+        self.batch = batch
+        self.index = index
 
     @property
     def tensor(self):
@@ -159,6 +162,40 @@ def column_tensor(records, column, device):
             parts.append(torch.from_numpy(np.ascontiguousarray(a)).to(device))
     dt = torch.float64 if any(p.dtype == torch.float64 for p in parts) else torch.float32
     return torch.stack([p.to(dt) for p in parts]).contiguous()
+
+
+class quiet_gc:
+    """Building the records of a 2000-source field allocates ~20 000 small acyclic objects (three proxies per galaxy, the
+    per-galaxy shift arrays ...).  Each 700 of them trigger a generation-0 collection of Python's cyclic garbage collector,
+    every hundredth of those a full collection that walks the whole interpreter heap — 37 ms measured on the GPU box with
+    torch imported, i.e. eight deblending passes' worth of device time, once every ~10 passes.  None of these objects can
+    be part of a cycle, so the collector is paused while they are created and its previous state restored afterwards."""
+
+    def __enter__(self):
+        import gc
+
+        self._was = gc.isenabled()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        if self._was:
+            import gc
+
+            gc.enable()
+        return False
+
+
+def with_quiet_gc(fn):
+    """decorator: run `fn` under quiet_gc."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        with quiet_gc():
+            return fn(*a, **kw)
+
+    return wrapper
 
 
 def make_records(columns: dict):

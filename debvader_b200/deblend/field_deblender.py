@@ -188,6 +188,7 @@ class DeblendField:
         return _fieldops.mse(a, b)
 
     # ------------------------------------------------------------------------------------------
+    @_records.with_quiet_gc
     def deblend_field(self, galaxy_distances_to_center, cutout_images=None, optimise_positions=False, epistemic_criterion=100.0,
                       mse_criterion=100.0, field_image=None):
         """field_deblender.py:219-382.  Tiled: the records are those of the sources THIS rank owns, ``list_idx`` stays
