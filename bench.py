@@ -384,6 +384,15 @@ def field_extras(net, device, pk, quick=False):
                                  "api": "DeblendField.deblend_field + get_residual_field(as_tensor=True) + field_mse"}
     except Exception as e:
         out["cfg1_dc2_field"] = {"error": repr(e)}
+    # DRAM bytes per launch of the field kernels from the committed ncu pass (same sizes as above): `traffic` next to the
+    # algorithmic bytes the fractions are computed from
+    try:
+        ft = json.load(open(os.path.join(ROOT, "profiles", "field_traffic.json")))
+        for k, ent in ft.items():
+            if k in out and isinstance(ent, dict):
+                out[k]["traffic"] = {"dram_bytes_per_launch": ent["dram_bytes_per_launch"], "kernel": ent["kernel"], "source": ft.get("source")}
+    except Exception:
+        pass
     return out
 
 
@@ -628,17 +637,20 @@ def main():
     top = max(tc_lay, key=lambda l: l["ms"]) if tc_lay else {"layer": None, "tflops": 0.0, "ms": 0.0}
     sum_ms = sum(l["ms"] for l in lay) or 1.0
     net_tf = value / world * spec.FLOP_PER_STAMP / 1e12
-    traffic = None
+    traffic, traffic_detail = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this layer's kernel, from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = tj.get(args.precision, {}).get(top["layer"])
         if ent:
-            traffic = {"bytes_per_launch": ent["dram_bytes"], "stamps_per_launch": ent["stamps"], "source": tj.get("source")}
+            # per launch of THIS run (B stamps), scaled from the captured launch (traffic is linear in the stamps: no reuse across stamps)
+            traffic = int(ent["dram_bytes"] / ent["stamps"] * B)
+            traffic_detail = {"captured_bytes_per_launch": ent["dram_bytes"], "captured_stamps_per_launch": ent["stamps"], "stamps_per_launch": B,
+                              "algorithmic_flops_per_launch": int(2 * spec.LAYER_MACS.get(top["layer"], 0) * B), "source": tj.get("source")}
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": f"{top['layer']} ({KERNEL_OF.get(top['layer'], '?')}, tcgen05)",
                 "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(top["tflops"] / peak_tf, 4), "traffic": traffic, "share_of_step": round(top["ms"] / sum_ms, 4),
+                "frac": round(top["tflops"] / peak_tf, 4), "traffic": traffic, "traffic_detail": traffic_detail, "share_of_step": round(top["ms"] / sum_ms, 4),
                 "frac_of_burst": round(top["tflops"] / pk["bf16_tflops"], 4), "frac_of_sustained": round(top["tflops"] / pk["bf16_tflops_sustained"], 4),
                 "peak_source": pk["source"] + (" bf16 burst (timed region %.2f s < 1 s)" % (ms_total / 1e3) if burst else " bf16 sustained (timed region %.2f s)" % (ms_total / 1e3)), "flops": "algorithmic (nominal 2*MACs of the layer; the hi/lo split precisions execute 3x that on the tensor pipe, 2x in the fp16 tail of 'mixed')"}
     line = {

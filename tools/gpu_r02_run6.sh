@@ -3,7 +3,7 @@
 # GPU suite, smoke, bench (+reference arm), ncu launch list, ncu --set full of one chunk, field-kernel DRAM bytes, PCIe probe.
 bash tools/gpu_final.sh
 O=gpurun_out
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"extract_bulk_kernel|window_axpy_kernel|sqdiff_partial|axpy_bin" --launch-skip 10 -c 12 --csv --log-file $O/field_ncu.csv python tools/field_ncu_target.py > $O/field_ncu.log 2>&1; echo "field ncu rc=$?"
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"extract_bulk_kernel|window_axpy|sqdiff_partial|axpy_bin" --launch-skip 10 -c 12 --csv --log-file $O/field_ncu.csv python tools/field_ncu_target.py > $O/field_ncu.log 2>&1; echo "field ncu rc=$?"
 timeout 300 python tools/pcie_probe.py > $O/pcie_probe_1gpu.log 2>&1; echo "pcie rc=$?"
 python - <<'PY'
 import json
