@@ -662,7 +662,7 @@ def main():
                    "parallelism": f"dp{world} (stamps sharded, no data-path collective)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * STAMP_ELTS * 4, "d2h_bytes_per_step": B * STAMP_ELTS * 4,
                 "api": "debvader_b200.deblend_cutout.deblender.deblend(net, host ndarray) -> dbv_deblend_host", "timing": "wall clock, max over ranks",
-                "note": "returns the mean ndarray (device->host copy inside the timed region) and the distribution object, whose stddev stays on the device until a caller asks for it; input = pinned float32",
+                "note": "returns the mean ndarray (device->host copy inside the timed region) and the distribution object, whose stddev stays on the device until a caller asks for it; input = pinned float32. Copy ceiling of the pool's boxes (tools/pcie_probe.py, profiles/r02_pcie_probe_*gpu.log): 551-593 k stamps/s on one GPU (55 GB/s each way), 765 k stamps/s in total on 8 GPUs (23 GB/s H2D, 11.7 GB/s D2H per rank when eight ranks copy at once): at N = 8 this figure IS the box's ceiling, not a code limit",
                 "pageable_f64_input": {"value": e2e_f64, "unit": UNIT, "h2d_bytes_per_step": B * STAMP_ELTS * 8,
                                        "note": "the reference's natural input: a pageable float64 ndarray (deblender.py:18 casts it); the copy is staged by the driver and the cast runs on the device"},
                 "host_affinity": numa},
