@@ -414,13 +414,17 @@ __global__ void __launch_bounds__(AX_THREADS) window_axpy_kernel(const T* in, T*
 // INPLACE: only the column span of the stamps reaching a row is read and written (a first, warp-uniform walk over the list).
 // Stamps are applied in ascending index with one rounding per addition: bit-identical to the sequential host loop.
 template <typename T, typename TS, int C, bool INPLACE>
-__global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T* in, T* out, long long FH, long long F,
+__global__ void __launch_bounds__(AX_THREADS, INPLACE ? 6 : 4) window_axpy_rows_kernel(const T* in, T* out, long long FH, long long F,
                                                                          const TS* __restrict__ stamps, const int32_t* __restrict__ x0,
                                                                          const int32_t* __restrict__ y0, int N, int S, double alpha_d, int tiles_c,
                                                                          const int* __restrict__ bin_cnt, const int4* __restrict__ bin_list) {
   static_assert((C & 1) == 0 && (AX_TC * C / 2) % 32 == 0, "a tile row is a whole number of 32-vector groups");
   constexpr int RV = AX_TC * C / 2;  // 16-byte (f64) / 8-byte (f32) vectors per tile row
-  constexpr int NI = RV / 32;        // vectors per lane and row
+  // INPLACE is latency bound (a row = one round trip to DRAM) and its throughput is the number of rows in flight = warps per
+  // SM: there a warp takes HALF a row (3 vectors per lane instead of 6: ~40 registers, 6 CTAs = 48 warps per SM instead of 32)
+  constexpr int CS = INPLACE ? 2 : 1;  // warps per tile row
+  static_assert(RV % (32 * CS) == 0, "a warp's share of a row is a whole number of 32-vector groups");
+  constexpr int NI = RV / CS / 32;     // vectors per lane and row
   using V2 = typename Vec2<T>::type;
   using VS = typename Vec2<TS>::type;
   __shared__ int s_id[AX_CAP], s_x[AX_CAP], s_y[AX_CAP];
@@ -435,11 +439,13 @@ __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T
   const int binned = bin_cnt ? bin_cnt[blockIdx.x] : -1;
   if (INPLACE && binned == 0) return;
   // this lane's columns: vector v = lane + 32 i covers values 2v, 2v + 1 of the row = band pair (2v % C) of pixel tc0 + 2v / C
+  const int half = wid % CS;                    // which share of its rows this warp takes
+  const int vbase = half * (RV / CS) + lane;    // this lane's first vector of a row
   int Ycol[NI];
   bool okc[NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    Ycol[i] = tc0 + (2 * (lane + 32 * i)) / C;
+    Ycol[i] = tc0 + (2 * (vbase + 32 * i)) / C;
     okc[i] = Ycol[i] < F;
   }
   int start = 0;
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T
         // The in-place form is latency bound (each row of a warp waits for its field and stamp segments in turn, and the
         // registers that hold loaded values limit how many rows can be in flight): pull every segment this warp is going
         // to touch into L2 first — prefetches hold no registers, one 128-byte line per lane.
-        for (int pr = wid; pr < AX_TR; pr += AX_THREADS / 32) {
+        for (int pr = wid / CS; pr < AX_TR && half == 0; pr += AX_THREADS / 32 / CS) {  // one warp per row issues the prefetches
           const int X = tr0 + pr;
           if (X >= FH) break;
           for (int k = 0; k < cnt; ++k) {
@@ -511,10 +517,10 @@ __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T
           }
         }
       }
-      for (int pr = wid; pr < AX_TR; pr += AX_THREADS / 32) {
+      for (int pr = wid / CS; pr < AX_TR; pr += AX_THREADS / 32 / CS) {
         const int X = tr0 + pr;
         if (X >= FH) break;
-        const long long rowbase = ((long long)X * F + tc0) * C + 2 * lane;
+        const long long rowbase = ((long long)X * F + tc0) * C + 2 * vbase;
         unsigned touched = ~0u;
         if (INPLACE) {
           // column span [lo, hi) of the stamps reaching this row (warp-uniform, two operations per stamp): elements inside it
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(AX_THREADS, 4) window_axpy_rows_kernel(const T
           const int dx = X - s_x[k];
           if ((unsigned)dx >= (unsigned)S) continue;  // warp-uniform
           const int sy = s_y[k];
-          const TS* sp = stamps + s_id[k] * stamp_sz + ((long long)dx * S + (tc0 - sy)) * C + 2 * lane;
+          const TS* sp = stamps + s_id[k] * stamp_sz + ((long long)dx * S + (tc0 - sy)) * C + 2 * vbase;
           VS v[NI];
           bool hit[NI];
 #pragma unroll
