@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEBVADER_B200_LIB") or os.path.join(_HERE, "libdebvader_b200.so")  # env override: A/B builds of the same source
 
-ABI_VERSION = 4  # must equal DBV_ABI_VERSION in include/debvader_b200.h
+ABI_VERSION = 5  # must equal DBV_ABI_VERSION in include/debvader_b200.h
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4, "fp32tc": 5}
 F32, F64 = 0, 1
 

@@ -29,10 +29,12 @@
 extern "C" {
 #endif
 
-#define DBV_ABI_VERSION 4  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
+#define DBV_ABI_VERSION 5  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
                               3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective
                               4: dbv_window_axpy_rect (rectangular local regions, caller scratch, in-place),
-                                 dbv_sqdiff_sum_rect, dbv_shift_objective_batch, dbv_fp16_overflow */
+                                 dbv_sqdiff_sum_rect, dbv_shift_objective_batch, dbv_fp16_overflow
+                              5: DBV_PREC_FP32TC; the binning scratch of dbv_window_axpy_rect holds 16-byte records and must
+                                 be 16-byte aligned (its size still comes from dbv_window_axpy_scratch_bytes) */
 
 typedef enum {
   DBV_OK = 0,
