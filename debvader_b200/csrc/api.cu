@@ -805,6 +805,9 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
   if (dbv_env("DBV_NO_HALO") && li != I_CONV1) return DBV_OK;
+  // DBV_PREC_FP32TC: convT6 has the longest chain of the resident-halo layers (K = 576) and, with N = 64, room for only two
+  // partial accumulators per tile in TMEM (chains of 256 / 320): it runs on tc_conv_kernel with 128-value segments instead
+  if (c->precision == DBV_PREC_FP32TC && li == I_T6) return DBV_OK;
   const bool must = li == I_CONV1 || mixed_tail(c->precision, li) || consumes_cg8(li);  // these layers have no other tensor-core kernel
   if ((!R.has_tc && !must) || L.kind == L_DENSE) return DBV_OK;
   if (!halo_layer_supported(G.CBK, G.NT)) return DBV_OK;
