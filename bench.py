@@ -425,17 +425,32 @@ def field_tiled_extra(net, device, rank, world, quick=False):
             keep["mse"] = obj.field_mse(obj.field_tensor, keep["res"])
 
         with contextlib.redirect_stdout(io.StringIO()):
-            one()
+            for _ in range(2):  # two passes: the steady state alternates between two result buffers (the caller still holds the
+                one()           # previous residual while the next one is made), and a first cudaMalloc of 805 MB costs ~100 ms
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            import gc
+
+            gc_log = []
+
+            def _gc_cb(phase, info, _t=[0.0]):
+                if phase == "start":
+                    _t[0] = time.perf_counter()
+                elif info.get("generation", 0) >= 2:
+                    gc_log.append(round((time.perf_counter() - _t[0]) * 1e3, 2))
+
+            gc.callbacks.append(_gc_cb)
             iters = 5
-            a.record()
-            for _ in range(iters):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            evs[0].record()
+            for i in range(iters):
                 one()
-            b.record()
+                evs[i + 1].record()
             torch.cuda.synchronize()
+            gc.callbacks.remove(_gc_cb)
+            a, b = evs[0], evs[-1]
+            each = [round(evs[i].elapsed_time(evs[i + 1]), 3) for i in range(iters)]
         ms = torch.tensor([a.elapsed_time(b) / iters], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -465,6 +480,7 @@ def field_tiled_extra(net, device, rank, world, quick=False):
         return {"ms_per_field": float(ms.item()), "n_gpus": world, "field": f"{F}x{F}x{C} f64", "sources": N,
                 "tiles": list(par.tile_grid(world)), "halo_px": par.HALO, "field_share_per_rank": round(share, 4),
                 "bit_identical_to_single_gpu": bool(flag.item()), "mse_tiled": keep["mse"], "mse_single": mse_single,
+                "ms_each_pass_rank0": each, "full_gc_pauses_ms_rank0": gc_log,
                 "api": "DeblendField(net, field, tiled=True).deblend_field + get_residual_field(as_tensor=True) + field_mse",
                 "collectives": "one all_to_all_single of overlapping stamps + one all_reduce of a double per pass", "timing": "CUDA events, max over ranks"}
     finally:

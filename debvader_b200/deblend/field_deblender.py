@@ -268,9 +268,7 @@ class DeblendField:
             # the reference stores n separate zero maps (field_deblender.py:317-321): one shared read-only map here
             zero = np.zeros((S, S, C))
             zero.setflags(write=False)
-            epistemic = np.empty(n, dtype=object)
-            for i in range(n):
-                epistemic[i] = zero
+            epistemic = np.frompyfunc(lambda _i: zero, 1, 1)(np.arange(n))
             epistemic_norm = np.zeros(n)
 
         # everything above only ENQUEUED device work; the record columns are built on the host while the GPU runs, and the
@@ -298,15 +296,13 @@ class DeblendField:
             for i in range(n):
                 shifts[i] = np.array(fitted[i])
         else:
-            shifts = np.empty(n, dtype=object)
-            for i, row in enumerate(np.zeros((n, 2), dtype=np.int64)):  # np.array([0, 0]) per galaxy (field_deblender.py:354)
-                shifts[i] = row
-        mse_center = mse_dev.cpu().numpy() if n else np.zeros(0)
-        passed_cuts = ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))
-
+            # np.array([0, 0]) per galaxy (field_deblender.py:354): rows of one (n, 2) array, gathered by a C-level loop
+            shifts = np.frompyfunc(np.zeros((n, 2), dtype=np.int64).__getitem__, 1, 1)(np.arange(n))
         self.nb_of_detected_objects += [n_detected]
         self.nb_of_deblended_galaxies += [n_deblended]
 
+        # the records are assembled BEFORE the host waits for the device (the network is still running): only the column
+        # that depends on a device result — passed_cuts, from the centre-window MSE — is filled in afterwards
         cols = {
             "cutout_images": col_cut,
             "output_images_mean": col_mean,
@@ -316,9 +312,12 @@ class DeblendField:
             "galaxy_distances_to_center_x": gx,
             "galaxy_distances_to_center_y": gy,
             "epistemic_uncertainty": epistemic,
-            "passed_cuts": np.asarray(passed_cuts, dtype=bool),
+            "passed_cuts": np.zeros(n, dtype=bool),
         }
         self.res_deblend = _records.make_records(cols)
+        mse_center = mse_dev.cpu().numpy() if n else np.zeros(0)
+        if n:
+            self.res_deblend["passed_cuts"][:] = ~((epistemic_norm > epistemic_criterion) | (mse_center > mse_criterion))
         if not optimise_positions:  # integer shifts (0, 0): positions known without walking the records again
             self._pos_cache = (self.res_deblend, np.asarray(gx, dtype=np.float64), np.asarray(gy, dtype=np.float64))
         if tp is not None:

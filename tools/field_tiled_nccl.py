@@ -40,6 +40,7 @@ def field_pass_tiled(net, field_host_or_local, centres, iters=3):
         out["res"] = res
 
     one()
+    one()  # steady state alternates between two result buffers; the first cudaMalloc of a field-sized buffer costs ~100 ms
     torch.cuda.synchronize()
     if dist.is_initialized():
         dist.barrier()
