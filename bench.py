@@ -425,8 +425,9 @@ def field_tiled_extra(net, device, rank, world, quick=False):
             keep["mse"] = obj.field_mse(obj.field_tensor, keep["res"])
 
         with contextlib.redirect_stdout(io.StringIO()):
-            for _ in range(2):  # two passes: the steady state alternates between two result buffers (the caller still holds the
-                one()           # previous residual while the next one is made), and a first cudaMalloc of 805 MB costs ~100 ms
+            for _ in range(3):  # the steady state alternates between two result buffers (the caller still holds the previous
+                one()           # residual while the next one is made): a first cudaMalloc of 805 MB costs ~100 ms; NCCL's
+                                # point-to-point channels also settle over the first passes
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -441,7 +442,7 @@ def field_tiled_extra(net, device, rank, world, quick=False):
                     gc_log.append(round((time.perf_counter() - _t[0]) * 1e3, 2))
 
             gc.callbacks.append(_gc_cb)
-            iters = 5
+            iters = 8
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
             evs[0].record()
             for i in range(iters):
