@@ -96,3 +96,34 @@ def test_reader_on_the_real_index():
     assert {k: tuple(e["shape"]) for k, e in entries.items()} == dict(spec.tensor_table())
     with pytest.raises(FileNotFoundError):  # the 99.8 MB data shard is not part of the snapshot
         ckpt.load_checkpoint(latest)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/debvader/data/weights/dc2/checkpoint"), reason="build container only")
+def test_crc_of_the_real_shard():
+    """The one data shard the reference snapshot does contain (…data-00000-of-00002: the object graph, a string tensor): its
+    bytes, located through the index the way the reader locates every tensor, carry exactly the CRC-32C TensorFlow stored
+    for them — offsets, sizes, the string-tensor framing and the checksum are read as they were written."""
+    d = "/root/reference/src/debvader/data/weights/dc2"
+    prefix = ckpt.latest_checkpoint(d)
+    entries = ckpt.read_index(prefix + ".index", all_entries=True)
+    in_shard0 = {k: e for k, e in entries.items() if e["shard_id"] == 0 and e["size"] > 0}
+    assert list(in_shard0) == ["_CHECKPOINTABLE_OBJECT_GRAPH"]
+    e = in_shard0["_CHECKPOINTABLE_OBJECT_GRAPH"]
+    raw = open(prefix + ".data-00000-of-00002", "rb").read()
+    assert e["offset"] + e["size"] == len(raw) and e["crc32c"] is not None
+    assert ckpt.verify_entry(e, raw[e["offset"] : e["offset"] + e["size"]])
+    bad = bytearray(raw)
+    bad[100] ^= 1
+    assert not ckpt.verify_entry(e, bytes(bad)[e["offset"] : e["offset"] + e["size"]])
+    assert all(v["crc32c"] is not None for v in ckpt.read_index(prefix + ".index").values())  # every model tensor has one too
+
+
+def test_crc32c_known_answers_and_float_tensor_round_trip(tmp_path):
+    """CRC-32C check values (RFC 3720 appendix B.4) and verify=True on a checkpoint written by this module's test writer."""
+    assert ckpt.crc32c(b"123456789") == 0xE3069283
+    assert ckpt.crc32c(bytes(32)) == 0x8A9136AA
+    assert ckpt.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+    assert ckpt.crc32c(b"6789", ckpt.crc32c(b"12345")) == 0xE3069283  # Extend
+    a = np.arange(12, dtype="<f4").reshape(3, 4)
+    e = {"dtype": 1, "shape": [3, 4], "shard_id": 0, "offset": 0, "size": 48, "crc32c": ckpt.crc_mask(ckpt.crc32c(a.tobytes()))}
+    assert ckpt.verify_entry(e, a.tobytes()) and not ckpt.verify_entry(e, (a + 1).tobytes())
