@@ -76,6 +76,33 @@ def tensor_table():
     return t
 
 
+def _pfx(fmt, n):
+    return (fmt % (n, ""))[:-1]  # "layer_with_weights-a/layer_with_weights-n"
+
+
+def layer_types():
+    """[(checkpoint key prefix, Keras layer type)] of every weighted layer in order — the layer sequence the library and the
+    oracle implement (reference model/model.py:61-161): BatchNormalization, then per filter Conv2D / PReLU / Conv2D(stride 2)
+    / PReLU, the Flatten PReLU and the Dense head; decoder PReLU, Dense, PReLU, Dense, PReLU, per filter
+    Conv2DTranspose(stride 2) / PReLU / Conv2DTranspose / PReLU, and the Conv2D output layer.  Pinned by the object graph of
+    the shipped checkpoint (tests/golden/object_graph_names.json)."""
+    t = [(_pfx(ENC, 0), "batch_normalization")]
+    n = 1
+    for _ in DC2_FILTERS:
+        t += [(_pfx(ENC, n), "conv2d"), (_pfx(ENC, n + 1), "p_re_lu"), (_pfx(ENC, n + 2), "conv2d"), (_pfx(ENC, n + 3), "p_re_lu")]
+        n += 4
+    t += [(_pfx(ENC, n), "p_re_lu"), (_pfx(ENC, n + 1), "dense")]
+    t += [(_pfx(DEC, 0), "p_re_lu"), (_pfx(DEC, 1), "dense"), (_pfx(DEC, 2), "p_re_lu"), (_pfx(DEC, 3), "dense"),
+          (_pfx(DEC, 4), "p_re_lu")]
+    n = 5
+    for _ in DC2_FILTERS:
+        t += [(_pfx(DEC, n), "conv2d_transpose"), (_pfx(DEC, n + 1), "p_re_lu"), (_pfx(DEC, n + 2), "conv2d_transpose"),
+              (_pfx(DEC, n + 3), "p_re_lu")]
+        n += 4
+    t += [(_pfx(DEC, n), "conv2d")]
+    return t
+
+
 FLOP_PER_STAMP = 658_693_504  # SURVEY §2.4 / BASELINE.md: nominal 2*MACs, encoder 191 648 128 + decoder 467 045 376
 
 

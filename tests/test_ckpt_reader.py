@@ -127,3 +127,30 @@ def test_crc32c_known_answers_and_float_tensor_round_trip(tmp_path):
     a = np.arange(12, dtype="<f4").reshape(3, 4)
     e = {"dtype": 1, "shape": [3, 4], "shard_id": 0, "offset": 0, "size": 48, "crc32c": ckpt.crc_mask(ckpt.crc32c(a.tobytes()))}
     assert ckpt.verify_entry(e, a.tobytes()) and not ckpt.verify_entry(e, (a + 1).tobytes())
+
+
+def test_layer_types_match_the_object_graph_of_the_shipped_checkpoint(golden_dir):
+    """tests/golden/object_graph_names.json (tests/golden/make_object_graph.py: the TrackableObjectGraph TensorFlow saved
+    with the reference's DC2 weights) names the Keras layer behind every checkpoint key: the layer TYPES and their order —
+    which weighted layer is a BatchNormalization, a Conv2D, a PReLU, a Dense, a Conv2DTranspose — are the ones the library
+    and the oracle implement, and Keras numbered them in that order (conv2d, conv2d_1, ... : creation order = model order)."""
+    import json
+    import re
+
+    g = json.load(open(os.path.join(golden_dir, "object_graph_names.json")))["full_name"]
+    assert set(g) == {k for k, _ in spec.tensor_table()}
+    seen = {}
+    for prefix, kind in spec.layer_types():
+        mine = {k: v for k, v in g.items() if k.rsplit("/", 1)[0] == prefix}
+        assert mine, prefix
+        layer_names = {v.rsplit("/", 1)[0] for v in mine.values()}
+        assert len(layer_names) == 1, (prefix, layer_names)
+        name = layer_names.pop()
+        m = re.fullmatch(r"(.+?)(?:_(\d+))?", name)
+        assert m.group(1) == kind, (prefix, name, kind)
+        idx = int(m.group(2) or 0)
+        assert idx == seen.get(kind, 0), (prefix, name)  # Keras' per-type counter runs in model order
+        seen[kind] = idx + 1
+        for k, v in mine.items():  # variable names: kernel / bias / alpha / gamma ... as in the checkpoint key
+            assert k.rsplit("/", 1)[1] == v.rsplit("/", 1)[1]
+    assert seen == {"batch_normalization": 1, "conv2d": 9, "p_re_lu": 20, "dense": 3, "conv2d_transpose": 8}
