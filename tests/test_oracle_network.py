@@ -33,6 +33,33 @@ def test_fill_triangular_index_form():
     assert np.all(np.triu(L, 1) == 0)
 
 
+def test_fill_triangular_is_the_op_chain_tensorflow_recorded():
+    """The reference's own notebook (notebooks/deblender_to_onnx.ipynb, output of `net.summary()` for the for_onnx model,
+    model/model.py:43-58) lists the TensorFlow ops fill_triangular expanded into, with their shapes:
+    getitem (None, 528) = t[..., 32:]  ->  getitem_3 (None, 496) = x[..., n:]  +  reverse (None, 528)  ->  concat_1 (None, 1024)
+    ->  reshape (None, 32, 32)  ->  linalg.band_part (lower)  ->  diag_part / softplus / add / set_diag (None, 32, 32)
+    ->  matmul with the (None, 32, 1) draw  ->  add to t[..., :32].  The oracle's restatement is that chain, step by step."""
+    rng = np.random.default_rng(0)
+    t = rng.normal(size=(3, 560))
+    x = t[..., 32:]
+    assert x.shape == (3, 528)
+    n = 32
+    head, rev = x[..., n:], x[..., ::-1]
+    assert head.shape == (3, 496) and rev.shape == (3, 528)
+    cat = np.concatenate([head, rev], axis=-1)
+    assert cat.shape == (3, 1024)
+    lower = np.tril(cat.reshape(3, 32, 32))  # band_part(num_lower=-1, num_upper=0)
+    assert np.array_equal(vn.fill_triangular_lower(x), lower)
+    diag = np.log1p(np.exp(np.diagonal(lower, axis1=-2, axis2=-1))) + 1e-5  # softplus + diag_shift (model.py:50-52)
+    L = lower.copy()
+    L[:, np.arange(32), np.arange(32)] = diag
+    eps = rng.normal(size=(3, 32))
+    want = t[..., :32] + np.einsum("bij,bj->bi", L, eps)  # loc + matvec(scale_tril, samples)
+    got = vn.latent(t, eps)
+    got_z = got["z"] if isinstance(got, dict) else got[0]
+    np.testing.assert_allclose(got_z, want, rtol=1e-12, atol=1e-12)
+
+
 def test_transposed_conv_tiny_bruteforce():
     rng = np.random.default_rng(0)
     for s in (1, 2):
