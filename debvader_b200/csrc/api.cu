@@ -1,6 +1,7 @@
 // C-ABI of libdebvader_b200: context, weights, layer plans and the network entry points.
 // See include/debvader_b200.h for the contract and the reference citations.
 #include "kernels.h"
+#include "host_stage.h"
 
 #include <algorithm>
 #include <map>
@@ -179,6 +180,10 @@ struct dbv_ctx {
   float* stage_eps[2] = {nullptr, nullptr};
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool pipe_ready = false;
+  // pageable host input: pinned staging (two slots of the largest piece) filled by a pool of host threads (host_stage.h)
+  float* hstage[2] = {nullptr, nullptr};
+  size_t hstage_elems = 0;
+  dbv::HostStagePool* hpool = nullptr;
   // A ctx owns ONE set of activation buffers: whatever the device-pointer entry points last enqueued on a caller's stream
   // is marked by this event, and the host pipeline (which computes on its own stream) waits for it before its first piece
   cudaEvent_t ev_user = nullptr;
@@ -1067,6 +1072,9 @@ extern "C" int dbv_destroy(dbv_ctx* c) {
   for (auto e : c->prof_ev) cudaEventDestroy(e);
   if (c->ev_user) cudaEventDestroy(c->ev_user);
   if (c->ovf_host) cudaFreeHost(c->ovf_host);
+  for (int i = 0; i < 2; ++i)
+    if (c->hstage[i]) cudaFreeHost(c->hstage[i]);
+  delete c->hpool;
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1371,6 +1379,30 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
   const long long before = g_launches.load();
   const size_t esz = x_dtype == DBV_F64 ? 8 : 4;
   const std::vector<std::pair<int64_t, long long>> sched = host_schedule(B, c->chunk);
+  // Pageable input (an ordinary numpy array): host threads stage it — converting float64 to float32 on the way, which also
+  // halves the PCIe bytes — into pinned memory.  Pinned (registered) input goes to the device as it is.
+  bool stage = false;
+  if (B > 0) {
+    cudaPointerAttributes at{};
+    const cudaError_t pe = cudaPointerGetAttributes(&at, x_host);
+    if (pe != cudaSuccess) cudaGetLastError();  // unregistered memory is reported as an error by old runtimes
+    stage = !(pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged));
+  }
+  if (stage) {
+    long long mx = 0;
+    for (const auto& pc : sched) mx = std::max(mx, pc.second);
+    const size_t need = (size_t)mx * STAMP_ELTS;
+    if (need > c->hstage_elems) {
+      for (int i = 0; i < 2; ++i) {
+        if (c->hstage[i]) cudaFreeHost(c->hstage[i]);
+        c->hstage[i] = nullptr;
+      }
+      c->hstage_elems = 0;
+      for (int i = 0; i < 2; ++i) DBV_CUDA(cudaHostAlloc((void**)&c->hstage[i], need * sizeof(float), cudaHostAllocDefault));
+      c->hstage_elems = need;
+    }
+    if (!c->hpool) c->hpool = new HostStagePool(host_stage_default_threads());
+  }
   // the activation buffers may still be in use by a dbv_deblend / dbv_encode / dbv_decode call enqueued on a caller's stream
   if (c->ev_user) DBV_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_user, 0));
   // on an error in the middle of the pipeline the copies already enqueued may still be writing the caller's host buffers:
@@ -1397,13 +1429,20 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
       DBV_PIPE(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[s], 0));
       DBV_PIPE(cudaStreamWaitEvent(c->s_comp, c->ev_out[s], 0));
     }
-    void* dst = x_dtype == DBV_F64 ? c->stage_in[s] : (void*)c->stage_x[s];
-    DBV_PIPE(cudaMemcpyAsync(dst, (const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, n * esz, cudaMemcpyHostToDevice, c->s_h2d));
+    if (stage) {
+      // the H2D copy that last read this staging slot (piece k-2) must have finished before the slot is refilled
+      if (k >= 2) DBV_PIPE(cudaEventSynchronize(c->ev_in[s]));
+      c->hpool->convert((const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, x_dtype == DBV_F64, c->hstage[s], n);
+      DBV_PIPE(cudaMemcpyAsync(c->stage_x[s], c->hstage[s], n * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    } else {
+      void* dst = x_dtype == DBV_F64 ? c->stage_in[s] : (void*)c->stage_x[s];
+      DBV_PIPE(cudaMemcpyAsync(dst, (const char*)x_host + (size_t)b0 * STAMP_ELTS * esz, n * esz, cudaMemcpyHostToDevice, c->s_h2d));
+    }
     if (eps_host)
       DBV_PIPE(cudaMemcpyAsync(c->stage_eps[s], eps_host + b0 * LAT, (size_t)nb * LAT * 4, cudaMemcpyHostToDevice, c->s_h2d));
     DBV_PIPE(cudaEventRecord(c->ev_in[s], c->s_h2d));
     DBV_PIPE(cudaStreamWaitEvent(c->s_comp, c->ev_in[s], 0));
-    if (x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return drain(r);
+    if (!stage && x_dtype == DBV_F64 && (r = launch_cast_f64_f32((const double*)c->stage_in[s], c->stage_x[s], (long long)n, c->s_comp))) return drain(r);
     // outputs: the caller's resident device buffers when given, else the double-buffered staging slots
     float* d_mean = mean_dev ? mean_dev + (size_t)b0 * STAMP_ELTS : c->stage_mean[s];
     float* d_std = stddev_dev ? stddev_dev + (size_t)b0 * STAMP_ELTS : (stddev_host ? c->stage_std[s] : nullptr);
