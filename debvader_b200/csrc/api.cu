@@ -1386,6 +1386,8 @@ extern "C" int dbv_deblend_host(dbv_ctx* c, const void* x_host, int x_dtype, int
     cudaPointerAttributes at{};
     const cudaError_t pe = cudaPointerGetAttributes(&at, x_host);
     if (pe != cudaSuccess) cudaGetLastError();  // unregistered memory is reported as an error by old runtimes
+    if (pe == cudaSuccess && at.type == cudaMemoryTypeDevice)
+      return fail(DBV_ERR_INVALID, "dbv_deblend_host: x_host is a device pointer (device-resident stamps go through dbv_deblend)");
     stage = !(pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged));
   }
   if (stage) {
