@@ -343,9 +343,22 @@ def test_chunking_and_host_pipeline_agree_with_device_path(wts, data):
     a = big(x, eps=eps)
     b = small(x, eps=eps)
     assert torch.equal(a.mean().tensor, b.mean().tensor) and torch.equal(a.stddev().tensor, b.stddev().tensor)
-    m, s = small.deblend_host(x.astype(np.float64), eps=eps)  # float64 host input: cast on the device
+    # pageable float64 / float32 input: staged into pinned memory by the library's host threads (float64 converted on the way,
+    # csrc/host_stage.cu); pinned input: copied as it is, float64 cast on the device.  Same bits on every route.
+    m, s = small.deblend_host(x.astype(np.float64), eps=eps)
     np.testing.assert_array_equal(m, a.mean().numpy())
     np.testing.assert_array_equal(s, a.stddev().numpy())
+    for dt in (torch.float64, torch.float32):
+        pinned = torch.from_numpy(x).to(dt).pin_memory().numpy()
+        mp, sp = small.deblend_host(pinned, eps=eps)
+        np.testing.assert_array_equal(mp, m)
+        np.testing.assert_array_equal(sp, s)
+    m32, s32 = small.deblend_host(np.array(x, dtype=np.float32, copy=True), eps=eps)
+    np.testing.assert_array_equal(m32, m)
+    big_batch = np.concatenate([x] * 30).astype(np.float64)  # 1200 stamps: several pieces, both staging slots reused
+    mb, _ = big.deblend_host(big_batch, eps=np.concatenate([eps] * 30), want_stddev=False)
+    np.testing.assert_array_equal(mb[-40:], m)
+    np.testing.assert_array_equal(mb[:40], m)
     from debvader_b200.deblend_cutout.deblender import deblend
 
     mean, dist = deblend(small, x, eps=eps)
