@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdebvader_b200.so")
 LIB_ABLATE = os.path.join(HERE, "libdebvader_b200_ablate.so")
-SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "host_stage.cu"]
+SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "tc_halo2.cu", "host_stage.cu"]
 SOURCES_ABLATE = SOURCES + ["tc_probe.cu"]
 HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", "tc_pair_ptx.cuh", "host_stage.h", os.path.join("..", "..", "include", "debvader_b200.h"),
            os.path.join("..", "..", "include", "debvader_b200_debug.h")]

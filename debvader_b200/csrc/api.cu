@@ -564,7 +564,7 @@ static int build_pairh_layer(dbv_ctx* c, int li) {
 
 // Fill T with the plan for R output rows per band and nbuf halo buffers.  Returns 1 if the plan is valid
 // (fits shared memory / TMEM / descriptor fields), 0 if not, < 0 on error.
-static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& T) {
+static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& T, bool pair = false) {
   const LayerDesc& L = kLayers[li];
   const TcGeom& G = kTc[li];
   LayerRt& R = c->rt[li];
@@ -595,7 +595,10 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   // Row pitch of the halo tile: W + 1 — ONE shared zero column per row (slot 0 = x = -1): the right neighbour of x = W-1 is
   // the next row's slot 0, and the slot after the last row is zeroed slack.  conv1's pair trick (x+1, x+2) keeps W + 3.
   const int W = (ncls == 4) ? L.Hin : L.Hout, H = W, WP = c1 ? W + 3 : W + 1;
-  const int n_wblk = (int)taps.size() * nchunk * parts_w;
+  // CTA-pair plan (tc_halo2.cu): each CTA of the pair keeps ONE part of every (tap, chunk) weight block — the leader hi, its peer
+  // lo —, the MMAs have M = 256 and read the two halves of [B_hi | B_lo] from the two shared memories
+  if (pair && (!x3 || in.planes != 1 || c1 || cg8 || (L.kind == L_CONVT && L.stride == 2) || in.mode == OUT_BF16_PARITY)) return 0;
+  const int n_wblk = (int)taps.size() * nchunk * (pair ? 1 : parts_w);
   const int w_bytes = ((n_wblk * G.NT * ROWB_W + 1023) / 1024) * 1024;
   // stride-2 Conv2D: the input is stored as 4 parity planes (OUT_BF16_PARITY); every (plane, hi/lo, chunk) is its own region
   const int npar = (in.mode == OUT_BF16_PARITY) ? 4 : 1;
@@ -639,7 +642,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
     T.cls[cl].osy = T.cls[cl].osx = ncls == 4 ? 2 : 1;
   }
   const int f16 = layer_f16(c->precision, li);
-  auto idesc_of = [&](int n) { return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); };
+  auto idesc_of = [&](int n) { return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24); };
   const long long MSTEP = 128ll * ROWB;  // bytes between consecutive 128-position tiles of a band
   const int ksteps = c1 ? 1 : G.CBK / 16;
   const long long wblk_bytes = (long long)G.NT * ROWB_W;
@@ -669,6 +672,8 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
           for (int part = 0; part < parts_w; ++part) T.w_src[j++] = (uint8_t)((ct.second * nchunk + ch) * parts_w + part);
     }
     if (j != n_wblk) return fail(DBV_ERR_STATE, "%s: concatenated weight layout has %d blocks, expected %d", L.name, j, n_wblk);
+  } else if (pair) {
+    for (int j = 0; j < n_wblk; ++j) T.w_src[j] = (uint8_t)(j * parts_w);  // + cluster rank in the kernel: hi block / lo block
   } else {
     for (int j = 0; j < n_wblk; ++j) T.w_src[j] = (uint8_t)j;
   }
@@ -707,7 +712,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
             for (int pr = 0; pr < in.planes; ++pr)  // pr = 1: the lo activation plane (absent for single-plane inputs)
               for (int k = 0; k < ksteps; ++k) {
                 const long long a_off = a_region(ch, pr, taps[ti].plane) * region + (long long)((taps[ti].dy + pad_top) * WP + taps[ti].dx + pad) * ROWB + 32 * k + m * MSTEP;
-                const long long b_off = (long long)((ti * nchunk + ch) * parts_w) * wblk_bytes + 32 * k;
+                const long long b_off = (long long)((ti * nchunk + ch) * (pair ? 1 : parts_w)) * wblk_bytes + 32 * k;
                 if (!push_op(a_off, b_off, (x3 && pr == 0) ? 2 * G.NT : G.NT, dseg, !first)) return 0;
                 first = false;
               }
@@ -777,6 +782,7 @@ static int halo_plan(dbv_ctx* c, int li, int bandR, int nbuf, int U, HaloLayer& 
   T.wide = x3 ? 1 : 0;
   T.nseg = nseg;
   T.seg_cols = CW;
+  T.pair = pair ? 1 : 0;
   T.tail_pad = tail_pad;
   T.smem_bytes = (int)smem;
   T.bands_per_img = (H + bandR - 1) / bandR;
@@ -864,19 +870,23 @@ static int build_halo_layer(dbv_ctx* c, int li) {
     o.out = tr.hm;
     o.out2 = tr.hs;
   }
+  // the stride-1 layers of the fp16 tail of DBV_PREC_MIXED also have a CTA-pair form (tc_halo2.cu): both are timed
+  const bool try_pair = mixed_tail(c->precision, li) && ncls == 1 && halo_pair_supported(G.CBK, G.NT) && !dbv_env("DBV_NO_HALO_PAIR");
+  for (int pass = 0; pass < (try_pair ? 2 : 1); ++pass)
   for (const Cand& cd : cand) {
     const int r = cd.r, nbuf = cd.nbuf;
+    const bool pair = pass == 1;
     HaloLayer T;
-    int ok = halo_plan(c, li, r, nbuf, cd.U, T);
+    int ok = halo_plan(c, li, r, nbuf, cd.U, T, pair);
     if (ok < 0) return ok;
     if (!ok) continue;
     T.B = Bt;
     T.o = o;
-    T.total_bands = Bt * T.bands_per_img;
+    T.total_bands = (pair ? (Bt + 1) / 2 : Bt) * T.bands_per_img;
     float ms = 0.f;
     for (int it = 0; it < 4; ++it) {  // 1 warm-up + best of 3
       DBV_CUDA(cudaEventRecord(e0, 0));
-      int rr = launch_halo_layer(T, G.CBK, G.NT, kNumSMs, 0);
+      int rr = pair ? launch_halo_pair_layer(T, G.CBK, G.NT, kNumSMs, 0) : launch_halo_layer(T, G.CBK, G.NT, kNumSMs, 0);
       if (rr) return rr;
       DBV_CUDA(cudaEventRecord(e1, 0));
       DBV_CUDA(cudaEventSynchronize(e1));
@@ -884,7 +894,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
       DBV_CUDA(cudaEventElapsedTime(&t, e0, e1));
       ms = (it == 1) ? t : (it >= 2 ? std::min(ms, t) : ms);
     }
-    if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate R=%d nbuf=%d U=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, r, nbuf, cd.U, T.ntiles, T.smem_bytes, ms, Bt);
+    if (getenv("DBV_VERBOSE")) fprintf(stderr, "[dbv] %s: halo candidate%s R=%d nbuf=%d U=%d ntiles=%d smem=%d -> %.3f ms / %lld stamps\n", L.name, pair ? " (CTA pair)" : "", r, nbuf, cd.U, T.ntiles, T.smem_bytes, ms, Bt);
     if (ms < best_ms) { best_ms = ms; best = T; found = true; }
   }
   if (!found && must) return fail(DBV_ERR_STATE, "%s: no valid halo plan (there is no other tensor-core kernel for this layer in this precision)", L.name);
@@ -892,7 +902,7 @@ static int build_halo_layer(dbv_ctx* c, int li) {
   R.halo = best;
   R.has_halo = true;
   if (getenv("DBV_VERBOSE"))
-    fprintf(stderr, "[dbv] %s: halo plan R=%d nbuf=%d U=%d ntiles=%d regions=%d smem=%d (%.3f ms / %lld stamps)\n", L.name, best.R, best.nbuf, best.U,
+    fprintf(stderr, "[dbv] %s: halo plan%s R=%d nbuf=%d U=%d ntiles=%d regions=%d smem=%d (%.3f ms / %lld stamps)\n", L.name, best.pair ? " (CTA pair)" : "", best.R, best.nbuf, best.U,
             best.ntiles, best.n_regions, best.smem_bytes, best_ms, Bt);
   return DBV_OK;
 }
@@ -915,7 +925,8 @@ static int run_layer(dbv_ctx* c, int li, const void* input_f32, long long B, flo
     HaloLayer T = R.halo;
     T.B = B;
     T.o = o;
-    T.total_bands = B * T.bands_per_img;
+    T.total_bands = (T.pair ? (B + 1) / 2 : B) * T.bands_per_img;
+    if (T.pair) return launch_halo_pair_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
     return launch_halo_layer(T, kTc[li].CBK, kTc[li].NT, kNumSMs, st);
   }
   if (R.has_pairh) {

@@ -175,6 +175,8 @@ struct HaloLayer {
   uint32_t magic_wp;  // ceil(2^32 / WP): n / WP == __umulhi(n, magic) for n, WP < 2^16 (epilogue coordinates)
   int cg8;           // the input is OUT_BF16_CG8: ONE un-swizzled TMA box (u64 tensor map (2W, H, planes*Cin/8, B, 1)) fills all
                      // group-plane regions; the A operand is un-swizzled with LBO = region_bytes (K=16 = two groups)
+  int pair;          // 1: CTA-pair plan (tc_halo2.cu): M = 256 ops, each CTA keeps one weight part (block w_src[j] + cluster rank),
+                     // total_bands counts (band, stamp pair) items
   int nbuf;          // halo buffers in the ring (1 or 2)
   int U;             // sub-units per unit (plan parameter, kept for the logs)
   int nseg;          // DBV_PREC_FP32TC: a (class, tile)'s taps are spread over nseg accumulators seg_cols columns apart (shorter
@@ -190,6 +192,9 @@ struct HaloLayer {
   OutSpec o;
 };
 int launch_halo_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+// the same plan on CTA pairs (stride-1 layers with single-plane activations and hi/lo weights: the fp16 tail of DBV_PREC_MIXED)
+int launch_halo_pair_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st);
+bool halo_pair_supported(int CBK, int NT);
 bool halo_layer_supported(int CBK, int NT);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
