@@ -9,7 +9,7 @@
 // operand) and only HALF of the B operand — the leader the hi weight blocks, its peer the lo blocks, which is precisely how
 // cta_group::2 splits the N = 2*NT rows of B between the two shared memories.  Per SM an MMA then fetches 128 A rows + NT
 // B rows instead of 128 + 2*NT: by the single-CTA cost model 40 instead of 48 cycles at N = 64, 48 instead of 64 at N = 128.
-// Measured: it pays at N = 128 only (convT6: -6 %); at N = 64 / 32 the pair MMA is slower (see halo_pair_supported).
+// Measured per layer: see halo_pair_supported below.
 //
 //   both CTAs  warp 0     TMA producer: own weight half once, own halo band per item; all bytes of the pair complete on the
 //                         LEADER's barriers (cp.async.bulk.tensor ... .cta_group::2)
@@ -180,7 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1) tc
               for (int jj = 0; jj < NV / 4; ++jj) al[jj] = __ldg(alpha4 + off + (uint32_t)jj * npix);
             }
             if (!waited) {
-              mbar_wait_cluster(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+              mbar_wait_cluster_relaxed(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
               tc_fence_after();
               waited = true;
             }
@@ -210,12 +210,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1) tc
             }
           }
           if (!waited) {
-            mbar_wait_cluster(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
+            mbar_wait_cluster_relaxed(bar_tfull + 8 * slot, (u >> slot_shift) & 1u);
             tc_fence_after();
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * slot);
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + 8 * slot);
         }
         if (++j == PB) { j = 0; y0 += L.R; }
       }
@@ -248,13 +248,19 @@ static int launch_halo2_one(const HaloLayer& L, int max_ctas, cudaStream_t st) {
   return DBV_OK;
 }
 
-// Measured on B200 (tuner, 2368 stamps): convT6 (N = 2*NT = 128) 0.250 -> 0.234 ms; convT8 (N = 64) 0.393 -> 0.457 ms and the head
-// (N = 32) 0.288 -> 0.317 ms — a cta_group::2 MMA does not get cheaper than ~64 cycles, so the pair form only pays at N >= 128.
-// Only that instance is built; the <32, 32> / <32, 16> instantiations compile and run (same results) if ever wanted.
-bool halo_pair_supported(int CBK, int NT) { return CBK == 64 && NT == 64; }
+// Measured on B200 (plan tuner, 2368 stamps; single CTA -> pair): convT6 (N = 2*NT = 128) 0.250 -> 0.207 ms, convT8 (N = 64)
+// 0.393 -> 0.376 ms, head (N = 32) 0.288 -> 0.262 ms.  The first version handed the accumulator slots back with
+// mbarrier.arrive.release.cluster and was SLOWER than the single-CTA kernel for convT8 and the head (0.457 / 0.317 ms): a
+// release at cluster scope makes every epilogue warp wait until the activations it has just stored are visible to the other
+// SM, once per unit.  The hand-over publishes nothing through memory, so it is now a relaxed arrive (tc_pair_ptx.cuh); the
+// same change in tc_pair.cu / tc_pairh.cu bought 3-7 % on conv5 / convT5.  tools/mma2_rate.cu: a pair MMA costs 39 / 43 / 64 /
+// 128 cycles at N = 32 / 64 / 128 / 256 for twice the rows of a single-CTA MMA (40 / 48 / 64 / 128).
+bool halo_pair_supported(int CBK, int NT) { return (CBK == 64 && NT == 64) || (CBK == 32 && (NT == 32 || NT == 16)); }
 
 int launch_halo_pair_layer(const HaloLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
   if (CBK == 64 && NT == 64) return launch_halo2_one<64, 64>(L, max_ctas, st);
+  if (CBK == 32 && NT == 32) return launch_halo2_one<32, 32>(L, max_ctas, st);
+  if (CBK == 32 && NT == 16) return launch_halo2_one<32, 16>(L, max_ctas, st);
   return fail(DBV_ERR_UNSUPPORTED, "no CTA-pair halo kernel instance for CBK=%d NT=%d", CBK, NT);
 }
 

@@ -180,7 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1) tc_pa
       // the two groups split the tile's 32-channel chunks (group g takes chunks q = g, g+2, ...)
       ActRegs<NV> ra;
       if (grp < NCHK) act_prefetch<NV>(L.o, ok, oy, ox, cbase + grp * NV, boff, ra);
-      mbar_wait_cluster(bar_tfull + 8 * slot, (u >> 1) & 1u);
+      mbar_wait_cluster_relaxed(bar_tfull + 8 * slot, (u >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int q = grp; q < NCHK; q += 2) {
@@ -195,7 +195,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1) tc_pa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * slot);
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + 8 * slot);  // nothing to publish through memory: see tc_pair_ptx.cuh
     }
   }
 

@@ -32,12 +32,35 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same arrive without release semantics.  An epilogue warp that hands an accumulator slot back has nothing to publish
+// through memory: its tcgen05.ld's are complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync.  A
+// release at CLUSTER scope would additionally make the warp wait until all its earlier global stores (the activations it just
+// wrote) are visible to the other SM — hundreds of cycles per hand-over (measured: the pair halo kernel of convT8 0.457 ->
+// 0.376 ms per 2368 stamps).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope (remote arrivals)
   uint32_t done;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// wait without acquire semantics: the epilogue warps wait for an accumulator that arrives through tcgen05.commit and is read
+// with tcgen05.ld after tcgen05.fence::after_thread_sync — no generic-proxy memory is handed over, so the cluster-scope
+// acquire (which also drops the SM's cached read-only data, e.g. the PReLU slopes) is not needed
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)

@@ -185,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
           ActRegs<NV> ra;
           act_prefetch<NV>(L.o, ok, oy, ox, q * NV, 0, ra);
           if (!waited) {
-            mbar_wait_cluster(bar_tfull + 8 * slot, tph);
+            mbar_wait_cluster_relaxed(bar_tfull + 8 * slot, tph);
             tc_fence_after();
             waited = true;
           }
@@ -199,12 +199,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1) tc_pa
         }
       }
       if (!waited) {
-        mbar_wait_cluster(bar_tfull + 8 * slot, tph);
+        mbar_wait_cluster_relaxed(bar_tfull + 8 * slot, tph);
         tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * slot);
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + 8 * slot);  // nothing to publish through memory: see tc_pair_ptx.cuh
     }
   }
 
