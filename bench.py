@@ -42,7 +42,8 @@ BATCH = 4096
 CFG = ("dc2", (59, 59, 6), 32, [32, 64, 128, 256], [3, 3, 3, 3])
 STAMP_ELTS = 59 * 59 * 6
 # which hand-written kernel runs each layer in the tensor-core precisions (csrc/api.cu: kTc, consumes/has_pair/has_halo)
-KERNEL_OF = {**{k: "tc_halo_kernel" for k in ("enc_conv1", "enc_conv2", "enc_conv3", "dec_convT6", "dec_convT7", "dec_convT8", "dec_head")},
+KERNEL_OF = {**{k: "tc_halo_kernel" for k in ("enc_conv1", "enc_conv2", "enc_conv3", "dec_convT7")},
+             **{k: "tc_halo2_kernel (cta_group::2 resident halo) or tc_halo_kernel, whichever the plan tuner timed faster" for k in ("dec_convT6", "dec_convT8", "dec_head")},
              **{k: "tc_pairh_kernel (cta_group::2, halo box)" for k in ("enc_conv5", "enc_conv7", "dec_convT2", "dec_convT3", "dec_convT4", "dec_convT5")},
              **{k: "tc_pair_kernel (cta_group::2)" for k in ("enc_conv6", "enc_conv8", "dec_dense2", "dec_convT1")},
              **{k: "tc_conv_kernel" for k in ("enc_conv4", "enc_dense")},
