@@ -236,9 +236,10 @@ void tc_pair_stage_plan(TcLayer& L, int CBK, int NT) {
   L.wide = 0;
 }
 
-bool tc_pair_supported(int CBK, int NT) { return CBK == 64 && (NT == 128 || NT == 256); }
+bool tc_pair_supported(int CBK, int NT) { return CBK == 64 && (NT == 64 || NT == 128 || NT == 256); }
 
 int launch_tc_pair(const TcLayer& L, int CBK, int NT, int max_ctas, cudaStream_t st) {
+  if (CBK == 64 && NT == 64) return launch_pair_one<64, 64>(L, max_ctas, st);
   if (CBK == 64 && NT == 128) return launch_pair_one<64, 128>(L, max_ctas, st);
   if (CBK == 64 && NT == 256) return launch_pair_one<64, 256>(L, max_ctas, st);
   return fail(DBV_ERR_UNSUPPORTED, "no CTA-pair kernel instance for CBK=%d NT=%d", CBK, NT);
