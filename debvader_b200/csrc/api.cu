@@ -1203,6 +1203,11 @@ extern "C" int dbv_finalize_weights(dbv_ctx* c) {
     o.bias = R.bias;
     o.alpha = R.alpha;
     o.alpha2 = R.alpha2;
+    o.alpha_le1 = 1;  // every slope <= 1 (NaN counts as "no"): the epilogues may then use prelu(v) = max(v, a v)
+    for (const HostTensor* t : {A, A2})
+      if (t)
+        for (float a : t->data)
+          if (!(a <= 1.0f)) o.alpha_le1 = 0;
     o.relu = L.relu_head;
     o.ovf = (!fp32 && o.mode == OUT_BF16_NHWC && o.planes == 1 && o.f16 == 1 && c->precision == DBV_PREC_MIXED) ? c->ovf_dev : nullptr;
     const size_t el = out_elems_per_stamp(o);

@@ -39,6 +39,7 @@ struct OutSpec {
   const float* alpha;  // PReLU slopes of the (OH,OW,Cout) map in the library's layout [Cout/4][OH*OW][4] (see alpha_index), or null
   const float* alpha2; // second PReLU (encoder Flatten PReLU, model/model.py:95), same layout, or null
   int relu;
+  int alpha_le1;       // every PReLU slope of this layer (alpha and alpha2) is <= 1: prelu(v) = max(v, a v) (tc_ptx.cuh:prelu4)
   int* ovf;            // single-plane fp16 outputs (the tail of DBV_PREC_MIXED): host-mapped flag set to 1 when a value saturates
                        // at +-65504, so that leaving the fp16 range fails loudly instead of silently (dbv_fp16_overflow); or null
 };

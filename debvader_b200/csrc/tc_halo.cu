@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
     const int ncls = (DBV_DBG(L.dbg_skip) & 1) ? 0 : L.n_cls;  // units exist only if the MMA warp produces them
     const bool has_alpha = L.o.alpha != nullptr && !(DBV_DBG(L.dbg_skip) & 4);  // halo layers: PReLU(h,w,c) or (head) ReLU, never a second PReLU
     const float4* alpha4 = reinterpret_cast<const float4*>(L.o.alpha);
+    const bool le1 = L.o.alpha_le1 != 0;
     const uint32_t npix = (uint32_t)(L.o.OH * L.o.OW);
     // The output layout (mode / planes / 16-bit format) is constant for a launch: the loops are instantiated once per
     // layout actually used, with those OutSpec fields as compile-time constants, so that store_act's dispatch folds away
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
               tmem_ld_wait<NV>(v);
               tmem_ld_wait<NV>(w);
   #pragma unroll
-              for (int j = 0; j < NV; ++j) v[j] += w[j];
+              for (int j = 0; j < NV; j += 2) add2(v[j], v[j + 1], w[j], w[j + 1]);
               if constexpr (SEGS) {  // DBV_PREC_FP32TC: the other partial accumulators of this tile, promoted in fp32 registers
                 for (int sg = 1; sg < L.nseg; ++sg) {
                   float w2[NV];
@@ -293,12 +294,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) tc_halo_kernel(const __grid_c
                 for (int j = 0; j < NV; ++j) v[j] += L.bias_c[c0 + j];  // bias from the constant bank
                 if (has_alpha) {
   #pragma unroll
-                  for (int j = 0; j < NV / 4; ++j) {
-                    v[4 * j + 0] = prelu_f(v[4 * j + 0], al[j].x);
-                    v[4 * j + 1] = prelu_f(v[4 * j + 1], al[j].y);
-                    v[4 * j + 2] = prelu_f(v[4 * j + 2], al[j].z);
-                    v[4 * j + 3] = prelu_f(v[4 * j + 3], al[j].w);
-                  }
+                  for (int j = 0; j < NV / 4; ++j) prelu4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], al[j], le1);
                 } else if (L.o.relu) {
   #pragma unroll
                   for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);

@@ -145,6 +145,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1) tc
     const uint32_t tempty0 = map_to_rank(bar_tempty, 0);
     const bool has_alpha = L.o.alpha != nullptr;
     const float4* alpha4 = reinterpret_cast<const float4*>(L.o.alpha);
+    const bool le1 = L.o.alpha_le1 != 0;
     const uint32_t npix = (uint32_t)(L.o.OH * L.o.OW);
     auto run = [&](auto MODE, auto PLANES, auto F16) {
       OutSpec o = L.o;
@@ -190,18 +191,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1) tc
             tmem_ld_wait<NV>(v);
             tmem_ld_wait<NV>(w);
 #pragma unroll
-            for (int jj = 0; jj < NV; ++jj) v[jj] += w[jj];
+            for (int jj = 0; jj < NV; jj += 2) add2(v[jj], v[jj + 1], w[jj], w[jj + 1]);
             if (ok) {
 #pragma unroll
               for (int jj = 0; jj < NV; ++jj) v[jj] += L.bias_c[c0 + jj];
               if (has_alpha) {
 #pragma unroll
-                for (int jj = 0; jj < NV / 4; ++jj) {
-                  v[4 * jj + 0] = prelu_f(v[4 * jj + 0], al[jj].x);
-                  v[4 * jj + 1] = prelu_f(v[4 * jj + 1], al[jj].y);
-                  v[4 * jj + 2] = prelu_f(v[4 * jj + 2], al[jj].z);
-                  v[4 * jj + 3] = prelu_f(v[4 * jj + 3], al[jj].w);
-                }
+                for (int jj = 0; jj < NV / 4; ++jj) prelu4(v[4 * jj + 0], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3], al[jj], le1);
               } else if (L.o.relu) {
 #pragma unroll
                 for (int jj = 0; jj < NV; ++jj) v[jj] = fmaxf(v[jj], 0.f);

@@ -192,11 +192,35 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 constexpr uint32_t kSmemDescLoConst = 1u << 16;
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-// packed fp32 add (sm_100 FADD2): (a0, a1) += (b0, b1) in one instruction — the epilogues are instruction-issue bound
+// packed fp32 arithmetic (sm_100 FADD2 / FMUL2): two lanes per instruction — the halo epilogues are instruction-issue bound
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
   asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; add.rn.f32x2 ra, ra, rb; mov.b64 {%0, %1}, ra; }"
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& r0, float& r1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r0), "=f"(r1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// PReLU of four channels with slopes (a.x .. a.w).  When every slope of the layer is <= 1 (le1: checked on the host when the
+// weights are loaded; trained slopes are small), prelu(v) = max(v, a * v) — for v > 0, a v <= v; for v < 0, a v >= v — which is
+// one packed multiply per two channels + one FMNMX per channel instead of compare + multiply + select per channel.
+__device__ __forceinline__ void prelu4(float& v0, float& v1, float& v2, float& v3, const float4& a, bool le1) {
+  if (le1) {
+    float t0, t1, t2, t3;
+    mul2(t0, t1, v0, v1, a.x, a.y);
+    mul2(t2, t3, v2, v3, a.z, a.w);
+    v0 = fmaxf(v0, t0);
+    v1 = fmaxf(v1, t1);
+    v2 = fmaxf(v2, t2);
+    v3 = fmaxf(v3, t3);
+  } else {
+    v0 = v0 > 0.f ? v0 : a.x * v0;
+    v1 = v1 > 0.f ? v1 : a.y * v1;
+    v2 = v2 > 0.f ? v2 : a.z * v2;
+    v3 = v3 > 0.f ? v3 : a.w * v3;
+  }
 }
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while its

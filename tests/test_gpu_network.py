@@ -210,6 +210,30 @@ def test_fp32tc_other_weights_and_stamps(seed):
     net.close()
 
 
+def test_prelu_slopes_above_one_and_negative(wts, data):
+    """The halo epilogues compute prelu(v) as max(v, a v) when every slope of the layer is <= 1 (checked when the weights are
+    loaded) and as the exact select otherwise: networks whose slopes reach 1.5 or are negative — which trained DC2 weights do
+    not need, but the architecture allows — still match the oracle."""
+    rng = np.random.default_rng(5)
+    w = dict(wts)
+    for k, v in wts.items():
+        if k.endswith("alpha"):
+            a = v * np.float32(6.0)  # U(0, 0.25) -> U(0, 1.5)
+            a[rng.random(a.shape) < 0.1] *= np.float32(-0.5)
+            w[k] = a.astype(np.float32)
+    x, eps = data
+    x, eps = x[:12], eps[:12]
+    o = TorchOracle(w, dtype=torch.float64).forward(x.astype(np.float64), eps.astype(np.float64))
+    peak = float(o["mean"].abs().max())
+    for precision, tol in (("bf16x3", 1e-3), ("mixed", 1e-3), ("fp32tc", 1e-5)):
+        net = _net(w, precision, chunk=64)
+        d = net(x, eps=eps)
+        e = float((d.mean().tensor.double().cpu() - o["mean"]).abs().max()) / peak
+        print(f"slopes up to 1.5 / negative, {precision}: err/peak={e:.3e}")
+        assert e <= tol, (precision, e)
+        net.close()
+
+
 def _scaled(w, gamma=1.0, kernels=1.0):
     out = dict(w)
     k = "layer_with_weights-0/layer_with_weights-0/gamma"
