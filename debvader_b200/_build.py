@@ -24,10 +24,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdebvader_b200.so")
 LIB_ABLATE = os.path.join(HERE, "libdebvader_b200_ablate.so")
-SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "tc_halo2.cu", "host_stage.cu"]
+SOURCES = ["api.cu", "field_kernels.cu", "simt_kernels.cu", "tc_conv.cu", "tc_pair.cu", "tc_pairh.cu", "tc_halo.cu", "tc_halo2.cu", "host_stage.cu", "detect_kernels.cu"]
 SOURCES_ABLATE = SOURCES + ["tc_probe.cu"]
 HEADERS = ["common.cuh", "epilogue.cuh", "kernels.h", "tc_ptx.cuh", "tc_pair_ptx.cuh", "host_stage.h", os.path.join("..", "..", "include", "debvader_b200.h"),
            os.path.join("..", "..", "include", "debvader_b200_debug.h")]
+# detect_kernels.cu is compared bit for bit with oracle/detect_numpy.py: no fused multiply-adds (numpy rounds every product and sum)
+EXTRA_FLAGS = {"detect_kernels.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -67,7 +69,7 @@ def build(force: bool = False, verbose: bool = False, ablate: bool = False) -> s
     for s in SOURCES_ABLATE if ablate else SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *flags, *EXTRA_FLAGS.get(s, []), "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

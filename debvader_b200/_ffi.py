@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEBVADER_B200_LIB") or os.path.join(_HERE, "libdebvader_b200.so")  # env override: A/B builds of the same source
 
-ABI_VERSION = 5  # must equal DBV_ABI_VERSION in include/debvader_b200.h
+ABI_VERSION = 6  # must equal DBV_ABI_VERSION in include/debvader_b200.h
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2, "fp16x3": 3, "mixed": 4, "fp32tc": 5}
 F32, F64 = 0, 1
 
@@ -65,6 +65,11 @@ def _declare(lib):
         "dbv_global_launch_count": (c_i64, []),
         "dbv_set_profiling": (C.c_int, [c_vp, C.c_int]),
         "dbv_layer_times": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
+        "dbv_layer_kernel": (C.c_int, [c_vp, C.c_char_p, c_vp, C.c_int]),
+        "dbv_detect_scratch_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+        "dbv_detect": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                 c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        "dbv_detect_plane": (c_vp, [c_vp, c_i64, c_i64, c_i64, C.c_int]),
         "dbv_debug_activation": (C.c_int, [c_vp, C.c_char_p, c_i64, c_vp, c_vp]),
     }
     for name, (res, args) in sig.items():

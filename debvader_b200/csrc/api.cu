@@ -1527,6 +1527,26 @@ extern "C" int dbv_layer_times(dbv_ctx* c, int max_layers, float* ms_out, char* 
   return n;
 }
 
+extern "C" int dbv_layer_kernel(dbv_ctx* c, const char* name, char* out, int out_bytes) {
+  // which __global__ function (as the ncu launch list names it) runs this layer under the ctx's precision and tuned plan
+  int r = check_ready(c, "dbv_layer_kernel");
+  if (r) return r;
+  DBV_REQUIRE(name && out && out_bytes >= 48, "dbv_layer_kernel: bad argument");
+  if (!strcmp(name, "enc_bn_pack")) { snprintf(out, out_bytes, "bn_pack8_kernel"); return DBV_OK; }
+  if (!strcmp(name, "latent")) { snprintf(out, out_bytes, "latent_kernel"); return DBV_OK; }
+  for (int li = 0; li < kNumLayers; ++li) {
+    if (strcmp(name, kLayers[li].name)) continue;
+    const LayerRt& R = c->rt[li];
+    if (R.has_halo) snprintf(out, out_bytes, "%s<%d, %d>", R.halo.pair ? "tc_halo2_kernel" : "tc_halo_kernel", kTc[li].CBK, kTc[li].NT);
+    else if (R.has_pairh) snprintf(out, out_bytes, "tc_pairh_kernel<%d>", kTc[li].NT);
+    else if (R.has_pair) snprintf(out, out_bytes, "tc_pair_kernel<%d, %d>", kTc[li].CBK, kTc[li].NT);
+    else if (R.has_tc) { const TcGeom G = tc_geom(c->precision, li); snprintf(out, out_bytes, "tc_conv_kernel<%d, %d>", G.CBK, G.NT); }
+    else snprintf(out, out_bytes, "simt_kernel");
+    return DBV_OK;
+  }
+  return fail(DBV_ERR_INVALID, "dbv_layer_kernel: unknown layer '%s'", name);
+}
+
 extern "C" int dbv_debug_activation(dbv_ctx* c, const char* name, int64_t B, float* out, void* stream) {
   int r = check_ready(c, "dbv_debug_activation");
   if (r) return r;

@@ -1,0 +1,686 @@
+// Object detection on the device: the step reference detect/detection.py:5-56 delegates to the CPU library
+// `sep` (sep.Background + sep.extract on the r band), restated stage by stage from the published algorithm
+// (Bertin & Arnouts 1996; Barbary 2016) — see oracle/detect_numpy.py, whose arithmetic this file reproduces BIT FOR BIT:
+//
+//   B1  det_mesh_kernel       per 64x64 mesh: mean / sigma, one +-2 sigma clip, level histogram, iterated 3-sigma clipping
+//   B2  det_mesh_post_kernel  bad-mesh fill, 3x3 median filter, global background / rms (medians), threshold, y-spline
+//   B3  det_nodes_kernel + det_foreground_kernel   bicubic-spline background map, foreground = band - background
+//   E1  det_filter_kernel     normalised 7x7 matched filter (zero outside the image), threshold test -> initial labels
+//   E2  det_ccl_*             8-connected components by union-find on the label image (root = smallest raster index)
+//   E3  det_stats / mark / count / scan / scatter   pixel count, bounding columns and LARGEST raster index per object; the
+//                             objects with >= minarea pixels listed by ascending largest raster index = the order in which
+//                             Lutz's one-pass scan completes them = sep's output order
+//   E4  det_moments_kernel    barycentre of the unfiltered foreground (double, raster order), centres rounded half-to-even
+//
+// Not restated: multi-threshold deblending and the `clean` pass (a connected footprint is ONE detection).
+// Parity with `sep` itself is UNPINNED (sep is not installable here, the reference holds no golden detections); parity with
+// the oracle is exact.  The file is compiled with -fmad=false: every product and sum is rounded on its own, as numpy does.
+// All HBM-bound integer / float work: coalesced loads, shared-memory tiles, integer atomics only (deterministic).
+#ifdef DBV_EMULATE  // host build of the SAME kernels for the container's logic check (tools/detect_emul, no GPU there); never in the library
+#include "detect_emul.h"
+#else
+#include "common.cuh"
+#include <limits.h>
+#define DET_LAUNCH(kernel, grid, block, smem, ...)     \
+  do {                                                 \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__);    \
+    DBV_LAUNCH_CHECK();                                \
+  } while (0)
+#define DET_MEMSET(p, v, n) DBV_CUDA(cudaMemsetAsync(p, v, n, st))
+#define DET_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
+namespace dbv {
+
+constexpr int DET_BW = 64;            // mesh size (sep.Background defaults)
+constexpr int DET_MAXLEVELS = 4096;   // histogram levels
+constexpr float DET_BIG = 1e30f;
+constexpr int DET_CHUNK = 4096;       // pixels per CTA of the compaction kernels (256 threads x 16)
+constexpr int DET_MAXK = 15;          // largest filter mask side
+
+struct DetTaps { float v[DET_MAXK * DET_MAXK]; };  // passed by value: a launch parameter (constant bank), no shared state between calls
+
+// ---- band -> compact f64 plane ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void det_band_kernel(const T* __restrict__ field, long long H, long long W, long long pitch, int C, int band, double* __restrict__ out) {
+  const long long n = H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const long long y = p / W, x = p - y * W;
+    out[p] = (double)field[(y * pitch + x) * C + band];
+  }
+}
+
+// ---- B1 --------------------------------------------------------------------------------------------------------------
+// iterated clipping on the level histogram of one mesh (oracle: histogram_guess); doubles, integer counts: sums exact
+__device__ void det_histo_guess(const int* histo, int nlevels, double mean0, float qzero_f, float qscale_f, float* back, float* sigma) {
+  const int nm1 = nlevels - 1;
+  const double qzero = (double)qzero_f, qscale = (double)qscale_f;
+  int lcut = 0, hcut = nm1;
+  double sig = 10.0 * nm1, sig1 = 1.0, mea = mean0, med = mean0;
+  for (int n = 100; n > 0 && sig >= 0.1 && fabs(sig / sig1 - 1.0) > 1e-4; --n) {
+    sig1 = sig;
+    long long tot = 0, lowsum = 0, highsum = 0;
+    mea = 0.0;
+    sig = 0.0;
+    int lo = lcut, hi = hcut;
+    for (int i = lcut; i <= hcut; ++i) {
+      if (lowsum < highsum) lowsum += histo[lo++];
+      else highsum += histo[hi--];
+      const int c = histo[i];
+      tot += c;
+      const double ci = (double)c * (double)i;
+      mea += ci;
+      sig += ci * (double)i;
+    }
+    if (hi >= 0) {
+      const int a = histo[lo < nm1 ? lo : nm1], b = histo[hi];
+      const int big = a > b ? a : b;
+      med = (double)hi + 0.5 + (big > 0 ? (double)(highsum - lowsum) / (2.0 * (double)big) : 0.0);
+    } else {
+      med = 0.0;
+    }
+    if (tot) {
+      mea = mea / (double)tot;
+      sig = sig / (double)tot - mea * mea;
+    }
+    sig = sig > 0.0 ? sqrt(sig) : 0.0;
+    double t = med - 3.0 * sig;
+    lcut = t > 0.0 ? (int)(t + 0.5) : 0;
+    t = med + 3.0 * sig;
+    hcut = t < (double)nm1 ? (t > 0.0 ? (int)(t + 0.5) : (int)(t - 0.5)) : nm1;
+    if (hcut < lcut) hcut = lcut;
+  }
+  double bk;
+  if (sig > 0.0) {
+    if (fabs((mea - med) / sig) < 0.3) bk = qzero + (2.5 * med - 1.5 * mea) * qscale;
+    else bk = qzero + med * qscale;
+  } else {
+    bk = qzero + mea * qscale;
+  }
+  *back = (float)bk;
+  *sigma = (float)(sig * qscale);
+}
+
+// one CTA of 64 threads per mesh: thread r owns mesh row r (sequential double sums, rows then combined in order by thread 0)
+__global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, int H, int W, int nx, float* __restrict__ back0,
+                                                      float* __restrict__ sig0) {
+  __shared__ float tile[DET_BW][DET_BW + 1];
+  __shared__ int histo[DET_MAXLEVELS];
+  __shared__ double rs[DET_BW], rq[DET_BW], rn[DET_BW];
+  __shared__ float s_lcut, s_hcut, s_qscale, s_cste, s_qzero;
+  __shared__ int s_nlevels, s_bad;
+  __shared__ double s_mean2;
+  const int mx = blockIdx.x, my = blockIdx.y, t = threadIdx.x;
+  const int x0 = mx * DET_BW, y0 = my * DET_BW;
+  const int mw = min(DET_BW, W - x0), mh = min(DET_BW, H - y0);
+  for (int r = 0; r < mh; ++r)
+    if (t < mw) tile[r][t] = (float)band[(long long)(y0 + r) * W + x0 + t];
+  __syncthreads();
+  // pass 1: all pixels
+  if (t < mh) {
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < mw; ++c) {
+      const double v = (double)tile[t][c];
+      s += v;
+      q += v * v;
+    }
+    rs[t] = s;
+    rq[t] = q;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < mh; ++r) { s += rs[r]; q += rq[r]; }
+    const double n = (double)(mh * mw);
+    const double mean = s / n;
+    const double var = q / n - mean * mean;
+    const double sigma = var > 0.0 ? sqrt(var) : 0.0;
+    s_lcut = (float)(mean - 2.0 * sigma);
+    s_hcut = (float)(mean + 2.0 * sigma);
+  }
+  __syncthreads();
+  // pass 2: pixels inside the cuts
+  if (t < mh) {
+    const float lc = s_lcut, hc = s_hcut;
+    double s = 0.0, q = 0.0, n = 0.0;
+    for (int c = 0; c < mw; ++c) {
+      const float f = tile[t][c];
+      if (f >= lc && f <= hc) {
+        const double v = (double)f;
+        n += 1.0;
+        s += v;
+        q += v * v;
+      }
+    }
+    rs[t] = s;
+    rq[t] = q;
+    rn[t] = n;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0, q = 0.0, n = 0.0;
+    for (int r = 0; r < mh; ++r) { n += rn[r]; s += rs[r]; q += rq[r]; }
+    const double nall = (double)(mh * mw);
+    if (n < nall * 0.5 || n < 1.0) {
+      s_bad = 1;
+    } else {
+      s_bad = 0;
+      const double mean2 = s / n;
+      const double var2 = q / n - mean2 * mean2;
+      const double sigma2 = var2 > 0.0 ? sqrt(var2) : 0.0;
+      int nl = (int)(0.9973557010035817 /* sqrt(2/pi) * 5 / 4 */ * n + 1.0);
+      if (nl > DET_MAXLEVELS) nl = DET_MAXLEVELS;
+      const float qscale = sigma2 > 0.0 ? (float)(10.0 * sigma2 / (double)nl) : 1.0f;
+      const float qzero = (float)(mean2 - 5.0 * sigma2);
+      s_nlevels = nl;
+      s_qscale = qscale;
+      s_qzero = qzero;
+      s_cste = (float)(0.499999 - (double)qzero / (double)qscale);
+      s_mean2 = mean2;
+    }
+  }
+  for (int i = t; i < DET_MAXLEVELS; i += DET_BW) histo[i] = 0;
+  __syncthreads();
+  if (s_bad) {
+    if (t == 0) {
+      back0[my * nx + mx] = -DET_BIG;
+      sig0[my * nx + mx] = -DET_BIG;
+    }
+    return;
+  }
+  if (t < mh) {
+    const float qs = s_qscale, cs = s_cste;
+    const int nl = s_nlevels;
+    for (int c = 0; c < mw; ++c) {
+      const float lev = tile[t][c] / qs + cs;
+      if (lev > -1.0f && lev < (float)nl) {
+        const int b = (int)lev;
+        if (b >= 0 && b < nl) atomicAdd(&histo[b], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (t == 0) det_histo_guess(histo, s_nlevels, s_mean2, s_qzero, s_qscale, &back0[my * nx + mx], &sig0[my * nx + mx]);
+}
+
+// ---- B2 --------------------------------------------------------------------------------------------------------------
+__device__ float det_median_small(float* a, int n) {  // insertion sort of <= 9 values
+  for (int i = 1; i < n; ++i) {
+    const float v = a[i];
+    int j = i - 1;
+    for (; j >= 0 && a[j] > v; --j) a[j + 1] = a[j];
+    a[j + 1] = v;
+  }
+  return (n & 1) ? a[n / 2] : (a[n / 2 - 1] + a[n / 2]) * 0.5f;
+}
+
+// median of n floats by rank selection (every thread ranks its own elements; ties broken by index)
+__device__ float det_median_block(const float* a, int n, float* s_pick) {
+  __syncthreads();
+  const int k1 = n / 2, k0 = (n & 1) ? k1 : k1 - 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = a[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float w = a[j];
+      rank += (w < v) || (w == v && j < i);
+    }
+    if (rank == k0) s_pick[0] = v;
+    if (rank == k1) s_pick[1] = v;
+  }
+  __syncthreads();
+  const float m = (n & 1) ? s_pick[1] : (s_pick[0] + s_pick[1]) * 0.5f;
+  __syncthreads();
+  return m;
+}
+
+// second derivatives / 6 of the natural cubic spline through n samples `v` (stride sv), Thomas algorithm in float32
+// (oracle: _spline_d2); cp / u are n-element scratch rows with the same stride as d
+__device__ void det_spline_d2(const float* v, int sv, int n, float* d, float* cp, float* u, int sd) {
+  for (int k = 0; k < n; ++k) d[k * sd] = 0.f;
+  if (n < 3) return;
+  cp[0] = 0.f;
+  u[0] = 0.f;
+  for (int k = 1; k < n - 1; ++k) {
+    const float rhs = 6.0f * ((v[(k + 1) * sv] + v[(k - 1) * sv]) - 2.0f * v[k * sv]);
+    const float den = 4.0f - cp[(k - 1) * sd];
+    cp[k * sd] = 1.0f / den;
+    u[k * sd] = (rhs - u[(k - 1) * sd]) / den;
+  }
+  float m = 0.f;  // M[n-1]
+  for (int k = n - 2; k >= 1; --k) {
+    m = u[k * sd] - cp[k * sd] * m;
+    d[k * sd] = m / 6.0f;
+  }
+}
+
+// one CTA: the mesh maps are tiny (64 x 64 for a 4096^2 field)
+__global__ void __launch_bounds__(256) det_mesh_post_kernel(const float* __restrict__ back0, const float* __restrict__ sig0, int ny, int nx,
+                                                            float* back1, float* sig1, float* back, float* sig, float* dback, float* cp,
+                                                            float* u, double thresh_sigma, float* stats) {
+  __shared__ float s_pick[2];
+  __shared__ int s_ngood;
+  const int n = ny * nx;
+  if (threadIdx.x == 0) s_ngood = 0;
+  __syncthreads();
+  int good = 0;
+  for (int m = threadIdx.x; m < n; m += blockDim.x) good += back0[m] > -DET_BIG;
+  if (good) atomicAdd(&s_ngood, good);
+  __syncthreads();
+  const int ngood = s_ngood;
+  // bad meshes: float32 mean of the nearest good ones (raster order)
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    float b = back0[m], s = sig0[m];
+    if (!(b > -DET_BIG) && ngood > 0) {
+      const int y = m / nx, x = m - y * nx;
+      long long best = LLONG_MAX;
+      for (int g = 0; g < n; ++g)
+        if (back0[g] > -DET_BIG) {
+          const long long dy = g / nx - y, dx = g % nx - x, d2 = dy * dy + dx * dx;
+          if (d2 < best) best = d2;
+        }
+      float sb = 0.f, ss = 0.f;
+      int k = 0;
+      for (int g = 0; g < n; ++g)
+        if (back0[g] > -DET_BIG) {
+          const long long dy = g / nx - y, dx = g % nx - x;
+          if (dy * dy + dx * dx == best) { sb += back0[g]; ss += sig0[g]; ++k; }
+        }
+      b = sb / (float)k;
+      s = ss / (float)k;
+    }
+    back1[m] = b;
+    sig1[m] = s;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    const int y = m / nx, x = m - y * nx;
+    float a[9], c[9];
+    int k = 0;
+    for (int yy = max(y - 1, 0); yy < min(y + 2, ny); ++yy)
+      for (int xx = max(x - 1, 0); xx < min(x + 2, nx); ++xx) {
+        a[k] = back1[yy * nx + xx];
+        c[k] = sig1[yy * nx + xx];
+        ++k;
+      }
+    back[m] = det_median_small(a, k);
+    sig[m] = det_median_small(c, k);
+  }
+  const float gback = det_median_block(back, n, s_pick);
+  const float grms = det_median_block(sig, n, s_pick);
+  if (threadIdx.x == 0) {
+    stats[0] = gback;
+    stats[1] = grms;
+    stats[2] = (float)(thresh_sigma * (double)grms);
+  }
+  for (int x = threadIdx.x; x < nx; x += blockDim.x) det_spline_d2(back + x, nx, ny, dback + x, cp + x, u + x, nx);
+}
+
+// ---- B3 --------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float det_spline_eval(float lo, float hi, float dlo, float dhi, float t) {
+  const float ct = 1.0f - t;
+  return ((ct * lo + t * hi) + ((ct * ct) * ct - ct) * dlo) + ((t * t) * t - t) * dhi;
+}
+__device__ __forceinline__ void det_spline_pos(int i, int n, int* lo, float* t) {
+  const float u = ((float)i + 0.5f) / (float)DET_BW - 0.5f;
+  int l = (int)floorf(u);
+  l = l < 0 ? 0 : (l > n - 2 ? n - 2 : l);
+  *lo = l;
+  *t = u - (float)l;
+}
+
+// one thread per image row: the mesh map interpolated along y at this row (node), then its x-spline (dnode)
+__global__ void det_nodes_kernel(const float* __restrict__ back, const float* __restrict__ dback, int H, int ny, int nx, float* node,
+                                 float* dnode, float* cp, float* u) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= H) return;
+  float* nd = node + (long long)y * nx;
+  if (ny > 1) {
+    int yl;
+    float t;
+    det_spline_pos(y, ny, &yl, &t);
+    for (int x = 0; x < nx; ++x)
+      nd[x] = det_spline_eval(back[yl * nx + x], back[(yl + 1) * nx + x], dback[yl * nx + x], dback[(yl + 1) * nx + x], t);
+  } else {
+    for (int x = 0; x < nx; ++x) nd[x] = back[x];
+  }
+  det_spline_d2(nd, 1, nx, dnode + (long long)y * nx, cp + (long long)y * nx, u + (long long)y * nx, 1);
+}
+
+__global__ void det_foreground_kernel(const double* __restrict__ band, const float* __restrict__ node, const float* __restrict__ dnode, int H,
+                                      int W, int nx, float* __restrict__ fg) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const float* nd = node + (long long)y * nx;
+  float b;
+  if (nx > 1) {
+    const float* dn = dnode + (long long)y * nx;
+    int xl;
+    float t;
+    det_spline_pos(x, nx, &xl, &t);
+    b = det_spline_eval(nd[xl], nd[xl + 1], dn[xl], dn[xl + 1], t);
+  } else {
+    b = nd[0];
+  }
+  const long long p = (long long)y * W + x;
+  fg[p] = (float)(band[p] - (double)b);
+}
+
+// ---- E1 --------------------------------------------------------------------------------------------------------------
+// 32 x 32 outputs per CTA from a zero-padded shared tile; taps accumulated in raster order (float32, one rounding per product
+// and per sum).  Writes the filtered image and the initial label image: own raster index above the threshold, -1 below.
+__global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict__ fg, int H, int W, int kh, int kw, const DetTaps taps,
+                                                         const float* __restrict__ stats, float* __restrict__ conv, int* __restrict__ label) {
+  DET_DYN_SMEM(float, sm);
+  const int tw = 32 + kw - 1, th = 32 + kh - 1;
+  const int x0 = blockIdx.x * 32 - kw / 2, y0 = blockIdx.y * 32 - kh / 2;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int y = y0 + ty, x = x0 + tx;
+    sm[i] = (y >= 0 && y < H && x >= 0 && x < W) ? fg[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  const float thresh = stats[2];
+  const int lx = threadIdx.x & 31;
+  for (int ly = threadIdx.x >> 5; ly < 32; ly += 8) {
+    const int x = blockIdx.x * 32 + lx, y = blockIdx.y * 32 + ly;
+    if (x >= W || y >= H) continue;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) acc = acc + taps.v[ky * kw + kx] * sm[(ly + ky) * tw + lx + kx];
+    const long long p = (long long)y * W + x;
+    conv[p] = acc;
+    label[p] = acc > thresh ? (int)p : -1;
+  }
+}
+
+// ---- E2: union-find on the label image ------------------------------------------------------------------------------------
+__device__ __forceinline__ int det_find(int* L, int i) {
+  volatile int* V = L;
+  int p = V[i];
+  while (p != i) {
+    i = p;
+    p = V[i];
+  }
+  return i;
+}
+__device__ void det_unite(int* L, int a, int b) {
+  bool done;
+  do {
+    a = det_find(L, a);
+    b = det_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// links to the already-scanned neighbours W, NW, N, NE; NW is implied when W or N is set, NE when N is set
+__global__ void det_ccl_merge_kernel(int* L, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int p = y * W + x;
+  if (L[p] < 0) return;
+  const bool w = x > 0 && L[p - 1] >= 0;
+  const bool n = y > 0 && L[p - W] >= 0;
+  const bool nw = x > 0 && y > 0 && L[p - W - 1] >= 0;
+  const bool ne = x + 1 < W && y > 0 && L[p - W + 1] >= 0;
+  if (w) det_unite(L, p, p - 1);
+  if (n) det_unite(L, p, p - W);
+  if (nw && !w && !n) det_unite(L, p, p - W - 1);
+  if (ne && !n) det_unite(L, p, p - W + 1);
+}
+
+__global__ void det_ccl_flatten_kernel(int* L, long long n) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n || L[p] < 0) return;
+  L[p] = det_find(L, (int)p);
+}
+
+// ---- E3 --------------------------------------------------------------------------------------------------------------
+__global__ void det_stats_kernel(const int* __restrict__ L, int H, int W, int* npix, int* last, int* xmin, int* xmax) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int p = y * W + x;
+  const int r = L[p];
+  if (r < 0) return;
+  atomicAdd(&npix[r], 1);
+  atomicMax(&last[r], p);
+  atomicMin(&xmin[r], x);
+  atomicMax(&xmax[r], x);
+}
+
+__global__ void det_mark_kernel(const int* __restrict__ L, long long n, const int* __restrict__ npix, const int* __restrict__ last, int minarea,
+                                unsigned char* flag) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (L[p] == (int)p && npix[p] >= minarea) flag[last[p]] = 1;
+}
+
+// flags are compacted in raster order: per-CTA counts, one-CTA exclusive scan, scatter
+__global__ void __launch_bounds__(256) det_count_kernel(const unsigned char* __restrict__ flag, long long n, int* cnt) {
+  const long long base = (long long)blockIdx.x * DET_CHUNK + threadIdx.x * 16;
+  int c = 0;
+  for (int j = 0; j < 16; ++j)
+    if (base + j < n) c += flag[base + j];
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  if (c) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) cnt[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024) det_scan_kernel(const int* __restrict__ cnt, int nblk, int* off, int* n_out) {
+  __shared__ int buf[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblk ? cnt[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int a = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (i < nblk) off[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_out[0] = carry;
+}
+
+__global__ void __launch_bounds__(256) det_scatter_kernel(const unsigned char* __restrict__ flag, long long n, const int* __restrict__ off,
+                                                          long long max_objects, int* endpos) {
+  __shared__ int buf[256];
+  const long long base = (long long)blockIdx.x * DET_CHUNK + threadIdx.x * 16;
+  int c = 0;
+  for (int j = 0; j < 16; ++j)
+    if (base + j < n) c += flag[base + j];
+  buf[threadIdx.x] = c;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    const int a = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+    __syncthreads();
+    buf[threadIdx.x] += a;
+    __syncthreads();
+  }
+  long long k = (long long)off[blockIdx.x] + buf[threadIdx.x] - c;
+  for (int j = 0; j < 16; ++j)
+    if (base + j < n && flag[base + j]) {
+      if (k < max_objects) endpos[k] = (int)(base + j);
+      ++k;
+    }
+}
+
+// ---- E4 --------------------------------------------------------------------------------------------------------------
+// one thread per object: its pixels in raster order over the bounding box, double sums (oracle: np.cumsum(...)[-1])
+__global__ void det_moments_kernel(const int* __restrict__ L, const float* __restrict__ fg, const float* __restrict__ conv, int W,
+                                   const int* __restrict__ endpos, const int* __restrict__ n_found, long long max_objects,
+                                   const int* __restrict__ npix, const int* __restrict__ xmin, const int* __restrict__ xmax, int cy, int cx,
+                                   double* xy, double* centres, int* npix_out) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long n = n_found[0] < max_objects ? n_found[0] : max_objects;
+  if (k >= n) return;
+  const int e = endpos[k], r = L[e];
+  const int y0 = r / W, y1 = e / W, x0 = xmin[r], x1 = xmax[r];
+  double tv = 0.0, mx = 0.0, my = 0.0, tc = 0.0, cmx = 0.0, cmy = 0.0;
+  for (int y = y0; y <= y1; ++y)
+    for (int x = x0; x <= x1; ++x) {
+      const int p = y * W + x;
+      if (L[p] != r) continue;
+      const double v = (double)fg[p], c = (double)conv[p];
+      const double dx = (double)(x - x0), dy = (double)(y - y0);
+      tv += v;
+      mx += v * dx;
+      my += v * dy;
+      tc += c;
+      cmx += c * dx;
+      cmy += c * dy;
+    }
+  if (!(tv > 0.0)) { tv = tc; mx = cmx; my = cmy; }  // faint detections: weight with the filtered values (> thresh > 0)
+  const double X = mx / tv + (double)x0, Y = my / tv + (double)y0;
+  xy[2 * k] = X;
+  xy[2 * k + 1] = Y;
+  centres[2 * k] = rint(Y - (double)cy);      // (row, col) offsets from the field centre, detection.py:48-54
+  centres[2 * k + 1] = rint(X - (double)cx);
+  npix_out[k] = npix[r];
+}
+
+struct DetLayout {
+  size_t band, fg, conv, label, npix, last, xmin, xmax, flag, mesh, rows, cnt, off, endpos, total;
+  int ny, nx, nblk;
+};
+static DetLayout det_layout(long long H, long long W, long long max_objects) {
+  DetLayout L{};
+  const size_t n = (size_t)H * W;
+  L.ny = (int)((H - 1) / DET_BW + 1);
+  L.nx = (int)((W - 1) / DET_BW + 1);
+  L.nblk = (int)((n + DET_CHUNK - 1) / DET_CHUNK);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  L.band = take(n * 8);
+  L.fg = take(n * 4);
+  L.conv = take(n * 4);
+  L.label = take(n * 4);
+  L.npix = take(n * 4);
+  L.last = take(n * 4);
+  L.xmin = take(n * 4);
+  L.xmax = take(n * 4);
+  L.flag = take(n);
+  L.mesh = take((size_t)L.ny * L.nx * 4 * 9);  // back0 sig0 back1 sig1 back sig dback cp u
+  L.rows = take((size_t)H * L.nx * 4 * 4);     // node dnode cp u
+  L.cnt = take((size_t)L.nblk * 4);
+  L.off = take((size_t)L.nblk * 4);
+  L.endpos = take((size_t)max_objects * 4);
+  L.total = o;
+  return L;
+}
+
+}  // namespace dbv
+
+using namespace dbv;
+
+extern "C" int64_t dbv_detect_scratch_bytes(int64_t H, int64_t W, int64_t max_objects) {
+  if (H <= 0 || W <= 0 || max_objects <= 0) return 0;
+  return (int64_t)det_layout(H, W, max_objects).total;
+}
+
+extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, int64_t pitch, int C, int band, const float* taps, int kh,
+                          int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t max_objects, void* scratch,
+                          int64_t scratch_bytes, int32_t* n_found, double* xy, double* centres, int32_t* npix_out, float* stats,
+                          void* stream) {
+  DBV_REQUIRE(field && taps && scratch && n_found && xy && centres && npix_out && stats, "dbv_detect: null pointer");
+  DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_detect: bad dtype %d", dtype);
+  DBV_REQUIRE(H > 0 && W > 0 && H * W < (1ll << 31) && pitch >= W && C > 0 && band >= 0 && band < C, "dbv_detect: bad field geometry");
+  DBV_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && kh <= DET_MAXK && kw <= DET_MAXK, "dbv_detect: the filter mask must be odd-sized, at most %d x %d", DET_MAXK, DET_MAXK);
+  DBV_REQUIRE(minarea >= 1 && max_objects > 0 && thresh_sigma > 0.0, "dbv_detect: bad minarea / max_objects / thresh");
+  const DetLayout Y = det_layout(H, W, max_objects);
+  DBV_REQUIRE(scratch_bytes >= (int64_t)Y.total, "dbv_detect: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)Y.total);
+  DBV_REQUIRE(((uintptr_t)scratch & 255) == 0, "dbv_detect: scratch must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)scratch;
+  const long long n = H * W;
+  const int ny = Y.ny, nx = Y.nx, nm = ny * nx;
+  double* d_band = (double*)(base + Y.band);
+  float* d_fg = (float*)(base + Y.fg);
+  float* d_conv = (float*)(base + Y.conv);
+  int* d_label = (int*)(base + Y.label);
+  int* d_npix = (int*)(base + Y.npix);
+  int* d_last = (int*)(base + Y.last);
+  int* d_xmin = (int*)(base + Y.xmin);
+  int* d_xmax = (int*)(base + Y.xmax);
+  unsigned char* d_flag = (unsigned char*)(base + Y.flag);
+  float* m = (float*)(base + Y.mesh);
+  float *back0 = m, *sig0 = m + nm, *back1 = m + 2 * nm, *sig1 = m + 3 * nm, *back = m + 4 * nm, *sig = m + 5 * nm, *dback = m + 6 * nm,
+        *mcp = m + 7 * nm, *mu = m + 8 * nm;
+  float* rw = (float*)(base + Y.rows);
+  const size_t hn = (size_t)H * nx;
+  float *node = rw, *dnode = rw + hn, *rcp = rw + 2 * hn, *ru = rw + 3 * hn;
+  int* d_cnt = (int*)(base + Y.cnt);
+  int* d_off = (int*)(base + Y.off);
+  int* d_end = (int*)(base + Y.endpos);
+
+  DetTaps tp{};
+  for (int i = 0; i < kh * kw; ++i) tp.v[i] = taps[i];
+  const int gb = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)field, H, W, pitch, C, band, d_band);
+  else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)field, H, W, pitch, C, band, d_band);
+  DET_LAUNCH(det_mesh_kernel, dim3(nx, ny), DET_BW, 0, d_band, (int)H, (int)W, nx, back0, sig0);
+  DET_LAUNCH(det_mesh_post_kernel, 1, 256, 0, back0, sig0, ny, nx, back1, sig1, back, sig, dback, mcp, mu, thresh_sigma, stats);
+  DET_LAUNCH(det_nodes_kernel, (unsigned)((H + 127) / 128), 128, 0, back, dback, (int)H, ny, nx, node, dnode, rcp, ru);
+  const dim3 grow((unsigned)((W + 255) / 256), (unsigned)H);
+  DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, (int)H, (int)W, nx, d_fg);
+  const size_t fsm = sizeof(float) * (32 + kw - 1) * (32 + kh - 1);
+  DET_LAUNCH(det_filter_kernel, dim3((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32)), 256, fsm, d_fg, (int)H, (int)W, kh, kw, tp, stats, d_conv,
+             d_label);
+  DET_LAUNCH(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)H, (int)W);
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  DET_LAUNCH(det_ccl_flatten_kernel, gn, 256, 0, d_label, n);
+  DET_MEMSET(d_npix, 0, n * 4);
+  DET_MEMSET(d_last, 0xFF, n * 4);
+  DET_MEMSET(d_xmax, 0xFF, n * 4);
+  DET_MEMSET(d_xmin, 0x7F, n * 4);
+  DET_MEMSET(d_flag, 0, n);
+  DET_LAUNCH(det_stats_kernel, grow, 256, 0, d_label, (int)H, (int)W, d_npix, d_last, d_xmin, d_xmax);
+  DET_LAUNCH(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, d_flag);
+  DET_LAUNCH(det_count_kernel, Y.nblk, 256, 0, d_flag, n, d_cnt);
+  DET_LAUNCH(det_scan_kernel, 1, 1024, 0, d_cnt, Y.nblk, d_off, n_found);
+  DET_LAUNCH(det_scatter_kernel, Y.nblk, 256, 0, d_flag, n, d_off, max_objects, d_end);
+  DET_LAUNCH(det_moments_kernel, (unsigned)((max_objects + 127) / 128), 128, 0, d_label, d_fg, d_conv, (int)W, d_end, n_found, max_objects, d_npix, d_xmin,
+             d_xmax, cy, cx, xy, centres, npix_out);
+  return DBV_OK;
+}
+
+// debug / parity access to the intermediate planes of the last dbv_detect call that used `scratch`:
+// what = 0 foreground f32 (H,W), 1 filtered f32 (H,W), 2 labels i32 (H,W), 3 mesh background f32 (ny,nx), 4 mesh sigma f32 (ny,nx),
+// 5 raw mesh background, 6 raw mesh sigma.  Returns a device pointer inside scratch (no copy).
+extern "C" const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int64_t max_objects, int what) {
+  if (!scratch || H <= 0 || W <= 0 || max_objects <= 0) return nullptr;
+  const DetLayout Y = det_layout(H, W, max_objects);
+  char* base = (char*)scratch;
+  const size_t nm = (size_t)Y.ny * Y.nx;
+  switch (what) {
+    case 0: return base + Y.fg;
+    case 1: return base + Y.conv;
+    case 2: return base + Y.label;
+    case 3: return base + Y.mesh + 4 * nm * 4;
+    case 4: return base + Y.mesh + 5 * nm * 4;
+    case 5: return base + Y.mesh;
+    case 6: return base + Y.mesh + 1 * nm * 4;
+  }
+  return nullptr;
+}

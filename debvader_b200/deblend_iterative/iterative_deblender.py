@@ -9,7 +9,8 @@ on ``len(None)`` (iterative_deblender.py:141).
 The field never leaves the device between steps: residual fields are CUDA tensors, the field MSE is a
 device reduction, and a detector that declares ``accepts_tensor = True`` is handed the tensor itself
 (the reference's ``detect_objects`` wraps the CPU library ``sep`` and needs a host array: that download
-is then the only full-field transfer of a step).  With ``tiled=True`` (one process per GPU) every rank
+is then the only full-field transfer of a step; ``detector="device"`` runs the detection kernels of
+csrc/detect_kernels.cu on the device-resident field instead).  With ``tiled=True`` (one process per GPU) every rank
 keeps its owner tile + halo only; a detector with ``accepts_local = True`` is called as
 ``detector(region_tensor, local_field)`` and must return the GLOBAL list of centres, identical on every
 rank — any other detector gets the gathered host field (on every rank, so that all ranks see the same list).
@@ -18,14 +19,20 @@ import numpy as np
 import torch
 
 from ..deblend.field_deblender import DeblendField
-from ..detect.detection import detect_objects
+from ..detect.detection import DeviceDetector, detect_objects
 
 
 class IterativeDeblendField(DeblendField):
     def __init__(self, net, field_image, cutout_size=59, nb_of_bands=6, epistemic_uncertainty_estimation=False, normalise=False,
                  detector=None, *, tiled=False, group=None):
         super().__init__(net, field_image, cutout_size, nb_of_bands, epistemic_uncertainty_estimation, normalise, tiled=tiled, group=group)
-        self.detector = detector or detect_objects  # extension: any callable field -> (N,2) centres
+        # extension: any callable field -> (N,2) centres; "device" = the CUDA detector (detect/detection.py:DeviceDetector),
+        # which takes the device-resident residual field as it is: no field-sized transfer per iteration
+        if isinstance(detector, str):
+            if detector not in ("device", "sep"):
+                raise ValueError(f"unknown detector {detector!r}")
+            detector = DeviceDetector(device=self._field_dev.device) if detector == "device" else detect_objects
+        self.detector = detector or detect_objects
 
     def iterative_deblending(self, galaxy_distances_to_center=None, cutout_images=None, optimise_positions=False,
                              epistemic_criterion=100.0, mse_criterion=100.0):

@@ -1,6 +1,21 @@
-"""reference detect/detection.py:5-56 — SExtractor detection through the third-party `sep`
-C library.  Detection is OUT OF SCOPE of the B200 hot path (centres are an input to it); this is
-the same call sequence with a lazy import so the package works without `sep` installed."""
+"""reference detect/detection.py:5-56 — SExtractor detection on the r band.
+
+The reference delegates to the third-party CPU library `sep` (``sep.Background`` + ``sep.extract``).  Two backends here:
+
+``backend="sep"``     the reference's own call sequence, with a lazy import so that the package works without `sep`
+                      (the default for host arrays: the reference's behaviour, library included).
+``backend="device"``  the same pipeline as hand-written CUDA kernels on a field that stays on the GPU (SURVEY §8f-3;
+                      csrc/detect_kernels.cu through ``dbv_detect``): mesh background, 7x7 matched filter, threshold
+                      1.5 x global rms, 8-connected components of >= 4 pixels in the order SExtractor's scan completes them,
+                      barycentres -> (row, col) offsets from the field centre.  The default for CUDA tensors, and what
+                      ``IterativeDeblendField(..., detector="device")`` uses: no field-sized transfer per iteration.
+                      Restated from the published algorithm and bit-exact with oracle/detect_numpy.py; parity with `sep`
+                      itself is UNPINNED (not installable where this was built).  Not restated: multi-threshold deblending
+                      and sep's `clean` pass — a connected footprint is one detection; the iterative loop finds the other
+                      members of a blend in the residual of the next step.
+"""
+import ctypes as C
+
 import numpy as np
 
 # 7x7 convolution mask of a gaussian PSF with FWHM = 3.0 pixels (detection.py:25-35)
@@ -15,23 +30,155 @@ FILTER_KERNEL = np.array(
         [0.004963, 0.021388, 0.051328, 0.068707, 0.051328, 0.021388, 0.004963],
     ]
 )
+DETECT_THRESH = 1.5  # detection.py:19
+MINAREA = 4  # detection.py:22
+R_BAND = 2  # detection.py:14
 
 
-def detect_objects(field_image):
-    """Detect objects on the r band (index 2) with sep; returns (row, col) offsets from the centre."""
+def normalised_taps(kernel=FILTER_KERNEL):
+    """float32 taps divided by the float32 running sum of their absolute values (sep normalises the mask it is given)."""
+    k = np.ascontiguousarray(kernel, np.float32)
+    s = np.float32(0.0)
+    for v in k.ravel():
+        s = np.float32(s + abs(v))
+    return np.ascontiguousarray(k / s, np.float32)
+
+
+class DeviceDetector:
+    """``detector(field) -> (N, 2)`` float64 centres on the GPU.  ``accepts_tensor``: IterativeDeblendField hands it the
+    device-resident residual field itself.  Work buffers are kept per field shape; one instance serves one stream at a time."""
+
+    accepts_tensor = True
+
+    def __init__(self, device=None, max_objects=1 << 17, thresh=DETECT_THRESH, minarea=MINAREA, band=R_BAND, kernel=FILTER_KERNEL):
+        self.device = device
+        self.max_objects = int(max_objects)
+        self.thresh, self.minarea, self.band = float(thresh), int(minarea), int(band)
+        self.taps = normalised_taps(kernel)
+        self._buf = {}
+        self.last = None  # details of the last call (device tensors)
+
+    def _buffers(self, H, W, dev):
+        import torch
+
+        from .. import _ffi
+
+        key = (H, W, str(dev))
+        b = self._buf.get(key)
+        if b is None:
+            nbytes = int(_ffi.lib().dbv_detect_scratch_bytes(H, W, self.max_objects))
+            M = self.max_objects
+            b = {
+                "scratch": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev),
+                "n": torch.zeros(1, dtype=torch.int32, device=dev),
+                "xy": torch.empty((M, 2), dtype=torch.float64, device=dev),
+                "centres": torch.empty((M, 2), dtype=torch.float64, device=dev),
+                "npix": torch.empty(M, dtype=torch.int32, device=dev),
+                "stats": torch.zeros(4, dtype=torch.float32, device=dev),
+                "nbytes": nbytes,
+            }
+            off = (-b["scratch"].data_ptr()) % 256
+            b["base"] = b["scratch"].data_ptr() + off
+            self._buf = {key: b}  # one shape at a time: a 4096^2 field needs ~0.6 GB of planes
+        return b
+
+    def run(self, field_image):
+        """Enqueue the detection; returns the buffer dict (device tensors; ``n`` not yet read)."""
+        import torch
+
+        from .. import _ffi
+
+        t = field_image
+        if not isinstance(t, torch.Tensor):
+            dev = torch.device(self.device if self.device is not None else "cuda")
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(field_image))).to(dev)
+        if not t.is_cuda:
+            raise ValueError("the device detector needs a CUDA tensor (or a host array to upload)")
+        if t.ndim == 4:
+            if t.shape[0] != 1:
+                raise ValueError(f"field_image must have shape (1, F, F, C), got {tuple(t.shape)}")
+            t = t[0]
+        if t.ndim != 3 or t.dtype not in (torch.float64, torch.float32) or not t.is_contiguous():
+            raise ValueError("field_image must be a contiguous (1, F, F, C) float64 / float32 tensor")
+        H, W, Cn = (int(v) for v in t.shape)
+        if not 0 <= self.band < Cn:
+            raise ValueError(f"band {self.band} outside the field's {Cn} bands")
+        b = self._buffers(H, W, t.device)
+        with torch.cuda.device(t.device):
+            _ffi.check(_ffi.lib().dbv_detect(
+                _ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, H, W, W, Cn, self.band,
+                self.taps.ctypes.data_as(C.c_void_p), int(self.taps.shape[0]), int(self.taps.shape[1]), self.thresh, self.minarea,
+                int(H / 2), int(W / 2), self.max_objects, C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["n"]), _ffi.ptr(b["xy"]),
+                _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["stats"]), _ffi.stream_ptr()))
+        b["shape"] = (H, W)
+        self.last = b
+        return b
+
+    def __call__(self, field_image, return_details=False):
+        b = self.run(field_image)
+        n = int(b["n"].item())  # the one synchronisation: the host index planner needs the centres anyway
+        if n > self.max_objects:
+            raise RuntimeError(f"{n} objects detected, more than max_objects={self.max_objects}")
+        centres = b["centres"][:n].cpu().numpy()
+        if return_details:
+            st = b["stats"].cpu().numpy()
+            return centres, {"x": b["xy"][:n, 0].cpu().numpy(), "y": b["xy"][:n, 1].cpu().numpy(), "npix": b["npix"][:n].cpu().numpy(),
+                             "globalback": st[0], "globalrms": st[1], "thresh": st[2]}
+        return centres
+
+    def plane(self, what):
+        """intermediate plane of the last call as a torch tensor view copy: 'fg', 'conv', 'label', 'back', 'sigma', 'back_raw', 'sigma_raw'"""
+        import torch
+
+        from .. import _ffi
+
+        b = self.last
+        H, W = b["shape"]
+        code = {"fg": 0, "conv": 1, "label": 2, "back": 3, "sigma": 4, "back_raw": 5, "sigma_raw": 6}[what]
+        p = _ffi.lib().dbv_detect_plane(C.c_void_p(b["base"]), H, W, self.max_objects, code)
+        off = int(p) - b["scratch"].data_ptr()
+        ny, nx = (H - 1) // 64 + 1, (W - 1) // 64 + 1
+        shape = (H, W) if code < 3 else (ny, nx)
+        nbytes = shape[0] * shape[1] * 4
+        raw = b["scratch"][off : off + nbytes].clone()
+        return raw.view(torch.int32 if code == 2 else torch.float32).reshape(shape)
+
+
+_default_device_detector = None
+
+
+def detect_objects_device(field_image, return_details=False):
+    """backend="device" of detect_objects with a module-level DeviceDetector."""
+    global _default_device_detector
+    if _default_device_detector is None:
+        _default_device_detector = DeviceDetector()
+    return _default_device_detector(field_image, return_details=return_details)
+
+
+def detect_objects(field_image, backend=None):
+    """Detect objects on the r band (index 2); returns (row, col) offsets from the field centre (detection.py:5-56).
+
+    backend: "sep" (the reference's CPU library), "device" (CUDA kernels), None = "device" for CUDA tensors, "sep" otherwise."""
+    is_cuda = hasattr(field_image, "is_cuda") and field_image.is_cuda
+    if backend is None:
+        backend = "device" if is_cuda else "sep"
+    if backend == "device":
+        return detect_objects_device(field_image)
+    if backend != "sep":
+        raise ValueError(f"unknown detection backend {backend!r}")
     try:
         import sep
     except ImportError as e:  # pragma: no cover
-        raise ImportError("detect_objects needs the third-party `sep` package (SExtractor); "
-                          "pass galaxy_distances_to_center / a detector= callable instead") from e
+        raise ImportError("detect_objects(backend='sep') needs the third-party `sep` package (SExtractor); use backend='device', "
+                          "IterativeDeblendField(..., detector='device'), or pass galaxy_distances_to_center / a detector= callable") from e
     if hasattr(field_image, "detach"):
         field_image = field_image.detach().cpu().numpy()
     field_image = np.asarray(field_image).copy()
     field_size = field_image.shape[1]
-    r_band = field_image[0, :, :, 2].copy()
+    r_band = field_image[0, :, :, R_BAND].copy()
     bkg = sep.Background(r_band)
-    objects = sep.extract(data=r_band - bkg, thresh=1.5, err=bkg.globalrms, deblend_cont=0.00001, deblend_nthresh=64,
-                          minarea=4, filter_kernel=FILTER_KERNEL, filter_type="conv")
+    objects = sep.extract(data=r_band - bkg, thresh=DETECT_THRESH, err=bkg.globalrms, deblend_cont=0.00001, deblend_nthresh=64,
+                          minarea=MINAREA, filter_kernel=FILTER_KERNEL, filter_type="conv")
     out = [(np.round(-int(field_size / 2) + objects["y"][i]), np.round(-int(field_size / 2) + objects["x"][i]))
            for i in range(len(objects["y"]))]
     return np.array(out)

@@ -29,12 +29,13 @@
 extern "C" {
 #endif
 
-#define DBV_ABI_VERSION 5  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
+#define DBV_ABI_VERSION 6  /* 2: dbv_deblend_host gained mean_dev / stddev_dev; precisions FP16X3, MIXED
                               3: dbv_window_axpy_ex, dbv_spline_* (sub-pixel placement), dbv_shift_objective
                               4: dbv_window_axpy_rect (rectangular local regions, caller scratch, in-place),
                                  dbv_sqdiff_sum_rect, dbv_shift_objective_batch, dbv_fp16_overflow
                               5: DBV_PREC_FP32TC; the binning scratch of dbv_window_axpy_rect holds 16-byte records and must
-                                 be 16-byte aligned (its size still comes from dbv_window_axpy_scratch_bytes) */
+                                 be 16-byte aligned (its size still comes from dbv_window_axpy_scratch_bytes)
+                              6: dbv_detect* (device detector), dbv_layer_kernel */
 
 typedef enum {
   DBV_OK = 0,
@@ -224,6 +225,30 @@ int dbv_sqdiff_sum_rect(const void* a_dev, const void* b_dev, int dtype, int64_t
  * stream the call was enqueued on.  Always 0 for the other precisions. */
 int dbv_fp16_overflow(dbv_ctx* ctx, int reset);
 
+/* ---- detection ---------------------------------------------------------------------
+ * Replaces the two calls reference detect/detection.py:5-56 makes into the CPU library `sep`
+ * (sep.Background(r_band) :15 and sep.extract(r_band - bkg, thresh=1.5, err=bkg.globalrms, minarea=4,
+ * filter_kernel=<7x7>, filter_type="conv") :37-46) and the centre arithmetic of :48-54, on a field that stays on the
+ * device.  Restated from the published SExtractor algorithm (oracle/detect_numpy.py, bit-exact with it): mesh
+ * background, matched filter, threshold, 8-connected components of >= minarea pixels in the order Lutz's scan
+ * completes them, barycentres.  NOT restated: multi-threshold deblending and the `clean` pass.  Parity with sep
+ * itself is unpinned (sep is not installable where this was built).
+ *   field   (H, pitch, C) f64 or f32 on the device; band = the plane detection runs on (2 = r)
+ *   taps    HOST pointer, kh*kw float32, already divided by the sum of their absolute values
+ *   cy, cx  subtracted from the barycentres before rounding (the reference: int(F/2))
+ *   outputs (device): n_found[0] = objects found (may exceed max_objects: only the first max_objects are written),
+ *           xy (max_objects,2) f64 = (x, y) barycentres in pixels, centres (max_objects,2) f64 = (row, col) offsets
+ *           rounded half-to-even, npix (max_objects) i32, stats[0..2] = global background, global rms, threshold
+ *   scratch 256-byte aligned device memory of dbv_detect_scratch_bytes(H, W, max_objects) bytes, private to the call
+ * Everything is enqueued on `stream`; no host synchronisation. */
+int64_t dbv_detect_scratch_bytes(int64_t H, int64_t W, int64_t max_objects);
+int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, int64_t pitch, int C, int band, const float* taps, int kh,
+               int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t max_objects, void* scratch,
+               int64_t scratch_bytes, int32_t* n_found, double* xy, double* centres, int32_t* npix, float* stats, void* stream);
+/* device pointer to an intermediate plane of the last dbv_detect call on `scratch` (per-stage parity tests): 0 foreground
+ * f32 (H,W), 1 filtered f32 (H,W), 2 labels i32 (H,W), 3 / 4 filtered mesh background / sigma f32 (ny,nx), 5 / 6 raw ones */
+const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int64_t max_objects, int what);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */
 int64_t dbv_launch_count(const dbv_ctx* ctx);
@@ -232,6 +257,9 @@ int64_t dbv_global_launch_count(void);
  * profiling was enabled (the caller synchronises first); returns the number of layers. */
 int dbv_set_profiling(dbv_ctx* ctx, int enabled);
 int dbv_layer_times(dbv_ctx* ctx, int max_layers, float* ms_out, char* names_out /* max_layers*32 bytes */);
+/* the __global__ function (named as the ncu launch list names it, leading template arguments only) that runs `layer`
+ * under the ctx's precision and tuned plan; out_bytes >= 48.  bench.py groups the per-layer times by it. */
+int dbv_layer_kernel(dbv_ctx* ctx, const char* layer, char* out, int out_bytes);
 /* copy an internal activation buffer (debug / per-layer parity): writes fp32 NHWC */
 int dbv_debug_activation(dbv_ctx* ctx, const char* name, int64_t B, float* out_dev, void* stream);
 

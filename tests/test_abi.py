@@ -45,7 +45,7 @@ def test_product_library_has_no_environment_switches_or_debug_exports(lib):
 
 
 def test_abi_version(lib):
-    assert lib.dbv_abi_version() == _ffi.ABI_VERSION == 5
+    assert lib.dbv_abi_version() == _ffi.ABI_VERSION == 6
     assert lib.dbv_mse_scratch_bytes() > 0
 
 
