@@ -3,11 +3,12 @@
 // (Bertin & Arnouts 1996; Barbary 2016) — see oracle/detect_numpy.py, whose arithmetic this file reproduces BIT FOR BIT:
 //
 //   B1  det_mesh_kernel       per 64x64 mesh: mean / sigma, one +-2 sigma clip, level histogram, iterated 3-sigma clipping
-//   B2  det_mesh_post_kernel  bad-mesh fill, 3x3 median filter, global background / rms (medians), threshold, y-spline
+//   B2  det_mesh_{fill,median,rank,final}_kernel  bad-mesh fill, 3x3 median filter, global background / rms (medians by rank
+//                             selection), threshold, y-spline of the mesh map
 //   B3  det_nodes_kernel + det_foreground_kernel   bicubic-spline background map, foreground = band - background
-//   E1  det_filter_kernel     normalised 7x7 matched filter (zero outside the image), threshold test -> initial labels
-//   E2  det_ccl_*             8-connected components by union-find on the label image (root = smallest raster index)
-//   E3  det_stats / mark / count / scan / scatter   pixel count, bounding columns and LARGEST raster index per object; the
+//   E1  det_filter_tiled_kernel<7> (det_filter_kernel for other mask sizes)   normalised 7x7 matched filter (zero outside the image), threshold test -> initial labels
+//   E2  det_ccl_merge_kernel  8-connected components by union-find on the label image (root = smallest raster index)
+//   E3  det_ccl_flatten_stats / mark / count / scan / scatter   pixel count, bounding columns and LARGEST raster index per object; the
 //                             objects with >= minarea pixels listed by ascending largest raster index = the order in which
 //                             Lutz's one-pass scan completes them = sep's output order
 //   E4  det_moments_kernel    barycentre of the unfiltered foreground (double, raster order), centres rounded half-to-even
@@ -51,64 +52,25 @@ __global__ void det_band_kernel(const T* __restrict__ field, long long H, long l
 }
 
 // ---- B1 --------------------------------------------------------------------------------------------------------------
-// iterated clipping on the level histogram of one mesh (oracle: histogram_guess); doubles, integer counts: sums exact
-__device__ void det_histo_guess(const int* histo, int nlevels, double mean0, float qzero_f, float qscale_f, float* back, float* sigma) {
-  const int nm1 = nlevels - 1;
-  const double qzero = (double)qzero_f, qscale = (double)qscale_f;
-  int lcut = 0, hcut = nm1;
-  double sig = 10.0 * nm1, sig1 = 1.0, mea = mean0, med = mean0;
-  for (int n = 100; n > 0 && sig >= 0.1 && fabs(sig / sig1 - 1.0) > 1e-4; --n) {
-    sig1 = sig;
-    long long tot = 0, lowsum = 0, highsum = 0;
-    mea = 0.0;
-    sig = 0.0;
-    int lo = lcut, hi = hcut;
-    for (int i = lcut; i <= hcut; ++i) {
-      if (lowsum < highsum) lowsum += histo[lo++];
-      else highsum += histo[hi--];
-      const int c = histo[i];
-      tot += c;
-      const double ci = (double)c * (double)i;
-      mea += ci;
-      sig += ci * (double)i;
-    }
-    if (hi >= 0) {
-      const int a = histo[lo < nm1 ? lo : nm1], b = histo[hi];
-      const int big = a > b ? a : b;
-      med = (double)hi + 0.5 + (big > 0 ? (double)(highsum - lowsum) / (2.0 * (double)big) : 0.0);
-    } else {
-      med = 0.0;
-    }
-    if (tot) {
-      mea = mea / (double)tot;
-      sig = sig / (double)tot - mea * mea;
-    }
-    sig = sig > 0.0 ? sqrt(sig) : 0.0;
-    double t = med - 3.0 * sig;
-    lcut = t > 0.0 ? (int)(t + 0.5) : 0;
-    t = med + 3.0 * sig;
-    hcut = t < (double)nm1 ? (t > 0.0 ? (int)(t + 0.5) : (int)(t - 0.5)) : nm1;
-    if (hcut < lcut) hcut = lcut;
-  }
-  double bk;
-  if (sig > 0.0) {
-    if (fabs((mea - med) / sig) < 0.3) bk = qzero + (2.5 * med - 1.5 * mea) * qscale;
-    else bk = qzero + med * qscale;
-  } else {
-    bk = qzero + mea * qscale;
-  }
-  *back = (float)bk;
-  *sigma = (float)(sig * qscale);
-}
+// One CTA of 64 threads per mesh: thread r owns mesh row r (sequential double sums, the rows then combined in order by thread 0:
+// the oracle's summation order).  The level histogram is counted with shared-memory integer atomics and turned into an exclusive
+// prefix sum in place, so that the iterated clipping (oracle: histogram_guess) costs O(range / 64 + log^2) per iteration
+// instead of a serial pass over <= 4096 levels:
+//   * the three sums over [lcut, hcut] are sums of integers (< 2^53): any order gives the oracle's doubles exactly — strided over the CTA;
+//   * the two-pointer walk "advance the side with the smaller running count" is the merge of the two prefix-sum sequences
+//     P(j) = count of the first j levels, Q(i) = count of the last i levels, ties to the high side: after n = hcut - lcut + 1 steps
+//     it has taken k = #{ j < n : j + #{ i < n : Q(i) <= P(j) } < n } low steps — two nested binary searches on the prefix sums.
+__device__ __forceinline__ int det_cnt(const int* pre, int i) { return pre[i + 1] - pre[i]; }
 
-// one CTA of 64 threads per mesh: thread r owns mesh row r (sequential double sums, rows then combined in order by thread 0)
 __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, int H, int W, int nx, float* __restrict__ back0,
                                                       float* __restrict__ sig0) {
   __shared__ float tile[DET_BW][DET_BW + 1];
-  __shared__ int histo[DET_MAXLEVELS];
+  __shared__ int pre[DET_MAXLEVELS + 1];  // level counts, then their exclusive prefix sums (pre[nlevels .. 4096] = total)
   __shared__ double rs[DET_BW], rq[DET_BW], rn[DET_BW];
+  __shared__ long long p0[DET_BW], p1[DET_BW], p2[DET_BW];
+  __shared__ int part[DET_BW];
   __shared__ float s_lcut, s_hcut, s_qscale, s_cste, s_qzero;
-  __shared__ int s_nlevels, s_bad;
+  __shared__ int s_nlevels, s_bad, s_lo, s_hi, s_go;
   __shared__ double s_mean2;
   const int mx = blockIdx.x, my = blockIdx.y, t = threadIdx.x;
   const int x0 = mx * DET_BW, y0 = my * DET_BW;
@@ -179,7 +141,7 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
       s_mean2 = mean2;
     }
   }
-  for (int i = t; i < DET_MAXLEVELS; i += DET_BW) histo[i] = 0;
+  for (int i = t; i <= DET_MAXLEVELS; i += DET_BW) pre[i] = 0;
   __syncthreads();
   if (s_bad) {
     if (t == 0) {
@@ -188,19 +150,123 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
     }
     return;
   }
+  const int nl = s_nlevels, nm1 = nl - 1;
   if (t < mh) {
     const float qs = s_qscale, cs = s_cste;
-    const int nl = s_nlevels;
     for (int c = 0; c < mw; ++c) {
       const float lev = tile[t][c] / qs + cs;
       if (lev > -1.0f && lev < (float)nl) {
         const int b = (int)lev;
-        if (b >= 0 && b < nl) atomicAdd(&histo[b], 1);
+        if (b >= 0 && b < nl) atomicAdd(&pre[b], 1);
       }
     }
   }
   __syncthreads();
-  if (t == 0) det_histo_guess(histo, s_nlevels, s_mean2, s_qzero, s_qscale, &back0[my * nx + mx], &sig0[my * nx + mx]);
+  // counts -> exclusive prefix sums, in place: thread t scans levels [64 t, 64 t + 64)
+  {
+    int s = 0;
+    for (int i = 0; i < DET_BW; ++i) s += pre[t * DET_BW + i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+      int run = 0;
+      for (int i = 0; i < DET_BW; ++i) {
+        const int v = part[i];
+        part[i] = run;
+        run += v;
+      }
+      pre[DET_MAXLEVELS] = run;
+    }
+    __syncthreads();
+    int run = part[t];
+    for (int i = 0; i < DET_BW; ++i) {
+      const int v = pre[t * DET_BW + i];
+      pre[t * DET_BW + i] = run;
+      run += v;
+    }
+  }
+  // iterated clipping around the histogram median (doubles; thread 0 keeps the state, the CTA sums the levels in range)
+  double sig = 10.0 * nm1, sig1 = 1.0, mea = s_mean2, med = s_mean2;
+  int lcut = 0, hcut = nm1, iters = 100;
+  if (t == 0) {
+    s_lo = lcut;
+    s_hi = hcut;
+    s_go = (iters > 0 && sig >= 0.1 && fabs(sig / sig1 - 1.0) > 1e-4);
+  }
+  __syncthreads();
+  while (s_go) {
+    const int lc = s_lo, hc = s_hi;
+    long long a0 = 0, a1 = 0, a2 = 0;
+    for (int i = lc + t; i <= hc; i += DET_BW) {
+      const long long c = det_cnt(pre, i);
+      a0 += c;
+      a1 += c * i;
+      a2 += c * i * (long long)i;
+    }
+    p0[t] = a0;
+    p1[t] = a1;
+    p2[t] = a2;
+    __syncthreads();
+    if (t == 0) {
+      long long tot = 0, m1 = 0, m2 = 0;
+      for (int i = 0; i < DET_BW; ++i) { tot += p0[i]; m1 += p1[i]; m2 += p2[i]; }
+      --iters;
+      sig1 = sig;
+      mea = (double)m1;
+      sig = (double)m2;
+      // the two-pointer walk over [lcut, hcut] by merge path (see the header of this section)
+      const int n = hcut - lcut + 1;
+      const int base_lo = pre[lcut], base_hi = pre[hcut + 1];
+      int ka = 0, kb = n;
+      while (ka < kb) {
+        const int j = (ka + kb) >> 1;
+        const int pj = pre[lcut + j] - base_lo;
+        int ia = 0, ib = n;
+        while (ia < ib) {
+          const int i = (ia + ib) >> 1;
+          if (base_hi - pre[hcut + 1 - i] <= pj) ia = i + 1;
+          else ib = i;
+        }
+        if (j + ia < n) ka = j + 1;
+        else kb = j;
+      }
+      const int lo = lcut + ka, hi = hcut - (n - ka);
+      const long long lowsum = pre[lo] - base_lo, highsum = base_hi - pre[hi + 1];
+      if (hi >= 0) {
+        const int ca = det_cnt(pre, lo < nm1 ? lo : nm1), cb = det_cnt(pre, hi);
+        const int big = ca > cb ? ca : cb;
+        med = (double)hi + 0.5 + (big > 0 ? (double)(highsum - lowsum) / (2.0 * (double)big) : 0.0);
+      } else {
+        med = 0.0;
+      }
+      if (tot) {
+        mea = mea / (double)tot;
+        sig = sig / (double)tot - mea * mea;
+      }
+      sig = sig > 0.0 ? sqrt(sig) : 0.0;
+      double v = med - 3.0 * sig;
+      lcut = v > 0.0 ? (int)(v + 0.5) : 0;
+      v = med + 3.0 * sig;
+      hcut = v < (double)nm1 ? (v > 0.0 ? (int)(v + 0.5) : (int)(v - 0.5)) : nm1;
+      if (hcut < lcut) hcut = lcut;
+      s_lo = lcut;
+      s_hi = hcut;
+      s_go = (iters > 0 && sig >= 0.1 && fabs(sig / sig1 - 1.0) > 1e-4);
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double qzero = (double)s_qzero, qscale = (double)s_qscale;
+    double bk;
+    if (sig > 0.0) {
+      if (fabs((mea - med) / sig) < 0.3) bk = qzero + (2.5 * med - 1.5 * mea) * qscale;
+      else bk = qzero + med * qscale;
+    } else {
+      bk = qzero + mea * qscale;
+    }
+    back0[my * nx + mx] = (float)bk;
+    sig0[my * nx + mx] = (float)(sig * qscale);
+  }
 }
 
 // ---- B2 --------------------------------------------------------------------------------------------------------------
@@ -212,26 +278,6 @@ __device__ float det_median_small(float* a, int n) {  // insertion sort of <= 9 
     a[j + 1] = v;
   }
   return (n & 1) ? a[n / 2] : (a[n / 2 - 1] + a[n / 2]) * 0.5f;
-}
-
-// median of n floats by rank selection (every thread ranks its own elements; ties broken by index)
-__device__ float det_median_block(const float* a, int n, float* s_pick) {
-  __syncthreads();
-  const int k1 = n / 2, k0 = (n & 1) ? k1 : k1 - 1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = a[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const float w = a[j];
-      rank += (w < v) || (w == v && j < i);
-    }
-    if (rank == k0) s_pick[0] = v;
-    if (rank == k1) s_pick[1] = v;
-  }
-  __syncthreads();
-  const float m = (n & 1) ? s_pick[1] : (s_pick[0] + s_pick[1]) * 0.5f;
-  __syncthreads();
-  return m;
 }
 
 // second derivatives / 6 of the natural cubic spline through n samples `v` (stride sv), Thomas algorithm in float32
@@ -254,66 +300,83 @@ __device__ void det_spline_d2(const float* v, int sv, int n, float* d, float* cp
   }
 }
 
-// one CTA: the mesh maps are tiny (64 x 64 for a 4096^2 field)
-__global__ void __launch_bounds__(256) det_mesh_post_kernel(const float* __restrict__ back0, const float* __restrict__ sig0, int ny, int nx,
-                                                            float* back1, float* sig1, float* back, float* sig, float* dback, float* cp,
-                                                            float* u, double thresh_sigma, float* stats) {
-  __shared__ float s_pick[2];
-  __shared__ int s_ngood;
-  const int n = ny * nx;
-  if (threadIdx.x == 0) s_ngood = 0;
-  __syncthreads();
-  int good = 0;
-  for (int m = threadIdx.x; m < n; m += blockDim.x) good += back0[m] > -DET_BIG;
-  if (good) atomicAdd(&s_ngood, good);
-  __syncthreads();
-  const int ngood = s_ngood;
-  // bad meshes: float32 mean of the nearest good ones (raster order)
-  for (int m = threadIdx.x; m < n; m += blockDim.x) {
-    float b = back0[m], s = sig0[m];
-    if (!(b > -DET_BIG) && ngood > 0) {
-      const int y = m / nx, x = m - y * nx;
-      long long best = LLONG_MAX;
-      for (int g = 0; g < n; ++g)
-        if (back0[g] > -DET_BIG) {
-          const long long dy = g / nx - y, dx = g % nx - x, d2 = dy * dy + dx * dx;
-          if (d2 < best) best = d2;
-        }
-      float sb = 0.f, ss = 0.f;
-      int k = 0;
-      for (int g = 0; g < n; ++g)
-        if (back0[g] > -DET_BIG) {
-          const long long dy = g / nx - y, dx = g % nx - x;
-          if (dy * dy + dx * dx == best) { sb += back0[g]; ss += sig0[g]; ++k; }
-        }
+// bad meshes: float32 mean of the nearest good ones (raster order); thread per mesh
+__global__ void det_mesh_fill_kernel(const float* __restrict__ back0, const float* __restrict__ sig0, int ny, int nx, float* __restrict__ back1,
+                                     float* __restrict__ sig1) {
+  const int n = ny * nx, m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  float b = back0[m], s = sig0[m];
+  if (!(b > -DET_BIG)) {
+    const int y = m / nx, x = m - y * nx;
+    long long best = LLONG_MAX;
+    for (int g = 0; g < n; ++g)
+      if (back0[g] > -DET_BIG) {
+        const long long dy = g / nx - y, dx = g % nx - x, d2 = dy * dy + dx * dx;
+        if (d2 < best) best = d2;
+      }
+    float sb = 0.f, ss = 0.f;
+    int k = 0;
+    for (int g = 0; g < n; ++g)
+      if (back0[g] > -DET_BIG) {
+        const long long dy = g / nx - y, dx = g % nx - x;
+        if (dy * dy + dx * dx == best) { sb += back0[g]; ss += sig0[g]; ++k; }
+      }
+    if (k) {
       b = sb / (float)k;
       s = ss / (float)k;
     }
-    back1[m] = b;
-    sig1[m] = s;
   }
-  __syncthreads();
-  for (int m = threadIdx.x; m < n; m += blockDim.x) {
-    const int y = m / nx, x = m - y * nx;
-    float a[9], c[9];
-    int k = 0;
-    for (int yy = max(y - 1, 0); yy < min(y + 2, ny); ++yy)
-      for (int xx = max(x - 1, 0); xx < min(x + 2, nx); ++xx) {
-        a[k] = back1[yy * nx + xx];
-        c[k] = sig1[yy * nx + xx];
-        ++k;
-      }
-    back[m] = det_median_small(a, k);
-    sig[m] = det_median_small(c, k);
+  back1[m] = b;
+  sig1[m] = s;
+}
+
+// 3x3 median filter of both mesh maps (clipped at the rims); thread per mesh
+__global__ void det_mesh_median_kernel(const float* __restrict__ back1, const float* __restrict__ sig1, int ny, int nx, float* __restrict__ back,
+                                       float* __restrict__ sig) {
+  const int n = ny * nx, m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const int y = m / nx, x = m - y * nx;
+  float a[9], c[9];
+  int k = 0;
+  for (int yy = max(y - 1, 0); yy < min(y + 2, ny); ++yy)
+    for (int xx = max(x - 1, 0); xx < min(x + 2, nx); ++xx) {
+      a[k] = back1[yy * nx + xx];
+      c[k] = sig1[yy * nx + xx];
+      ++k;
+    }
+  back[m] = det_median_small(a, k);
+  sig[m] = det_median_small(c, k);
+}
+
+// global medians by rank selection: thread i ranks element i among all n (ties broken by index) and, if it is one of the two
+// middle ranks, writes itself into pick[2 * map + {0, 1}]; blockIdx.y = 0 background map, 1 sigma map
+__global__ void det_mesh_rank_kernel(const float* __restrict__ back, const float* __restrict__ sig, int n, float* __restrict__ pick) {
+  const float* a = blockIdx.y ? sig : back;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k1 = n / 2, k0 = (n & 1) ? k1 : k1 - 1;
+  const float v = a[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const float w = a[j];
+    rank += (w < v) || (w == v && j < i);
   }
-  const float gback = det_median_block(back, n, s_pick);
-  const float grms = det_median_block(sig, n, s_pick);
-  if (threadIdx.x == 0) {
+  if (rank == k0) pick[2 * blockIdx.y] = v;
+  if (rank == k1) pick[2 * blockIdx.y + 1] = v;
+}
+
+// global background / rms / threshold, and the y-spline of the background map (thread per mesh column)
+__global__ void det_mesh_final_kernel(const float* __restrict__ pick, int ny, int nx, const float* __restrict__ back, float* dback, float* cp, float* u,
+                                      double thresh_sigma, float* stats) {
+  const int n = ny * nx, x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x == 0) {
+    const float gback = (n & 1) ? pick[1] : (pick[0] + pick[1]) * 0.5f;
+    const float grms = (n & 1) ? pick[3] : (pick[2] + pick[3]) * 0.5f;
     stats[0] = gback;
     stats[1] = grms;
     stats[2] = (float)(thresh_sigma * (double)grms);
   }
-  for (int x = threadIdx.x; x < nx; x += blockDim.x) det_spline_d2(back + x, nx, ny, dback + x, cp + x, u + x, nx);
+  if (x < nx) det_spline_d2(back + x, nx, ny, dback + x, cp + x, u + x, nx);
 }
 
 // ---- B3 --------------------------------------------------------------------------------------------------------------
@@ -394,6 +457,50 @@ __global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict
   }
 }
 
+// the 7x7 mask of the reference (and any other K x K one instantiated below): a thread keeps FOUR vertically adjacent outputs and
+// streams the K + 3 tile rows they share through registers (K shared-memory loads per row instead of 4 K); every output still adds
+// its taps in raster order, one rounding per product and per sum, so the result is bit-identical to det_filter_kernel
+template <int K>
+__global__ void __launch_bounds__(256) det_filter_tiled_kernel(const float* __restrict__ fg, int H, int W, const DetTaps taps,
+                                                               const float* __restrict__ stats, float* __restrict__ conv, int* __restrict__ label) {
+  DET_DYN_SMEM(float, sm);
+  constexpr int tw = 32 + K - 1, th = 32 + K - 1;
+  const int x0 = blockIdx.x * 32 - K / 2, y0 = blockIdx.y * 32 - K / 2;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int y = y0 + ty, x = x0 + tx;
+    sm[i] = (y >= 0 && y < H && x >= 0 && x < W) ? fg[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  const float thresh = stats[2];
+  const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < K + 3; ++j) {
+    float v[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) v[kx] = sm[(ly0 + j) * tw + lx + kx];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ky = j - r;
+      if (ky >= 0 && ky < K) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc[r] = acc[r] + taps.v[ky * K + kx] * v[kx];
+      }
+    }
+  }
+  const int x = blockIdx.x * 32 + lx;
+  if (x >= W) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = blockIdx.y * 32 + ly0 + r;
+    if (y >= H) break;
+    const long long p = (long long)y * W + x;
+    conv[p] = acc[r];
+    label[p] = acc[r] > thresh ? (int)p : -1;
+  }
+}
+
 // ---- E2: union-find on the label image ------------------------------------------------------------------------------------
 __device__ __forceinline__ int det_find(int* L, int i) {
   volatile int* V = L;
@@ -439,25 +546,22 @@ __global__ void det_ccl_merge_kernel(int* L, int H, int W) {
   if (ne && !n) det_unite(L, p, p - W + 1);
 }
 
-__global__ void det_ccl_flatten_kernel(int* L, long long n) {
-  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (p >= n || L[p] < 0) return;
-  L[p] = det_find(L, (int)p);
-}
-
-// ---- E3 --------------------------------------------------------------------------------------------------------------
-__global__ void det_stats_kernel(const int* __restrict__ L, int H, int W, int* npix, int* last, int* xmin, int* xmax) {
+// every pixel takes its root as label (the trees are final once the merge kernel has finished) and adds itself to the root's
+// statistics: pixel count, largest raster index, bounding columns — integer atomics, order-independent
+__global__ void det_ccl_flatten_stats_kernel(int* L, int H, int W, int* npix, int* last, int* xmin, int* xmax) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W) return;
   const int p = y * W + x;
-  const int r = L[p];
-  if (r < 0) return;
+  if (L[p] < 0) return;
+  const int r = det_find(L, p);
+  L[p] = r;
   atomicAdd(&npix[r], 1);
   atomicMax(&last[r], p);
   atomicMin(&xmin[r], x);
   atomicMax(&xmax[r], x);
 }
 
+// ---- E3 --------------------------------------------------------------------------------------------------------------
 __global__ void det_mark_kernel(const int* __restrict__ L, long long n, const int* __restrict__ npix, const int* __restrict__ last, int minarea,
                                 unsigned char* flag) {
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -581,7 +685,7 @@ static DetLayout det_layout(long long H, long long W, long long max_objects) {
   L.xmin = take(n * 4);
   L.xmax = take(n * 4);
   L.flag = take(n);
-  L.mesh = take((size_t)L.ny * L.nx * 4 * 9);  // back0 sig0 back1 sig1 back sig dback cp u
+  L.mesh = take((size_t)L.ny * L.nx * 4 * 9 + 16);  // back0 sig0 back1 sig1 back sig dback cp u, then the 4 median picks
   L.rows = take((size_t)H * L.nx * 4 * 4);     // node dnode cp u
   L.cnt = take((size_t)L.nblk * 4);
   L.off = take((size_t)L.nblk * 4);
@@ -626,7 +730,7 @@ extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, in
   unsigned char* d_flag = (unsigned char*)(base + Y.flag);
   float* m = (float*)(base + Y.mesh);
   float *back0 = m, *sig0 = m + nm, *back1 = m + 2 * nm, *sig1 = m + 3 * nm, *back = m + 4 * nm, *sig = m + 5 * nm, *dback = m + 6 * nm,
-        *mcp = m + 7 * nm, *mu = m + 8 * nm;
+        *mcp = m + 7 * nm, *mu = m + 8 * nm, *pick = m + 9 * nm;
   float* rw = (float*)(base + Y.rows);
   const size_t hn = (size_t)H * nx;
   float *node = rw, *dnode = rw + hn, *rcp = rw + 2 * hn, *ru = rw + 3 * hn;
@@ -640,22 +744,26 @@ extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, in
   if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)field, H, W, pitch, C, band, d_band);
   else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)field, H, W, pitch, C, band, d_band);
   DET_LAUNCH(det_mesh_kernel, dim3(nx, ny), DET_BW, 0, d_band, (int)H, (int)W, nx, back0, sig0);
-  DET_LAUNCH(det_mesh_post_kernel, 1, 256, 0, back0, sig0, ny, nx, back1, sig1, back, sig, dback, mcp, mu, thresh_sigma, stats);
+  const unsigned gm = (unsigned)((nm + 127) / 128);
+  DET_LAUNCH(det_mesh_fill_kernel, gm, 128, 0, back0, sig0, ny, nx, back1, sig1);
+  DET_LAUNCH(det_mesh_median_kernel, gm, 128, 0, back1, sig1, ny, nx, back, sig);
+  DET_LAUNCH(det_mesh_rank_kernel, dim3(gm, 2), 128, 0, back, sig, nm, pick);
+  DET_LAUNCH(det_mesh_final_kernel, (unsigned)((nx + 127) / 128), 128, 0, pick, ny, nx, back, dback, mcp, mu, thresh_sigma, stats);
   DET_LAUNCH(det_nodes_kernel, (unsigned)((H + 127) / 128), 128, 0, back, dback, (int)H, ny, nx, node, dnode, rcp, ru);
   const dim3 grow((unsigned)((W + 255) / 256), (unsigned)H);
   DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, (int)H, (int)W, nx, d_fg);
   const size_t fsm = sizeof(float) * (32 + kw - 1) * (32 + kh - 1);
-  DET_LAUNCH(det_filter_kernel, dim3((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32)), 256, fsm, d_fg, (int)H, (int)W, kh, kw, tp, stats, d_conv,
-             d_label);
+  const dim3 gf((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32));
+  if (kh == 7 && kw == 7) DET_LAUNCH(det_filter_tiled_kernel<7>, gf, 256, fsm, d_fg, (int)H, (int)W, tp, stats, d_conv, d_label);
+  else DET_LAUNCH(det_filter_kernel, gf, 256, fsm, d_fg, (int)H, (int)W, kh, kw, tp, stats, d_conv, d_label);
   DET_LAUNCH(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)H, (int)W);
   const unsigned gn = (unsigned)((n + 255) / 256);
-  DET_LAUNCH(det_ccl_flatten_kernel, gn, 256, 0, d_label, n);
   DET_MEMSET(d_npix, 0, n * 4);
   DET_MEMSET(d_last, 0xFF, n * 4);
   DET_MEMSET(d_xmax, 0xFF, n * 4);
   DET_MEMSET(d_xmin, 0x7F, n * 4);
   DET_MEMSET(d_flag, 0, n);
-  DET_LAUNCH(det_stats_kernel, grow, 256, 0, d_label, (int)H, (int)W, d_npix, d_last, d_xmin, d_xmax);
+  DET_LAUNCH(det_ccl_flatten_stats_kernel, grow, 256, 0, d_label, (int)H, (int)W, d_npix, d_last, d_xmin, d_xmax);
   DET_LAUNCH(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, d_flag);
   DET_LAUNCH(det_count_kernel, Y.nblk, 256, 0, d_flag, n, d_cnt);
   DET_LAUNCH(det_scan_kernel, 1, 1024, 0, d_cnt, Y.nblk, d_off, n_found);

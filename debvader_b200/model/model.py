@@ -260,6 +260,12 @@ class Deblender:
         k = _ffi.check(_ffi.lib().dbv_layer_times(self._ctx, n, ms, names))
         return [(names.raw[32 * i : 32 * i + 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(k)]
 
+    def layer_kernel(self, name: str) -> str:
+        """the __global__ function (as the ncu launch list names it) that runs `name` under this precision and tuned plan"""
+        buf = C.create_string_buffer(64)
+        _ffi.check(_ffi.lib().dbv_layer_kernel(self._ctx, name.encode(), buf, 64))
+        return buf.value.decode()
+
     def debug_activation(self, name: str, B: int, shape):
         out = torch.empty((B,) + tuple(shape), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
