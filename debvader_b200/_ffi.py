@@ -70,6 +70,10 @@ def _declare(lib):
         "dbv_detect": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                  c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "dbv_detect_plane": (c_vp, [c_vp, c_i64, c_i64, c_i64, C.c_int]),
+        "dbv_detect_plane_region": (c_vp, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, C.c_int]),
+        "dbv_detect_scratch_bytes_region": (c_i64, [c_i64] * 5),
+        "dbv_detect_meshes": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+        "dbv_detect_objects": (C.c_int, [c_i64] * 6 + [c_vp] * 3 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [c_i64] * 5 + [c_vp, c_i64] + [c_vp] * 8),
         "dbv_debug_activation": (C.c_int, [c_vp, C.c_char_p, c_i64, c_vp, c_vp]),
     }
     for name, (res, args) in sig.items():

@@ -39,7 +39,17 @@ constexpr float DET_BIG = 1e30f;
 constexpr int DET_CHUNK = 4096;       // pixels per CTA of the compaction kernels (256 threads x 16)
 constexpr int DET_MAXK = 15;          // largest filter mask side
 
-struct DetTaps { float v[DET_MAXK * DET_MAXK]; };  // passed by value: a launch parameter (constant bank), no shared state between calls
+struct DetTaps { float v[DET_MAXK * DET_MAXK]; };
+// A call works on a REGION of the field (the whole field on one GPU; a rank's owner tile + halo when the field is tiled over GPUs):
+// the mesh grid, the spline positions and the output coordinates are those of the WHOLE field, indices inside kernels are region-local.
+struct DetGeom {
+  int H, W;                // the whole field
+  int RH, RW;              // the region
+  int gy0, gx0;            // origin of the region in the field
+  int ny, nx;              // mesh grid of the whole field
+  int vy0, vy1, vx0, vx1;  // region-local area where the filtered image is exact (region minus kh/2, kw/2 on edges inside the field)
+  int oy0, oy1, ox0, ox1;  // owner tile in field coordinates: an object belongs to the call whose tile holds its last pixel
+};  // passed by value: a launch parameter (constant bank), no shared state between calls
 
 // ---- band -> compact f64 plane ---------------------------------------------------------------------------------------
 template <typename T>
@@ -62,7 +72,7 @@ __global__ void det_band_kernel(const T* __restrict__ field, long long H, long l
 //     it has taken k = #{ j < n : j + #{ i < n : Q(i) <= P(j) } < n } low steps — two nested binary searches on the prefix sums.
 __device__ __forceinline__ int det_cnt(const int* pre, int i) { return pre[i + 1] - pre[i]; }
 
-__global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, int H, int W, int nx, float* __restrict__ back0,
+__global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, const DetGeom G, float* __restrict__ back0,
                                                       float* __restrict__ sig0) {
   __shared__ float tile[DET_BW][DET_BW + 1];
   __shared__ int pre[DET_MAXLEVELS + 1];  // level counts, then their exclusive prefix sums (pre[nlevels .. 4096] = total)
@@ -73,10 +83,13 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   __shared__ int s_nlevels, s_bad, s_lo, s_hi, s_go;
   __shared__ double s_mean2;
   const int mx = blockIdx.x, my = blockIdx.y, t = threadIdx.x;
-  const int x0 = mx * DET_BW, y0 = my * DET_BW;
-  const int mw = min(DET_BW, W - x0), mh = min(DET_BW, H - y0);
+  const int nx = G.nx;
+  const int x0 = mx * DET_BW, y0 = my * DET_BW;  // field coordinates
+  const int mw = min(DET_BW, G.W - x0), mh = min(DET_BW, G.H - y0);
+  // a mesh is computed by the call whose region holds all of it (tiled fields: the other meshes come from the other ranks)
+  if (y0 < G.gy0 || y0 + mh > G.gy0 + G.RH || x0 < G.gx0 || x0 + mw > G.gx0 + G.RW) return;
   for (int r = 0; r < mh; ++r)
-    if (t < mw) tile[r][t] = (float)band[(long long)(y0 + r) * W + x0 + t];
+    if (t < mw) tile[r][t] = (float)band[(long long)(y0 - G.gy0 + r) * G.RW + (x0 - G.gx0) + t];
   __syncthreads();
   // pass 1: all pixels
   if (t < mh) {
@@ -393,15 +406,16 @@ __device__ __forceinline__ void det_spline_pos(int i, int n, int* lo, float* t) 
 }
 
 // one thread per image row: the mesh map interpolated along y at this row (node), then its x-spline (dnode)
-__global__ void det_nodes_kernel(const float* __restrict__ back, const float* __restrict__ dback, int H, int ny, int nx, float* node,
+__global__ void det_nodes_kernel(const float* __restrict__ back, const float* __restrict__ dback, const DetGeom G, float* node,
                                  float* dnode, float* cp, float* u) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
-  if (y >= H) return;
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;  // region row
+  if (y >= G.RH) return;
+  const int ny = G.ny, nx = G.nx;
   float* nd = node + (long long)y * nx;
   if (ny > 1) {
     int yl;
     float t;
-    det_spline_pos(y, ny, &yl, &t);
+    det_spline_pos(G.gy0 + y, ny, &yl, &t);
     for (int x = 0; x < nx; ++x)
       nd[x] = det_spline_eval(back[yl * nx + x], back[(yl + 1) * nx + x], dback[yl * nx + x], dback[(yl + 1) * nx + x], t);
   } else {
@@ -410,9 +424,10 @@ __global__ void det_nodes_kernel(const float* __restrict__ back, const float* __
   det_spline_d2(nd, 1, nx, dnode + (long long)y * nx, cp + (long long)y * nx, u + (long long)y * nx, 1);
 }
 
-__global__ void det_foreground_kernel(const double* __restrict__ band, const float* __restrict__ node, const float* __restrict__ dnode, int H,
-                                      int W, int nx, float* __restrict__ fg) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+__global__ void det_foreground_kernel(const double* __restrict__ band, const float* __restrict__ node, const float* __restrict__ dnode,
+                                      const DetGeom G, float* __restrict__ fg) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;  // region pixel
+  const int W = G.RW, nx = G.nx;
   if (x >= W) return;
   const float* nd = node + (long long)y * nx;
   float b;
@@ -420,7 +435,7 @@ __global__ void det_foreground_kernel(const double* __restrict__ band, const flo
     const float* dn = dnode + (long long)y * nx;
     int xl;
     float t;
-    det_spline_pos(x, nx, &xl, &t);
+    det_spline_pos(G.gx0 + x, nx, &xl, &t);
     b = det_spline_eval(nd[xl], nd[xl + 1], dn[xl], dn[xl + 1], t);
   } else {
     b = nd[0];
@@ -432,9 +447,10 @@ __global__ void det_foreground_kernel(const double* __restrict__ band, const flo
 // ---- E1 --------------------------------------------------------------------------------------------------------------
 // 32 x 32 outputs per CTA from a zero-padded shared tile; taps accumulated in raster order (float32, one rounding per product
 // and per sum).  Writes the filtered image and the initial label image: own raster index above the threshold, -1 below.
-__global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict__ fg, int H, int W, int kh, int kw, const DetTaps taps,
+__global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict__ fg, const DetGeom G, int kh, int kw, const DetTaps taps,
                                                          const float* __restrict__ stats, float* __restrict__ conv, int* __restrict__ label) {
   DET_DYN_SMEM(float, sm);
+  const int H = G.RH, W = G.RW;
   const int tw = 32 + kw - 1, th = 32 + kh - 1;
   const int x0 = blockIdx.x * 32 - kw / 2, y0 = blockIdx.y * 32 - kh / 2;
   for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
@@ -453,7 +469,8 @@ __global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict
       for (int kx = 0; kx < kw; ++kx) acc = acc + taps.v[ky * kw + kx] * sm[(ly + ky) * tw + lx + kx];
     const long long p = (long long)y * W + x;
     conv[p] = acc;
-    label[p] = acc > thresh ? (int)p : -1;
+    // on a region edge inside the field the taps beyond the region are missing: those pixels carry no label (their objects belong to a neighbour)
+    label[p] = (acc > thresh && y >= G.vy0 && y < G.vy1 && x >= G.vx0 && x < G.vx1) ? (int)p : -1;
   }
 }
 
@@ -461,9 +478,10 @@ __global__ void __launch_bounds__(256) det_filter_kernel(const float* __restrict
 // streams the K + 3 tile rows they share through registers (K shared-memory loads per row instead of 4 K); every output still adds
 // its taps in raster order, one rounding per product and per sum, so the result is bit-identical to det_filter_kernel
 template <int K>
-__global__ void __launch_bounds__(256) det_filter_tiled_kernel(const float* __restrict__ fg, int H, int W, const DetTaps taps,
+__global__ void __launch_bounds__(256) det_filter_tiled_kernel(const float* __restrict__ fg, const DetGeom G, const DetTaps taps,
                                                                const float* __restrict__ stats, float* __restrict__ conv, int* __restrict__ label) {
   DET_DYN_SMEM(float, sm);
+  const int H = G.RH, W = G.RW;
   constexpr int tw = 32 + K - 1, th = 32 + K - 1;
   const int x0 = blockIdx.x * 32 - K / 2, y0 = blockIdx.y * 32 - K / 2;
   for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
@@ -497,7 +515,7 @@ __global__ void __launch_bounds__(256) det_filter_tiled_kernel(const float* __re
     if (y >= H) break;
     const long long p = (long long)y * W + x;
     conv[p] = acc[r];
-    label[p] = acc[r] > thresh ? (int)p : -1;
+    label[p] = (acc[r] > thresh && y >= G.vy0 && y < G.vy1 && x >= G.vx0 && x < G.vx1) ? (int)p : -1;
   }
 }
 
@@ -548,8 +566,9 @@ __global__ void det_ccl_merge_kernel(int* L, int H, int W) {
 
 // every pixel takes its root as label (the trees are final once the merge kernel has finished) and adds itself to the root's
 // statistics: pixel count, largest raster index, bounding columns — integer atomics, order-independent
-__global__ void det_ccl_flatten_stats_kernel(int* L, int H, int W, int* npix, int* last, int* xmin, int* xmax) {
+__global__ void det_ccl_flatten_stats_kernel(int* L, const DetGeom G, int* npix, int* last, int* xmin, int* xmax, int* touch) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int W = G.RW;
   if (x >= W) return;
   const int p = y * W + x;
   if (L[p] < 0) return;
@@ -559,14 +578,19 @@ __global__ void det_ccl_flatten_stats_kernel(int* L, int H, int W, int* npix, in
   atomicMax(&last[r], p);
   atomicMin(&xmin[r], x);
   atomicMax(&xmax[r], x);
+  // a pixel on the rim of the exact area, on a side that is not the field's edge: the object may continue beyond what this call sees
+  if ((y == G.vy0 && G.vy0 > 0) || (y == G.vy1 - 1 && G.vy1 < G.RH) || (x == G.vx0 && G.vx0 > 0) || (x == G.vx1 - 1 && G.vx1 < G.RW)) touch[r] = 1;
 }
 
 // ---- E3 --------------------------------------------------------------------------------------------------------------
 __global__ void det_mark_kernel(const int* __restrict__ L, long long n, const int* __restrict__ npix, const int* __restrict__ last, int minarea,
-                                unsigned char* flag) {
+                                const DetGeom G, unsigned char* flag) {
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p >= n) return;
-  if (L[p] == (int)p && npix[p] >= minarea) flag[last[p]] = 1;
+  if (L[p] == (int)p && npix[p] >= minarea) {
+    const int e = last[p], ey = G.gy0 + e / G.RW, ex = G.gx0 + e % G.RW;
+    if (ey >= G.oy0 && ey < G.oy1 && ex >= G.ox0 && ex < G.ox1) flag[e] = 1;
+  }
 }
 
 // flags are compacted in raster order: per-CTA counts, one-CTA exclusive scan, scatter
@@ -632,13 +656,15 @@ __global__ void __launch_bounds__(256) det_scatter_kernel(const unsigned char* _
 
 // ---- E4 --------------------------------------------------------------------------------------------------------------
 // one thread per object: its pixels in raster order over the bounding box, double sums (oracle: np.cumsum(...)[-1])
-__global__ void det_moments_kernel(const int* __restrict__ L, const float* __restrict__ fg, const float* __restrict__ conv, int W,
+__global__ void det_moments_kernel(const int* __restrict__ L, const float* __restrict__ fg, const float* __restrict__ conv, const DetGeom G,
                                    const int* __restrict__ endpos, const int* __restrict__ n_found, long long max_objects,
-                                   const int* __restrict__ npix, const int* __restrict__ xmin, const int* __restrict__ xmax, int cy, int cx,
-                                   double* xy, double* centres, int* npix_out) {
+                                   const int* __restrict__ npix, const int* __restrict__ xmin, const int* __restrict__ xmax,
+                                   const int* __restrict__ touch, int cy, int cx, double* xy, double* centres, int* npix_out,
+                                   long long* last_out, int* flags) {
   const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long n = n_found[0] < max_objects ? n_found[0] : max_objects;
   if (k >= n) return;
+  const int W = G.RW;
   const int e = endpos[k], r = L[e];
   const int y0 = r / W, y1 = e / W, x0 = xmin[r], x1 = xmax[r];
   double tv = 0.0, mx = 0.0, my = 0.0, tc = 0.0, cmx = 0.0, cmy = 0.0;
@@ -656,21 +682,23 @@ __global__ void det_moments_kernel(const int* __restrict__ L, const float* __res
       cmy += c * dy;
     }
   if (!(tv > 0.0)) { tv = tc; mx = cmx; my = cmy; }  // faint detections: weight with the filtered values (> thresh > 0)
-  const double X = mx / tv + (double)x0, Y = my / tv + (double)y0;
+  const double X = mx / tv + (double)(x0 + G.gx0), Y = my / tv + (double)(y0 + G.gy0);  // field coordinates
   xy[2 * k] = X;
   xy[2 * k + 1] = Y;
   centres[2 * k] = rint(Y - (double)cy);      // (row, col) offsets from the field centre, detection.py:48-54
   centres[2 * k + 1] = rint(X - (double)cx);
   npix_out[k] = npix[r];
+  last_out[k] = (long long)(G.gy0 + e / W) * G.W + (G.gx0 + e % W);  // the order key, in the raster of the whole field
+  if (touch[r]) flags[0] = 1;  // an object of this call's tile leaves the area it can see: the caller must detect on the assembled field
 }
 
 struct DetLayout {
-  size_t band, fg, conv, label, npix, last, xmin, xmax, flag, mesh, rows, cnt, off, endpos, total;
+  size_t band, fg, conv, label, npix, last, xmin, xmax, touch, flag, mesh, rows, cnt, off, endpos, last64, flags, total;
   int ny, nx, nblk;
 };
-static DetLayout det_layout(long long H, long long W, long long max_objects) {
+static DetLayout det_layout(long long H, long long W, long long RH, long long RW, long long max_objects) {
   DetLayout L{};
-  const size_t n = (size_t)H * W;
+  const size_t n = (size_t)RH * RW;
   L.ny = (int)((H - 1) / DET_BW + 1);
   L.nx = (int)((W - 1) / DET_BW + 1);
   L.nblk = (int)((n + DET_CHUNK - 1) / DET_CHUNK);
@@ -684,41 +712,91 @@ static DetLayout det_layout(long long H, long long W, long long max_objects) {
   L.last = take(n * 4);
   L.xmin = take(n * 4);
   L.xmax = take(n * 4);
+  L.touch = take(n * 4);
   L.flag = take(n);
   L.mesh = take((size_t)L.ny * L.nx * 4 * 9 + 16);  // back0 sig0 back1 sig1 back sig dback cp u, then the 4 median picks
-  L.rows = take((size_t)H * L.nx * 4 * 4);     // node dnode cp u
+  L.rows = take((size_t)RH * L.nx * 4 * 4);        // node dnode cp u
   L.cnt = take((size_t)L.nblk * 4);
   L.off = take((size_t)L.nblk * 4);
   L.endpos = take((size_t)max_objects * 4);
+  L.last64 = take((size_t)max_objects * 8);
+  L.flags = take(16);
   L.total = o;
   return L;
+}
+
+static DetGeom det_geom(long long H, long long W, long long RH, long long RW, long long gy0, long long gx0, int kh, int kw, const DetLayout& Y) {
+  DetGeom G{};
+  G.H = (int)H; G.W = (int)W; G.RH = (int)RH; G.RW = (int)RW; G.gy0 = (int)gy0; G.gx0 = (int)gx0;
+  G.ny = Y.ny; G.nx = Y.nx;
+  G.vy0 = gy0 > 0 ? kh / 2 : 0;
+  G.vy1 = (int)RH - (gy0 + RH < H ? kh / 2 : 0);
+  G.vx0 = gx0 > 0 ? kw / 2 : 0;
+  G.vx1 = (int)RW - (gx0 + RW < W ? kw / 2 : 0);
+  G.oy0 = 0; G.oy1 = (int)H; G.ox0 = 0; G.ox1 = (int)W;
+  return G;
 }
 
 }  // namespace dbv
 
 using namespace dbv;
 
+extern "C" int64_t dbv_detect_scratch_bytes_region(int64_t H, int64_t W, int64_t RH, int64_t RW, int64_t max_objects) {
+  if (H <= 0 || W <= 0 || RH <= 0 || RW <= 0 || RH > H || RW > W || max_objects <= 0) return 0;
+  return (int64_t)det_layout(H, W, RH, RW, max_objects).total;
+}
 extern "C" int64_t dbv_detect_scratch_bytes(int64_t H, int64_t W, int64_t max_objects) {
-  if (H <= 0 || W <= 0 || max_objects <= 0) return 0;
-  return (int64_t)det_layout(H, W, max_objects).total;
+  return dbv_detect_scratch_bytes_region(H, W, H, W, max_objects);
 }
 
-extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, int64_t pitch, int C, int band, const float* taps, int kh,
-                          int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t max_objects, void* scratch,
-                          int64_t scratch_bytes, int32_t* n_found, double* xy, double* centres, int32_t* npix_out, float* stats,
-                          void* stream) {
-  DBV_REQUIRE(field && taps && scratch && n_found && xy && centres && npix_out && stats, "dbv_detect: null pointer");
-  DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_detect: bad dtype %d", dtype);
-  DBV_REQUIRE(H > 0 && W > 0 && H * W < (1ll << 31) && pitch >= W && C > 0 && band >= 0 && band < C, "dbv_detect: bad field geometry");
-  DBV_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && kh <= DET_MAXK && kw <= DET_MAXK, "dbv_detect: the filter mask must be odd-sized, at most %d x %d", DET_MAXK, DET_MAXK);
-  DBV_REQUIRE(minarea >= 1 && max_objects > 0 && thresh_sigma > 0.0, "dbv_detect: bad minarea / max_objects / thresh");
-  const DetLayout Y = det_layout(H, W, max_objects);
-  DBV_REQUIRE(scratch_bytes >= (int64_t)Y.total, "dbv_detect: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)Y.total);
-  DBV_REQUIRE(((uintptr_t)scratch & 255) == 0, "dbv_detect: scratch must be 256-byte aligned");
+// phase A: the band plane of the region and the statistics of every mesh that lies wholly inside it, written at the mesh's place
+// in the caller's field-sized (ny, nx) maps (other entries untouched: a tiled caller presets -inf and max-reduces over the ranks)
+extern "C" int dbv_detect_meshes(const void* region, int dtype, int64_t RH, int64_t RW, int64_t pitch, int C, int band, int64_t gy0,
+                                 int64_t gx0, int64_t H, int64_t W, int64_t max_objects, void* scratch, int64_t scratch_bytes,
+                                 float* back0, float* sig0, void* stream) {
+  DBV_REQUIRE(region && scratch && back0 && sig0, "dbv_detect_meshes: null pointer");
+  DBV_REQUIRE(dtype == DBV_F64 || dtype == DBV_F32, "dbv_detect_meshes: bad dtype %d", dtype);
+  DBV_REQUIRE(H > 0 && W > 0 && RH > 0 && RW > 0 && gy0 >= 0 && gx0 >= 0 && gy0 + RH <= H && gx0 + RW <= W && H * W < (1ll << 31) && pitch >= RW &&
+                  C > 0 && band >= 0 && band < C && max_objects > 0,
+              "dbv_detect_meshes: bad geometry");
+  const DetLayout Y = det_layout(H, W, RH, RW, max_objects);
+  DBV_REQUIRE(scratch_bytes >= (int64_t)Y.total, "dbv_detect_meshes: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)Y.total);
+  DBV_REQUIRE(((uintptr_t)scratch & 255) == 0, "dbv_detect_meshes: scratch must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  (void)st;
+  double* d_band = (double*)((char*)scratch + Y.band);
+  const DetGeom G = det_geom(H, W, RH, RW, gy0, gx0, 1, 1, Y);
+  const long long n = RH * RW;
+  const int gb = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)region, RH, RW, pitch, C, band, d_band);
+  else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)region, RH, RW, pitch, C, band, d_band);
+  DET_LAUNCH(det_mesh_kernel, dim3(Y.nx, Y.ny), DET_BW, 0, d_band, G, back0, sig0);
+  return DBV_OK;
+}
+
+// phase B: everything after the mesh statistics, on the region whose band plane phase A left in `scratch`; back0 / sig0 = the
+// COMPLETE field-sized mesh maps.  Objects are reported by the call whose owner tile [oy0, oy1) x [ox0, ox1) holds their last pixel;
+// flags[0] is set when such an object reaches the rim of what the region can see (the caller then detects on the assembled field).
+extern "C" int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t gx0, int64_t H, int64_t W, const float* back0, const float* sig0,
+                                  const float* taps, int kh, int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t oy0,
+                                  int64_t oy1, int64_t ox0, int64_t ox1, int64_t max_objects, void* scratch, int64_t scratch_bytes,
+                                  int32_t* n_found, double* xy, double* centres, int32_t* npix_out, int64_t* last_out, int32_t* flags,
+                                  float* stats, void* stream) {
+  DBV_REQUIRE(back0 && sig0 && taps && scratch && n_found && xy && centres && npix_out && last_out && flags && stats, "dbv_detect_objects: null pointer");
+  DBV_REQUIRE(H > 0 && W > 0 && RH > 0 && RW > 0 && gy0 >= 0 && gx0 >= 0 && gy0 + RH <= H && gx0 + RW <= W && H * W < (1ll << 31),
+              "dbv_detect_objects: bad geometry");
+  DBV_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && kh <= DET_MAXK && kw <= DET_MAXK, "dbv_detect_objects: the filter mask must be odd-sized, at most %d x %d", DET_MAXK, DET_MAXK);
+  DBV_REQUIRE(minarea >= 1 && max_objects > 0 && thresh_sigma > 0.0, "dbv_detect_objects: bad minarea / max_objects / thresh");
+  const DetLayout Y = det_layout(H, W, RH, RW, max_objects);
+  DBV_REQUIRE(scratch_bytes >= (int64_t)Y.total, "dbv_detect_objects: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)Y.total);
+  DBV_REQUIRE(((uintptr_t)scratch & 255) == 0, "dbv_detect_objects: scratch must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  (void)st;
   char* base = (char*)scratch;
-  const long long n = H * W;
+  const long long n = RH * RW;
   const int ny = Y.ny, nx = Y.nx, nm = ny * nx;
+  DetGeom G = det_geom(H, W, RH, RW, gy0, gx0, kh, kw, Y);
+  G.oy0 = (int)oy0; G.oy1 = (int)oy1; G.ox0 = (int)ox0; G.ox1 = (int)ox1;
   double* d_band = (double*)(base + Y.band);
   float* d_fg = (float*)(base + Y.fg);
   float* d_conv = (float*)(base + Y.conv);
@@ -727,58 +805,75 @@ extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, in
   int* d_last = (int*)(base + Y.last);
   int* d_xmin = (int*)(base + Y.xmin);
   int* d_xmax = (int*)(base + Y.xmax);
+  int* d_touch = (int*)(base + Y.touch);
   unsigned char* d_flag = (unsigned char*)(base + Y.flag);
   float* m = (float*)(base + Y.mesh);
-  float *back0 = m, *sig0 = m + nm, *back1 = m + 2 * nm, *sig1 = m + 3 * nm, *back = m + 4 * nm, *sig = m + 5 * nm, *dback = m + 6 * nm,
-        *mcp = m + 7 * nm, *mu = m + 8 * nm, *pick = m + 9 * nm;
+  float *back1 = m + 2 * nm, *sig1 = m + 3 * nm, *back = m + 4 * nm, *sig = m + 5 * nm, *dback = m + 6 * nm, *mcp = m + 7 * nm, *mu = m + 8 * nm,
+        *pick = m + 9 * nm;
   float* rw = (float*)(base + Y.rows);
-  const size_t hn = (size_t)H * nx;
+  const size_t hn = (size_t)RH * nx;
   float *node = rw, *dnode = rw + hn, *rcp = rw + 2 * hn, *ru = rw + 3 * hn;
   int* d_cnt = (int*)(base + Y.cnt);
   int* d_off = (int*)(base + Y.off);
   int* d_end = (int*)(base + Y.endpos);
-
   DetTaps tp{};
   for (int i = 0; i < kh * kw; ++i) tp.v[i] = taps[i];
-  const int gb = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)field, H, W, pitch, C, band, d_band);
-  else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)field, H, W, pitch, C, band, d_band);
-  DET_LAUNCH(det_mesh_kernel, dim3(nx, ny), DET_BW, 0, d_band, (int)H, (int)W, nx, back0, sig0);
+
   const unsigned gm = (unsigned)((nm + 127) / 128);
   DET_LAUNCH(det_mesh_fill_kernel, gm, 128, 0, back0, sig0, ny, nx, back1, sig1);
   DET_LAUNCH(det_mesh_median_kernel, gm, 128, 0, back1, sig1, ny, nx, back, sig);
   DET_LAUNCH(det_mesh_rank_kernel, dim3(gm, 2), 128, 0, back, sig, nm, pick);
   DET_LAUNCH(det_mesh_final_kernel, (unsigned)((nx + 127) / 128), 128, 0, pick, ny, nx, back, dback, mcp, mu, thresh_sigma, stats);
-  DET_LAUNCH(det_nodes_kernel, (unsigned)((H + 127) / 128), 128, 0, back, dback, (int)H, ny, nx, node, dnode, rcp, ru);
-  const dim3 grow((unsigned)((W + 255) / 256), (unsigned)H);
-  DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, (int)H, (int)W, nx, d_fg);
+  DET_LAUNCH(det_nodes_kernel, (unsigned)((RH + 127) / 128), 128, 0, back, dback, G, node, dnode, rcp, ru);
+  const dim3 grow((unsigned)((RW + 255) / 256), (unsigned)RH);
+  DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, G, d_fg);
   const size_t fsm = sizeof(float) * (32 + kw - 1) * (32 + kh - 1);
-  const dim3 gf((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32));
-  if (kh == 7 && kw == 7) DET_LAUNCH(det_filter_tiled_kernel<7>, gf, 256, fsm, d_fg, (int)H, (int)W, tp, stats, d_conv, d_label);
-  else DET_LAUNCH(det_filter_kernel, gf, 256, fsm, d_fg, (int)H, (int)W, kh, kw, tp, stats, d_conv, d_label);
-  DET_LAUNCH(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)H, (int)W);
+  const dim3 gf((unsigned)((RW + 31) / 32), (unsigned)((RH + 31) / 32));
+  if (kh == 7 && kw == 7) DET_LAUNCH(det_filter_tiled_kernel<7>, gf, 256, fsm, d_fg, G, tp, stats, d_conv, d_label);
+  else DET_LAUNCH(det_filter_kernel, gf, 256, fsm, d_fg, G, kh, kw, tp, stats, d_conv, d_label);
+  DET_LAUNCH(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)RH, (int)RW);
   const unsigned gn = (unsigned)((n + 255) / 256);
   DET_MEMSET(d_npix, 0, n * 4);
   DET_MEMSET(d_last, 0xFF, n * 4);
   DET_MEMSET(d_xmax, 0xFF, n * 4);
   DET_MEMSET(d_xmin, 0x7F, n * 4);
+  DET_MEMSET(d_touch, 0, n * 4);
   DET_MEMSET(d_flag, 0, n);
-  DET_LAUNCH(det_ccl_flatten_stats_kernel, grow, 256, 0, d_label, (int)H, (int)W, d_npix, d_last, d_xmin, d_xmax);
-  DET_LAUNCH(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, d_flag);
+  DET_MEMSET(flags, 0, 4);
+  DET_LAUNCH(det_ccl_flatten_stats_kernel, grow, 256, 0, d_label, G, d_npix, d_last, d_xmin, d_xmax, d_touch);
+  DET_LAUNCH(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, G, d_flag);
   DET_LAUNCH(det_count_kernel, Y.nblk, 256, 0, d_flag, n, d_cnt);
   DET_LAUNCH(det_scan_kernel, 1, 1024, 0, d_cnt, Y.nblk, d_off, n_found);
   DET_LAUNCH(det_scatter_kernel, Y.nblk, 256, 0, d_flag, n, d_off, max_objects, d_end);
-  DET_LAUNCH(det_moments_kernel, (unsigned)((max_objects + 127) / 128), 128, 0, d_label, d_fg, d_conv, (int)W, d_end, n_found, max_objects, d_npix, d_xmin,
-             d_xmax, cy, cx, xy, centres, npix_out);
+  DET_LAUNCH(det_moments_kernel, (unsigned)((max_objects + 127) / 128), 128, 0, d_label, d_fg, d_conv, G, d_end, n_found, max_objects, d_npix, d_xmin,
+             d_xmax, d_touch, cy, cx, xy, centres, npix_out, (long long*)last_out, flags);
   return DBV_OK;
 }
 
-// debug / parity access to the intermediate planes of the last dbv_detect call that used `scratch`:
-// what = 0 foreground f32 (H,W), 1 filtered f32 (H,W), 2 labels i32 (H,W), 3 mesh background f32 (ny,nx), 4 mesh sigma f32 (ny,nx),
-// 5 raw mesh background, 6 raw mesh sigma.  Returns a device pointer inside scratch (no copy).
-extern "C" const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int64_t max_objects, int what) {
-  if (!scratch || H <= 0 || W <= 0 || max_objects <= 0) return nullptr;
-  const DetLayout Y = det_layout(H, W, max_objects);
+// the whole field in one call (one GPU): phase A into the scratch's own mesh maps, then phase B with the field as its own owner tile
+extern "C" int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, int64_t pitch, int C, int band, const float* taps, int kh,
+                          int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t max_objects, void* scratch,
+                          int64_t scratch_bytes, int32_t* n_found, double* xy, double* centres, int32_t* npix_out, float* stats,
+                          void* stream) {
+  DBV_REQUIRE(field && scratch, "dbv_detect: null pointer");
+  DBV_REQUIRE(H > 0 && W > 0 && max_objects > 0, "dbv_detect: bad field geometry");
+  const DetLayout Y = det_layout(H, W, H, W, max_objects);
+  DBV_REQUIRE(scratch_bytes >= (int64_t)Y.total, "dbv_detect: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)Y.total);
+  char* base = (char*)scratch;
+  float* m = (float*)(base + Y.mesh);
+  const int nm = Y.ny * Y.nx;
+  int r = dbv_detect_meshes(field, dtype, H, W, pitch, C, band, 0, 0, H, W, max_objects, scratch, scratch_bytes, m, m + nm, stream);
+  if (r) return r;
+  return dbv_detect_objects(H, W, 0, 0, H, W, m, m + nm, taps, kh, kw, thresh_sigma, minarea, cy, cx, 0, H, 0, W, max_objects, scratch,
+                            scratch_bytes, n_found, xy, centres, npix_out, (int64_t*)(base + Y.last64), (int32_t*)(base + Y.flags), stats, stream);
+}
+
+// debug / parity access to the intermediate planes of the last call that used `scratch` (region-sized planes):
+// what = 0 foreground f32 (RH,RW), 1 filtered f32 (RH,RW), 2 labels i32 (RH,RW), 3 mesh background f32 (ny,nx), 4 mesh sigma f32 (ny,nx),
+// 5 raw mesh background, 6 raw mesh sigma (5 / 6: the scratch's own maps, filled by dbv_detect only).  Returns a device pointer inside scratch.
+extern "C" const void* dbv_detect_plane_region(void* scratch, int64_t H, int64_t W, int64_t RH, int64_t RW, int64_t max_objects, int what) {
+  if (!scratch || H <= 0 || W <= 0 || RH <= 0 || RW <= 0 || max_objects <= 0) return nullptr;
+  const DetLayout Y = det_layout(H, W, RH, RW, max_objects);
   char* base = (char*)scratch;
   const size_t nm = (size_t)Y.ny * Y.nx;
   switch (what) {
@@ -791,4 +886,7 @@ extern "C" const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int
     case 6: return base + Y.mesh + 1 * nm * 4;
   }
   return nullptr;
+}
+extern "C" const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int64_t max_objects, int what) {
+  return dbv_detect_plane_region(scratch, H, W, H, W, max_objects, what);
 }

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ..deblend.field_deblender import DeblendField
-from ..detect.detection import DeviceDetector, detect_objects
+from ..detect.detection import DeviceDetector, TiledDeviceDetector, detect_objects
 
 
 class IterativeDeblendField(DeblendField):
@@ -31,7 +31,11 @@ class IterativeDeblendField(DeblendField):
         if isinstance(detector, str):
             if detector not in ("device", "sep"):
                 raise ValueError(f"unknown detector {detector!r}")
-            detector = DeviceDetector(device=self._field_dev.device) if detector == "device" else detect_objects
+            if detector == "device":
+                detector = (TiledDeviceDetector(group=group, device=self._field_dev.device) if self._local is not None
+                            else DeviceDetector(device=self._field_dev.device))
+            else:
+                detector = detect_objects
         self.detector = detector or detect_objects
 
     def iterative_deblending(self, galaxy_distances_to_center=None, cutout_images=None, optimise_positions=False,

@@ -144,6 +144,132 @@ class DeviceDetector:
         return raw.view(torch.int32 if code == 2 else torch.float32).reshape(shape)
 
 
+class TiledDeviceDetector(DeviceDetector):
+    """The device detector on a field tiled over GPUs (one process per GPU; ``debvader_b200.parallel.LocalField``): every rank works
+    on its owner tile + halo only and all ranks return the SAME global list of centres — the single-GPU list, bit for bit.
+
+    Data path: mesh statistics of the rank's own meshes -> ONE all-reduce(MAX) of the (2, ny, nx) mesh maps (32 KB for a 4096^2
+    field) -> background / filter / components on the region -> the objects whose last pixel lies in the owner tile -> one
+    all-gather of (order key, row, col) per object, merged by the order key.  No field-sized transfer.  Falls back to detection
+    on the assembled field (``parallel.gather_field``) when that is needed for exactness: tiles not aligned to the 64-px mesh
+    grid, or an owned object reaching the rim of the region (footprints wider than the 30-px halo minus the filter's 3 px)."""
+
+    accepts_local = True
+
+    def __init__(self, group=None, **kw):
+        super().__init__(**kw)
+        self.group = group
+        self.fallbacks = 0
+        self._rbuf = {}
+
+    @staticmethod
+    def meshes_covered(field_size, world, halo):
+        """every 64x64 mesh of the field lies wholly inside some rank's region"""
+        from .. import parallel
+
+        regs = parallel.region_bounds(field_size, world, halo)
+        n = (field_size - 1) // 64 + 1
+        for my in range(n):
+            y0, y1 = 64 * my, min(64 * my + 64, field_size)
+            for mx in range(n):
+                x0, x1 = 64 * mx, min(64 * mx + 64, field_size)
+                if not any(R0 <= y0 and y1 <= R1 and C0 <= x0 and x1 <= C1 for R0, R1, C0, C1 in regs):
+                    return False
+        return True
+
+    def _region_buffers(self, F, RH, RW, dev):
+        import torch
+
+        from .. import _ffi
+
+        key = (F, RH, RW, str(dev))
+        b = self._rbuf.get(key)
+        if b is None:
+            M = self.max_objects
+            nbytes = int(_ffi.lib().dbv_detect_scratch_bytes_region(F, F, RH, RW, M))
+            n = (F - 1) // 64 + 1
+            b = {"scratch": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev), "nbytes": nbytes,
+                 "maps": torch.empty((2, n, n), dtype=torch.float32, device=dev),
+                 "n": torch.zeros(1, dtype=torch.int32, device=dev), "flags": torch.zeros(4, dtype=torch.int32, device=dev),
+                 "xy": torch.empty((M, 2), dtype=torch.float64, device=dev), "centres": torch.empty((M, 2), dtype=torch.float64, device=dev),
+                 "npix": torch.empty(M, dtype=torch.int32, device=dev), "last": torch.empty(M, dtype=torch.int64, device=dev),
+                 "stats": torch.zeros(4, dtype=torch.float32, device=dev)}
+            b["base"] = b["scratch"].data_ptr() + (-b["scratch"].data_ptr()) % 256
+            self._rbuf = {key: b}
+        return b
+
+    def __call__(self, field_image, local=None, return_details=False):
+        import torch
+        import torch.distributed as dist
+
+        from .. import _ffi, parallel
+
+        if local is None or local.world == 1:
+            return super().__call__(local.data if (local is not None and field_image is None) else field_image, return_details=return_details)
+        t = local.data if field_image is None else field_image
+        if t.ndim == 4:
+            t = t[0]
+        if t.dtype not in (torch.float64, torch.float32) or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError("the tiled detector needs the rank's contiguous CUDA region tensor")
+        F = local.field_size
+        R0, R1, C0, C1 = local.region
+        r0, r1, c0, c1 = local.tile
+        RH, RW, Cn = (int(v) for v in t.shape)
+        if (RH, RW) != (R1 - R0, C1 - C0):
+            raise ValueError(f"region tensor {tuple(t.shape)} does not match the rank's region {local.region}")
+        if not self.meshes_covered(F, local.world, local.halo):
+            return self._on_assembled_field(local, field_image, return_details)
+        b = self._region_buffers(F, RH, RW, t.device)
+        lib = _ffi.lib()
+        with torch.cuda.device(t.device):
+            b["maps"].fill_(float("-inf"))
+            _ffi.check(lib.dbv_detect_meshes(_ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, RH, RW, RW, Cn, self.band, R0, C0, F, F, self.max_objects,
+                                             C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), _ffi.stream_ptr()))
+            dist.all_reduce(b["maps"], op=dist.ReduceOp.MAX, group=self.group)
+            _ffi.check(lib.dbv_detect_objects(RH, RW, R0, C0, F, F, _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), self.taps.ctypes.data_as(C.c_void_p),
+                                              int(self.taps.shape[0]), int(self.taps.shape[1]), self.thresh, self.minarea, int(F / 2), int(F / 2),
+                                              r0, r1, c0, c1, self.max_objects, C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["n"]), _ffi.ptr(b["xy"]),
+                                              _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["last"]), _ffi.ptr(b["flags"]), _ffi.ptr(b["stats"]),
+                                              _ffi.stream_ptr()))
+            # every rank learns every rank's (count, flag); then one padded all-gather of the objects
+            head = torch.stack([b["n"][0], b["flags"][0]]).to(torch.int64)
+            heads = torch.empty((local.world, 2), dtype=torch.int64, device=t.device)
+            dist.all_gather_into_tensor(heads, head, group=self.group)
+            heads = heads.cpu().numpy()
+        if heads[:, 1].any() or (heads[:, 0] > self.max_objects).any():
+            return self._on_assembled_field(local, field_image, return_details)
+        nmax = int(heads[:, 0].max())
+        if nmax == 0:
+            out = np.zeros((0, 2))
+            return (out, {"x": np.zeros(0), "y": np.zeros(0), "npix": np.zeros(0, np.int32)}) if return_details else out
+        with torch.cuda.device(t.device):
+            mine = torch.zeros((nmax, 6), dtype=torch.float64, device=t.device)
+            k = int(heads[local.rank, 0])
+            if k:
+                mine[:k, 0] = b["last"][:k].to(torch.float64)  # < 2^31: exact
+                mine[:k, 1:3] = b["centres"][:k]
+                mine[:k, 3:5] = b["xy"][:k]
+                mine[:k, 5] = b["npix"][:k].to(torch.float64)
+            allo = torch.empty((local.world, nmax, 6), dtype=torch.float64, device=t.device)
+            dist.all_gather_into_tensor(allo, mine, group=self.group)
+            allo = allo.cpu().numpy()
+        rows = np.concatenate([allo[r, : int(heads[r, 0])] for r in range(local.world)])
+        rows = rows[np.argsort(rows[:, 0], kind="stable")]
+        centres = np.ascontiguousarray(rows[:, 1:3])
+        if return_details:
+            st = b["stats"].cpu().numpy()
+            return centres, {"x": rows[:, 3], "y": rows[:, 4], "npix": rows[:, 5].astype(np.int32), "last": rows[:, 0].astype(np.int64),
+                             "globalback": st[0], "globalrms": st[1], "thresh": st[2]}
+        return centres
+
+    def _on_assembled_field(self, local, field_image, return_details):
+        from .. import parallel
+
+        self.fallbacks += 1
+        full = parallel.gather_field(local, field_image, self.group)
+        return DeviceDetector.__call__(self, full, return_details=return_details)
+
+
 _default_device_detector = None
 
 

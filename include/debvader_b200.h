@@ -245,9 +245,30 @@ int64_t dbv_detect_scratch_bytes(int64_t H, int64_t W, int64_t max_objects);
 int dbv_detect(const void* field, int dtype, int64_t H, int64_t W, int64_t pitch, int C, int band, const float* taps, int kh,
                int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t max_objects, void* scratch,
                int64_t scratch_bytes, int32_t* n_found, double* xy, double* centres, int32_t* npix, float* stats, void* stream);
-/* device pointer to an intermediate plane of the last dbv_detect call on `scratch` (per-stage parity tests): 0 foreground
- * f32 (H,W), 1 filtered f32 (H,W), 2 labels i32 (H,W), 3 / 4 filtered mesh background / sigma f32 (ny,nx), 5 / 6 raw ones */
+/* The same detection on a field TILED over GPUs (one rank = owner tile + halo = a (RH, RW) region at (gy0, gx0) of the (H, W)
+ * field; reference: none — the reference is single-process).  Two phases around ONE exchange of the tiny mesh maps:
+ *   dbv_detect_meshes   band plane of the region into `scratch`, statistics of every 64x64 mesh lying wholly inside the region
+ *                       written at the mesh's place in the caller's field-sized (ny, nx) maps back0 / sig0 (other entries are
+ *                       left alone: preset -inf, then max-reduce the maps over the ranks);
+ *   dbv_detect_objects  everything else on the region, with the COMPLETE maps: the mesh post-processing (replicated), background,
+ *                       filter (exact kh/2, kw/2 pixels inside the region's inner edges), components, and the objects whose LAST
+ *                       pixel lies in the owner tile [oy0, oy1) x [ox0, ox1) (field coordinates), in ascending order of
+ *                       last_out = raster index of that pixel in the whole field.  Merging the ranks' lists by last_out gives
+ *                       the single-GPU list bit for bit.  flags[0] != 0: an owned object reaches the rim of what the region
+ *                       sees — detect on the assembled field instead.
+ * dbv_detect == both phases with the field as its own region and owner tile. */
+int64_t dbv_detect_scratch_bytes_region(int64_t H, int64_t W, int64_t RH, int64_t RW, int64_t max_objects);
+int dbv_detect_meshes(const void* region, int dtype, int64_t RH, int64_t RW, int64_t pitch, int C, int band, int64_t gy0, int64_t gx0,
+                      int64_t H, int64_t W, int64_t max_objects, void* scratch, int64_t scratch_bytes, float* back0, float* sig0,
+                      void* stream);
+int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t gx0, int64_t H, int64_t W, const float* back0, const float* sig0,
+                       const float* taps, int kh, int kw, double thresh_sigma, int minarea, int cy, int cx, int64_t oy0, int64_t oy1,
+                       int64_t ox0, int64_t ox1, int64_t max_objects, void* scratch, int64_t scratch_bytes, int32_t* n_found,
+                       double* xy, double* centres, int32_t* npix, int64_t* last_out, int32_t* flags, float* stats, void* stream);
+/* device pointer to an intermediate plane of the last call on `scratch` (per-stage parity tests): 0 foreground f32, 1 filtered
+ * f32, 2 labels i32 (region-sized), 3 / 4 filtered mesh background / sigma f32 (ny,nx), 5 / 6 raw ones (dbv_detect only) */
 const void* dbv_detect_plane(void* scratch, int64_t H, int64_t W, int64_t max_objects, int what);
+const void* dbv_detect_plane_region(void* scratch, int64_t H, int64_t W, int64_t RH, int64_t RW, int64_t max_objects, int what);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 /* number of kernels this library has launched on behalf of ctx (bench.py's gpu_launches) */

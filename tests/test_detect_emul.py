@@ -85,3 +85,79 @@ def test_emulated_kernels_match_the_oracle_bit_for_bit(emu, case, golden_dir):
                    centres=int((e["centres"] != c_ref).sum()))
     assert not any(rep.values()), rep
     assert e["n"] > 0
+
+
+def run_emulated_tiled(lib, field, world, max_objects=512, halo=30):
+    """the field split into owner tiles + halo as debvader_b200.parallel does, one emulated 'rank' after the other:
+    dbv_detect_meshes per rank -> max-reduce of the mesh maps -> dbv_detect_objects per rank -> objects merged by their order key"""
+    from debvader_b200 import parallel
+
+    lib.dbv_detect_scratch_bytes_region.restype = C.c_int64
+    lib.dbv_detect_scratch_bytes_region.argtypes = [C.c_int64] * 5
+    lib.dbv_detect_meshes.restype = C.c_int
+    lib.dbv_detect_meshes.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 3 + [C.c_int, C.c_int] + [C.c_int64] * 5 + [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dbv_detect_objects.restype = C.c_int
+    lib.dbv_detect_objects.argtypes = [C.c_int64] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_int64] * 5 + \
+        [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+    F = field.shape[1]
+    Cn = field.shape[3]
+    ny = nx = (F - 1) // 64 + 1
+    taps = det.normalised_taps()
+    regions, tiles = parallel.region_bounds(F, world, halo), parallel.tile_bounds(F, world)
+    ranks = []
+    maps = np.full((2, ny, nx), -np.inf, np.float32)
+    for (R0, R1, C0, C1) in regions:
+        reg = np.ascontiguousarray(field[0, R0:R1, C0:C1])
+        RH, RW = reg.shape[:2]
+        nbytes = lib.dbv_detect_scratch_bytes_region(F, F, RH, RW, max_objects)
+        raw = np.zeros(nbytes + 256, np.uint8)
+        base = raw.ctypes.data + (-raw.ctypes.data) % 256
+        mine = np.full((2, ny, nx), -np.inf, np.float32)
+        rc = lib.dbv_detect_meshes(reg.ctypes.data, 1 if reg.dtype == np.float64 else 0, RH, RW, RW, Cn, 2, R0, C0, F, F, max_objects, base, nbytes,
+                                   mine[0].ctypes.data, mine[1].ctypes.data, None)
+        assert rc == 0
+        maps = np.maximum(maps, mine)  # the all-reduce(MAX) of the tiled detector
+        ranks.append((reg, raw, base, nbytes, RH, RW, R0, C0))
+    assert np.isfinite(maps).all(), "a mesh lies in no rank's region"
+    objs, flagged = [], 0
+    for (reg, raw, base, nbytes, RH, RW, R0, C0), (r0, r1, c0, c1) in zip(ranks, tiles):
+        n = np.zeros(1, np.int32)
+        xy = np.zeros((max_objects, 2))
+        cen = np.zeros((max_objects, 2))
+        npix = np.zeros(max_objects, np.int32)
+        last = np.zeros(max_objects, np.int64)
+        flags = np.zeros(4, np.int32)
+        stats = np.zeros(4, np.float32)
+        rc = lib.dbv_detect_objects(RH, RW, R0, C0, F, F, maps[0].ctypes.data, maps[1].ctypes.data, taps.ctypes.data, 7, 7, 1.5, 4, int(F / 2), int(F / 2),
+                                    r0, r1, c0, c1, max_objects, base, nbytes, n.ctypes.data, xy.ctypes.data, cen.ctypes.data, npix.ctypes.data,
+                                    last.ctypes.data, flags.ctypes.data, stats.ctypes.data, None)
+        assert rc == 0
+        k = int(n[0])
+        flagged += int(flags[0])
+        objs += [(int(last[i]), xy[i, 0], xy[i, 1], int(npix[i]), cen[i, 0], cen[i, 1]) for i in range(k)]
+    objs.sort(key=lambda o: o[0])
+    return objs, flagged, stats
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_emulated_tiled_detection_equals_the_whole_field(emu, world):
+    """owner tile + 30-px halo per rank, mesh maps max-reduced, objects owned by the tile of their last pixel: the merged list is the
+    whole-field list, bit for bit (256^2 field: tiles of 128 / 64 px, i.e. mesh-aligned)"""
+    field = make_field(256, 45, seed=31, gradient=0.02)[0]
+    c_ref, o = D.detect(field, det.FILTER_KERNEL, return_details=True)
+    objs, flagged, stats = run_emulated_tiled(emu, field, world)
+    assert flagged == 0
+    assert stats[1] == o["globalrms"] and stats[2] == o["thresh"]
+    assert [t[0] for t in objs] == list(o["last"])
+    assert [t[3] for t in objs] == list(o["npix"])
+    np.testing.assert_array_equal(np.array([t[1] for t in objs]), o["x"])
+    np.testing.assert_array_equal(np.array([t[2] for t in objs]), o["y"])
+    np.testing.assert_array_equal(np.array([[t[4], t[5]] for t in objs]), c_ref)
+
+
+def test_emulated_tiled_detection_flags_an_object_that_leaves_the_region(emu):
+    field = make_field(256, 10, seed=32)[0]
+    yy, xx = np.mgrid[0:256, 0:256]
+    field[0] += (40.0 * np.exp(-((xx - 131) ** 2 + (yy - 100) ** 2) / (2 * 14.0 ** 2)))[..., None]  # footprint ~ 60 px across the tile edge at x = 128
+    objs, flagged, _ = run_emulated_tiled(emu, field, 2)
+    assert flagged >= 1

@@ -142,3 +142,35 @@ def test_iterative_deblending_with_the_device_detector(golden_dir):
     np.testing.assert_array_equal(np.array(list(res["galaxy_distances_to_center_x"][:n0])), first[idx, 0])
     np.testing.assert_array_equal(np.array(list(res["galaxy_distances_to_center_y"][:n0])), first[idx, 1])
     net.close()
+
+
+def test_tiled_detector_outside_a_distributed_job_is_the_plain_detector():
+    from debvader_b200 import parallel
+
+    field, _ = make_field(320, 40, seed=15)
+    t = torch.as_tensor(field).cuda()
+    local = parallel.LocalField.from_full(t, 0, 1)
+    np.testing.assert_array_equal(det.TiledDeviceDetector()(local.data, local), det.DeviceDetector()(t))
+    assert det.TiledDeviceDetector.meshes_covered(4096, 8, 30) and det.TiledDeviceDetector.meshes_covered(4097, 8, 30)
+    assert not det.TiledDeviceDetector.meshes_covered(4097, 8, 0)  # without a halo a mesh astride a tile edge belongs to nobody
+
+
+def test_two_gpu_tiled_detection_is_bit_identical():
+    """2 ranks over NCCL: owner tile + halo each, mesh statistics all-reduced, objects all-gathered — the single-GPU list on every
+    rank; a footprint wider than the halo takes the assembled-field path.  Skipped on a one-GPU box; the tiling logic of the
+    kernels is also run on CPU by tests/test_detect_emul.py (2 and 8 emulated ranks)."""
+    import json
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(root, "tools", "detect_tiled_nccl.py"), "1024", "300"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["plain"]["identical_to_single_gpu_on_every_rank"] and line["plain"]["assembled_field_fallbacks"] == 0
+    assert line["wide_object"]["identical_to_single_gpu_on_every_rank"] and line["wide_object"]["assembled_field_fallbacks"] > 0
+    assert line["plain"]["region_share"] < 0.6
