@@ -82,4 +82,21 @@ with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
         kn = col(r, "Kernel Name").split("(")[0].replace("void ", "")
         db = traffic[prec].get(nm, {}).get("dram_bytes", 0) / 1e6
         f.write(f"| {nm} | `{kn}` | {col(r, keep[0])} | {col(r, keep[2])[:5]} | {col(r, keep[3])[:5]} | {col(r, keep[4])[:5]} | {col(r, keep[5])[:5]} | {col(r, keep[6])[:5]} | {db:.0f} |\n")
+    # ---- the device detector: per-kernel times / DRAM bytes of one 4096^2 detection (tools/detect_ncu_target.py under ncu)
+    dn = os.path.join(G, "detect_ncu.csv")
+    if os.path.exists(dn):
+        shutil.copy(dn, os.path.join(P, f"{tag}_detect_ncu.csv"))
+        rows = [r for r in csv.reader(open(dn)) if len(r) > 10 and r[0].isdigit()]
+        d = collections.OrderedDict()
+        for r in rows:
+            d.setdefault((int(r[0]), r[4].split("(")[0].replace("void ", "")), {})[r[12]] = float(r[14].replace(",", ""))
+        f.write("\n## device detector: one detection of a 4096^2 x 6 f64 field with 2000 sources (`ncu --metrics gpu__time_duration.sum,dram__bytes_*`; "
+                "20 consecutive launches = one call; CUDA-event time of the call without a profiler: see `field.detect.ms` above)\n\n"
+                "| kernel | us | DRAM read MB | DRAM write MB |\n|---|---|---|---|\n")
+        tot_us = 0.0
+        for (i, k), v in d.items():
+            us = v.get("gpu__time_duration.sum", 0.0) / 1e3
+            tot_us += us
+            f.write(f"| `{k}` | {us:.1f} | {v.get('dram__bytes_read.sum', 0) / 1e6:.1f} | {v.get('dram__bytes_write.sum', 0) / 1e6:.1f} |\n")
+        f.write(f"| sum | {tot_us:.1f} | | |\n")
 print("wrote profiles/%s_*" % tag)
