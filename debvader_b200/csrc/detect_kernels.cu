@@ -69,7 +69,8 @@ __global__ void det_band_kernel(const T* __restrict__ field, long long H, long l
 //   * the three sums over [lcut, hcut] are sums of integers (< 2^53): any order gives the oracle's doubles exactly — strided over the CTA;
 //   * the two-pointer walk "advance the side with the smaller running count" is the merge of the two prefix-sum sequences
 //     P(j) = count of the first j levels, Q(i) = count of the last i levels, ties to the high side: after n = hcut - lcut + 1 steps
-//     it has taken k = #{ j < n : j + #{ i < n : Q(i) <= P(j) } < n } low steps — two nested binary searches on the prefix sums.
+//     it has taken k = #{ j < n : j + #{ i < n : Q(i) <= P(j) } < n } = #{ j < n : Q(n - 1 - j) > P(j) } low steps, and the predicate is
+//     monotone in j — one binary search on the prefix sums.
 __device__ __forceinline__ int det_cnt(const int* pre, int i) { return pre[i + 1] - pre[i]; }
 
 __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, const DetGeom G, float* __restrict__ back0,
@@ -230,17 +231,11 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
       // the two-pointer walk over [lcut, hcut] by merge path (see the header of this section)
       const int n = hcut - lcut + 1;
       const int base_lo = pre[lcut], base_hi = pre[hcut + 1];
+      // low step j is taken within the first n steps  <=>  fewer than n - j high counts are <= P(j)  <=>  Q(n - 1 - j) > P(j)  (Q monotone)
       int ka = 0, kb = n;
       while (ka < kb) {
         const int j = (ka + kb) >> 1;
-        const int pj = pre[lcut + j] - base_lo;
-        int ia = 0, ib = n;
-        while (ia < ib) {
-          const int i = (ia + ib) >> 1;
-          if (base_hi - pre[hcut + 1 - i] <= pj) ia = i + 1;
-          else ib = i;
-        }
-        if (j + ia < n) ka = j + 1;
+        if (base_hi - pre[hcut + 2 - n + j] > pre[lcut + j] - base_lo) ka = j + 1;
         else kb = j;
       }
       const int lo = lcut + ka, hi = hcut - (n - ka);
@@ -294,21 +289,26 @@ __device__ float det_median_small(float* a, int n) {  // insertion sort of <= 9 
 }
 
 // second derivatives / 6 of the natural cubic spline through n samples `v` (stride sv), Thomas algorithm in float32
-// (oracle: _spline_d2); cp / u are n-element scratch rows with the same stride as d
-__device__ void det_spline_d2(const float* v, int sv, int n, float* d, float* cp, float* u, int sd) {
+// (oracle: _spline_d2); cp / u are n-element scratch rows of stride ss (shared memory, [k][thread]: the recurrence is a chain of
+// dependent divisions, so the scratch must not add a global-memory round trip to every link)
+__device__ void det_spline_d2(const float* v, int sv, int n, float* d, int sd, float* cp, float* u, int ss) {
   for (int k = 0; k < n; ++k) d[k * sd] = 0.f;
   if (n < 3) return;
-  cp[0] = 0.f;
-  u[0] = 0.f;
+  float cpk = 0.f, uk = 0.f, vm = v[0], vc = v[sv];
   for (int k = 1; k < n - 1; ++k) {
-    const float rhs = 6.0f * ((v[(k + 1) * sv] + v[(k - 1) * sv]) - 2.0f * v[k * sv]);
-    const float den = 4.0f - cp[(k - 1) * sd];
-    cp[k * sd] = 1.0f / den;
-    u[k * sd] = (rhs - u[(k - 1) * sd]) / den;
+    const float vp = v[(k + 1) * sv];
+    const float rhs = 6.0f * ((vp + vm) - 2.0f * vc);
+    const float den = 4.0f - cpk;
+    cpk = 1.0f / den;
+    uk = (rhs - uk) / den;
+    cp[k * ss] = cpk;
+    u[k * ss] = uk;
+    vm = vc;
+    vc = vp;
   }
   float m = 0.f;  // M[n-1]
   for (int k = n - 2; k >= 1; --k) {
-    m = u[k * sd] - cp[k * sd] * m;
+    m = u[k * ss] - cp[k * ss] * m;
     d[k * sd] = m / 6.0f;
   }
 }
@@ -363,8 +363,14 @@ __global__ void det_mesh_median_kernel(const float* __restrict__ back1, const fl
 
 // global medians by rank selection: thread i ranks element i among all n (ties broken by index) and, if it is one of the two
 // middle ranks, writes itself into pick[2 * map + {0, 1}]; blockIdx.y = 0 background map, 1 sigma map
-__global__ void det_mesh_rank_kernel(const float* __restrict__ back, const float* __restrict__ sig, int n, float* __restrict__ pick) {
+__global__ void det_mesh_rank_kernel(const float* __restrict__ back, const float* __restrict__ sig, int n, int staged, float* __restrict__ pick) {
+  DET_DYN_SMEM(float, sa);
   const float* a = blockIdx.y ? sig : back;
+  if (staged) {  // the whole map fits in shared memory (a 4096^2 field: 16 KB): every thread then scans it from there
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sa[j] = a[j];
+    __syncthreads();
+    a = sa;
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k1 = n / 2, k0 = (n & 1) ? k1 : k1 - 1;
@@ -379,9 +385,13 @@ __global__ void det_mesh_rank_kernel(const float* __restrict__ back, const float
 }
 
 // global background / rms / threshold, and the y-spline of the background map (thread per mesh column)
-__global__ void det_mesh_final_kernel(const float* __restrict__ pick, int ny, int nx, const float* __restrict__ back, float* dback, float* cp, float* u,
-                                      double thresh_sigma, float* stats) {
+__global__ void det_mesh_final_kernel(const float* __restrict__ pick, int ny, int nx, const float* __restrict__ back, float* dback, float* gcp, float* gu,
+                                      int staged, double thresh_sigma, float* stats) {
+  DET_DYN_SMEM(float, sm);
   const int n = ny * nx, x = blockIdx.x * blockDim.x + threadIdx.x;
+  float* cp = staged ? sm + threadIdx.x : gcp + x;
+  float* u = staged ? sm + blockDim.x * ny + threadIdx.x : gu + x;
+  const int ss = staged ? (int)blockDim.x : nx;
   if (x == 0) {
     const float gback = (n & 1) ? pick[1] : (pick[0] + pick[1]) * 0.5f;
     const float grms = (n & 1) ? pick[3] : (pick[2] + pick[3]) * 0.5f;
@@ -389,7 +399,7 @@ __global__ void det_mesh_final_kernel(const float* __restrict__ pick, int ny, in
     stats[1] = grms;
     stats[2] = (float)(thresh_sigma * (double)grms);
   }
-  if (x < nx) det_spline_d2(back + x, nx, ny, dback + x, cp + x, u + x, nx);
+  if (x < nx) det_spline_d2(back + x, nx, ny, dback + x, nx, cp, u, ss);
 }
 
 // ---- B3 --------------------------------------------------------------------------------------------------------------
@@ -407,10 +417,14 @@ __device__ __forceinline__ void det_spline_pos(int i, int n, int* lo, float* t) 
 
 // one thread per image row: the mesh map interpolated along y at this row (node), then its x-spline (dnode)
 __global__ void det_nodes_kernel(const float* __restrict__ back, const float* __restrict__ dback, const DetGeom G, float* node,
-                                 float* dnode, float* cp, float* u) {
+                                 float* dnode, float* gcp, float* gu, int staged) {
+  DET_DYN_SMEM(float, sm);
   const int y = blockIdx.x * blockDim.x + threadIdx.x;  // region row
   if (y >= G.RH) return;
   const int ny = G.ny, nx = G.nx;
+  float* cp = staged ? sm + threadIdx.x : gcp + (long long)y * nx;
+  float* u = staged ? sm + blockDim.x * nx + threadIdx.x : gu + (long long)y * nx;
+  const int ss = staged ? (int)blockDim.x : 1;
   float* nd = node + (long long)y * nx;
   if (ny > 1) {
     int yl;
@@ -421,7 +435,7 @@ __global__ void det_nodes_kernel(const float* __restrict__ back, const float* __
   } else {
     for (int x = 0; x < nx; ++x) nd[x] = back[x];
   }
-  det_spline_d2(nd, 1, nx, dnode + (long long)y * nx, cp + (long long)y * nx, u + (long long)y * nx, 1);
+  det_spline_d2(nd, 1, nx, dnode + (long long)y * nx, 1, cp, u, ss);
 }
 
 __global__ void det_foreground_kernel(const double* __restrict__ band, const float* __restrict__ node, const float* __restrict__ dnode,
@@ -655,41 +669,59 @@ __global__ void __launch_bounds__(256) det_scatter_kernel(const unsigned char* _
 }
 
 // ---- E4 --------------------------------------------------------------------------------------------------------------
-// one thread per object: its pixels in raster order over the bounding box, double sums (oracle: np.cumsum(...)[-1])
-__global__ void det_moments_kernel(const int* __restrict__ L, const float* __restrict__ fg, const float* __restrict__ conv, const DetGeom G,
-                                   const int* __restrict__ endpos, const int* __restrict__ n_found, long long max_objects,
-                                   const int* __restrict__ npix, const int* __restrict__ xmin, const int* __restrict__ xmax,
-                                   const int* __restrict__ touch, int cy, int cx, double* xy, double* centres, int* npix_out,
-                                   long long* last_out, int* flags) {
-  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// one 32-thread CTA per object (grid-stride over the objects): the lanes fetch 32 pixels of a bounding-box row at a time (coalesced,
+// all loads in flight together) into shared memory, lane 0 adds the member pixels in raster order — the oracle's sequential double sums
+// (np.cumsum(...)[-1]) without a memory round trip per pixel
+__global__ void __launch_bounds__(32) det_moments_kernel(const int* __restrict__ L, const float* __restrict__ fg, const float* __restrict__ conv,
+                                                         const DetGeom G, const int* __restrict__ endpos, const int* __restrict__ n_found,
+                                                         long long max_objects, const int* __restrict__ npix, const int* __restrict__ xmin,
+                                                         const int* __restrict__ xmax, const int* __restrict__ touch, int cy, int cx, double* xy,
+                                                         double* centres, int* npix_out, long long* last_out, int* flags) {
+  __shared__ float s_v[32], s_c[32];
+  __shared__ int s_in[32];
   const long long n = n_found[0] < max_objects ? n_found[0] : max_objects;
-  if (k >= n) return;
-  const int W = G.RW;
-  const int e = endpos[k], r = L[e];
-  const int y0 = r / W, y1 = e / W, x0 = xmin[r], x1 = xmax[r];
-  double tv = 0.0, mx = 0.0, my = 0.0, tc = 0.0, cmx = 0.0, cmy = 0.0;
-  for (int y = y0; y <= y1; ++y)
-    for (int x = x0; x <= x1; ++x) {
-      const int p = y * W + x;
-      if (L[p] != r) continue;
-      const double v = (double)fg[p], c = (double)conv[p];
-      const double dx = (double)(x - x0), dy = (double)(y - y0);
-      tv += v;
-      mx += v * dx;
-      my += v * dy;
-      tc += c;
-      cmx += c * dx;
-      cmy += c * dy;
+  const int W = G.RW, lane = threadIdx.x;
+  for (long long k = blockIdx.x; k < n; k += gridDim.x) {
+    const int e = endpos[k], r = L[e];
+    const int y0 = r / W, y1 = e / W, x0 = xmin[r], x1 = xmax[r];
+    double tv = 0.0, mx = 0.0, my = 0.0, tc = 0.0, cmx = 0.0, cmy = 0.0;
+    for (int y = y0; y <= y1; ++y)
+      for (int xb = x0; xb <= x1; xb += 32) {
+        const int x = xb + lane;
+        const int p = y * W + x;
+        const int in = (x <= x1) && (L[p] == r);
+        s_in[lane] = in;
+        s_v[lane] = in ? fg[p] : 0.f;
+        s_c[lane] = in ? conv[p] : 0.f;
+        __syncthreads();
+        if (lane == 0) {
+          const double dy = (double)(y - y0);
+          for (int l = 0; l < 32; ++l) {
+            if (!s_in[l]) continue;
+            const double v = (double)s_v[l], c = (double)s_c[l];
+            const double dx = (double)(xb + l - x0);
+            tv += v;
+            mx += v * dx;
+            my += v * dy;
+            tc += c;
+            cmx += c * dx;
+            cmy += c * dy;
+          }
+        }
+        __syncthreads();
+      }
+    if (lane == 0) {
+      if (!(tv > 0.0)) { tv = tc; mx = cmx; my = cmy; }  // faint detections: weight with the filtered values (> thresh > 0)
+      const double X = mx / tv + (double)(x0 + G.gx0), Y = my / tv + (double)(y0 + G.gy0);  // field coordinates
+      xy[2 * k] = X;
+      xy[2 * k + 1] = Y;
+      centres[2 * k] = rint(Y - (double)cy);      // (row, col) offsets from the field centre, detection.py:48-54
+      centres[2 * k + 1] = rint(X - (double)cx);
+      npix_out[k] = npix[r];
+      last_out[k] = (long long)(G.gy0 + e / W) * G.W + (G.gx0 + e % W);  // the order key, in the raster of the whole field
+      if (touch[r]) flags[0] = 1;  // an object of this call's tile leaves the area it can see: the caller must detect on the assembled field
     }
-  if (!(tv > 0.0)) { tv = tc; mx = cmx; my = cmy; }  // faint detections: weight with the filtered values (> thresh > 0)
-  const double X = mx / tv + (double)(x0 + G.gx0), Y = my / tv + (double)(y0 + G.gy0);  // field coordinates
-  xy[2 * k] = X;
-  xy[2 * k + 1] = Y;
-  centres[2 * k] = rint(Y - (double)cy);      // (row, col) offsets from the field centre, detection.py:48-54
-  centres[2 * k + 1] = rint(X - (double)cx);
-  npix_out[k] = npix[r];
-  last_out[k] = (long long)(G.gy0 + e / W) * G.W + (G.gx0 + e % W);  // the order key, in the raster of the whole field
-  if (touch[r]) flags[0] = 1;  // an object of this call's tile leaves the area it can see: the caller must detect on the assembled field
+  }
 }
 
 struct DetLayout {
@@ -822,9 +854,13 @@ extern "C" int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t g
   const unsigned gm = (unsigned)((nm + 127) / 128);
   DET_LAUNCH(det_mesh_fill_kernel, gm, 128, 0, back0, sig0, ny, nx, back1, sig1);
   DET_LAUNCH(det_mesh_median_kernel, gm, 128, 0, back1, sig1, ny, nx, back, sig);
-  DET_LAUNCH(det_mesh_rank_kernel, dim3(gm, 2), 128, 0, back, sig, nm, pick);
-  DET_LAUNCH(det_mesh_final_kernel, (unsigned)((nx + 127) / 128), 128, 0, pick, ny, nx, back, dback, mcp, mu, thresh_sigma, stats);
-  DET_LAUNCH(det_nodes_kernel, (unsigned)((RH + 127) / 128), 128, 0, back, dback, G, node, dnode, rcp, ru);
+  const int staged = nm <= 10240;
+  DET_LAUNCH(det_mesh_rank_kernel, dim3(gm, 2), 128, staged ? sizeof(float) * nm : 0, back, sig, nm, staged, pick);
+  // the spline recurrences keep their scratch in shared memory ([k][thread], 32 threads per CTA) whenever it fits in 48 KB
+  const int st_y = ny <= 192, st_x = nx <= 192;
+  DET_LAUNCH(det_mesh_final_kernel, (unsigned)((nx + 31) / 32), 32, st_y ? sizeof(float) * 2 * 32 * ny : 0, pick, ny, nx, back, dback, mcp, mu, st_y, thresh_sigma,
+             stats);
+  DET_LAUNCH(det_nodes_kernel, (unsigned)((RH + 31) / 32), 32, st_x ? sizeof(float) * 2 * 32 * nx : 0, back, dback, G, node, dnode, rcp, ru, st_x);
   const dim3 grow((unsigned)((RW + 255) / 256), (unsigned)RH);
   DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, G, d_fg);
   const size_t fsm = sizeof(float) * (32 + kw - 1) * (32 + kh - 1);
@@ -845,7 +881,7 @@ extern "C" int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t g
   DET_LAUNCH(det_count_kernel, Y.nblk, 256, 0, d_flag, n, d_cnt);
   DET_LAUNCH(det_scan_kernel, 1, 1024, 0, d_cnt, Y.nblk, d_off, n_found);
   DET_LAUNCH(det_scatter_kernel, Y.nblk, 256, 0, d_flag, n, d_off, max_objects, d_end);
-  DET_LAUNCH(det_moments_kernel, (unsigned)((max_objects + 127) / 128), 128, 0, d_label, d_fg, d_conv, G, d_end, n_found, max_objects, d_npix, d_xmin,
+  DET_LAUNCH(det_moments_kernel, (unsigned)(max_objects < 148 * 32 ? max_objects : 148 * 32), 32, 0, d_label, d_fg, d_conv, G, d_end, n_found, max_objects, d_npix, d_xmin,
              d_xmax, d_touch, cy, cx, xy, centres, npix_out, (long long*)last_out, flags);
   return DBV_OK;
 }
