@@ -89,8 +89,15 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   const int mw = min(DET_BW, G.W - x0), mh = min(DET_BW, G.H - y0);
   // a mesh is computed by the call whose region holds all of it (tiled fields: the other meshes come from the other ranks)
   if (y0 < G.gy0 || y0 + mh > G.gy0 + G.RH || x0 < G.gx0 || x0 + mw > G.gx0 + G.RW) return;
-  for (int r = 0; r < mh; ++r)
-    if (t < mw) tile[r][t] = (float)band[(long long)(y0 - G.gy0 + r) * G.RW + (x0 - G.gx0) + t];
+  // eight rows in flight per thread: the CTA has only two warps to hide a DRAM round trip with
+  for (int r0 = 0; r0 < mh; r0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (t < mw && r0 + i < mh) ? band[(long long)(y0 - G.gy0 + r0 + i) * G.RW + (x0 - G.gx0) + t] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t < mw && r0 + i < mh) tile[r0 + i][t] = (float)v[i];
+  }
   __syncthreads();
   // pass 1: all pixels
   if (t < mh) {
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   // counts -> exclusive prefix sums, in place: thread t scans levels [64 t, 64 t + 64)
   {
     int s = 0;
-    for (int i = 0; i < DET_BW; ++i) s += pre[t * DET_BW + i];
+    for (int i = 0; i < DET_BW; ++i) s += pre[t * DET_BW + ((i + t) & (DET_BW - 1))];  // skewed: the chunks are 64 words apart (one bank)
     part[t] = s;
     __syncthreads();
     if (t == 0) {

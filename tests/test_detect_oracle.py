@@ -157,3 +157,19 @@ def test_detect_objects_wiring():
 
     assert _ffi.lib().dbv_detect_scratch_bytes(4096, 4096, 1 << 17) < 1 << 30
     assert _ffi.lib().dbv_detect_scratch_bytes(0, 4096, 16) == 0
+
+
+def test_against_sep_when_its_detections_are_in_the_golden(golden_dir):
+    """tests/golden/make_golden_detect.py --sep (run where the reference's `sep` is installable) stores sep's own detections of the
+    packaged field next to the oracle's.  Until then parity with sep is UNPINNED and this test is skipped.  What can match: the
+    isolated objects and their order (this restatement has no multi-threshold deblending / clean pass, sep's gatherup is randomised)."""
+    g = np.load(os.path.join(golden_dir, "detect_dc2.npz"))
+    if "sep_centres" not in g.files:
+        pytest.skip("no sep detections in tests/golden/detect_dc2.npz (sep not installable where the golden was made): parity unpinned")
+    ours, theirs = g["centres"], g["sep_centres"]
+    d = np.abs(ours[:, None, :] - theirs[None]).max(-1)
+    matched = d.min(1) <= 1
+    assert matched.mean() > 0.8
+    # the matched objects appear in the same relative order in both lists
+    j = d.argmin(1)[matched]
+    assert (np.diff(j) > 0).mean() > 0.9
