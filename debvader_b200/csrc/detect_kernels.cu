@@ -62,8 +62,8 @@ __global__ void det_band_kernel(const T* __restrict__ field, long long H, long l
 }
 
 // ---- B1 --------------------------------------------------------------------------------------------------------------
-// One CTA of 64 threads per mesh: thread r owns mesh row r (sequential double sums, the rows then combined in order by thread 0:
-// the oracle's summation order).  The level histogram is counted with shared-memory integer atomics and turned into an exclusive
+// One CTA of 64 threads per mesh: thread c owns mesh column c (sequential double sums down the column, the columns then combined in
+// order by thread 0: the oracle's summation order).  The level histogram is counted with shared-memory integer atomics and turned into an exclusive
 // prefix sum in place, so that the iterated clipping (oracle: histogram_guess) costs O(range / 64 + log^2) per iteration
 // instead of a serial pass over <= 4096 levels:
 //   * the three sums over [lcut, hcut] are sums of integers (< 2^53): any order gives the oracle's doubles exactly — strided over the CTA;
@@ -75,7 +75,6 @@ __device__ __forceinline__ int det_cnt(const int* pre, int i) { return pre[i + 1
 
 __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__ band, const DetGeom G, float* __restrict__ back0,
                                                       float* __restrict__ sig0) {
-  __shared__ float tile[DET_BW][DET_BW + 1];
   __shared__ int pre[DET_MAXLEVELS + 1];  // level counts, then their exclusive prefix sums (pre[nlevels .. 4096] = total)
   __shared__ double rs[DET_BW], rq[DET_BW], rn[DET_BW];
   __shared__ long long p0[DET_BW], p1[DET_BW], p2[DET_BW];
@@ -89,23 +88,24 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   const int mw = min(DET_BW, G.W - x0), mh = min(DET_BW, G.H - y0);
   // a mesh is computed by the call whose region holds all of it (tiled fields: the other meshes come from the other ranks)
   if (y0 < G.gy0 || y0 + mh > G.gy0 + G.RH || x0 < G.gx0 || x0 + mw > G.gx0 + G.RW) return;
-  // eight rows in flight per thread: the CTA has only two warps to hide a DRAM round trip with
-  for (int r0 = 0; r0 < mh; r0 += 8) {
-    double v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (t < mw && r0 + i < mh) ? band[(long long)(y0 - G.gy0 + r0 + i) * G.RW + (x0 - G.gx0) + t] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (t < mw && r0 + i < mh) tile[r0 + i][t] = (float)v[i];
-  }
-  __syncthreads();
-  // pass 1: all pixels
-  if (t < mh) {
+  // thread t owns mesh COLUMN t: every pass reads the mesh row by row, the 64 threads one 512-byte segment at a time (coalesced; the
+  // 32 KB of the mesh stay in L1 / L2 between the passes), so the CTA needs no shared-memory copy of the mesh and twice as many CTAs fit
+  const double* col = band + (long long)(y0 - G.gy0) * G.RW + (x0 - G.gx0) + t;
+  const long long pitch = G.RW;
+  // pass 1: all pixels (sequential double sums down the column, the columns then combined in order by thread 0: the oracle's order)
+  if (t < mw) {
     double s = 0.0, q = 0.0;
-    for (int c = 0; c < mw; ++c) {
-      const double v = (double)tile[t][c];
-      s += v;
-      q += v * v;
+    for (int r0 = 0; r0 < mh; r0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = r0 + i < mh ? (float)col[(r0 + i) * pitch] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (r0 + i < mh) {
+          const double v = (double)f[i];
+          s += v;
+          q += v * v;
+        }
     }
     rs[t] = s;
     rq[t] = q;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   __syncthreads();
   if (t == 0) {
     double s = 0.0, q = 0.0;
-    for (int r = 0; r < mh; ++r) { s += rs[r]; q += rq[r]; }
+    for (int c = 0; c < mw; ++c) { s += rs[c]; q += rq[c]; }
     const double n = (double)(mh * mw);
     const double mean = s / n;
     const double var = q / n - mean * mean;
@@ -123,17 +123,21 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   }
   __syncthreads();
   // pass 2: pixels inside the cuts
-  if (t < mh) {
+  if (t < mw) {
     const float lc = s_lcut, hc = s_hcut;
     double s = 0.0, q = 0.0, n = 0.0;
-    for (int c = 0; c < mw; ++c) {
-      const float f = tile[t][c];
-      if (f >= lc && f <= hc) {
-        const double v = (double)f;
-        n += 1.0;
-        s += v;
-        q += v * v;
-      }
+    for (int r0 = 0; r0 < mh; r0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = r0 + i < mh ? (float)col[(r0 + i) * pitch] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (r0 + i < mh && f[i] >= lc && f[i] <= hc) {
+          const double v = (double)f[i];
+          n += 1.0;
+          s += v;
+          q += v * v;
+        }
     }
     rs[t] = s;
     rq[t] = q;
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
   __syncthreads();
   if (t == 0) {
     double s = 0.0, q = 0.0, n = 0.0;
-    for (int r = 0; r < mh; ++r) { n += rn[r]; s += rs[r]; q += rq[r]; }
+    for (int c = 0; c < mw; ++c) { n += rn[c]; s += rs[c]; q += rq[c]; }
     const double nall = (double)(mh * mw);
     if (n < nall * 0.5 || n < 1.0) {
       s_bad = 1;
@@ -172,13 +176,20 @@ __global__ void __launch_bounds__(64) det_mesh_kernel(const double* __restrict__
     return;
   }
   const int nl = s_nlevels, nm1 = nl - 1;
-  if (t < mh) {
+  if (t < mw) {
     const float qs = s_qscale, cs = s_cste;
-    for (int c = 0; c < mw; ++c) {
-      const float lev = tile[t][c] / qs + cs;
-      if (lev > -1.0f && lev < (float)nl) {
-        const int b = (int)lev;
-        if (b >= 0 && b < nl) atomicAdd(&pre[b], 1);
+    for (int r0 = 0; r0 < mh; r0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = r0 + i < mh ? (float)col[(r0 + i) * pitch] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r0 + i >= mh) continue;
+        const float lev = f[i] / qs + cs;
+        if (lev > -1.0f && lev < (float)nl) {
+          const int b = (int)lev;
+          if (b >= 0 && b < nl) atomicAdd(&pre[b], 1);
+        }
       }
     }
   }
@@ -809,6 +820,10 @@ extern "C" int dbv_detect_meshes(const void* region, int dtype, int64_t RH, int6
   const int gb = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)region, RH, RW, pitch, C, band, d_band);
   else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)region, RH, RW, pitch, C, band, d_band);
+#ifndef DBV_EMULATE
+  // 20 KB of static shared memory per 64-thread CTA of mostly serial work: ask for the largest shared-memory carve-out (11 CTAs per SM)
+  DBV_CUDA(cudaFuncSetAttribute(det_mesh_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#endif
   DET_LAUNCH(det_mesh_kernel, dim3(Y.nx, Y.ny), DET_BW, 0, d_band, G, back0, sig0);
   return DBV_OK;
 }

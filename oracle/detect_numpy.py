@@ -42,14 +42,14 @@ f64 = np.float64
 
 
 def _seq_sum_mesh(a, valid):
-    """(ny, BW, nx, BW) float64 -> per-mesh sums in the order: columns of a mesh row one after the other, then the rows."""
+    """(ny, BW, nx, BW) float64 -> per-mesh sums in the order: the rows of a mesh column one after the other, then the columns."""
     a = np.where(valid, a, 0.0)
-    row = np.zeros(a.shape[:3], f64)  # (ny, BW, nx)
-    for c in range(BW):
-        row = row + a[:, :, :, c]
-    tot = np.zeros((a.shape[0], a.shape[2]), f64)
+    col = np.zeros((a.shape[0], a.shape[2], a.shape[3]), f64)  # (ny, nx, BW)
     for r in range(BW):
-        tot = tot + row[:, r, :]
+        col = col + a[:, r, :, :]
+    tot = np.zeros((a.shape[0], a.shape[2]), f64)
+    for c in range(BW):
+        tot = tot + col[:, :, c]
     return tot
 
 
