@@ -409,6 +409,18 @@ def field_extras(net, device, pk, quick=False):
         out["detect"] = {"ms": t_det, "ms_call_with_centres_on_host": t_call, "objects": int(len(cen)), "sources": N, "field": "4096x4096x6 f64, r band",
                          "api": "debvader_b200.detect.detection.DeviceDetector (dbv_detect): mesh background, 7x7 matched filter, threshold, components, order, barycentres",
                          "note": "restated from the published SExtractor algorithm, bit-exact with oracle/detect_numpy.py; parity with sep itself unpinned; no multi-threshold deblending / clean pass"}
+        try:  # DRAM bytes of one detection from the committed ncu pass (tools/detect_ncu_target.py, same field): the HBM roofline of the detector
+            import csv
+
+            rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r02_final_detect_ncu.csv"))) if len(r) > 14 and r[0].isdigit()]
+            dram = sum(float(r[14].replace(",", "")) for r in rows if r[12].startswith("dram__bytes"))
+            out["detect"]["roofline"] = {"bound": "hbm", "dram_bytes_per_detection": int(dram), "achieved_GBps_moved": round(dram / t_det / 1e6, 1),
+                                         "peak_GBps": pk["hbm_gbs"], "frac_moved": round(dram / t_det / 1e6 / pk["hbm_gbs"], 4),
+                                         "floor_ms": round(dram / pk["hbm_gbs"] / 1e6, 3),
+                                         "note": "16 small kernels, half of the bytes = the one strided pass over the 6-band field (805 MB for the r band of a 4096^2 f64 field); the rest is latency / launch bound (per-mesh serial statistics 0.30 ms)",
+                                         "source": "profiles/r02_final_detect_ncu.csv"}
+        except Exception:
+            pass
         import contextlib
         import io
 

@@ -27,6 +27,7 @@
     kernel<<<grid, block, smem, st>>>(__VA_ARGS__);    \
     DBV_LAUNCH_CHECK();                                \
   } while (0)
+#define DET_LAUNCH_NOSYNC DET_LAUNCH  // (the emulation runs barrier-free kernels without OS threads)
 #define DET_MEMSET(p, v, n) DBV_CUDA(cudaMemsetAsync(p, v, n, st))
 #define DET_DYN_SMEM(T, name) extern __shared__ T name[]
 #endif
@@ -818,8 +819,8 @@ extern "C" int dbv_detect_meshes(const void* region, int dtype, int64_t RH, int6
   const DetGeom G = det_geom(H, W, RH, RW, gy0, gx0, 1, 1, Y);
   const long long n = RH * RW;
   const int gb = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  if (dtype == DBV_F64) DET_LAUNCH(det_band_kernel<double>, gb, 256, 0, (const double*)region, RH, RW, pitch, C, band, d_band);
-  else DET_LAUNCH(det_band_kernel<float>, gb, 256, 0, (const float*)region, RH, RW, pitch, C, band, d_band);
+  if (dtype == DBV_F64) DET_LAUNCH_NOSYNC(det_band_kernel<double>, gb, 256, 0, (const double*)region, RH, RW, pitch, C, band, d_band);
+  else DET_LAUNCH_NOSYNC(det_band_kernel<float>, gb, 256, 0, (const float*)region, RH, RW, pitch, C, band, d_band);
 #ifndef DBV_EMULATE
   // 20 KB of static shared memory per 64-thread CTA of mostly serial work: ask for the largest shared-memory carve-out (11 CTAs per SM)
   DBV_CUDA(cudaFuncSetAttribute(det_mesh_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -874,22 +875,22 @@ extern "C" int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t g
   for (int i = 0; i < kh * kw; ++i) tp.v[i] = taps[i];
 
   const unsigned gm = (unsigned)((nm + 127) / 128);
-  DET_LAUNCH(det_mesh_fill_kernel, gm, 128, 0, back0, sig0, ny, nx, back1, sig1);
-  DET_LAUNCH(det_mesh_median_kernel, gm, 128, 0, back1, sig1, ny, nx, back, sig);
+  DET_LAUNCH_NOSYNC(det_mesh_fill_kernel, gm, 128, 0, back0, sig0, ny, nx, back1, sig1);
+  DET_LAUNCH_NOSYNC(det_mesh_median_kernel, gm, 128, 0, back1, sig1, ny, nx, back, sig);
   const int staged = nm <= 10240;
   DET_LAUNCH(det_mesh_rank_kernel, dim3(gm, 2), 128, staged ? sizeof(float) * nm : 0, back, sig, nm, staged, pick);
   // the spline recurrences keep their scratch in shared memory ([k][thread], 32 threads per CTA) whenever it fits in 48 KB
   const int st_y = ny <= 192, st_x = nx <= 192;
-  DET_LAUNCH(det_mesh_final_kernel, (unsigned)((nx + 31) / 32), 32, st_y ? sizeof(float) * 2 * 32 * ny : 0, pick, ny, nx, back, dback, mcp, mu, st_y, thresh_sigma,
+  DET_LAUNCH_NOSYNC(det_mesh_final_kernel, (unsigned)((nx + 31) / 32), 32, st_y ? sizeof(float) * 2 * 32 * ny : 0, pick, ny, nx, back, dback, mcp, mu, st_y, thresh_sigma,
              stats);
-  DET_LAUNCH(det_nodes_kernel, (unsigned)((RH + 31) / 32), 32, st_x ? sizeof(float) * 2 * 32 * nx : 0, back, dback, G, node, dnode, rcp, ru, st_x);
+  DET_LAUNCH_NOSYNC(det_nodes_kernel, (unsigned)((RH + 31) / 32), 32, st_x ? sizeof(float) * 2 * 32 * nx : 0, back, dback, G, node, dnode, rcp, ru, st_x);
   const dim3 grow((unsigned)((RW + 255) / 256), (unsigned)RH);
-  DET_LAUNCH(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, G, d_fg);
+  DET_LAUNCH_NOSYNC(det_foreground_kernel, grow, 256, 0, d_band, node, dnode, G, d_fg);
   const size_t fsm = sizeof(float) * (32 + kw - 1) * (32 + kh - 1);
   const dim3 gf((unsigned)((RW + 31) / 32), (unsigned)((RH + 31) / 32));
   if (kh == 7 && kw == 7) DET_LAUNCH(det_filter_tiled_kernel<7>, gf, 256, fsm, d_fg, G, tp, stats, d_conv, d_label);
   else DET_LAUNCH(det_filter_kernel, gf, 256, fsm, d_fg, G, kh, kw, tp, stats, d_conv, d_label);
-  DET_LAUNCH(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)RH, (int)RW);
+  DET_LAUNCH_NOSYNC(det_ccl_merge_kernel, grow, 256, 0, d_label, (int)RH, (int)RW);
   const unsigned gn = (unsigned)((n + 255) / 256);
   DET_MEMSET(d_npix, 0, n * 4);
   DET_MEMSET(d_last, 0xFF, n * 4);
@@ -898,8 +899,8 @@ extern "C" int dbv_detect_objects(int64_t RH, int64_t RW, int64_t gy0, int64_t g
   DET_MEMSET(d_touch, 0, n * 4);
   DET_MEMSET(d_flag, 0, n);
   DET_MEMSET(flags, 0, 4);
-  DET_LAUNCH(det_ccl_flatten_stats_kernel, grow, 256, 0, d_label, G, d_npix, d_last, d_xmin, d_xmax, d_touch);
-  DET_LAUNCH(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, G, d_flag);
+  DET_LAUNCH_NOSYNC(det_ccl_flatten_stats_kernel, grow, 256, 0, d_label, G, d_npix, d_last, d_xmin, d_xmax, d_touch);
+  DET_LAUNCH_NOSYNC(det_mark_kernel, gn, 256, 0, d_label, n, d_npix, d_last, minarea, G, d_flag);
   DET_LAUNCH(det_count_kernel, Y.nblk, 256, 0, d_flag, n, d_cnt);
   DET_LAUNCH(det_scan_kernel, 1, 1024, 0, d_cnt, Y.nblk, d_off, n_found);
   DET_LAUNCH(det_scatter_kernel, Y.nblk, 256, 0, d_flag, n, d_off, max_objects, d_end);

@@ -145,6 +145,42 @@ class DeviceDetector:
         return raw.view(torch.int32 if code == 2 else torch.float32).reshape(shape)
 
 
+def reduce_mesh_maps(maps, group=None):
+    """tiled detection, exchange 1: every rank has written the statistics of ITS meshes into a (2, ny, nx) tensor preset to -inf;
+    one all-reduce(MAX) completes the maps on every rank (a mesh computed by two ranks has the same bits on both)."""
+    import torch.distributed as dist
+
+    dist.all_reduce(maps, op=dist.ReduceOp.MAX, group=group)
+    return maps
+
+
+def merge_owned_objects(rows, flag, world, group=None):
+    """tiled detection, exchange 2: ``rows`` = (k, 6) float64 tensor [order key, centre row, centre col, x, y, npix] of the objects this
+    rank owns, ``flag`` != 0 when one of them reaches the rim of the rank's region.  Every rank learns every rank's (k, flag), then one
+    padded all-gather; returns ``(merged (N, 6) ndarray in ascending order key — identical on every rank —, heads)`` or ``(None,
+    heads)`` when any rank raised its flag (the caller then detects on the assembled field)."""
+    import torch
+    import torch.distributed as dist
+
+    k = int(rows.shape[0])
+    head = torch.tensor([k, int(flag)], dtype=torch.int64, device=rows.device)
+    heads = [torch.empty_like(head) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    heads = torch.stack(heads).cpu().numpy()
+    if heads[:, 1].any():
+        return None, heads
+    nmax = int(heads[:, 0].max())
+    if nmax == 0:
+        return np.zeros((0, 6)), heads
+    mine = torch.zeros((nmax, 6), dtype=torch.float64, device=rows.device)
+    if k:
+        mine[:k] = rows
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    allr = np.concatenate([parts[r][: int(heads[r, 0])].cpu().numpy() for r in range(world)])
+    return allr[np.argsort(allr[:, 0], kind="stable")], heads
+
+
 class TiledDeviceDetector(DeviceDetector):
     """The device detector on a field tiled over GPUs (one process per GPU; ``debvader_b200.parallel.LocalField``): every rank works
     on its owner tile + halo only and all ranks return the SAME global list of centres — the single-GPU list, bit for bit.
@@ -226,40 +262,27 @@ class TiledDeviceDetector(DeviceDetector):
             b["maps"].fill_(float("-inf"))
             _ffi.check(lib.dbv_detect_meshes(_ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, RH, RW, RW, Cn, self.band, R0, C0, F, F, self.max_objects,
                                              C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), _ffi.stream_ptr()))
-            dist.all_reduce(b["maps"], op=dist.ReduceOp.MAX, group=self.group)
+            reduce_mesh_maps(b["maps"], self.group)
             _ffi.check(lib.dbv_detect_objects(RH, RW, R0, C0, F, F, _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), self.taps.ctypes.data_as(C.c_void_p),
                                               int(self.taps.shape[0]), int(self.taps.shape[1]), self.thresh, self.minarea, int(F / 2), int(F / 2),
                                               r0, r1, c0, c1, self.max_objects, C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["n"]), _ffi.ptr(b["xy"]),
                                               _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["last"]), _ffi.ptr(b["flags"]), _ffi.ptr(b["stats"]),
                                               _ffi.stream_ptr()))
-            # every rank learns every rank's (count, flag); then one padded all-gather of the objects
-            head = torch.stack([b["n"][0], b["flags"][0]]).to(torch.int64)
-            heads = torch.empty((local.world, 2), dtype=torch.int64, device=t.device)
-            dist.all_gather_into_tensor(heads, head, group=self.group)
-            heads = heads.cpu().numpy()
-        if heads[:, 1].any() or (heads[:, 0] > self.max_objects).any():
-            return self._on_assembled_field(local, field_image, return_details)
-        nmax = int(heads[:, 0].max())
-        if nmax == 0:
-            out = np.zeros((0, 2))
-            return (out, {"x": np.zeros(0), "y": np.zeros(0), "npix": np.zeros(0, np.int32)}) if return_details else out
-        with torch.cuda.device(t.device):
-            mine = torch.zeros((nmax, 6), dtype=torch.float64, device=t.device)
-            k = int(heads[local.rank, 0])
+            nf = b["n"].cpu().numpy()[0], b["flags"].cpu().numpy()[0]  # one synchronisation
+            k = min(int(nf[0]), self.max_objects)
+            rows = torch.empty((k, 6), dtype=torch.float64, device=t.device)
             if k:
-                mine[:k, 0] = b["last"][:k].to(torch.float64)  # < 2^31: exact
-                mine[:k, 1:3] = b["centres"][:k]
-                mine[:k, 3:5] = b["xy"][:k]
-                mine[:k, 5] = b["npix"][:k].to(torch.float64)
-            allo = torch.empty((local.world, nmax, 6), dtype=torch.float64, device=t.device)
-            dist.all_gather_into_tensor(allo, mine, group=self.group)
-            allo = allo.cpu().numpy()
-        rows = np.concatenate([allo[r, : int(heads[r, 0])] for r in range(local.world)])
-        rows = rows[np.argsort(rows[:, 0], kind="stable")]
-        centres = np.ascontiguousarray(rows[:, 1:3])
+                rows[:, 0] = b["last"][:k].to(torch.float64)  # < 2^31: exact
+                rows[:, 1:3] = b["centres"][:k]
+                rows[:, 3:5] = b["xy"][:k]
+                rows[:, 5] = b["npix"][:k].to(torch.float64)
+            merged, _ = merge_owned_objects(rows, int(nf[1]) or int(nf[0] > self.max_objects), local.world, self.group)
+        if merged is None:
+            return self._on_assembled_field(local, field_image, return_details)
+        centres = np.ascontiguousarray(merged[:, 1:3])
         if return_details:
             st = b["stats"].cpu().numpy()
-            return centres, {"x": rows[:, 3], "y": rows[:, 4], "npix": rows[:, 5].astype(np.int32), "last": rows[:, 0].astype(np.int64),
+            return centres, {"x": merged[:, 3], "y": merged[:, 4], "npix": merged[:, 5].astype(np.int32), "last": merged[:, 0].astype(np.int64),
                              "globalback": st[0], "globalrms": st[1], "thresh": st[2]}
         return centres
 

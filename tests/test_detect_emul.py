@@ -161,3 +161,91 @@ def test_emulated_tiled_detection_flags_an_object_that_leaves_the_region(emu):
     field[0] += (40.0 * np.exp(-((xx - 131) ** 2 + (yy - 100) ** 2) / (2 * 14.0 ** 2)))[..., None]  # footprint ~ 60 px across the tile edge at x = 128
     objs, flagged, _ = run_emulated_tiled(emu, field, 2)
     assert flagged >= 1
+
+
+def _tiled_worker(rank, world, port, so_path, q):
+    """one gloo rank of the tiled detector: the emulated kernels for the device work, the PRODUCT's exchange functions
+    (detect/detection.py: reduce_mesh_maps, merge_owned_objects) over torch.distributed for the two collectives"""
+    import torch
+    import torch.distributed as dist
+
+    from debvader_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = C.CDLL(so_path)
+        lib.dbv_detect_scratch_bytes_region.restype = C.c_int64
+        lib.dbv_detect_scratch_bytes_region.argtypes = [C.c_int64] * 5
+        lib.dbv_detect_meshes.restype = C.c_int
+        lib.dbv_detect_meshes.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 3 + [C.c_int, C.c_int] + [C.c_int64] * 5 + [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.dbv_detect_objects.restype = C.c_int
+        lib.dbv_detect_objects.argtypes = [C.c_int64] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_int64] * 5 + \
+            [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        results = {}
+        for tag, wide in (("plain", False), ("wide", True)):
+            field = make_field(128, 14, seed=41)[0]
+            if wide:
+                yy, xx = np.mgrid[0:128, 0:128]
+                field[0] += (40.0 * np.exp(-((xx - 66) ** 2 + (yy - 50) ** 2) / (2 * 12.0 ** 2)))[..., None]
+            F, M = 128, 256
+            assert det.TiledDeviceDetector.meshes_covered(F, world, 30)
+            R0, R1, C0, C1 = parallel.region_bounds(F, world, 30)[rank]
+            r0, r1, c0, c1 = parallel.tile_bounds(F, world)[rank]
+            reg = np.ascontiguousarray(field[0, R0:R1, C0:C1])
+            RH, RW = reg.shape[:2]
+            nbytes = lib.dbv_detect_scratch_bytes_region(F, F, RH, RW, M)
+            raw = np.zeros(nbytes + 256, np.uint8)
+            base = raw.ctypes.data + (-raw.ctypes.data) % 256
+            maps = torch.full((2, 2, 2), float("-inf"), dtype=torch.float32)
+            assert lib.dbv_detect_meshes(reg.ctypes.data, 1, RH, RW, RW, 6, 2, R0, C0, F, F, M, base, nbytes, maps[0].data_ptr(), maps[1].data_ptr(), None) == 0
+            det.reduce_mesh_maps(maps)
+            assert torch.isfinite(maps).all()
+            taps = det.normalised_taps()
+            n, flags, stats = np.zeros(1, np.int32), np.zeros(4, np.int32), np.zeros(4, np.float32)
+            xy, cen, npix, last = np.zeros((M, 2)), np.zeros((M, 2)), np.zeros(M, np.int32), np.zeros(M, np.int64)
+            assert lib.dbv_detect_objects(RH, RW, R0, C0, F, F, maps[0].data_ptr(), maps[1].data_ptr(), taps.ctypes.data, 7, 7, 1.5, 4, 64, 64, r0, r1, c0, c1, M, base,
+                                          nbytes, n.ctypes.data, xy.ctypes.data, cen.ctypes.data, npix.ctypes.data, last.ctypes.data, flags.ctypes.data,
+                                          stats.ctypes.data, None) == 0
+            k = int(n[0])
+            rows = torch.from_numpy(np.concatenate([last[:k, None].astype(np.float64), cen[:k], xy[:k], npix[:k, None].astype(np.float64)], axis=1))
+            merged, heads = det.merge_owned_objects(rows, int(flags[0]), world)
+            results[tag] = (None if merged is None else merged.copy(), heads.copy())
+        q.put((rank, results))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tiled_detector_exchanges_over_gloo(emu):
+    """world_size 2 over gloo: the N > 1 choreography of TiledDeviceDetector (all-reduce(MAX) of the mesh maps preset to -inf, counts +
+    flags, padded all-gather, merge by the order key, the collective decision to take the assembled-field path) with the emulated
+    kernels standing in for the GPU — every rank ends with the whole-field oracle's list"""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    so = os.path.join(EMU, "_build", "libdetect_emul.so")
+    procs = [ctx.Process(target=_tiled_worker, args=(r, 2, port, so, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c_ref, o = D.detect(make_field(128, 14, seed=41)[0], det.FILTER_KERNEL, return_details=True)
+    assert len(c_ref) > 5
+    for rank in (0, 1):
+        merged, heads = got[rank]["plain"]
+        assert heads[:, 1].sum() == 0 and heads[:, 0].sum() == len(c_ref)
+        np.testing.assert_array_equal(merged[:, 0].astype(np.int64), o["last"])
+        np.testing.assert_array_equal(merged[:, 1:3], c_ref)
+        np.testing.assert_array_equal(merged[:, 3], o["x"])
+        np.testing.assert_array_equal(merged[:, 5].astype(np.int64), o["npix"])
+        merged_w, heads_w = got[rank]["wide"]
+        assert merged_w is None and heads_w[:, 1].any()  # both ranks decide together to detect on the assembled field

@@ -82,7 +82,25 @@ static inline void emu_launch(dim3 grid, dim3 block, size_t smem, const std::fun
         for (auto& x : th) x.join();
       }
 }
+// kernels without __syncthreads(): the CUDA threads of a CTA run one after the other on the calling thread (a std::thread per pixel is slow)
+static inline void emu_launch_seq(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  gridDim = grid;
+  blockDim = block;
+  const unsigned nt = block.x * block.y * block.z;
+  std::vector<char> dyn(smem + 16);
+  g_emu_dynsmem = dyn.data();
+  g_emu_bar = nullptr;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx)
+        for (unsigned t = 0; t < nt; ++t) {
+          threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+          blockIdx = {bx, by, bz};
+          body();
+        }
+}
 typedef void* cudaStream_t;
 #define DET_LAUNCH(kernel, grid, block, smem, ...) emu_launch(dim3(grid), dim3(block), smem, [&] { kernel(__VA_ARGS__); })
+#define DET_LAUNCH_NOSYNC(kernel, grid, block, smem, ...) emu_launch_seq(dim3(grid), dim3(block), smem, [&] { kernel(__VA_ARGS__); })
 #define DET_MEMSET(p, v, n) memset(p, v, n)
 #define DET_DYN_SMEM(T, name) T* name = (T*)g_emu_dynsmem
