@@ -249,3 +249,34 @@ def test_tiled_detector_exchanges_over_gloo(emu):
         np.testing.assert_array_equal(merged[:, 5].astype(np.int64), o["npix"])
         merged_w, heads_w = got[rank]["wide"]
         assert merged_w is None and heads_w[:, 1].any()  # both ranks decide together to detect on the assembled field
+
+
+@pytest.mark.parametrize("case", ["zeros", "constant", "tiny_12x9", "lone_pixels", "step_background"])
+def test_emulated_kernels_on_degenerate_fields(emu, case):
+    """edge cases: zero / constant fields (sigma = 0: one histogram level, threshold 0, nothing above it), a field smaller than the filter
+    footprint of its own corners, detections below minarea, a background step across meshes — no hang, no NaN, same answer as the oracle"""
+    rng = np.random.default_rng(51)
+    if case == "zeros":
+        field = np.zeros((1, 70, 70, 6))
+    elif case == "constant":
+        field = np.full((1, 70, 70, 6), 3.25)
+    elif case == "tiny_12x9":
+        field = rng.normal(0, 0.03, (1, 12, 9, 6))
+        field[0, 4:8, 3:6] += 1.0
+    elif case == "lone_pixels":
+        field = rng.normal(0, 0.03, (1, 70, 70, 6))
+        field[0, 10, 10] += 0.5   # the filter spreads it, but too faintly for 4 pixels above the threshold
+        field[0, 40:43, 40:43] += 2.0
+    else:
+        field = rng.normal(0, 0.03, (1, 130, 130, 6))
+        field[0, :, 64:] += 0.5
+    c_ref, o = D.detect(field, det.FILTER_KERNEL, return_details=True)
+    e = run_emulated(emu, field)
+    assert e["n"] == len(c_ref)
+    assert np.array_equal(e["conv"], o["conv"]) and np.array_equal(e["fg"], o["fg"]) and np.array_equal(e["back"], o["back"])
+    assert e["stats"][1] == o["globalrms"] and np.isfinite(e["stats"]).all()
+    np.testing.assert_array_equal(e["centres"], c_ref)
+    if case in ("zeros", "constant"):
+        assert e["n"] == 0
+    if case == "lone_pixels":
+        assert e["n"] >= 1
