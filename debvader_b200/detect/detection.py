@@ -58,6 +58,32 @@ class DeviceDetector:
         self._buf = {}
         self.last = None  # details of the last call (device tensors)
 
+    # ---- device plumbing: the five places that touch CUDA.  tests/test_detect_emul.py overrides them to drive ALL of the host logic
+    # below (buffers, calls, synchronisation, the tiled exchanges and fall-backs) on CPU tensors with the kernels compiled as host C++.
+    def _lib(self):
+        from .. import _ffi
+
+        return _ffi.lib()
+
+    def _check(self, rc):
+        from .. import _ffi
+
+        return _ffi.check(rc)
+
+    def _device_ctx(self, t):
+        import torch
+
+        return torch.cuda.device(t.device)
+
+    def _stream(self):
+        from .. import _ffi
+
+        return _ffi.stream_ptr()
+
+    def _require_device(self, t):
+        if not t.is_cuda:
+            raise ValueError("the device detector needs a CUDA tensor (or a host array to upload)")
+
     def _buffers(self, H, W, dev):
         import torch
 
@@ -66,7 +92,7 @@ class DeviceDetector:
         key = (H, W, str(dev))
         b = self._buf.get(key)
         if b is None:
-            nbytes = int(_ffi.lib().dbv_detect_scratch_bytes(H, W, self.max_objects))
+            nbytes = int(self._lib().dbv_detect_scratch_bytes(H, W, self.max_objects))
             M = self.max_objects
             b = {
                 "scratch": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev),
@@ -93,8 +119,7 @@ class DeviceDetector:
         if not isinstance(t, torch.Tensor):
             dev = torch.device(self.device if self.device is not None else "cuda")
             t = torch.as_tensor(np.ascontiguousarray(np.asarray(field_image))).to(dev)
-        if not t.is_cuda:
-            raise ValueError("the device detector needs a CUDA tensor (or a host array to upload)")
+        self._require_device(t)
         if t.ndim == 4:
             if t.shape[0] != 1:
                 raise ValueError(f"field_image must have shape (1, F, F, C), got {tuple(t.shape)}")
@@ -105,12 +130,12 @@ class DeviceDetector:
         if not 0 <= band < Cn:
             raise ValueError(f"band {band} outside the field's {Cn} bands")
         b = self._buffers(H, W, t.device)
-        with torch.cuda.device(t.device):
-            _ffi.check(_ffi.lib().dbv_detect(
+        with self._device_ctx(t):
+            self._check(self._lib().dbv_detect(
                 _ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, H, W, W, Cn, band,
                 self.taps.ctypes.data_as(C.c_void_p), int(self.taps.shape[0]), int(self.taps.shape[1]), self.thresh, self.minarea,
                 int(H / 2), int(W / 2), self.max_objects, C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["n"]), _ffi.ptr(b["xy"]),
-                _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["stats"]), _ffi.stream_ptr()))
+                _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["stats"]), self._stream()))
         b["shape"] = (H, W)
         self.last = b
         return b
@@ -136,7 +161,7 @@ class DeviceDetector:
         b = self.last
         H, W = b["shape"]
         code = {"fg": 0, "conv": 1, "label": 2, "back": 3, "sigma": 4, "back_raw": 5, "sigma_raw": 6}[what]
-        p = _ffi.lib().dbv_detect_plane(C.c_void_p(b["base"]), H, W, self.max_objects, code)
+        p = self._lib().dbv_detect_plane(C.c_void_p(b["base"]), H, W, self.max_objects, code)
         off = int(p) - b["scratch"].data_ptr()
         ny, nx = (H - 1) // 64 + 1, (W - 1) // 64 + 1
         shape = (H, W) if code < 3 else (ny, nx)
@@ -223,7 +248,7 @@ class TiledDeviceDetector(DeviceDetector):
         b = self._rbuf.get(key)
         if b is None:
             M = self.max_objects
-            nbytes = int(_ffi.lib().dbv_detect_scratch_bytes_region(F, F, RH, RW, M))
+            nbytes = int(self._lib().dbv_detect_scratch_bytes_region(F, F, RH, RW, M))
             n = (F - 1) // 64 + 1
             b = {"scratch": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev), "nbytes": nbytes,
                  "maps": torch.empty((2, n, n), dtype=torch.float32, device=dev),
@@ -246,8 +271,9 @@ class TiledDeviceDetector(DeviceDetector):
         t = local.data if field_image is None else field_image
         if t.ndim == 4:
             t = t[0]
-        if t.dtype not in (torch.float64, torch.float32) or not t.is_contiguous() or not t.is_cuda:
-            raise ValueError("the tiled detector needs the rank's contiguous CUDA region tensor")
+        self._require_device(t)
+        if t.dtype not in (torch.float64, torch.float32) or not t.is_contiguous():
+            raise ValueError("the tiled detector needs the rank's contiguous region tensor (float64 / float32)")
         F = local.field_size
         R0, R1, C0, C1 = local.region
         r0, r1, c0, c1 = local.tile
@@ -257,17 +283,17 @@ class TiledDeviceDetector(DeviceDetector):
         if not self.meshes_covered(F, local.world, local.halo):
             return self._on_assembled_field(local, field_image, return_details)
         b = self._region_buffers(F, RH, RW, t.device)
-        lib = _ffi.lib()
-        with torch.cuda.device(t.device):
+        lib = self._lib()
+        with self._device_ctx(t):
             b["maps"].fill_(float("-inf"))
-            _ffi.check(lib.dbv_detect_meshes(_ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, RH, RW, RW, Cn, self.band, R0, C0, F, F, self.max_objects,
-                                             C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), _ffi.stream_ptr()))
+            self._check(lib.dbv_detect_meshes(_ffi.ptr(t), 1 if t.dtype == torch.float64 else 0, RH, RW, RW, Cn, self.band, R0, C0, F, F, self.max_objects,
+                                             C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), self._stream()))
             reduce_mesh_maps(b["maps"], self.group)
-            _ffi.check(lib.dbv_detect_objects(RH, RW, R0, C0, F, F, _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), self.taps.ctypes.data_as(C.c_void_p),
+            self._check(lib.dbv_detect_objects(RH, RW, R0, C0, F, F, _ffi.ptr(b["maps"][0]), _ffi.ptr(b["maps"][1]), self.taps.ctypes.data_as(C.c_void_p),
                                               int(self.taps.shape[0]), int(self.taps.shape[1]), self.thresh, self.minarea, int(F / 2), int(F / 2),
                                               r0, r1, c0, c1, self.max_objects, C.c_void_p(b["base"]), b["nbytes"], _ffi.ptr(b["n"]), _ffi.ptr(b["xy"]),
                                               _ffi.ptr(b["centres"]), _ffi.ptr(b["npix"]), _ffi.ptr(b["last"]), _ffi.ptr(b["flags"]), _ffi.ptr(b["stats"]),
-                                              _ffi.stream_ptr()))
+                                              self._stream()))
             nf = b["n"].cpu().numpy()[0], b["flags"].cpu().numpy()[0]  # one synchronisation
             k = min(int(nf[0]), self.max_objects)
             rows = torch.empty((k, 6), dtype=torch.float64, device=t.device)
@@ -302,11 +328,11 @@ class TiledDeviceDetector(DeviceDetector):
         mh, mw = max(b[1] - b[0] for b in tb), max(b[3] - b[2] for b in tb)
         pad = torch.zeros((mh, mw), dtype=tile.dtype, device=tile.device)
         pad[: tile.shape[0], : tile.shape[1]] = tile
-        parts = torch.empty((local.world, mh, mw), dtype=tile.dtype, device=tile.device)
-        dist.all_gather_into_tensor(parts, pad, group=self.group)
+        parts = [torch.empty_like(pad) for _ in range(local.world)]
+        dist.all_gather(parts, pad, group=self.group)
         full = torch.empty((1, F, F, 1), dtype=tile.dtype, device=tile.device)
         for r, (r0, r1, c0, c1) in enumerate(tb):
-            full[0, r0:r1, c0:c1, 0] = parts[r, : r1 - r0, : c1 - c0]
+            full[0, r0:r1, c0:c1, 0] = parts[r][: r1 - r0, : c1 - c0]
         del parts, pad
         return DeviceDetector.__call__(self, full, return_details=return_details, band=0)
 

@@ -163,9 +163,51 @@ def test_emulated_tiled_detection_flags_an_object_that_leaves_the_region(emu):
     assert flagged >= 1
 
 
+def _declare(lib):
+    """ctypes signatures of the emulated library = include/debvader_b200.h"""
+    i64, vp = C.c_int64, C.c_void_p
+    lib.dbv_detect_scratch_bytes.restype = i64
+    lib.dbv_detect_scratch_bytes.argtypes = [i64] * 3
+    lib.dbv_detect_scratch_bytes_region.restype = i64
+    lib.dbv_detect_scratch_bytes_region.argtypes = [i64] * 5
+    lib.dbv_detect.restype = C.c_int
+    lib.dbv_detect.argtypes = [vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, i64, vp, i64] + [vp] * 6
+    lib.dbv_detect_meshes.restype = C.c_int
+    lib.dbv_detect_meshes.argtypes = [vp, C.c_int] + [i64] * 3 + [C.c_int, C.c_int] + [i64] * 5 + [vp, i64, vp, vp, vp]
+    lib.dbv_detect_objects.restype = C.c_int
+    lib.dbv_detect_objects.argtypes = [i64] * 6 + [vp] * 3 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [i64] * 5 + [vp, i64] + [vp] * 8
+    lib.dbv_detect_plane.restype = vp
+    lib.dbv_detect_plane.argtypes = [vp, i64, i64, i64, C.c_int]
+    return lib
+
+
+def _emulated_detector_class(lib):
+    """the PRODUCT's TiledDeviceDetector with its five device hooks pointed at the emulated library and CPU tensors: everything else —
+    buffers, the two phases, synchronisation, both exchanges, the collective fall-back decision, the assembled-band path — is product code"""
+    import contextlib
+
+    class EmuTiled(det.TiledDeviceDetector):
+        def _lib(self):
+            return lib
+
+        def _check(self, rc):
+            assert rc == 0, rc
+            return rc
+
+        def _device_ctx(self, t):
+            return contextlib.nullcontext()
+
+        def _stream(self):
+            return None
+
+        def _require_device(self, t):
+            pass
+
+    return EmuTiled
+
+
 def _tiled_worker(rank, world, port, so_path, q):
-    """one gloo rank of the tiled detector: the emulated kernels for the device work, the PRODUCT's exchange functions
-    (detect/detection.py: reduce_mesh_maps, merge_owned_objects) over torch.distributed for the two collectives"""
+    """one gloo rank: TiledDeviceDetector itself (detect/detection.py) on this rank's LocalField, CPU tensors, emulated kernels"""
     import torch
     import torch.distributed as dist
 
@@ -174,52 +216,30 @@ def _tiled_worker(rank, world, port, so_path, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        lib = C.CDLL(so_path)
-        lib.dbv_detect_scratch_bytes_region.restype = C.c_int64
-        lib.dbv_detect_scratch_bytes_region.argtypes = [C.c_int64] * 5
-        lib.dbv_detect_meshes.restype = C.c_int
-        lib.dbv_detect_meshes.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 3 + [C.c_int, C.c_int] + [C.c_int64] * 5 + [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.dbv_detect_objects.restype = C.c_int
-        lib.dbv_detect_objects.argtypes = [C.c_int64] * 6 + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_int64] * 5 + \
-            [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        Emu = _emulated_detector_class(_declare(C.CDLL(so_path)))
         results = {}
         for tag, wide in (("plain", False), ("wide", True)):
             field = make_field(128, 14, seed=41)[0]
             if wide:
                 yy, xx = np.mgrid[0:128, 0:128]
                 field[0] += (40.0 * np.exp(-((xx - 66) ** 2 + (yy - 50) ** 2) / (2 * 12.0 ** 2)))[..., None]
-            F, M = 128, 256
-            assert det.TiledDeviceDetector.meshes_covered(F, world, 30)
-            R0, R1, C0, C1 = parallel.region_bounds(F, world, 30)[rank]
-            r0, r1, c0, c1 = parallel.tile_bounds(F, world)[rank]
-            reg = np.ascontiguousarray(field[0, R0:R1, C0:C1])
-            RH, RW = reg.shape[:2]
-            nbytes = lib.dbv_detect_scratch_bytes_region(F, F, RH, RW, M)
-            raw = np.zeros(nbytes + 256, np.uint8)
-            base = raw.ctypes.data + (-raw.ctypes.data) % 256
-            maps = torch.full((2, 2, 2), float("-inf"), dtype=torch.float32)
-            assert lib.dbv_detect_meshes(reg.ctypes.data, 1, RH, RW, RW, 6, 2, R0, C0, F, F, M, base, nbytes, maps[0].data_ptr(), maps[1].data_ptr(), None) == 0
-            det.reduce_mesh_maps(maps)
-            assert torch.isfinite(maps).all()
-            taps = det.normalised_taps()
-            n, flags, stats = np.zeros(1, np.int32), np.zeros(4, np.int32), np.zeros(4, np.float32)
-            xy, cen, npix, last = np.zeros((M, 2)), np.zeros((M, 2)), np.zeros(M, np.int32), np.zeros(M, np.int64)
-            assert lib.dbv_detect_objects(RH, RW, R0, C0, F, F, maps[0].data_ptr(), maps[1].data_ptr(), taps.ctypes.data, 7, 7, 1.5, 4, 64, 64, r0, r1, c0, c1, M, base,
-                                          nbytes, n.ctypes.data, xy.ctypes.data, cen.ctypes.data, npix.ctypes.data, last.ctypes.data, flags.ctypes.data,
-                                          stats.ctypes.data, None) == 0
-            k = int(n[0])
-            rows = torch.from_numpy(np.concatenate([last[:k, None].astype(np.float64), cen[:k], xy[:k], npix[:k, None].astype(np.float64)], axis=1))
-            merged, heads = det.merge_owned_objects(rows, int(flags[0]), world)
-            results[tag] = (None if merged is None else merged.copy(), heads.copy())
+            R0, R1, C0, C1 = parallel.region_bounds(128, world, 30)[rank]
+            local = parallel.LocalField(torch.from_numpy(np.ascontiguousarray(field[:, R0:R1, C0:C1])), 128, rank, world)
+            d = Emu(device="cpu", max_objects=256)
+            centres, info = d(local.data, local, return_details=True)
+            again = d(local.data, local)  # buffers are reused
+            assert np.array_equal(again, centres)
+            results[tag] = (centres, info["x"], info["npix"], d.fallbacks)
         q.put((rank, results))
     finally:
         dist.destroy_process_group()
 
 
-def test_tiled_detector_exchanges_over_gloo(emu):
-    """world_size 2 over gloo: the N > 1 choreography of TiledDeviceDetector (all-reduce(MAX) of the mesh maps preset to -inf, counts +
-    flags, padded all-gather, merge by the order key, the collective decision to take the assembled-field path) with the emulated
-    kernels standing in for the GPU — every rank ends with the whole-field oracle's list"""
+def test_tiled_detector_class_over_gloo(emu):
+    """world_size 2 over gloo: the product's TiledDeviceDetector end to end — all-reduce(MAX) of the mesh maps preset to -inf, counts +
+    flags, padded all-gather, merge by the order key, and, for a footprint wider than the halo, the collective decision to assemble the
+    detection band on every rank and detect on it — with the emulated kernels standing in for the GPU.  Every rank must end with the
+    whole-field oracle's list."""
     import socket
 
     import torch.multiprocessing as mp
@@ -238,17 +258,43 @@ def test_tiled_detector_exchanges_over_gloo(emu):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    c_ref, o = D.detect(make_field(128, 14, seed=41)[0], det.FILTER_KERNEL, return_details=True)
+    field = make_field(128, 14, seed=41)[0]
+    c_ref, o = D.detect(field, det.FILTER_KERNEL, return_details=True)
+    yy, xx = np.mgrid[0:128, 0:128]
+    wide = field.copy()
+    wide[0] += (40.0 * np.exp(-((xx - 66) ** 2 + (yy - 50) ** 2) / (2 * 12.0 ** 2)))[..., None]
+    w_ref, w_o = D.detect(wide, det.FILTER_KERNEL, return_details=True)
     assert len(c_ref) > 5
     for rank in (0, 1):
-        merged, heads = got[rank]["plain"]
-        assert heads[:, 1].sum() == 0 and heads[:, 0].sum() == len(c_ref)
-        np.testing.assert_array_equal(merged[:, 0].astype(np.int64), o["last"])
-        np.testing.assert_array_equal(merged[:, 1:3], c_ref)
-        np.testing.assert_array_equal(merged[:, 3], o["x"])
-        np.testing.assert_array_equal(merged[:, 5].astype(np.int64), o["npix"])
-        merged_w, heads_w = got[rank]["wide"]
-        assert merged_w is None and heads_w[:, 1].any()  # both ranks decide together to detect on the assembled field
+        centres, x, npix, fallbacks = got[rank]["plain"]
+        assert fallbacks == 0
+        np.testing.assert_array_equal(centres, c_ref)
+        np.testing.assert_array_equal(x, o["x"])
+        np.testing.assert_array_equal(npix, o["npix"])
+        centres, x, npix, fallbacks = got[rank]["wide"]
+        assert fallbacks == 2  # both calls took the assembled-band path, on both ranks
+        np.testing.assert_array_equal(centres, w_ref)
+        np.testing.assert_array_equal(x, w_o["x"])
+
+
+def test_single_gpu_detector_class_on_the_emulated_library(emu):
+    """DeviceDetector's own host logic (buffers, run / call, plane views, host arrays) with the emulated kernels"""
+    import torch
+
+    Emu = _emulated_detector_class(_declare(emu))
+    field = make_field(100, 8, seed=43)[0]
+    c_ref, o = D.detect(field, det.FILTER_KERNEL, return_details=True)
+    d = Emu(device="cpu", max_objects=64)
+    c, info = d(torch.from_numpy(field), return_details=True)
+    np.testing.assert_array_equal(c, c_ref)
+    np.testing.assert_array_equal(info["y"], o["y"])
+    assert np.array_equal(d.plane("conv").numpy(), o["conv"]) and np.array_equal(d.plane("back").numpy(), o["back"])
+    np.testing.assert_array_equal(d(field), c_ref)  # a host array is "uploaded" to the detector's device
+    with pytest.raises(ValueError):
+        d(torch.from_numpy(field[:, :, :, :2]))  # no band 2
+    small = Emu(device="cpu", max_objects=2)
+    with pytest.raises(RuntimeError, match="more than max_objects"):
+        small(torch.from_numpy(field))
 
 
 @pytest.mark.parametrize("case", ["zeros", "constant", "tiny_12x9", "lone_pixels", "step_background"])
